@@ -1,0 +1,184 @@
+/*
+ * basevar_b200.h -- C ABI of the B200-native `basevar basetype` per-site statistical core.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer; the seam
+ * it exposes is the C++ class `BaseType` and the free function `strand_bias`:
+ *
+ *   reference interface                                         replaced by
+ *   ----------------------------------------------------------  ---------------------------------
+ *   struct BatchInfo                    src/basetype.h:25-43     bv_tile (packed SoA planes)
+ *   BaseType::BaseType(BatchInfo*,af)   src/basetype.h:105       bv_tile_submit / bv_tile_run_device
+ *                                       src/basetype.cpp:22-72   (site histogram kernel stage)
+ *   BaseType::lrt()                     src/basetype.h:117-118   same call (EM + LRT + QUAL stage)
+ *                                       src/basetype.cpp:130-199
+ *   EM / e_step / m_step                src/algorithm.h:148-255  same call
+ *   chi2_test -> kf_gammaq              src/algorithm.h:44-46    same call
+ *   strand_bias(...)                    src/basetype.h:178-181   same call (fwd/rev counts + FS)
+ *                                       src/basetype.cpp:244-295
+ *   fisher_exact_test -> kt_fisher_exact src/algorithm.h:62-74   same call
+ *   getters get_alt_bases/get_lrt_af/   src/basetype.h:120-151   fields of bv_site_out
+ *     get_var_qual/get_total_depth/get_base_depth
+ *   per-site driver _basevar_caller     src/basetype_caller.cpp:667-765   caller loops over bv_site_out
+ *
+ * Everything is `extern "C"`, plain pointers and sizes, POD structs; no exception crosses the
+ * boundary.  Every entry point returns BV_OK (0) or a negative status; bv_last_error() gives text.
+ * A context is bound to one CUDA device and must not be shared between host threads; use one
+ * context per (GPU, host worker).  Calls on one slot are stream ordered.
+ *
+ * There is NO CPU fallback: without a usable CUDA device bv_create() fails with BV_ERR_CUDA.
+ */
+#ifndef BASEVAR_B200_H
+#define BASEVAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BV_VERSION_MAJOR 0
+#define BV_VERSION_MINOR 1
+
+/* ---- status codes ---------------------------------------------------------------------------- */
+#define BV_OK            0
+#define BV_ERR_ARG      -1   /* bad argument (null pointer, pitch not multiple of 16, tile too large) */
+#define BV_ERR_CUDA     -2   /* CUDA runtime error or no device; text in bv_last_error()            */
+#define BV_ERR_STATE    -3   /* slot busy / nothing submitted                                         */
+#define BV_ERR_NOMEM    -4
+
+/* ---- cell encoding of the packed SoA planes (one u8 per sample per site, per plane) ---------- */
+/* base plane: first character of BatchInfo::align_bases[i] (src/basetype.cpp:50)                  */
+#define BV_BASE_A      0
+#define BV_BASE_C      1
+#define BV_BASE_G      2
+#define BV_BASE_T      3
+#define BV_BASE_OTHER  4   /* any other single character: counted in total depth, never an allele    */
+                           /* (src/basetype.cpp:58-64 gives it the row {e/3,e/3,e/3,e/3})            */
+#define BV_BASE_N      5   /* 'N' = uncovered / masked: skipped (src/basetype.cpp:51)                 */
+#define BV_BASE_INS    6   /* "+SEQ": skipped by the SNP caller                                       */
+#define BV_BASE_DEL    7   /* "-SEQ": skipped by the SNP caller                                       */
+/* qual plane: phred = align_base_quals[i] - 33, 0..93 (src/basetype.cpp:47)                        */
+#define BV_QUAL_MAX    93
+/* strand plane: map_strands[i] */
+#define BV_STRAND_FWD  0   /* '+' */
+#define BV_STRAND_REV  1   /* '-' */
+#define BV_STRAND_NONE 2   /* '.' (uncovered) or '*' */
+
+/* ---- per-site flags --------------------------------------------------------------------------- */
+#define BV_FLAG_BAD_STRAND   0x01u /* counted cell whose strand is not +/-: reference throws (basetype.cpp:271) */
+#define BV_FLAG_BAD_QUAL     0x02u /* counted cell with phred > 93                                             */
+#define BV_FLAG_ZERO_SUBSET  0x04u /* a candidate subset has zero depth: reference throws (basetype.cpp:113)  */
+#define BV_FLAG_MONO_QUAL    0x08u /* QUAL came from the mono-allelic 5000 rule (basetype.cpp:182-185)        */
+#define BV_FLAG_NEAR_LRT     0x10u /* some LRT decision had |chi2 - threshold| < 1e-9*threshold (possible flip) */
+#define BV_FLAG_NEAR_MINAF   0x20u /* some depth/total is within 4 ulp of min_af (never flips: exact compare)  */
+#define BV_FLAG_EM_MAXITER   0x40u /* an EM used all em_max_iter iterations                                   */
+
+#define BV_EM_ABS_INT_TRUNC 0  /* as built by g++/glibc: abs() resolves to int abs(int) (algorithm.h:245)   */
+#define BV_EM_ABS_DOUBLE    1  /* fabs(): the evident intent                                                */
+
+#define BV_LOC_HOST   0
+#define BV_LOC_DEVICE 1
+
+/* ---- parameters ------------------------------------------------------------------------------- */
+typedef struct bv_params {
+    float    min_af;         /* CLI --min-af as FLOAT (basetype_utils.h:80), widened to double inside;    */
+                             /* caller applies min(100.0f/n_bam, min_af) (basetype_caller.cpp:122)        */
+    int32_t  lrt_threshold;  /* 24  (basetype.h:21)                                                       */
+    int32_t  em_max_iter;    /* 100 (algorithm.h:213)                                                     */
+    float    em_eps;         /* 0.001f (algorithm.h:213)                                                  */
+    int32_t  em_abs_mode;    /* BV_EM_ABS_*                                                               */
+    uint32_t max_samples;    /* capacity: largest n_samples of any tile                                   */
+    uint32_t max_sites;      /* capacity: largest n_sites of any tile submitted through a slot            */
+    uint32_t n_slots;        /* in-flight tile slots (each owns a stream + pinned staging); >= 1          */
+    uint32_t reserved;
+} bv_params;
+
+/* ---- one tile of the packed site-major SoA pileup --------------------------------------------- */
+typedef struct bv_tile {
+    const uint8_t* base;     /* [n_sites][pitch]  BV_BASE_*                                               */
+    const uint8_t* qual;     /* [n_sites][pitch]  phred                                                   */
+    const uint8_t* strand;   /* [n_sites][pitch]  BV_STRAND_*                                             */
+    const uint8_t* ref_base; /* [n_sites] raw ASCII of BatchInfo::ref_base[0] (may be lowercase or 'N')  */
+    uint64_t pitch;          /* bytes between consecutive site rows, multiple of 16, >= n_samples;        */
+                             /* padding cells [n_samples, pitch) are ignored                              */
+    uint32_t n_sites;
+    uint32_t n_samples;
+    int32_t  location;       /* BV_LOC_HOST (pinned or pageable) or BV_LOC_DEVICE                         */
+    int32_t  reserved;
+} bv_tile;
+
+/* ---- per-site result record: fixed 128 bytes --------------------------------------------------- */
+typedef struct bv_site_out {
+    uint32_t depth[4];       /* A,C,G,T read counts       (BaseType::get_base_depth)                      */
+    uint32_t depth_other;    /* BV_BASE_OTHER cells; total depth = sum(depth)+depth_other                 */
+    uint32_t n_indel;        /* BV_BASE_INS/DEL cells (skipped)                                           */
+    uint32_t fwd[4];         /* '+' strand count per base (strand_bias, any ALT set derivable on host)    */
+    uint32_t rev[4];         /* '-' strand count per base                                                 */
+    uint8_t  n_alt;          /* number of ALT alleles (0 => not a variant site)                           */
+    uint8_t  alt[4];         /* ALT base codes, in the reference's order (ACGT order of the active set)   */
+    uint8_t  n_active;       /* |active_bases| after backward elimination                                 */
+    uint8_t  flags;          /* BV_FLAG_*                                                                 */
+    uint8_t  em_calls;       /* number of EM invocations (saturating)                                     */
+    double   af[4];          /* AF by EM+LRT for alt[i] (BaseType::get_lrt_af); may be NaN (Q0 read)      */
+    double   qual;           /* BaseType::get_var_qual(); 0 when n_alt == 0                               */
+    double   chi2;           /* last chi_sqrt_value of the LRT loop (0 when the loop did not run)         */
+    double   fs_cvg;         /* FS of strand_bias(ref, all non-ref ACGT): the CVG row (caller.cpp:1245)   */
+    double   fs_vcf;         /* FS of strand_bias(ref, ALT set): the VCF row (caller.cpp:1164); 0 if !n_alt */
+} bv_site_out;
+
+/* ---- synthetic pileup model (bench / tests); integer thresholds only, so that the device       */
+/* generator and its host twin are bit-identical                                                   */
+typedef struct bv_synth_model {
+    uint64_t seed;
+    uint32_t cov_thr;        /* cell covered iff u32 draw < cov_thr                                       */
+    uint32_t var_thr;        /* site is variant iff u32 draw < var_thr                                    */
+    uint32_t multi_thr;      /* variant site gets extra ALT alleles iff u32 draw < multi_thr              */
+    uint32_t q_lo;           /* phred = q_lo + ((u32 draw * q_span) >> 32)                                */
+    uint32_t q_span;
+    uint32_t reserved;
+    uint32_t err_thr[96];    /* per phred: read is an error iff 24-bit draw < err_thr[q]                  */
+    uint32_t af_thr[1024];   /* inverse CDF of the ALT1 allele frequency as a u32 threshold               */
+    uint32_t af_extra_thr[256]; /* same for ALT2/ALT3 of multi-allelic sites                              */
+} bv_synth_model;
+
+typedef struct bv_ctx bv_ctx;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+int         bv_version(void);                                  /* major*1000 + minor */
+int         bv_create(int device, const bv_params* params, bv_ctx** out_ctx);
+void        bv_destroy(bv_ctx* ctx);
+const char* bv_last_error(const bv_ctx* ctx);                  /* ctx may be NULL: last global error */
+int         bv_set_params(bv_ctx* ctx, const bv_params* params); /* change min_af / em mode; capacities fixed */
+uint64_t    bv_launch_count(const bv_ctx* ctx);                /* kernels launched by this context so far */
+
+/* ---- tile pipeline (replaces: BatchInfo -> BaseType ctor -> lrt() -> strand_bias per site) ------ */
+/* Asynchronous.  Host tiles are copied H2D on the slot's stream (pinned memory makes the copy
+ * truly asynchronous), the site kernel runs, and the records are copied back to pinned staging. */
+int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile);
+/* Blocks until the slot is done and copies n_sites records to `out` (host memory). */
+int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out);
+
+/* Device-resident path: planes AND the output buffer are device pointers; nothing is copied.
+ * `stream` is a cudaStream_t (NULL = the legacy default stream).  Stream ordered, returns at once. */
+int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, void* stream);
+
+/* ---- synthetic pileups --------------------------------------------------------------------------- */
+int bv_synth_set_model(bv_ctx* ctx, const bv_synth_model* model);
+/* Fill device planes for sites [site0, site0+n_sites) of the synthetic genome; mapq may be NULL. */
+int bv_synth_fill_device(bv_ctx* ctx, uint64_t site0, uint32_t n_sites, uint32_t n_samples, uint64_t pitch,
+                         uint8_t* d_base, uint8_t* d_qual, uint8_t* d_strand, uint8_t* d_mapq,
+                         uint8_t* d_ref_base, void* stream);
+/* Host twin of the generator (plain C loop, no CUDA): same bytes as bv_synth_fill_device. */
+int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
+                       uint64_t pitch, uint8_t* base, uint8_t* qual, uint8_t* strand, uint8_t* mapq,
+                       uint8_t* ref_base);
+
+/* ---- pinned host memory helpers (for the packer / staging buffers of the caller) ---------------- */
+int bv_host_alloc(void** out_ptr, size_t bytes);   /* cudaHostAlloc */
+int bv_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASEVAR_B200_H */
