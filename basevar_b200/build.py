@@ -1,0 +1,44 @@
+"""Build the CUDA library in-tree: basevar_b200/libbasevar_b200.so (sm_100a only).
+
+    python -m basevar_b200.build            # rebuild if sources are newer than the .so
+    python -m basevar_b200.build --force
+
+-fmad=false: the x86-64 reference build contracts nothing, so the device code must not either
+(see csrc/bv_math.cuh).  -lineinfo keeps ncu's source page usable.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbasevar_b200.so")
+SOURCES = [os.path.join(CSRC, "bv_api.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("bv_site_kernel.cuh", "bv_math.cuh", "bv_synth.cuh")] + [
+    os.path.join(HERE, "..", "include", "basevar_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

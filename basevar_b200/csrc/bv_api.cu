@@ -1,0 +1,432 @@
+// bv_api.cu -- kernels' __global__ entry points and the C ABI of include/basevar_b200.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// (see basevar_b200/build.py).  No torch types, no CPU fallback: every entry point that computes needs a
+// CUDA device and fails with BV_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/basevar_b200.h"
+#include "bv_site_kernel.cuh"
+#include "bv_synth.cuh"
+
+namespace bv {
+
+constexpr int kWarpsPerCta = 16;
+constexpr int kLutBytes = 4 * kQStride * (int)sizeof(double);
+
+// ======================================================================================================
+// Site kernel v1: persistent CTAs, one warp per site, direct 128-bit streaming loads (two vectors of each
+// plane in flight per lane).
+// ======================================================================================================
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bv_site_kernel(const SiteKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* s_lut = reinterpret_cast<double*>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem + kLutBytes)[warp];
+
+    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) s_lut[i] = a.lut[i];
+    for (int i = lane; i < kHistWords; i += 32) ws.hist[i] = 0;
+    __syncthreads();
+
+    const uint32_t total_warps = gridDim.x * kWarpsPerCta;
+    const int nvec = (int)((a.n_samples + 15u) >> 4);   // 16-cell vectors per row (last one may be partial)
+    const int nfull = (int)(a.n_samples >> 4);          // vectors without padding cells
+    for (uint32_t site = blockIdx.x * kWarpsPerCta + warp; site < a.n_sites; site += total_warps) {
+        LaneCounts lc;
+        lc.fwd = lc.rev = lc.nos = 0ull;
+        lc.other = 0; lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
+        const size_t row = (size_t)site * a.pitch;
+        const uint4* pb = reinterpret_cast<const uint4*>(a.base + row);
+        const uint4* pq = reinterpret_cast<const uint4*>(a.qual + row);
+        const uint4* ps = reinterpret_cast<const uint4*>(a.strand + row);
+        for (int v = lane; v < nvec; v += 64) {
+            const int v2 = v + 32;
+            const bool has2 = v2 < nvec;
+            uint4 b0 = ld_stream(pb + v), q0 = ld_stream(pq + v), s0 = ld_stream(ps + v);
+            uint4 b1 = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u), q1 = b1, s1 = b1;
+            if (has2) { b1 = ld_stream(pb + v2); q1 = ld_stream(pq + v2); s1 = ld_stream(ps + v2); }
+            if (v < nfull) count_vec<false>(b0, q0, s0, 16, ws.hist, lc);
+            else count_vec<true>(b0, q0, s0, (int)a.n_samples - 16 * v, ws.hist, lc);
+            if (has2) {
+                if (v2 < nfull) count_vec<false>(b1, q1, s1, 16, ws.hist, lc);
+                else count_vec<true>(b1, q1, s1, (int)a.n_samples - 16 * v2, ws.hist, lc);
+            }
+        }
+        site_finish(ws, s_lut, a, site, lc);
+    }
+}
+
+// ======================================================================================================
+// Synthetic pileup generator: one thread writes one 16-cell vector of each plane.
+// ======================================================================================================
+__global__ void __launch_bounds__(256) bv_synth_kernel(const bv_synth_model* __restrict__ model, uint64_t site0,
+                                                      uint32_t n_sites, uint32_t n_samples, uint64_t pitch,
+                                                      uint8_t* base, uint8_t* qual, uint8_t* strand, uint8_t* mapq,
+                                                      uint8_t* ref_base) {
+    const uint32_t vec_per_row = (uint32_t)(pitch >> 4);
+    const uint64_t n_units = (uint64_t)n_sites * vec_per_row;
+    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < n_units;
+         u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t)(u / vec_per_row);
+        const uint32_t v = (uint32_t)(u - (uint64_t)s * vec_per_row);
+        const SynthSite ss = synth_site(model, site0 + s);
+        if (v == 0) ref_base[s] = "ACGT"[ss.ref];
+        uint32_t wb[4], wq[4], wst[4], wm[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t xb = 0, xq = 0, xs = 0, xm = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t i = v * 16 + w * 4 + k;
+                SynthCell c;
+                if (i < n_samples) c = synth_cell(model, ss, i);
+                else { c.base = BV_BASE_N; c.qual = 0; c.strand = BV_STRAND_NONE; c.mapq = 0; }
+                xb |= (uint32_t)c.base << (8 * k);
+                xq |= (uint32_t)c.qual << (8 * k);
+                xs |= (uint32_t)c.strand << (8 * k);
+                xm |= (uint32_t)c.mapq << (8 * k);
+            }
+            wb[w] = xb; wq[w] = xq; wst[w] = xs; wm[w] = xm;
+        }
+        const size_t off = (size_t)s * pitch + (size_t)v * 16;
+        *reinterpret_cast<uint4*>(base + off) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+        *reinterpret_cast<uint4*>(qual + off) = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+        *reinterpret_cast<uint4*>(strand + off) = make_uint4(wst[0], wst[1], wst[2], wst[3]);
+        if (mapq) *reinterpret_cast<uint4*>(mapq + off) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
+    }
+}
+
+}  // namespace bv
+
+// ======================================================================================================
+// Context
+// ======================================================================================================
+struct bv_slot {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_planes = nullptr;   // base | qual | strand, each max_sites * pitch_cap
+    uint8_t* d_ref = nullptr;
+    bv_site_out* d_out = nullptr;
+    bv_site_out* h_out = nullptr;  // pinned
+    uint32_t n_sites = 0;
+    bool busy = false;
+};
+
+struct bv_ctx {
+    int device = 0;
+    int num_sms = 0;
+    bv_params prm{};
+    char err[512] = {0};
+    double* d_lut = nullptr;
+    double* d_logfact = nullptr;
+    bv_synth_model* d_model = nullptr;
+    bool has_model = false;
+    uint64_t pitch_cap = 0;
+    bv_slot* slots = nullptr;
+    uint64_t launches = 0;
+};
+
+static char g_err[512] = "";
+
+static int set_err(bv_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    snprintf(g_err, sizeof(g_err), "%s", buf);
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s", buf);
+    return code;
+}
+
+#define BV_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return set_err(ctx, BV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                           __FILE__, __LINE__);                                                         \
+    } while (0)
+
+static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, bv::SiteKernelArgs* a) {
+    if (!t || !t->base || !t->qual || !t->strand || !t->ref_base || !d_out)
+        return set_err(ctx, BV_ERR_ARG, "bv_tile: null pointer");
+    if (t->pitch % 16 != 0 || t->pitch < t->n_samples)
+        return set_err(ctx, BV_ERR_ARG, "bv_tile: pitch %llu must be a multiple of 16 and >= n_samples %u",
+                       (unsigned long long)t->pitch, t->n_samples);
+    if (t->n_samples > ctx->prm.max_samples)
+        return set_err(ctx, BV_ERR_ARG, "bv_tile: n_samples %u > max_samples %u", t->n_samples, ctx->prm.max_samples);
+    if ((((uintptr_t)t->base) | ((uintptr_t)t->qual) | ((uintptr_t)t->strand)) & 15)
+        return set_err(ctx, BV_ERR_ARG, "bv_tile: plane pointers must be 16-byte aligned");
+    a->base = t->base; a->qual = t->qual; a->strand = t->strand; a->ref_base = t->ref_base;
+    a->out = d_out;
+    a->lut = ctx->d_lut;
+    a->logfact = ctx->d_logfact;
+    a->pitch = t->pitch;
+    a->n_sites = t->n_sites;
+    a->n_samples = t->n_samples;
+    a->min_af = (double)ctx->prm.min_af;     // float -> double: src/basetype_caller.cpp:122,506
+    a->em_eps = (double)ctx->prm.em_eps;     // const float epsilon: src/algorithm.h:213
+    a->lrt_threshold = (double)ctx->prm.lrt_threshold;
+    a->em_max_iter = ctx->prm.em_max_iter;
+    a->abs_mode = ctx->prm.em_abs_mode;
+    return BV_OK;
+}
+
+static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream) {
+    if (a.n_sites == 0) return BV_OK;
+    const size_t smem = bv::kLutBytes + (size_t)bv::kWarpsPerCta * sizeof(bv::WarpScratch);
+    uint32_t grid = (a.n_sites + bv::kWarpsPerCta - 1) / bv::kWarpsPerCta;
+    const uint32_t max_grid = (uint32_t)ctx->num_sms * 2u;
+    if (grid > max_grid) grid = max_grid;
+    bv::bv_site_kernel<<<grid, bv::kWarpsPerCta * 32, smem, stream>>>(a);
+    BV_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return BV_OK;
+}
+
+extern "C" {
+
+int bv_version(void) { return BV_VERSION_MAJOR * 1000 + BV_VERSION_MINOR; }
+
+const char* bv_last_error(const bv_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+uint64_t bv_launch_count(const bv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static int upload_tables(bv_ctx* ctx) {
+    // per-phred likelihood table: eps = exp((q) * MLN10TO10) with glibc exp, exactly the reference's expression
+    // (src/basetype.cpp:47, MLN10TO10 at src/basetype.h:20); 1-eps and eps/3 are single IEEE operations.
+    const double MLN10TO10 = -0.23025850929940458;
+    double lut[4 * bv::kQStride];
+    for (int q = 0; q < bv::kQStride; ++q) {
+        double eps = exp((double)q * MLN10TO10);
+        double ome = 1.0 - eps, e3 = eps / 3;
+        lut[bv::kLutOneMinusEps * bv::kQStride + q] = ome;
+        lut[bv::kLutEpsThird * bv::kQStride + q] = e3;
+        lut[bv::kLutLogMatch * bv::kQStride + q] = log(ome);
+        lut[bv::kLutLogMis * bv::kQStride + q] = log(e3);
+    }
+    BV_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(lut)));
+    BV_CUDA(ctx, cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    // log-factorials: lgamma(k+1) from glibc, the values lbinom() uses (htslib/kfunc.c:197-201)
+    const size_t n = (size_t)ctx->prm.max_samples + 2;
+    double* lf = (double*)malloc(n * sizeof(double));
+    if (!lf) return set_err(ctx, BV_ERR_NOMEM, "out of host memory");
+    for (size_t k = 0; k < n; ++k) lf[k] = lgamma((double)(k + 1));
+    cudaError_t e = cudaMalloc(&ctx->d_logfact, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_logfact, lf, n * sizeof(double), cudaMemcpyHostToDevice);
+    free(lf);
+    BV_CUDA(ctx, e);
+    return BV_OK;
+}
+
+int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
+    if (!params || !out_ctx) return set_err(nullptr, BV_ERR_ARG, "bv_create: null argument");
+    *out_ctx = nullptr;
+    if (params->max_samples == 0 || params->max_samples > 2000000u)
+        return set_err(nullptr, BV_ERR_ARG, "bv_create: max_samples must be in 1..2000000");
+    if (params->n_slots > 64) return set_err(nullptr, BV_ERR_ARG, "bv_create: n_slots > 64");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, BV_ERR_CUDA, "bv_create: no CUDA device (%s); this library has no CPU fallback",
+                       cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return set_err(nullptr, BV_ERR_ARG, "bv_create: bad device %d", device);
+    bv_ctx* ctx = new (std::nothrow) bv_ctx();
+    if (!ctx) return set_err(nullptr, BV_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->prm = *params;
+    int rc = BV_OK;
+    do {
+        if (cudaSetDevice(device) != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "cudaSetDevice failed"); break; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
+        ctx->num_sms = prop.multiProcessorCount;
+        const size_t smem = bv::kLutBytes + (size_t)bv::kWarpsPerCta * sizeof(bv::WarpScratch);
+        if (cudaFuncSetAttribute(bv::bv_site_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
+                         cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rc = upload_tables(ctx);
+        if (rc != BV_OK) break;
+        ctx->pitch_cap = ((uint64_t)params->max_samples + 15) / 16 * 16;
+        if (params->n_slots > 0 && params->max_sites > 0) {
+            ctx->slots = new (std::nothrow) bv_slot[params->n_slots];
+            if (!ctx->slots) { rc = set_err(nullptr, BV_ERR_NOMEM, "out of host memory"); break; }
+            const size_t plane = (size_t)params->max_sites * ctx->pitch_cap;
+            for (uint32_t i = 0; i < params->n_slots && rc == BV_OK; ++i) {
+                bv_slot& s = ctx->slots[i];
+                cudaError_t ce = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+                if (ce == cudaSuccess) ce = cudaMalloc(&s.d_planes, 3 * plane);
+                if (ce == cudaSuccess) ce = cudaMalloc(&s.d_ref, params->max_sites);
+                if (ce == cudaSuccess) ce = cudaMalloc(&s.d_out, (size_t)params->max_sites * sizeof(bv_site_out));
+                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_out, (size_t)params->max_sites * sizeof(bv_site_out), cudaHostAllocDefault);
+                if (ce != cudaSuccess) rc = set_err(nullptr, BV_ERR_CUDA, "slot allocation failed: %s", cudaGetErrorString(ce));
+            }
+        }
+    } while (0);
+    if (rc != BV_OK) { bv_destroy(ctx); return rc; }
+    *out_ctx = ctx;
+    return BV_OK;
+}
+
+void bv_destroy(bv_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->slots) {
+        for (uint32_t i = 0; i < ctx->prm.n_slots; ++i) {
+            bv_slot& s = ctx->slots[i];
+            if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+            cudaFree(s.d_planes); cudaFree(s.d_ref); cudaFree(s.d_out);
+            if (s.h_out) cudaFreeHost(s.h_out);
+        }
+        delete[] ctx->slots;
+    }
+    cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model);
+    delete ctx;
+}
+
+int bv_set_params(bv_ctx* ctx, const bv_params* p) {
+    if (!ctx || !p) return set_err(ctx, BV_ERR_ARG, "bv_set_params: null argument");
+    ctx->prm.min_af = p->min_af;
+    ctx->prm.lrt_threshold = p->lrt_threshold;
+    ctx->prm.em_max_iter = p->em_max_iter;
+    ctx->prm.em_eps = p->em_eps;
+    ctx->prm.em_abs_mode = p->em_abs_mode;
+    return BV_OK;
+}
+
+int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, void* stream) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (tile && tile->location != BV_LOC_DEVICE) return set_err(ctx, BV_ERR_ARG, "bv_tile_run_device: tile must be device resident");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    bv::SiteKernelArgs a;
+    int rc = fill_kernel_args(ctx, tile, d_out, &a);
+    if (rc != BV_OK) return rc;
+    return launch_site_kernel(ctx, a, (cudaStream_t)stream);
+}
+
+int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
+    if (!tile) return set_err(ctx, BV_ERR_ARG, "null tile");
+    bv_slot& s = ctx->slots[slot];
+    if (s.busy) return set_err(ctx, BV_ERR_STATE, "slot %d is busy: call bv_tile_wait first", slot);
+    if (tile->n_sites > ctx->prm.max_sites) return set_err(ctx, BV_ERR_ARG, "tile has %u sites > max_sites %u", tile->n_sites, ctx->prm.max_sites);
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    bv_tile dev = *tile;
+    if (tile->location == BV_LOC_HOST) {
+        if (!tile->base || !tile->qual || !tile->strand || !tile->ref_base) return set_err(ctx, BV_ERR_ARG, "bv_tile: null pointer");
+        if (tile->pitch % 16 != 0 || tile->pitch < tile->n_samples || tile->n_samples > ctx->prm.max_samples)
+            return set_err(ctx, BV_ERR_ARG, "bv_tile: bad pitch/n_samples");
+        // device rows are re-pitched to round16(n_samples) so that no padding crosses PCIe
+        const uint64_t dp = ((uint64_t)tile->n_samples + 15) / 16 * 16;
+        const size_t plane = (size_t)ctx->prm.max_sites * ctx->pitch_cap;
+        uint8_t* d[3] = {s.d_planes, s.d_planes + plane, s.d_planes + 2 * plane};
+        const uint8_t* h[3] = {tile->base, tile->qual, tile->strand};
+        for (int k = 0; k < 3 && tile->n_sites; ++k) {
+            if (dp == tile->pitch)
+                BV_CUDA(ctx, cudaMemcpyAsync(d[k], h[k], (size_t)tile->n_sites * dp, cudaMemcpyHostToDevice, s.stream));
+            else
+                BV_CUDA(ctx, cudaMemcpy2DAsync(d[k], dp, h[k], tile->pitch, dp, tile->n_sites, cudaMemcpyHostToDevice, s.stream));
+        }
+        if (tile->n_sites)
+            BV_CUDA(ctx, cudaMemcpyAsync(s.d_ref, tile->ref_base, tile->n_sites, cudaMemcpyHostToDevice, s.stream));
+        dev.base = d[0]; dev.qual = d[1]; dev.strand = d[2]; dev.ref_base = s.d_ref;
+        dev.pitch = dp;
+        dev.location = BV_LOC_DEVICE;
+    }
+    bv::SiteKernelArgs a;
+    int rc = fill_kernel_args(ctx, &dev, s.d_out, &a);
+    if (rc != BV_OK) return rc;
+    rc = launch_site_kernel(ctx, a, s.stream);
+    if (rc != BV_OK) return rc;
+    if (tile->n_sites)
+        BV_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, (size_t)tile->n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
+    s.n_sites = tile->n_sites;
+    s.busy = true;
+    return BV_OK;
+}
+
+int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
+    bv_slot& s = ctx->slots[slot];
+    if (!s.busy) return set_err(ctx, BV_ERR_STATE, "slot %d has nothing submitted", slot);
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    s.busy = false;
+    BV_CUDA(ctx, e);
+    if (out && s.n_sites) memcpy(out, s.h_out, (size_t)s.n_sites * sizeof(bv_site_out));
+    return BV_OK;
+}
+
+int bv_synth_set_model(bv_ctx* ctx, const bv_synth_model* model) {
+    if (!ctx || !model) return set_err(ctx, BV_ERR_ARG, "bv_synth_set_model: null argument");
+    if (model->q_lo + model->q_span > BV_QUAL_MAX + 1) return set_err(ctx, BV_ERR_ARG, "synthetic phred range exceeds 93");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_model) BV_CUDA(ctx, cudaMalloc(&ctx->d_model, sizeof(bv_synth_model)));
+    BV_CUDA(ctx, cudaMemcpy(ctx->d_model, model, sizeof(bv_synth_model), cudaMemcpyHostToDevice));
+    ctx->has_model = true;
+    return BV_OK;
+}
+
+int bv_synth_fill_device(bv_ctx* ctx, uint64_t site0, uint32_t n_sites, uint32_t n_samples, uint64_t pitch,
+                         uint8_t* d_base, uint8_t* d_qual, uint8_t* d_strand, uint8_t* d_mapq, uint8_t* d_ref_base,
+                         void* stream) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (!ctx->has_model) return set_err(ctx, BV_ERR_STATE, "bv_synth_set_model was not called");
+    if (!d_base || !d_qual || !d_strand || !d_ref_base) return set_err(ctx, BV_ERR_ARG, "null plane");
+    if (pitch % 16 != 0 || pitch < n_samples) return set_err(ctx, BV_ERR_ARG, "bad pitch");
+    if (n_sites == 0) return BV_OK;
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t units = (uint64_t)n_sites * (pitch >> 4);
+    uint64_t blocks = (units + 255) / 256;
+    const uint64_t cap = (uint64_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    bv::bv_synth_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ctx->d_model, site0, n_sites, n_samples, pitch,
+                                                                        d_base, d_qual, d_strand, d_mapq, d_ref_base);
+    BV_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return BV_OK;
+}
+
+int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples, uint64_t pitch,
+                       uint8_t* base, uint8_t* qual, uint8_t* strand, uint8_t* mapq, uint8_t* ref_base) {
+    if (!model || !base || !qual || !strand || !ref_base) return set_err(nullptr, BV_ERR_ARG, "null argument");
+    if (pitch < n_samples) return set_err(nullptr, BV_ERR_ARG, "bad pitch");
+    for (uint32_t s = 0; s < n_sites; ++s) {
+        const bv::SynthSite ss = bv::synth_site(model, site0 + s);
+        ref_base[s] = "ACGT"[ss.ref];
+        const size_t row = (size_t)s * pitch;
+        for (uint64_t i = 0; i < pitch; ++i) {
+            bv::SynthCell c;
+            if (i < n_samples) c = bv::synth_cell(model, ss, i);
+            else { c.base = BV_BASE_N; c.qual = 0; c.strand = BV_STRAND_NONE; c.mapq = 0; }
+            base[row + i] = c.base; qual[row + i] = c.qual; strand[row + i] = c.strand;
+            if (mapq) mapq[row + i] = c.mapq;
+        }
+    }
+    return BV_OK;
+}
+
+int bv_host_alloc(void** out_ptr, size_t bytes) {
+    if (!out_ptr) return set_err(nullptr, BV_ERR_ARG, "null argument");
+    cudaError_t e = cudaHostAlloc(out_ptr, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return set_err(nullptr, BV_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return BV_OK;
+}
+
+int bv_host_free(void* ptr) {
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) return set_err(nullptr, BV_ERR_CUDA, "cudaFreeHost failed: %s", cudaGetErrorString(e));
+    return BV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+"""Host-side driver of the CUDA basetype core, a thin layer over the C ABI (include/basevar_b200.h).
+
+``BaseTypeEngine`` plays the role of the reference's per-site loop in ``_variant_calling_unit`` /
+``_basevar_caller`` (src/basetype_caller.cpp:586-611, 738-743): it is handed the pileup of many sites
+(as packed SoA planes instead of one BatchInfo per site) and returns one record per site holding
+what ``BaseType`` + ``strand_bias`` would have produced.  Tiles are pipelined over ``n_slots`` CUDA
+streams (H2D copy, kernel, D2H copy per slot).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import BvError, BvTile, SITE_OUT_DTYPE
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class BaseTypeEngine:
+    def __init__(self, device=0, max_samples=1, max_sites=0, n_slots=0, min_af=0.01,
+                 abs_mode=capi.BV_EM_ABS_INT_TRUNC):
+        self.lib = capi.load_library()
+        self.params = capi.make_params(min_af, abs_mode, max_samples, max_sites, n_slots)
+        self._ctx = C.c_void_p()
+        rc = self.lib.bv_create(device, C.byref(self.params), C.byref(self._ctx))
+        if rc != capi.BV_OK:
+            raise BvError(f"bv_create failed ({rc}): {self.lib.bv_last_error(None).decode()}")
+        self.device = device
+
+    # -- lifecycle ---------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.bv_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != capi.BV_OK:
+            raise BvError(f"{what} failed ({rc}): {self.lib.bv_last_error(self._ctx).decode()}")
+
+    def set_params(self, min_af=None, abs_mode=None):
+        if min_af is not None:
+            self.params.min_af = float(np.float32(min_af))
+        if abs_mode is not None:
+            self.params.em_abs_mode = abs_mode
+        self._check(self.lib.bv_set_params(self._ctx, C.byref(self.params)), "bv_set_params")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.bv_launch_count(self._ctx))
+
+    # -- tiles from host memory --------------------------------------------------------------------
+    def call_host(self, base, qual, strand, ref_base, n_samples, out=None):
+        """Run planes [S][pitch] (numpy uint8, ideally pinned) through the slot pipeline.
+
+        Returns a numpy record array (capi.SITE_OUT_DTYPE) with one record per site."""
+        S, pitch = base.shape
+        assert qual.shape == base.shape and strand.shape == base.shape and ref_base.shape[0] == S
+        for a in (base, qual, strand, ref_base):
+            assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
+        if out is None:
+            out = np.zeros(S, dtype=SITE_OUT_DTYPE)
+        n_slots, step = self.params.n_slots, self.params.max_sites
+        assert n_slots >= 1 and step >= 1, "engine was created without slots"
+        pending = []  # (slot, site0)
+        slot = 0
+        for s0 in range(0, max(S, 1), step):
+            ns = min(step, S - s0)
+            if len(pending) == n_slots:
+                ps, p0 = pending.pop(0)
+                self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data), "bv_tile_wait")
+            t = BvTile(base[s0:].ctypes.data, qual[s0:].ctypes.data, strand[s0:].ctypes.data,
+                       ref_base[s0:].ctypes.data, pitch, ns, n_samples, capi.BV_LOC_HOST, 0)
+            self._check(self.lib.bv_tile_submit(self._ctx, slot, C.byref(t)), "bv_tile_submit")
+            pending.append((slot, s0))
+            slot = (slot + 1) % n_slots
+        for ps, p0 in pending:
+            self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data), "bv_tile_wait")
+        return out
+
+    # -- device-resident tiles ---------------------------------------------------------------------
+    def call_device(self, d_base, d_qual, d_strand, d_ref, n_sites, n_samples, pitch, d_out, stream=0):
+        """All arguments are device pointers (ints); stream is a cudaStream_t handle (int).  Asynchronous."""
+        t = BvTile(int(d_base), int(d_qual), int(d_strand), int(d_ref), pitch, n_sites, n_samples,
+                   capi.BV_LOC_DEVICE, 0)
+        self._check(self.lib.bv_tile_run_device(self._ctx, C.byref(t), C.c_void_p(int(d_out)),
+                                                C.c_void_p(int(stream))), "bv_tile_run_device")
+
+    # -- synthetic pileups -------------------------------------------------------------------------
+    def synth_set_model(self, model):
+        self._model = model
+        self._check(self.lib.bv_synth_set_model(self._ctx, C.byref(model)), "bv_synth_set_model")
+
+    def synth_fill_device(self, site0, n_sites, n_samples, pitch, d_base, d_qual, d_strand, d_mapq, d_ref, stream=0):
+        self._check(self.lib.bv_synth_fill_device(self._ctx, site0, n_sites, n_samples, pitch, int(d_base), int(d_qual),
+                                                  int(d_strand), int(d_mapq) if d_mapq else None, int(d_ref),
+                                                  C.c_void_p(int(stream))), "bv_synth_fill_device")
+
+
+def synth_fill_host(model, site0, n_sites, n_samples, pitch=None, with_mapq=False):
+    """Host twin of the device generator (no CUDA needed).  Returns (base, qual, strand, mapq|None, ref_base)."""
+    lib = capi.load_library()
+    if pitch is None:
+        pitch = (n_samples + 15) // 16 * 16
+    base = np.empty((n_sites, pitch), np.uint8)
+    qual = np.empty((n_sites, pitch), np.uint8)
+    strand = np.empty((n_sites, pitch), np.uint8)
+    mapq = np.empty((n_sites, pitch), np.uint8) if with_mapq else None
+    ref = np.empty(n_sites, np.uint8)
+    rc = lib.bv_synth_fill_host(C.byref(model), site0, n_sites, n_samples, pitch, base.ctypes.data, qual.ctypes.data,
+                                strand.ctypes.data, mapq.ctypes.data if with_mapq else None, ref.ctypes.data)
+    if rc != capi.BV_OK:
+        raise BvError(f"bv_synth_fill_host failed ({rc}): {lib.bv_last_error(None).decode()}")
+    return base, qual, strand, mapq, ref

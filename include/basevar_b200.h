@@ -73,6 +73,7 @@ extern "C" {
 #define BV_FLAG_NEAR_LRT     0x10u /* some LRT decision had |chi2 - threshold| < 1e-9*threshold (possible flip) */
 #define BV_FLAG_NEAR_MINAF   0x20u /* some depth/total is within 4 ulp of min_af (never flips: exact compare)  */
 #define BV_FLAG_EM_MAXITER   0x40u /* an EM used all em_max_iter iterations                                   */
+#define BV_FLAG_LRT_TIE      0x80u /* two candidate subsets had equal chi2 (to rounding): first one kept       */
 
 #define BV_EM_ABS_INT_TRUNC 0  /* as built by g++/glibc: abs() resolves to int abs(int) (algorithm.h:245)   */
 #define BV_EM_ABS_DOUBLE    1  /* fabs(): the evident intent                                                */
@@ -112,7 +113,7 @@ typedef struct bv_tile {
 typedef struct bv_site_out {
     uint32_t depth[4];       /* A,C,G,T read counts       (BaseType::get_base_depth)                      */
     uint32_t depth_other;    /* BV_BASE_OTHER cells; total depth = sum(depth)+depth_other                 */
-    uint32_t n_indel;        /* BV_BASE_INS/DEL cells (skipped)                                           */
+    uint32_t reserved0;      /* 0                                                                         */
     uint32_t fwd[4];         /* '+' strand count per base (strand_bias, any ALT set derivable on host)    */
     uint32_t rev[4];         /* '-' strand count per base                                                 */
     uint8_t  n_alt;          /* number of ALT alleles (0 => not a variant site)                           */

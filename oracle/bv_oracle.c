@@ -262,10 +262,7 @@ int bvo_site(const uint8_t* base, const uint8_t* qual, const uint8_t* strand, ui
     /* BaseType::BaseType, src/basetype.cpp:45-71 */
     for (uint32_t i = 0; i < n_samples; ++i) {
         uint8_t b = base[i];
-        if (b >= BV_BASE_N) {
-            if (b == BV_BASE_INS || b == BV_BASE_DEL) out->n_indel++;
-            continue;
-        }
+        if (b >= BV_BASE_N) continue; /* 'N' and indels are skipped, basetype.cpp:51 */
         uint8_t q = qual[i];
         if (q > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;
         double eps = exp((double)q * kMLN10TO10);

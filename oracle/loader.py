@@ -17,7 +17,7 @@ SITE_OUT_DTYPE = np.dtype(
     [
         ("depth", "<u4", (4,)),
         ("depth_other", "<u4"),
-        ("n_indel", "<u4"),
+        ("reserved0", "<u4"),
         ("fwd", "<u4", (4,)),
         ("rev", "<u4", (4,)),
         ("n_alt", "u1"),

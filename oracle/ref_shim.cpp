@@ -61,7 +61,6 @@ double run_site(SiteScratch& sc, const uint8_t* base, const uint8_t* qual, const
         bi.align_base_quals[i] = (char)(qual[i] + 33);
         bi.map_strands[i] = strand[i] == BV_STRAND_FWD ? '+' : strand[i] == BV_STRAND_REV ? '-' : '.';
         if (b != BV_BASE_N) bi.depth++;
-        if (b == BV_BASE_INS || b == BV_BASE_DEL) out->n_indel++;
         if (b == BV_BASE_OTHER) out->depth_other++;
         if (b < 4) {
             if (strand[i] == BV_STRAND_FWD) out->fwd[b]++;

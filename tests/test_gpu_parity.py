@@ -1,0 +1,204 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import basevar_b200 as bv
+from basevar_b200 import capi
+from oracle import loader as L
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(built_lib):
+    eng = bv.BaseTypeEngine(device=0, max_samples=20000, max_sites=4096, n_slots=3, min_af=0.01)
+    yield eng
+    eng.close()
+
+
+def _check(got, want, label, max_flips=0):
+    """Exact fields bit-exact, floats within util.RTOL; flips (threshold / tie sites, see util.compare_records)
+    are printed and bounded by max_flips."""
+    ie, fe, flips = util.compare_records(got, want)
+    msg = ""
+    if len(ie):
+        i = ie[0]
+        msg += f"\n{label}: {len(ie)} sites differ in exact fields, first site {i}:\n got  {util.describe(got[i])}\n want {util.describe(want[i])}"
+    if len(fe):
+        i = fe[0]
+        msg += f"\n{label}: {len(fe)} sites out of tolerance, first site {i}:\n got  {util.describe(got[i])}\n want {util.describe(want[i])}"
+    if len(flips):
+        print(f"{label}: {len(flips)} threshold/tie flips at sites {flips.tolist()[:20]}")
+    assert not msg, msg
+    assert len(flips) <= max_flips
+
+
+GOLDEN_SITES = [
+    ("A", [("A", 30, "-+"[i % 2]) for i in range(7)] + [("G", 30, "-+"[i % 2]) for i in range(3)]),
+    ("C", [("C", 20 + i % 20, "+" if i % 3 else "-") for i in range(50)] + [("T", 35, "+")] * 5 + [("A", 12, "-")] * 2 + [("N", 0, ".")] * 20),
+    ("G", [("T", 30, "+")] * 12),
+    ("A", [("A", 30, "-+"[i % 2]) for i in range(40)] + [("C", 30, "-+"[i % 2]) for i in range(30)] + [("G", 30, "+")] * 20 + [("T", 30, "-")] * 10),
+    ("A", [("A", 30 + i % 10, "+-"[i % 2]) for i in range(997)] + [("C", 25, "+")] * 3),
+    ("G", [("T", 0, "+")]),
+    ("A", [("A", 30, "+")] * 5 + [("G", 0, "+")] * 3),
+    ("A", [("+", 30, "+"), ("-", 30, "+"), ("N", 0, ".")]),
+    ("a", [("A", 30, "+")] * 2 + [("C", 30, "+")] * 2 + [("C", 35, "+")]),
+    ("N", [("A", 30, "+")] * 2 + [("C", 30, "+")] * 2 + [("C", 35, "+")]),
+    ("A", [("A", 40, "+")] * 600 + [("T", 40, "-")] * 400),
+    ("T", []),
+]
+
+
+@pytest.mark.parametrize("abs_mode", [0, 1])
+@pytest.mark.parametrize("min_af", [0.01, 0.05, 0.001])
+def test_golden_sites(engine, abs_mode, min_af):
+    b, q, s, r, n = L.planes_from_reads(GOLDEN_SITES)
+    engine.set_params(min_af=min_af, abs_mode=abs_mode)
+    got = engine.call_host(b, q, s, r, n)
+    want = L.oracle_tile(b, q, s, r, n, min_af, abs_mode)
+    _check(got, want, f"golden abs={abs_mode} min_af={min_af}")
+
+
+@pytest.mark.parametrize("abs_mode", [0, 1])
+@pytest.mark.parametrize(
+    "name,S,N,kw",
+    [
+        ("C2-like", 20000, 1000, dict(coverage=0.1, variant_frac=0.019)),
+        ("C2-dense-variants", 6000, 1000, dict(coverage=0.1, variant_frac=0.6, multi_frac=0.3)),
+        ("C1-like-N100", 8000, 100, dict(coverage=0.065, variant_frac=0.05)),
+        ("C3-like", 1500, 10000, dict(coverage=0.1, variant_frac=0.1)),
+        ("C5-like", 1500, 2000, dict(coverage=0.99326, variant_frac=0.5, multi_frac=0.5)),
+        ("odd-N", 3000, 1003, dict(coverage=0.3, variant_frac=0.3, multi_frac=0.5)),
+        ("tiny-N", 3000, 7, dict(coverage=0.8, variant_frac=0.5)),
+    ],
+)
+def test_synthetic_tiles(engine, name, S, N, kw, abs_mode):
+    model = bv.synth.make_model(seed=1234 + N, **kw)
+    b, q, s, _, r = bv.synth_fill_host(model, 0, S, N)
+    maf = bv.cli_min_af(0.01, N)
+    engine.set_params(min_af=maf, abs_mode=abs_mode)
+    got = engine.call_host(b, q, s, r, N)
+    want = L.oracle_tile(b, q, s, r, N, maf, abs_mode)
+    _check(got, want, f"{name} abs={abs_mode}", max_flips=2)
+    assert (want["n_alt"] > 0).sum() > 0
+
+
+@pytest.mark.parametrize("abs_mode", [0, 1])
+def test_fuzz_junk_indels_lowqual(engine, abs_mode):
+    rng = np.random.default_rng(7)
+    for (S, N, cov, qlo, qhi, maf) in [(3000, 100, 0.5, 0, 40, 0.01), (1500, 1000, 0.1, 0, 93, 0.01),
+                                       (800, 2000, 0.99, 2, 41, 0.01), (2000, 50, 0.3, 0, 93, 0.05),
+                                       (300, 5000, 0.1, 2, 41, 0.001)]:
+        b, q, s, r = util.random_tile(rng, S, N, cov, qlo, qhi, other=0.01, indel=0.01, bad_strand=0.001)
+        engine.set_params(min_af=maf, abs_mode=abs_mode)
+        got = engine.call_host(b, q, s, r, N)
+        want = L.oracle_tile(b, q, s, r, N, maf, abs_mode)
+        _check(got, want, f"fuzz N={N} abs={abs_mode}", max_flips=2)
+
+
+def test_padding_cells_are_ignored(engine):
+    """Cells in [n_samples, pitch) must not be read as data, whatever they hold."""
+    rng = np.random.default_rng(3)
+    N, S, pitch = 200, 500, 256
+    b, q, s, r = util.random_tile(rng, S, N, 0.5, 10, 40, pitch=pitch)
+    want = L.oracle_tile(b, q, s, r, N, 0.01, 0)
+    b2, q2, s2 = b.copy(), q.copy(), s.copy()
+    b2[:, N:] = rng.integers(0, 4, (S, pitch - N))
+    q2[:, N:] = 40
+    s2[:, N:] = 0
+    engine.set_params(min_af=0.01, abs_mode=0)
+    got = engine.call_host(b2, q2, s2, r, N)
+    _check(got, want, "padding")
+
+
+def test_device_generator_matches_host_twin_and_device_path(engine):
+    import torch
+    N, S = 1000, 3000
+    pitch = 1008
+    model = bv.synth.config_model("C2")
+    engine.synth_set_model(model)
+    dev = torch.device("cuda:0")
+    planes = [torch.empty((S, pitch), dtype=torch.uint8, device=dev) for _ in range(4)]
+    ref = torch.empty(S, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    engine.synth_fill_device(777, S, N, pitch, planes[0].data_ptr(), planes[1].data_ptr(), planes[2].data_ptr(),
+                             planes[3].data_ptr(), ref.data_ptr(), st)
+    torch.cuda.synchronize()
+    hb, hq, hs, hm, hr = bv.synth_fill_host(model, 777, S, N, pitch, with_mapq=True)
+    for d, h in zip(planes, (hb, hq, hs, hm)):
+        assert np.array_equal(d.cpu().numpy(), h)
+    assert np.array_equal(ref.cpu().numpy(), hr)
+    # device-resident call == host-tile call, bit for bit
+    maf = bv.cli_min_af(0.01, N)
+    engine.set_params(min_af=maf, abs_mode=0)
+    out = torch.zeros(S * 128, dtype=torch.uint8, device=dev)
+    engine.call_device(planes[0].data_ptr(), planes[1].data_ptr(), planes[2].data_ptr(), ref.data_ptr(), S, N, pitch,
+                       out.data_ptr(), st)
+    torch.cuda.synchronize()
+    got_dev = out.cpu().numpy().view(capi.SITE_OUT_DTYPE)
+    got_host = engine.call_host(hb, hq, hs, hr, N)
+    assert got_dev.tobytes() == got_host.tobytes()
+    want = L.oracle_tile(hb, hq, hs, hr, N, maf, 0)
+    _check(got_dev, want, "device path")
+
+
+def test_full_size_properties_c2(engine):
+    """BASELINE config 2 slice at full N: size-independent properties on a tile the oracle does not see whole:
+    depth conservation (sum of per-base depths == number of counted cells), fwd+rev == depth, idempotence."""
+    import torch
+    N, S, pitch = 1000, 200_000, 1008
+    model = bv.synth.config_model("C2")
+    engine.synth_set_model(model)
+    dev = torch.device("cuda:0")
+    base, qual, strand = (torch.empty((S, pitch), dtype=torch.uint8, device=dev) for _ in range(3))
+    ref = torch.empty(S, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    engine.synth_fill_device(0, S, N, pitch, base.data_ptr(), qual.data_ptr(), strand.data_ptr(), 0, ref.data_ptr(), st)
+    engine.set_params(min_af=bv.cli_min_af(0.01, N), abs_mode=0)
+    out1 = torch.zeros(S * 128, dtype=torch.uint8, device=dev)
+    out2 = torch.zeros(S * 128, dtype=torch.uint8, device=dev)
+    for o in (out1, out2):
+        engine.call_device(base.data_ptr(), qual.data_ptr(), strand.data_ptr(), ref.data_ptr(), S, N, pitch, o.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(out1, out2), "kernel is not deterministic"
+    rec = out1.cpu().numpy().view(capi.SITE_OUT_DTYPE)
+    counted = (base < 5).sum(dim=1).cpu().numpy()
+    assert np.array_equal(rec["depth"].sum(axis=1) + rec["depth_other"], counted)
+    assert np.array_equal(rec["fwd"] + rec["rev"], rec["depth"])
+    # spot-check 2000 random sites against the oracle
+    idx = np.sort(np.random.default_rng(0).choice(S, 2000, replace=False))
+    hb, hq, hs = (t[idx].cpu().numpy() for t in (base, qual, strand))
+    want = L.oracle_tile(np.ascontiguousarray(hb), np.ascontiguousarray(hq), np.ascontiguousarray(hs),
+                         np.ascontiguousarray(ref.cpu().numpy()[idx]), N, bv.cli_min_af(0.01, N), 0)
+    _check(rec[idx], want, "C2 spot check")
+
+
+def test_symmetric_allele_ties(engine):
+    """Two ALT alleles with identical read multisets tie exactly in the reference's LRT; std::min_element then
+    keeps the first subset.  The CUDA path must resolve such ties the same way."""
+    rng = np.random.default_rng(11)
+    sites = []
+    for _ in range(600):
+        n_ref = int(rng.integers(5, 120))
+        k = int(rng.integers(1, 6))
+        quals = rng.integers(0, 41, k).tolist()
+        ref, a1, a2 = rng.permutation(4)[:3]
+        reads = [("ACGT"[ref], int(rng.integers(10, 41)), "+-"[int(rng.integers(0, 2))]) for _ in range(n_ref)]
+        for a in (a1, a2):
+            reads += [("ACGT"[a], qq, "+-"[i % 2]) for i, qq in enumerate(quals)]
+        if rng.random() < 0.3:  # three-way tie
+            a3 = [x for x in range(4) if x not in (ref, a1, a2)][0]
+            reads += [("ACGT"[a3], qq, "+-"[i % 2]) for i, qq in enumerate(quals)]
+        order = rng.permutation(len(reads))
+        sites.append(("ACGT"[ref], [reads[i] for i in order]))
+    b, q, s, r, n = L.planes_from_reads(sites)
+    for abs_mode in (0, 1):
+        for maf in (0.01, 0.001):
+            engine.set_params(min_af=maf, abs_mode=abs_mode)
+            got = engine.call_host(b, q, s, r, n)
+            want = L.oracle_tile(b, q, s, r, n, maf, abs_mode)
+            # every site here has tied alleles: the reference resolves them by rounding noise, we keep the first
+            # subset; the flips are listed, everything else must agree
+            _check(got, want, f"ties abs={abs_mode} min_af={maf}", max_flips=60)
+            assert ((got["flags"] & capi.FLAG_LRT_TIE) != 0).sum() > 100
