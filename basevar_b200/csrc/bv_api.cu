@@ -22,8 +22,8 @@ constexpr int kWarpsPerCta = 16;
 constexpr int kLutBytes = 4 * kQStride * (int)sizeof(double);
 
 // ======================================================================================================
-// Site kernel v1: persistent CTAs, one warp per site, direct 128-bit streaming loads (two vectors of each
-// plane in flight per lane).
+// Site kernel: persistent CTAs, one warp per site, 128-bit streaming loads software-pipelined one vector
+// ahead (a row of <= 1024 samples is fully in flight before the first cell is counted).
 // ======================================================================================================
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bv_site_kernel(const SiteKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -36,30 +36,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bv_site_kernel(const Sit
     __syncthreads();
 
     const uint32_t total_warps = gridDim.x * kWarpsPerCta;
+    const uint32_t warp_global = blockIdx.x * kWarpsPerCta + warp;
     const int nvec = (int)((a.n_samples + 15u) >> 4);   // 16-cell vectors per row (last one may be partial)
-    const int nfull = (int)(a.n_samples >> 4);          // vectors without padding cells
-    for (uint32_t site = blockIdx.x * kWarpsPerCta + warp; site < a.n_sites; site += total_warps) {
+    for (uint32_t site = warp_global; site < a.n_sites; site += total_warps) {
         LaneCounts lc;
-        lc.fwd = lc.rev = lc.nos = 0ull;
-        lc.other = 0; lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
+        lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
         const size_t row = (size_t)site * a.pitch;
         const uint4* pb = reinterpret_cast<const uint4*>(a.base + row);
         const uint4* pq = reinterpret_cast<const uint4*>(a.qual + row);
         const uint4* ps = reinterpret_cast<const uint4*>(a.strand + row);
-        for (int v = lane; v < nvec; v += 64) {
-            const int v2 = v + 32;
-            const bool has2 = v2 < nvec;
-            uint4 b0 = ld_stream(pb + v), q0 = ld_stream(pq + v), s0 = ld_stream(ps + v);
-            uint4 b1 = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u), q1 = b1, s1 = b1;
-            if (has2) { b1 = ld_stream(pb + v2); q1 = ld_stream(pq + v2); s1 = ld_stream(ps + v2); }
-            if (v < nfull) count_vec<false>(b0, q0, s0, 16, ws.hist, lc);
-            else count_vec<true>(b0, q0, s0, (int)a.n_samples - 16 * v, ws.hist, lc);
-            if (has2) {
-                if (v2 < nfull) count_vec<false>(b1, q1, s1, 16, ws.hist, lc);
-                else count_vec<true>(b1, q1, s1, (int)a.n_samples - 16 * v2, ws.hist, lc);
-            }
+        int v = lane;
+        uint4 b0 = make_uint4(0, 0, 0, 0), q0 = b0, s0 = b0;
+        if (v < nvec) { b0 = ld_stream(pb + v); q0 = ld_stream(pq + v); s0 = ld_stream(ps + v); }
+        while (v < nvec) {
+            const int vn = v + 32;
+            uint4 b1 = make_uint4(0, 0, 0, 0), q1 = b1, s1 = b1;
+            if (vn < nvec) { b1 = ld_stream(pb + vn); q1 = ld_stream(pq + vn); s1 = ld_stream(ps + vn); }
+            count_vec(b0, q0, s0, (int)a.n_samples - 16 * v, ws.hist, lc);
+            b0 = b1; q0 = q1; s0 = s1;
+            v = vn;
         }
-        site_finish(ws, s_lut, a, site, lc);
+        site_finish(ws, s_lut, a, site, warp_global, lc);
     }
 }
 
@@ -126,6 +123,8 @@ struct bv_ctx {
     double* d_lut = nullptr;
     double* d_logfact = nullptr;
     bv_synth_model* d_model = nullptr;
+    uint32_t* d_bin_spill = nullptr;
+    double* d_lml_spill = nullptr;
     bool has_model = false;
     uint64_t pitch_cap = 0;
     bv_slot* slots = nullptr;
@@ -167,6 +166,8 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->out = d_out;
     a->lut = ctx->d_lut;
     a->logfact = ctx->d_logfact;
+    a->bin_spill = ctx->d_bin_spill;
+    a->lml_spill = ctx->d_lml_spill;
     a->pitch = t->pitch;
     a->n_sites = t->n_sites;
     a->n_samples = t->n_samples;
@@ -255,6 +256,12 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         }
         rc = upload_tables(ctx);
         if (rc != BV_OK) break;
+        {   // per-warp overflow scratch of the EM (only touched by sites with very many distinct bins)
+            const size_t warps = (size_t)ctx->num_sms * 2 * bv::kWarpsPerCta;
+            cudaError_t ce = cudaMalloc(&ctx->d_bin_spill, warps * (bv::kMaxBins - bv::kSmemBins) * sizeof(uint32_t));
+            if (ce == cudaSuccess) ce = cudaMalloc(&ctx->d_lml_spill, warps * bv::kMaxBins * sizeof(double));
+            if (ce != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(ce)); break; }
+        }
         ctx->pitch_cap = ((uint64_t)params->max_samples + 15) / 16 * 16;
         if (params->n_slots > 0 && params->max_sites > 0) {
             ctx->slots = new (std::nothrow) bv_slot[params->n_slots];
@@ -289,6 +296,7 @@ void bv_destroy(bv_ctx* ctx) {
         delete[] ctx->slots;
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model);
+    cudaFree(ctx->d_bin_spill); cudaFree(ctx->d_lml_spill);
     delete ctx;
 }
 

@@ -136,7 +136,9 @@ __device__ __noinline__ double fisher_two_sided(const double* __restrict__ lf, i
 
 // src/basetype.cpp:277-283
 __device__ __forceinline__ double fs_from_table(const double* __restrict__ lf, int rf, int rr, int af, int ar) {
-    double fs = -10 * log10(fisher_two_sided(lf, rf, rr, af, ar));
+    const double p = fisher_two_sided(lf, rf, rr, af, ar);
+    if (p == 1.0) return 0.0;   // -10*log10(1) = -0.0, scrubbed to +0.0 by the reference's `fs == 0` branch
+    double fs = -10 * log10(p);
     if (isinf(fs)) fs = 10000;
     else if (fs == 0) fs = 0.0;
     return fs;

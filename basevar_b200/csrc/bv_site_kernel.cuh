@@ -2,18 +2,21 @@
 //
 // One warp owns one genomic site at a time (sites are the embarrassingly parallel axis, samples the
 // reduction axis).  For its site the warp
-//   1. streams the three u8 planes of the site row (base, qual, strand) with 128-bit loads and counts
-//      every read into a warp-private shared-memory histogram hist[base 0..4][phred 0..95] plus
-//      per-lane packed strand counters                      (BaseType::BaseType, src/basetype.cpp:45-71;
-//                                                            strand_bias counting, src/basetype.cpp:252-274)
-//   2. compacts the non-empty (base, phred) bins in place, in (base, phred) order
-//   3. runs EM + LRT backward elimination on the bins: all reads of one bin are exchangeable in
-//      e_step/m_step (src/algorithm.h:148-198), so a bin of c reads contributes c * (per-read term);
-//      lanes own bins, allele sums are warp-shuffle reductions   (EM, src/algorithm.h:210-255;
-//                                                                 _f / lrt, src/basetype.cpp:105-199)
-//   4. QUAL (chi2 survival via kf_gammaq) and the two Fisher strand-bias tests  (src/basetype.cpp:180-194,
-//                                                                                 :244-295)
-//   5. writes the fixed 128-byte bv_site_out record.
+//   1. streams the three u8 planes of the site row (base, qual, strand) with 128-bit loads and counts every
+//      read into a warp-private shared-memory histogram hist[strand 0..1][base 0..4][phred 0..95]
+//                                                            (BaseType::BaseType, src/basetype.cpp:45-71;
+//                                                             strand_bias counting, src/basetype.cpp:252-274)
+//   2. sweeps the touched phred range once: per-base depths and the 2x4 strand table by warp reductions
+//   3. decides the active alleles (depth/total >= min_af).  With ONE active allele the reference's EM has a
+//      closed form (AF == 1.0 exactly) and nothing else is computed.  Otherwise the non-empty (base, phred)
+//      bins are compacted and EM + LRT backward elimination run on the bins: all reads of one bin are
+//      exchangeable in e_step/m_step (src/algorithm.h:148-198), so a bin of c reads contributes c * (per-read
+//      term); lanes own bins, allele sums are warp-shuffle reductions
+//                                                            (EM, src/algorithm.h:210-255;
+//                                                             _f / lrt, src/basetype.cpp:105-199)
+//   4. QUAL (chi2 survival via kf_gammaq) and the two Fisher strand-bias tests
+//                                                            (src/basetype.cpp:180-194, :244-295)
+//   5. writes the fixed 128-byte bv_site_out record with one coalesced store.
 //
 // The only FP64 work that scales with the number of samples is gone: the sample axis is byte loads and
 // integer shared-memory atomics; FP64 work is O(bins) per site.  Per-read likelihood values (1-eps,
@@ -27,12 +30,15 @@
 
 namespace bv {
 
-constexpr int kQStride = 96;               // phred slots per base row of the histogram (0..93 used)
-constexpr int kHistWords = 5 * kQStride;   // A,C,G,T,other
-constexpr int kLutOneMinusEps = 0;         // lut[0][q] = 1 - eps(q)
-constexpr int kLutEpsThird = 1;            // lut[1][q] = eps(q) / 3
-constexpr int kLutLogMatch = 2;            // lut[2][q] = log(1 - eps(q))   (glibc)
-constexpr int kLutLogMis = 3;              // lut[3][q] = log(eps(q) / 3)   (glibc)
+constexpr int kQStride = 96;                 // phred slots per histogram row (0..93 used)
+constexpr int kHistRows = 10;                // (strand 0..1) x (A,C,G,T,other)
+constexpr int kHistWords = kHistRows * kQStride;
+constexpr int kSmemBins = 160;               // compact bins kept in shared memory; more spill to global scratch
+constexpr int kMaxBins = 5 * kQStride;       // 480
+constexpr int kLutOneMinusEps = 0;           // lut[0][q] = 1 - eps(q)
+constexpr int kLutEpsThird = 1;              // lut[1][q] = eps(q) / 3
+constexpr int kLutLogMatch = 2;              // lut[2][q] = log(1 - eps(q))   (glibc)
+constexpr int kLutLogMis = 3;                // lut[3][q] = log(eps(q) / 3)   (glibc)
 
 struct SiteKernelArgs {
     const uint8_t* base;
@@ -42,6 +48,8 @@ struct SiteKernelArgs {
     bv_site_out* out;
     const double* lut;       // [4][kQStride]
     const double* logfact;   // [max_samples + 2], lgamma(k+1) from glibc
+    uint32_t* bin_spill;     // [total warps][kMaxBins - kSmemBins] overflow bins (rare: > 160 distinct bins)
+    double* lml_spill;       // [total warps][kMaxBins] EM state of bins beyond the register-resident ones
     uint64_t pitch;
     uint32_t n_sites;
     uint32_t n_samples;
@@ -54,13 +62,16 @@ struct SiteKernelArgs {
 
 // Per-warp shared-memory working set.
 struct __align__(16) WarpScratch {
-    uint32_t hist[kHistWords];  // dense histogram while streaming; packed compact bins afterwards
-    double lml[kHistWords];     // log marginal likelihood of each compact bin (EM state)
-    bv_site_out rec;            // record staging for one coalesced 128-byte store
+    uint32_t hist[kHistWords];   // dense histogram, all-zero between sites
+    uint32_t bins[kSmemBins];    // compact non-empty (base, phred) bins: (base << 29) | (phred << 22) | count
+    bv_site_out rec;             // record staging for one coalesced 128-byte store
 };
 
-__device__ __forceinline__ uint32_t pack_bin(uint32_t code, uint32_t count) { return (code << 22) | count; }
-__device__ __forceinline__ uint32_t bin_code(uint32_t p) { return p >> 22; }
+__device__ __forceinline__ uint32_t pack_bin(uint32_t b, uint32_t q, uint32_t count) {
+    return (b << 29) | (q << 22) | count;
+}
+__device__ __forceinline__ uint32_t bin_base(uint32_t p) { return p >> 29; }
+__device__ __forceinline__ uint32_t bin_qual(uint32_t p) { return (p >> 22) & 0x7fu; }
 __device__ __forceinline__ uint32_t bin_count(uint32_t p) { return p & 0x3fffffu; }
 
 // streaming loads: read once, do not pollute L1
@@ -72,71 +83,80 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
     return r;
 }
 
-// Per-lane counters of one site row.
+// Per-lane state of one site row.
 struct LaneCounts {
-    unsigned long long fwd, rev, nos;  // 4 x 16-bit fields (A,C,G,T) per strand class
-    uint32_t other, qmin, qmax, flags;
+    uint32_t qmin, qmax, flags;
 };
 
-// Count the (up to 4) cells of one 32-bit word of each plane.  MASKED: only the first `valid` cells exist
-// (tail of the row; cells in [n_samples, pitch) are padding).
-template <bool MASKED>
-__device__ __forceinline__ void count_word(uint32_t wb, uint32_t wq, uint32_t ws, int valid, uint32_t* hist,
+// Count the (up to 4) cells of one 32-bit word of each plane; vmask keeps only cells below n_samples.
+__device__ __forceinline__ void count_word(uint32_t wb, uint32_t wq, uint32_t ws, uint32_t vmask, uint32_t* hist,
                                            LaneCounts& lc) {
     // bit 7 of each byte of `nc` is set iff the base code is >= 5 (N / indel / junk): not counted
-    uint32_t nc = ((((wb | 0x80808080u) - 0x05050505u) | wb) & 0x80808080u);
-    uint32_t m = ~nc & 0x80808080u;
-    if (MASKED) m &= (valid <= 0) ? 0u : (valid >= 4 ? 0xffffffffu : (0xffffffffu >> (8 * (4 - valid))));
+    const uint32_t nc = (((wb | 0x80808080u) - 0x05050505u) | wb) & 0x80808080u;
+    uint32_t m = ~nc & 0x80808080u & vmask;
     while (m) {
-        int sh = __ffs(m) - 8;  // bit index of the cell's LSB
-        uint32_t b = (wb >> sh) & 0xffu;
+        const int sh = __ffs(m) - 8;  // bit index of the cell's LSB
+        m &= m - 1;
+        const uint32_t b = (wb >> sh) & 0xffu;
         uint32_t q = (wq >> sh) & 0xffu;
         uint32_t s = (ws >> sh) & 0xffu;
-        m &= m - 1;
         if (q > BV_QUAL_MAX) { lc.flags |= BV_FLAG_BAD_QUAL; q = BV_QUAL_MAX; }
-        atomicAdd(&hist[b * kQStride + q], 1u);
+        if (s > BV_STRAND_REV) { lc.flags |= BV_FLAG_BAD_STRAND; s = BV_STRAND_FWD; }
+        atomicAdd(&hist[(s * 5 + b) * kQStride + q], 1u);
         lc.qmin = min(lc.qmin, q);
         lc.qmax = max(lc.qmax, q);
-        if (b < 4) {
-            unsigned long long inc = 1ull << (16 * b);
-            if (s == BV_STRAND_FWD) lc.fwd += inc;
-            else if (s == BV_STRAND_REV) lc.rev += inc;
-            else { lc.nos += inc; lc.flags |= BV_FLAG_BAD_STRAND; }
-        } else {
-            lc.other += 1;
-            if (s > BV_STRAND_REV) lc.flags |= BV_FLAG_BAD_STRAND;
-        }
     }
 }
 
-template <bool MASKED>
-__device__ __forceinline__ void count_vec(const uint4& vb, const uint4& vq, const uint4& vs, int valid,
-                                          uint32_t* hist, LaneCounts& lc) {
-    count_word<MASKED>(vb.x, vq.x, vs.x, valid, hist, lc);
-    count_word<MASKED>(vb.y, vq.y, vs.y, valid - 4, hist, lc);
-    count_word<MASKED>(vb.z, vq.z, vs.z, valid - 8, hist, lc);
-    count_word<MASKED>(vb.w, vq.w, vs.w, valid - 12, hist, lc);
+__device__ __forceinline__ void count_vec(const uint4& vb, const uint4& vq, const uint4& vs, int valid, uint32_t* hist,
+                                          LaneCounts& lc) {
+    // valid = number of real cells in this 16-cell vector (>= 16 for all but the row's last vector)
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        const int left = valid - 4 * k;
+        const uint32_t vmask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+        // select word k without dynamic register indexing
+        const uint32_t wb = k == 0 ? vb.x : k == 1 ? vb.y : k == 2 ? vb.z : vb.w;
+        const uint32_t wq = k == 0 ? vq.x : k == 1 ? vq.y : k == 2 ? vq.z : vq.w;
+        const uint32_t wst = k == 0 ? vs.x : k == 1 ? vs.y : k == 2 ? vs.z : vs.w;
+        count_word(wb, wq, wst, vmask, hist, lc);
+    }
 }
 
-// ---- EM on compact bins (src/algorithm.h:210-255) ----------------------------------------------------------
-// subset: bit j set => allele j in the candidate combination.  f_io: initial frequencies in (NOT renormalised,
-// src/basetype.cpp:93-103), estimated frequencies out.  Returns sum of log marginal likelihoods under the
+// ---- compact-bin storage: first kSmemBins in shared memory, the (rare) rest in a per-warp global scratch ------
+struct BinStore {
+    const uint32_t* sbins;
+    const uint32_t* gbins;
+    double* lml;   // per-warp global scratch, one slot per bin
+    __device__ __forceinline__ uint32_t bin(int i) const { return i < kSmemBins ? sbins[i] : gbins[i - kSmemBins]; }
+};
+
+constexpr int kRegBins = 2;   // bins per lane whose EM state (log marginal likelihood) lives in registers
+
+// ---- EM on compact bins (src/algorithm.h:210-255) ----------------------------------------------------------------
+// subset: bit j set => allele j in the candidate combination.  f[0..3]: initial frequencies in (NOT renormalised,
+// src/basetype.cpp:93-103), estimated frequencies out.  Returns the sum of log marginal likelihoods under the
 // second-to-last frequency vector, exactly what _f() sums (src/basetype.cpp:119-120).
-__device__ __noinline__ double em_bins(const uint32_t* bins, int nb, double* lml, const double* s_lut, int subset,
-                                       double total, double* f_io, const SiteKernelArgs& a, uint32_t& flags) {
+struct Freq4 {
+    double v0, v1, v2, v3;
+};
+
+__device__ __noinline__ double em_bins(const BinStore& bs, int nb, const double* s_lut, int subset, double total,
+                                       Freq4& f, const SiteKernelArgs& a, uint32_t& flags) {
     const int lane = threadIdx.x & 31;
-    double f0 = f_io[0], f1 = f_io[1], f2 = f_io[2], f3 = f_io[3];
+    double f0 = f.v0, f1 = f.v1, f2 = f.v2, f3 = f.v3;
+    double lml_r[kRegBins];
+#pragma unroll
+    for (int r = 0; r < kRegBins; ++r) lml_r[r] = 0.0;
     int it = a.em_max_iter;
     bool first = true;
     for (;;) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0, delta = 0;
         bool big = false;
-        for (int i = lane; i < nb; i += 32) {
-            uint32_t p = bins[i];
-            uint32_t code = bin_code(p);
-            uint32_t b = code / kQStride, q = code - b * kQStride;
-            double cd = (double)bin_count(p);
-            double ome = s_lut[kLutOneMinusEps * kQStride + q], e3 = s_lut[kLutEpsThird * kQStride + q];
+        auto visit = [&](uint32_t p, double lml_prev) -> double {
+            const uint32_t b = bin_base(p), q = bin_qual(p);
+            const double cd = (double)bin_count(p);
+            const double ome = s_lut[kLutOneMinusEps * kQStride + q], e3 = s_lut[kLutEpsThird * kQStride + q];
             // e_step (algorithm.h:160-172): lik*freq summed in A,C,G,T order; alleles outside the subset have
             // freq 0 and add an exact +0.0, so they are skipped
             double l0 = 0, l1 = 0, l2 = 0, l3 = 0, m = 0;
@@ -144,9 +164,9 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, int nb, double* lml
             if (subset & 2) { l1 = (b == 1 ? ome : e3) * f1; m += l1; }
             if (subset & 4) { l2 = (b == 2 ? ome : e3) * f2; m += l2; }
             if (subset & 8) { l3 = (b == 3 ? ome : e3) * f3; m += l3; }
-            double llh = log(m);
+            const double llh = log(m);
             if (!first) {
-                double diff = llh - lml[i];
+                const double diff = llh - lml_prev;
                 if (a.abs_mode == BV_EM_ABS_INT_TRUNC) {
                     // (double)abs((int)diff): non-zero iff |diff| >= 1; NaN/inf convert to INT_MIN whose
                     // "abs" stays negative and ends the loop (results are NaN by then)
@@ -155,13 +175,19 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, int nb, double* lml
                     delta += cd * fabs(diff);
                 }
             }
-            lml[i] = llh;
             // m_step (algorithm.h:184-198): column sums of the posteriors; c equal reads add c * post
             if (subset & 1) s0 += cd * (l0 / m);
             if (subset & 2) s1 += cd * (l1 / m);
             if (subset & 4) s2 += cd * (l2 / m);
             if (subset & 8) s3 += cd * (l3 / m);
+            return llh;
+        };
+#pragma unroll
+        for (int r = 0; r < kRegBins; ++r) {
+            const int i = lane + 32 * r;
+            if (i < nb) lml_r[r] = visit(bs.bin(i), lml_r[r]);
         }
+        for (int i = lane + 32 * kRegBins; i < nb; i += 32) bs.lml[i] = visit(bs.bin(i), first ? 0.0 : bs.lml[i]);
         if (subset & 1) f0 = warp_sum(s0) / total;
         if (subset & 2) f1 = warp_sum(s1) / total;
         if (subset & 4) f2 = warp_sum(s2) / total;
@@ -175,155 +201,204 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, int nb, double* lml
         if (!more || it == 0) break;
     }
     double ll = 0;
-    for (int i = lane; i < nb; i += 32) ll += (double)bin_count(bins[i]) * lml[i];
-    ll = warp_sum(ll);
-    f_io[0] = f0; f_io[1] = f1; f_io[2] = f2; f_io[3] = f3;
-    return ll;
+#pragma unroll
+    for (int r = 0; r < kRegBins; ++r) {
+        const int i = lane + 32 * r;
+        if (i < nb) ll += (double)bin_count(bs.bin(i)) * lml_r[r];
+    }
+    for (int i = lane + 32 * kRegBins; i < nb; i += 32) ll += (double)bin_count(bs.bin(i)) * bs.lml[i];
+    f.v0 = f0; f.v1 = f1; f.v2 = f2; f.v3 = f3;
+    return warp_sum(ll);
 }
 
 // Log-likelihood of the single-allele model {b} (an EM whose answer is closed form):
 // after the first m_step f_b == 1.0 exactly (every posterior is x/x), so every later marginal is L_b itself and
 // the reported log marginal is log(1-eps) or log(eps/3) -- both tabulated on the host with glibc.  A bin of base b
 // with phred 0 has L_b == 0: the reference then divides 0/0 and everything becomes NaN.
-__device__ __forceinline__ double single_allele_ll(const uint32_t* bins, int nb, const double* s_lut, int b_allele,
-                                                   bool& is_nan) {
+__device__ __noinline__ double single_allele_ll(const BinStore& bs, int nb, const double* s_lut, int b_allele,
+                                                bool& is_nan) {
     const int lane = threadIdx.x & 31;
     double ll = 0;
     bool bad = false;
     for (int i = lane; i < nb; i += 32) {
-        uint32_t p = bins[i];
-        uint32_t code = bin_code(p);
-        uint32_t b = code / kQStride, q = code - b * kQStride;
-        double cd = (double)bin_count(p);
-        bool match = ((int)b == b_allele);
+        const uint32_t p = bs.bin(i);
+        const uint32_t b = bin_base(p), q = bin_qual(p);
+        const bool match = ((int)b == b_allele);
         if (match && q == 0) bad = true;
-        ll += cd * s_lut[(match ? kLutLogMatch : kLutLogMis) * kQStride + q];
+        ll += (double)bin_count(p) * s_lut[(match ? kLutLogMatch : kLutLogMis) * kQStride + q];
     }
     is_nan = __any_sync(0xffffffffu, bad);
     return warp_sum(ll);
 }
 
-// The LRT loop only ever asks for the (n-1)-subsets of the current n active bases.  In the lexicographic
-// position order of src/external/combinations.h:19-84 the i-th of them drops position n-1-i.
-__device__ __forceinline__ int subset_posmask(int n_active, int i) {
-    return ((1 << n_active) - 1) ^ (1 << (n_active - 1 - i));
+__device__ __forceinline__ double sel4(int j, double v0, double v1, double v2, double v3) {
+    return j == 0 ? v0 : j == 1 ? v1 : j == 2 ? v2 : v3;
 }
-
-// ---- the warp-per-site core: everything after the row has been histogrammed -------------------------------------
-__device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut, const SiteKernelArgs& a,
-                                            uint32_t site, LaneCounts& lc) {
-    const int lane = threadIdx.x & 31;
-    // ---- reduce lane counters ----
-    uint32_t fwd[4], rev[4], dep[4];
+__device__ __forceinline__ uint32_t sel4u(int j, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    return j == 0 ? v0 : j == 1 ? v1 : j == 2 ? v2 : v3;
+}
+// position of the k-th (k >= 0) set bit of a 4-bit mask
+__device__ __forceinline__ int nth_set_bit(uint32_t mask, int k) {
+    int pos = -1;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-        uint32_t f = (uint32_t)(lc.fwd >> (16 * b)) & 0xffffu;
-        uint32_t r = (uint32_t)(lc.rev >> (16 * b)) & 0xffffu;
-        uint32_t x = (uint32_t)(lc.nos >> (16 * b)) & 0xffffu;
-        fwd[b] = __reduce_add_sync(0xffffffffu, f);
-        rev[b] = __reduce_add_sync(0xffffffffu, r);
-        dep[b] = fwd[b] + rev[b] + __reduce_add_sync(0xffffffffu, x);
+        if (mask & (1u << b)) {
+            if (k == 0 && pos < 0) pos = b;
+            --k;
+        }
     }
-    const uint32_t other = __reduce_add_sync(0xffffffffu, lc.other);
+    return pos;
+}
+
+// exact `(double)dep / (double)total >= min_af` (src/basetype.cpp:137) with the trivial cases short-cut
+__device__ __forceinline__ bool is_active(uint32_t dep, uint32_t total, double dtot, double min_af) {
+    if (dep == 0) return 0.0 >= min_af;
+    if (dep == total) return 1.0 >= min_af;
+    return (double)dep / dtot >= min_af;
+}
+
+// ---- the warp-per-site core: everything after the row has been histogrammed ----------------------------------------
+__device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut, const SiteKernelArgs& a,
+                                            uint32_t site, uint32_t warp_global, LaneCounts& lc) {
+    const int lane = threadIdx.x & 31;
     uint32_t flags = __reduce_or_sync(0xffffffffu, lc.flags);
     const uint32_t qmin = __reduce_min_sync(0xffffffffu, lc.qmin);
     const uint32_t qmax = __reduce_max_sync(0xffffffffu, lc.qmax);
-    const uint32_t total = dep[0] + dep[1] + dep[2] + dep[3] + other;
-
-    // ---- compact the non-empty bins in place, (base, phred) order ----
     __syncwarp();
-    int nb = 0;
-    if (total > 0) {
-        for (int b = 0; b < 5; ++b) {
-            for (uint32_t q0 = qmin; q0 <= qmax; q0 += 32) {
-                uint32_t q = q0 + lane;
-                uint32_t idx = b * kQStride + q;
-                uint32_t v = 0;
-                if (q <= qmax) { v = ws.hist[idx]; }
-                __syncwarp();
-                if (q <= qmax && v) ws.hist[idx] = 0;
-                uint32_t bal = __ballot_sync(0xffffffffu, v != 0);
-                __syncwarp();
-                if (v) ws.hist[nb + __popc(bal & ((1u << lane) - 1u))] = pack_bin(idx, v);
-                nb += __popc(bal);
-                __syncwarp();
-            }
+
+    // ---- sweep 1: depths and strand table from the touched phred range ----
+    // rows 0..4 = '+' strand A,C,G,T,other; rows 5..9 = '-' strand.  A counted cell whose strand is neither sets
+    // BV_FLAG_BAD_STRAND and is counted as '+': the reference throws on such a site (src/basetype.cpp:271-273), so
+    // only its depths and flags are specified.
+    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+    if (qmin <= qmax) {
+        for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
+            f0 += ws.hist[0 * kQStride + q]; f1 += ws.hist[1 * kQStride + q]; f2 += ws.hist[2 * kQStride + q];
+            f3 += ws.hist[3 * kQStride + q]; f4 += ws.hist[4 * kQStride + q];
+            r0 += ws.hist[5 * kQStride + q]; r1 += ws.hist[6 * kQStride + q]; r2 += ws.hist[7 * kQStride + q];
+            r3 += ws.hist[8 * kQStride + q]; r4 += ws.hist[9 * kQStride + q];
         }
+        f0 = __reduce_add_sync(0xffffffffu, f0); f1 = __reduce_add_sync(0xffffffffu, f1);
+        f2 = __reduce_add_sync(0xffffffffu, f2); f3 = __reduce_add_sync(0xffffffffu, f3);
+        r0 = __reduce_add_sync(0xffffffffu, r0); r1 = __reduce_add_sync(0xffffffffu, r1);
+        r2 = __reduce_add_sync(0xffffffffu, r2); r3 = __reduce_add_sync(0xffffffffu, r3);
+        f4 = __reduce_add_sync(0xffffffffu, f4 + r4);
     }
-    uint32_t* bins = ws.hist;
+    const uint32_t d0 = f0 + r0, d1 = f1 + r1, d2 = f2 + r2, d3 = f3 + r3, other = f4;
+    const uint32_t total = d0 + d1 + d2 + d3 + other;
+    const double dtot = (double)total;
 
     // ---- reference base ----
     int ref_char = a.ref_base[site];
     if (ref_char >= 'a' && ref_char <= 'z') ref_char -= 32;  // toupper (src/basetype.cpp:171)
     const int ref_code = ref_char == 'A' ? 0 : ref_char == 'C' ? 1 : ref_char == 'G' ? 2 : ref_char == 'T' ? 3 : -1;
 
-    // ---- lrt (src/basetype.cpp:130-199) ----
-    int act[4];
-    int n_act = 0;
-    const double dtot = (double)total;
+    // ---- lrt (src/basetype.cpp:130-199): active set ----
+    uint32_t act = 0;   // bit b set => base b active
     if (total > 0) {
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if ((double)dep[b] / dtot >= a.min_af) act[n_act++] = b;   // exact-boundary compare (:137)
+        act |= is_active(d0, total, dtot, a.min_af) ? 1u : 0u;
+        act |= is_active(d1, total, dtot, a.min_af) ? 2u : 0u;
+        act |= is_active(d2, total, dtot, a.min_af) ? 4u : 0u;
+        act |= is_active(d3, total, dtot, a.min_af) ? 8u : 0u;
     }
-    double f_act[4] = {0, 0, 0, 0};
+    int n_act = __popc(act);
+    Freq4 fa = {0, 0, 0, 0};   // frequencies of the accepted model
     double chi = 0.0;
     uint32_t em_calls = 0;
+
     if (n_act == 1) {
         // One active allele: the reference still runs one EM; its answer is closed form (see single_allele_ll):
         // AF == 1.0 exactly, or NaN when a phred-0 read of that base exists.
-        bool bad;
-        (void)single_allele_ll(bins, nb, s_lut, act[0], bad);
-        f_act[act[0]] = bad ? __longlong_as_double(0x7ff8000000000000ll) : 1.0;
+        const int b = __ffs(act) - 1;
+        bool bad = false;
+        if (qmin == 0) {
+            bad = (ws.hist[b * kQStride] + ws.hist[(5 + b) * kQStride]) != 0;
+        }
+        const double v = bad ? __longlong_as_double(0x7ff8000000000000ll) : 1.0;
+        fa.v0 = b == 0 ? v : 0.0; fa.v1 = b == 1 ? v : 0.0; fa.v2 = b == 2 ? v : 0.0; fa.v3 = b == 3 ? v : 0.0;
         em_calls = 1;
-    } else if (n_act > 1) {
-        int mask = 0;
-        for (int k = 0; k < n_act; ++k) { mask |= 1 << act[k]; f_act[act[k]] = (double)dep[act[k]] / dtot; }
-        double lr_alt = em_bins(bins, nb, ws.lml, s_lut, mask, dtot, f_act, a, flags);
+    }
+    __syncwarp();
+
+    // ---- sweep 2: histogram back to zero; with >= 2 active alleles also compact the bins ----
+    int nb = 0;
+    uint32_t* gbins = a.bin_spill + (size_t)warp_global * (kMaxBins - kSmemBins);
+    if (qmin <= qmax) {
+        if (n_act >= 2) {
+            for (int b = 0; b < 5; ++b) {
+                for (uint32_t q0 = qmin; q0 <= qmax; q0 += 32) {
+                    const uint32_t q = q0 + lane;
+                    uint32_t v = 0;
+                    if (q <= qmax) {
+                        v = ws.hist[b * kQStride + q] + ws.hist[(5 + b) * kQStride + q];
+                        ws.hist[b * kQStride + q] = 0;
+                        ws.hist[(5 + b) * kQStride + q] = 0;
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, v != 0);
+                    if (v) {
+                        const int pos = nb + __popc(bal & ((1u << lane) - 1u));
+                        const uint32_t p = pack_bin(b, q, v);
+                        if (pos < kSmemBins) ws.bins[pos] = p; else gbins[pos - kSmemBins] = p;
+                    }
+                    nb += __popc(bal);
+                }
+            }
+        } else {
+            for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
+#pragma unroll
+                for (int r = 0; r < kHistRows; ++r) ws.hist[r * kQStride + q] = 0;
+            }
+        }
+    }
+    __syncwarp();
+
+    if (n_act >= 2) {
+        BinStore bs;
+        bs.sbins = ws.bins;
+        bs.gbins = gbins;
+        bs.lml = a.lml_spill + (size_t)warp_global * kMaxBins;
+        const double i0 = (double)d0 / dtot, i1 = (double)d1 / dtot, i2 = (double)d2 / dtot, i3 = (double)d3 / dtot;
+        fa.v0 = (act & 1) ? i0 : 0.0; fa.v1 = (act & 2) ? i1 : 0.0; fa.v2 = (act & 4) ? i2 : 0.0; fa.v3 = (act & 8) ? i3 : 0.0;
+        double lr_alt = em_bins(bs, nb, s_lut, (int)act, dtot, fa, a, flags);
         em_calls = 1;
         for (int n = n_act - 1; n > 0; --n) {
-            const int ns = n_act;   // C(n_act, n_act-1)
-            double best_chi = 0, best_lr = 0, best_f[4] = {0, 0, 0, 0};
-            int best_pm = 0;
-            for (int i = 0; i < ns; ++i) {
-                const int pm = subset_posmask(n_act, i);
-                double f[4] = {0, 0, 0, 0};
-                int sm = 0, single = -1;
-                for (int k = 0; k < n_act; ++k)
-                    if (pm & (1 << k)) { sm |= 1 << act[k]; f[act[k]] = (double)dep[act[k]] / dtot; single = act[k]; }
+            // the n-subsets of the n+1 active bases in the lexicographic order of
+            // src/external/combinations.h:19-84: the i-th subset drops the (n-i)-th active base
+            double best_chi = 0, best_lr = 0;
+            Freq4 best_f = {0, 0, 0, 0};
+            uint32_t best_set = 0;
+            for (int i = 0; i <= n; ++i) {
+                const uint32_t sub = act & ~(1u << nth_set_bit(act, n - i));
+                Freq4 g = {(sub & 1) ? i0 : 0.0, (sub & 2) ? i1 : 0.0, (sub & 4) ? i2 : 0.0, (sub & 8) ? i3 : 0.0};
+                if (g.v0 + g.v1 + g.v2 + g.v3 == 0) flags |= BV_FLAG_ZERO_SUBSET;   // the reference throws (basetype.cpp:113)
                 double lr;
                 if (n == 1) {
+                    const int single = __ffs(sub) - 1;
                     bool bad;
-                    lr = single_allele_ll(bins, nb, s_lut, single, bad);
-                    f[single] = 1.0;
-                    if (bad) { lr = __longlong_as_double(0x7ff8000000000000ll); f[single] = lr; }
+                    lr = single_allele_ll(bs, nb, s_lut, single, bad);
+                    double v = 1.0;
+                    if (bad) { lr = __longlong_as_double(0x7ff8000000000000ll); v = lr; }
+                    g.v0 = single == 0 ? v : 0.0; g.v1 = single == 1 ? v : 0.0; g.v2 = single == 2 ? v : 0.0; g.v3 = single == 3 ? v : 0.0;
                 } else {
-                    lr = em_bins(bins, nb, ws.lml, s_lut, sm, dtot, f, a, flags);
+                    lr = em_bins(bs, nb, s_lut, (int)sub, dtot, g, a, flags);
                 }
                 if (em_calls < 255) ++em_calls;
-                double c = 2 * (lr_alt - lr);
+                const double c = 2 * (lr_alt - lr);
                 // std::min_element keeps the FIRST minimum (algorithm.h:24-27).  Alleles with identical read
-                // multisets give bit-identical chi in the reference (its per-read sums are symmetric under
-                // relabelling); here the bin order is not symmetric, so values that agree to rounding noise
-                // are treated as the tie they are and the earlier subset stays.
+                // multisets have equal likelihood; the reference's pick between them hangs on the rounding noise
+                // of its read-order sums.  Values that agree to rounding noise are treated as the tie they are:
+                // the earlier subset stays and the site is flagged.
                 const double tie_tol = 1e-11 * (fabs(lr_alt) + fabs(lr));
                 if (i > 0 && fabs(c - best_chi) <= tie_tol) flags |= BV_FLAG_LRT_TIE;
                 if (i == 0 || c < best_chi - tie_tol) {
-                    best_chi = c; best_lr = lr; best_pm = pm;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) best_f[j] = f[j];
+                    best_chi = c; best_lr = lr; best_set = sub; best_f = g;
                 }
             }
             lr_alt = best_lr;
             chi = best_chi;
             if (fabs(chi - a.lrt_threshold) < 1e-9 * a.lrt_threshold) flags |= BV_FLAG_NEAR_LRT;
             if (chi < a.lrt_threshold) {
-                int k2 = 0;
-                for (int k = 0; k < n_act; ++k)
-                    if (best_pm & (1 << k)) act[k2++] = act[k];
-                n_act = n;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) f_act[j] = best_f[j];
+                act = best_set; n_act = n; fa = best_f;
             } else {
                 break;
             }
@@ -331,48 +406,47 @@ __device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut
     }
 
     // ---- ALT / QUAL (src/basetype.cpp:170-196) ----
-    int n_alt = 0;
-    int alt[4] = {0, 0, 0, 0};
-    double af[4] = {0, 0, 0, 0};
-    for (int k = 0; k < n_act; ++k)
-        if (act[k] != ref_code) { alt[n_alt] = act[k]; af[n_alt] = f_act[act[k]]; ++n_alt; }
+    const uint32_t alt_set = (ref_code >= 0) ? (act & ~(1u << ref_code)) : act;
+    const int n_alt = __popc(alt_set);
     double qual = 0.0;
     if (n_alt) {
-        double r = (double)dep[act[0]] / dtot;
+        const int first_act = __ffs(act) - 1;
+        const double r = (double)sel4u(first_act, d0, d1, d2, d3) / dtot;
         if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
         else qual = qual_from_chi(chi);
     }
 
     // ---- strand bias (src/basetype.cpp:244-295): CVG row = ref vs all non-ref ACGT; VCF row = ref vs ALT ----
-    double fs_cvg, fs_vcf = 0.0;
+    double fs_cvg = 0.0, fs_vcf = 0.0;
     {
-        int rf = 0, rr = 0, af_ = 0, ar = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            if (b == ref_code) { rf += fwd[b]; rr += rev[b]; } else { af_ += fwd[b]; ar += rev[b]; }
-        }
+        const int rf = ref_code < 0 ? 0 : (int)sel4u(ref_code, f0, f1, f2, f3);
+        const int rr = ref_code < 0 ? 0 : (int)sel4u(ref_code, r0, r1, r2, r3);
+        const int af_ = (int)(f0 + f1 + f2 + f3) - rf, ar = (int)(r0 + r1 + r2 + r3) - rr;
         fs_cvg = fs_from_table(a.logfact, rf, rr, af_, ar);
         if (n_alt) {
-            int vf = 0, vr = 0;
-            for (int k = 0; k < n_alt; ++k) { vf += fwd[alt[k]]; vr += rev[alt[k]]; }
+            const int vf = (int)(((alt_set & 1) ? f0 : 0u) + ((alt_set & 2) ? f1 : 0u) + ((alt_set & 4) ? f2 : 0u) + ((alt_set & 8) ? f3 : 0u));
+            const int vr = (int)(((alt_set & 1) ? r0 : 0u) + ((alt_set & 2) ? r1 : 0u) + ((alt_set & 4) ? r2 : 0u) + ((alt_set & 8) ? r3 : 0u));
             if (vf == af_ && vr == ar) fs_vcf = fs_cvg;   // same 2x2 table
             else fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
         }
     }
 
     // ---- record ----
-    __syncwarp();
-    for (int i = lane; i < nb; i += 32) ws.hist[i] = 0;   // histogram back to all-zero for the next site
     if (lane == 0) {
         bv_site_out& r = ws.rec;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) { r.depth[b] = dep[b]; r.fwd[b] = fwd[b]; r.rev[b] = rev[b]; }
+        r.depth[0] = d0; r.depth[1] = d1; r.depth[2] = d2; r.depth[3] = d3;
         r.depth_other = other;
         r.reserved0 = 0;
+        r.fwd[0] = f0; r.fwd[1] = f1; r.fwd[2] = f2; r.fwd[3] = f3;
+        r.rev[0] = r0; r.rev[1] = r1; r.rev[2] = r2; r.rev[3] = r3;
         r.n_alt = (uint8_t)n_alt;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { r.alt[k] = (uint8_t)alt[k]; r.af[k] = af[k]; }
-        r.n_active = (uint8_t)((total > 0) ? n_act : 0);
+        for (int k = 0; k < 4; ++k) {
+            const int b = k < n_alt ? nth_set_bit(alt_set, k) : 0;
+            r.alt[k] = (uint8_t)b;
+            r.af[k] = k < n_alt ? sel4(b, fa.v0, fa.v1, fa.v2, fa.v3) : 0.0;
+        }
+        r.n_active = (uint8_t)n_act;
         r.flags = (uint8_t)flags;
         r.em_calls = (uint8_t)em_calls;
         r.qual = qual;

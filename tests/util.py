@@ -30,10 +30,16 @@ def compare_records(got, want, check_diag=True, rtol=RTOL):
     assert got.shape == want.shape
     n = got.shape[0]
     int_fail = np.zeros(n, bool)
-    for f in ("depth", "depth_other", "fwd", "rev"):
+    # a counted cell with a strand symbol other than +/- makes the reference throw (src/basetype.cpp:271-273):
+    # for such sites only the flag and the depths are specified
+    badst = ((got["flags"] | want["flags"]) & capi.FLAG_BAD_STRAND) != 0
+    for f in ("depth", "depth_other"):
         x = got[f] != want[f]
         int_fail |= x.reshape(n, -1).any(axis=1)
-    flt_fail = ~close(got["fs_cvg"], want["fs_cvg"], rtol)
+    for f in ("fwd", "rev"):
+        x = got[f] != want[f]
+        int_fail |= x.reshape(n, -1).any(axis=1) & ~badst
+    flt_fail = ~close(got["fs_cvg"], want["fs_cvg"], rtol) & ~badst
     soft = ((got["flags"] | want["flags"]) & (capi.FLAG_NEAR_LRT | capi.FLAG_LRT_TIE)) != 0
     call_diff = (got["n_alt"] != want["n_alt"]) | (got["alt"] != want["alt"]).any(axis=1)
     if check_diag:
@@ -45,7 +51,7 @@ def compare_records(got, want, check_diag=True, rtol=RTOL):
         live = same_call & (got["n_alt"] > k)
         flt_fail |= live & ~close(got["af"][:, k], want["af"][:, k], rtol)
     flt_fail |= same_call & (got["n_alt"] > 0) & ~close(got["qual"], want["qual"], rtol) & ~soft
-    flt_fail |= same_call & (got["n_alt"] > 0) & ~close(got["fs_vcf"], want["fs_vcf"], rtol)
+    flt_fail |= same_call & (got["n_alt"] > 0) & ~close(got["fs_vcf"], want["fs_vcf"], rtol) & ~badst
     if check_diag:
         flt_fail |= same_call & ~soft & ~close(got["chi2"], want["chi2"], rtol, atol=1e-9)
         mask = capi.FLAG_BAD_STRAND
