@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bv_site_kernel(const Sit
     const uint32_t total_warps = gridDim.x * kWarpsPerCta;
     const uint32_t warp_global = blockIdx.x * kWarpsPerCta + warp;
     const int nvec = (int)((a.n_samples + 15u) >> 4);   // 16-cell vectors per row (last one may be partial)
+    const int niter = (nvec + 31) >> 5;                 // warp iterations per row
     for (uint32_t site = warp_global; site < a.n_sites; site += total_warps) {
         LaneCounts lc;
         lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
@@ -45,12 +46,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bv_site_kernel(const Sit
         const uint4* pb = reinterpret_cast<const uint4*>(a.base + row);
         const uint4* pq = reinterpret_cast<const uint4*>(a.qual + row);
         const uint4* ps = reinterpret_cast<const uint4*>(a.strand + row);
+        // every lane runs the same number of iterations (count_word ends in a full-warp barrier); lanes past the end
+        // of the row carry an all-'N' vector
+        const uint4 kAllN = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
         int v = lane;
-        uint4 b0 = make_uint4(0, 0, 0, 0), q0 = b0, s0 = b0;
+        uint4 b0 = kAllN, q0 = kAllN, s0 = kAllN;
         if (v < nvec) { b0 = ld_stream(pb + v); q0 = ld_stream(pq + v); s0 = ld_stream(ps + v); }
-        while (v < nvec) {
+        for (int it = 0; it < niter; ++it) {
             const int vn = v + 32;
-            uint4 b1 = make_uint4(0, 0, 0, 0), q1 = b1, s1 = b1;
+            uint4 b1 = kAllN, q1 = kAllN, s1 = kAllN;
             if (vn < nvec) { b1 = ld_stream(pb + vn); q1 = ld_stream(pq + vn); s1 = ld_stream(ps + vn); }
             count_vec(b0, q0, s0, (int)a.n_samples - 16 * v, ws.hist, lc);
             b0 = b1; q0 = q1; s0 = s1;

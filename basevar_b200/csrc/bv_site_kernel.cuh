@@ -30,11 +30,11 @@
 
 namespace bv {
 
-constexpr int kQStride = 96;                 // phred slots per histogram row (0..93 used)
+constexpr int kQStride = 128;                // phred slots per histogram row (0..93 used; 7-bit index never overflows)
 constexpr int kHistRows = 10;                // (strand 0..1) x (A,C,G,T,other)
 constexpr int kHistWords = kHistRows * kQStride;
 constexpr int kSmemBins = 160;               // compact bins kept in shared memory; more spill to global scratch
-constexpr int kMaxBins = 5 * kQStride;       // 480
+constexpr int kMaxBins = 5 * kQStride;       // upper bound on distinct (base, phred) bins
 constexpr int kLutOneMinusEps = 0;           // lut[0][q] = 1 - eps(q)
 constexpr int kLutEpsThird = 1;              // lut[1][q] = eps(q) / 3
 constexpr int kLutLogMatch = 2;              // lut[2][q] = log(1 - eps(q))   (glibc)
@@ -88,39 +88,54 @@ struct LaneCounts {
     uint32_t qmin, qmax, flags;
 };
 
-// Count the (up to 4) cells of one 32-bit word of each plane; vmask keeps only cells below n_samples.
-__device__ __forceinline__ void count_word(uint32_t wb, uint32_t wq, uint32_t ws, uint32_t vmask, uint32_t* hist,
-                                           LaneCounts& lc) {
-    // bit 7 of each byte of `nc` is set iff the base code is >= 5 (N / indel / junk): not counted
-    const uint32_t nc = (((wb | 0x80808080u) - 0x05050505u) | wb) & 0x80808080u;
-    uint32_t m = ~nc & 0x80808080u & vmask;
-    while (m) {
-        const int sh = __ffs(m) - 8;  // bit index of the cell's LSB
-        m &= m - 1;
-        const uint32_t b = (wb >> sh) & 0xffu;
-        uint32_t q = (wq >> sh) & 0xffu;
-        uint32_t s = (ws >> sh) & 0xffu;
-        if (q > BV_QUAL_MAX) { lc.flags |= BV_FLAG_BAD_QUAL; q = BV_QUAL_MAX; }
-        if (s > BV_STRAND_REV) { lc.flags |= BV_FLAG_BAD_STRAND; s = BV_STRAND_FWD; }
-        atomicAdd(&hist[(s * 5 + b) * kQStride + q], 1u);
-        lc.qmin = min(lc.qmin, q);
-        lc.qmax = max(lc.qmax, q);
+// Count the 4 cells of one 32-bit word of each plane.  Histogram slot of a read: (base << 8) | (strand << 7) | phred.
+__device__ __forceinline__ void count_word(uint32_t wb, uint32_t wq, uint32_t ws, uint32_t* hist, LaneCounts& lc) {
+    // bit 7 of each byte of `m` is set iff the base code is < 5 (A,C,G,T,other): the cell is counted
+    uint32_t m = ~((((wb | 0x80808080u) - 0x05050505u) | wb)) & 0x80808080u;
+    if (m) {
+        // rare input errors, checked per word: a counted cell with phred > 93 or a strand symbol other than +/-
+        const uint32_t bytes = (m >> 7) * 0xffu;
+        const uint32_t badq = ((wq + 0x22222222u) | wq) & m, bads = ws & 0xfefefefeu & bytes;
+        if (badq | bads) lc.flags |= (badq ? BV_FLAG_BAD_QUAL : 0u) | (bads ? BV_FLAG_BAD_STRAND : 0u);
+        const uint32_t sq = (wq & 0x7f7f7f7fu) | ((ws & 0x01010101u) << 7);   // per byte: strand << 7 | phred
+        do {
+            int top;                         // bit 7 of the highest counted cell
+            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(m));
+            const int sh = top - 7;
+            m ^= 1u << top;
+            const uint32_t b = (wb >> sh) & 0xffu;
+            const uint32_t x = (sq >> sh) & 0xffu;
+            atomicAdd(&hist[(b << 8) | x], 1u);
+            const uint32_t q = x & 0x7fu;
+            lc.qmin = min(lc.qmin, q);
+            lc.qmax = max(lc.qmax, q);
+        } while (m);
     }
+    // Lanes leave the cell loop after different trip counts; without an explicit barrier the warp stays split
+    // into fragments for the rest of the row (measured: 6.5 active lanes per streaming load).
+    __syncwarp();
 }
 
-__device__ __forceinline__ void count_vec(const uint4& vb, const uint4& vq, const uint4& vs, int valid, uint32_t* hist,
-                                          LaneCounts& lc) {
-    // valid = number of real cells in this 16-cell vector (>= 16 for all but the row's last vector)
-#pragma unroll 1
+// valid = number of real cells in this 16-cell vector (>= 16 for all but the row's last vector): padding cells
+// are turned into 'N'
+__device__ __forceinline__ void mask_tail(uint4& vb, int valid) {
+    uint32_t w[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int left = valid - 4 * k;
-        const uint32_t vmask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
-        // select word k without dynamic register indexing
-        const uint32_t wb = k == 0 ? vb.x : k == 1 ? vb.y : k == 2 ? vb.z : vb.w;
-        const uint32_t wq = k == 0 ? vq.x : k == 1 ? vq.y : k == 2 ? vq.z : vq.w;
-        const uint32_t wst = k == 0 ? vs.x : k == 1 ? vs.y : k == 2 ? vs.z : vs.w;
-        count_word(wb, wq, wst, vmask, hist, lc);
+        const uint32_t keep = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+        w[k] = (w[k] & keep) | (0x05050505u & ~keep);
     }
+    vb = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ void count_vec(uint4 vb, const uint4& vq, const uint4& vs, int valid, uint32_t* hist,
+                                          LaneCounts& lc) {
+    if (valid < 16) mask_tail(vb, valid);
+    count_word(vb.x, vq.x, vs.x, hist, lc);
+    count_word(vb.y, vq.y, vs.y, hist, lc);
+    count_word(vb.z, vq.z, vs.z, hist, lc);
+    count_word(vb.w, vq.w, vs.w, hist, lc);
 }
 
 // ---- compact-bin storage: first kSmemBins in shared memory, the (rare) rest in a per-warp global scratch ------
@@ -267,16 +282,17 @@ __device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut
     __syncwarp();
 
     // ---- sweep 1: depths and strand table from the touched phred range ----
-    // rows 0..4 = '+' strand A,C,G,T,other; rows 5..9 = '-' strand.  A counted cell whose strand is neither sets
-    // BV_FLAG_BAD_STRAND and is counted as '+': the reference throws on such a site (src/basetype.cpp:271-273), so
+    // row 2*base + strand ('+' = 0, '-' = 1).  A counted cell whose strand is neither sets
+    // BV_FLAG_BAD_STRAND and is counted by the low bit of its code: the reference throws on such a site (src/basetype.cpp:271-273), so
     // only its depths and flags are specified.
     uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
     if (qmin <= qmax) {
         for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
-            f0 += ws.hist[0 * kQStride + q]; f1 += ws.hist[1 * kQStride + q]; f2 += ws.hist[2 * kQStride + q];
-            f3 += ws.hist[3 * kQStride + q]; f4 += ws.hist[4 * kQStride + q];
-            r0 += ws.hist[5 * kQStride + q]; r1 += ws.hist[6 * kQStride + q]; r2 += ws.hist[7 * kQStride + q];
-            r3 += ws.hist[8 * kQStride + q]; r4 += ws.hist[9 * kQStride + q];
+            f0 += ws.hist[0 * kQStride + q]; r0 += ws.hist[1 * kQStride + q];
+            f1 += ws.hist[2 * kQStride + q]; r1 += ws.hist[3 * kQStride + q];
+            f2 += ws.hist[4 * kQStride + q]; r2 += ws.hist[5 * kQStride + q];
+            f3 += ws.hist[6 * kQStride + q]; r3 += ws.hist[7 * kQStride + q];
+            f4 += ws.hist[8 * kQStride + q]; r4 += ws.hist[9 * kQStride + q];
         }
         f0 = __reduce_add_sync(0xffffffffu, f0); f1 = __reduce_add_sync(0xffffffffu, f1);
         f2 = __reduce_add_sync(0xffffffffu, f2); f3 = __reduce_add_sync(0xffffffffu, f3);
@@ -312,7 +328,7 @@ __device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut
         const int b = __ffs(act) - 1;
         bool bad = false;
         if (qmin == 0) {
-            bad = (ws.hist[b * kQStride] + ws.hist[(5 + b) * kQStride]) != 0;
+            bad = (ws.hist[(2 * b) * kQStride] + ws.hist[(2 * b + 1) * kQStride]) != 0;
         }
         const double v = bad ? __longlong_as_double(0x7ff8000000000000ll) : 1.0;
         fa.v0 = b == 0 ? v : 0.0; fa.v1 = b == 1 ? v : 0.0; fa.v2 = b == 2 ? v : 0.0; fa.v3 = b == 3 ? v : 0.0;
@@ -330,9 +346,9 @@ __device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut
                     const uint32_t q = q0 + lane;
                     uint32_t v = 0;
                     if (q <= qmax) {
-                        v = ws.hist[b * kQStride + q] + ws.hist[(5 + b) * kQStride + q];
-                        ws.hist[b * kQStride + q] = 0;
-                        ws.hist[(5 + b) * kQStride + q] = 0;
+                        v = ws.hist[(2 * b) * kQStride + q] + ws.hist[(2 * b + 1) * kQStride + q];
+                        ws.hist[(2 * b) * kQStride + q] = 0;
+                        ws.hist[(2 * b + 1) * kQStride + q] = 0;
                     }
                     const uint32_t bal = __ballot_sync(0xffffffffu, v != 0);
                     if (v) {
