@@ -65,6 +65,81 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bv_site_kernel(const Sit
 }
 
 // ======================================================================================================
+// Site kernel, TMA-staged (the product path): persistent CTAs, one warp per site, per-warp mbarrier ring.
+// ======================================================================================================
+constexpr int kTmaWarpsPerCta = 20;
+
+struct __align__(128) TmaWarpScratch {
+    Stage stage[kStages];
+    WarpScratch ws;
+    uint64_t full[kStages];
+};
+
+__global__ void __launch_bounds__(kTmaWarpsPerCta * 32, 1) bv_site_kernel_tma(const SiteKernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_tma[];
+    double* s_lut = reinterpret_cast<double*>(smem_tma);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TmaWarpScratch& W = reinterpret_cast<TmaWarpScratch*>(smem_tma + kLutBytes)[warp];
+
+    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) s_lut[i] = a.lut[i];
+    for (int i = lane; i < kHistWords; i += 32) W.ws.hist[i] = 0;
+    if (lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&W.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t total_warps = gridDim.x * kTmaWarpsPerCta;
+    const uint32_t warp_global = blockIdx.x * kTmaWarpsPerCta + warp;
+    const uint32_t row_bytes = (a.n_samples + 15u) & ~15u;               // bytes of a row that hold cells
+    const uint32_t nchunk = (row_bytes + kChunk - 1) / kChunk;           // >= 1 when n_samples > 0
+    if (warp_global >= a.n_sites || nchunk == 0) return;
+    const uint32_t my_sites = (a.n_sites - warp_global + total_warps - 1) / total_warps;
+    const uint64_t n_units = (uint64_t)my_sites * nchunk;
+
+    // producer state (lane 0): next unit to issue
+    uint64_t pu = 0;
+    uint32_t p_site = warp_global, p_chunk = 0;
+    auto issue = [&]() {
+        if (pu < n_units) {
+            if (lane == 0) {
+                const int st = (int)(pu % kStages);
+                const uint32_t off = p_chunk * kChunk;
+                const uint32_t bytes = min((uint32_t)kChunk, row_bytes - off);
+                const size_t g = (size_t)p_site * a.pitch + off;
+                mbar_expect_tx(&W.full[st], 3 * bytes);
+                bulk_g2s(W.stage[st].base, a.base + g, bytes, &W.full[st]);
+                bulk_g2s(W.stage[st].qual, a.qual + g, bytes, &W.full[st]);
+                bulk_g2s(W.stage[st].strand, a.strand + g, bytes, &W.full[st]);
+            }
+            ++pu;
+            if (++p_chunk == nchunk) { p_chunk = 0; p_site += total_warps; }
+        }
+    };
+#pragma unroll 1
+    for (int s = 0; s < kStages - 1; ++s) issue();
+
+    uint32_t site = warp_global, chunk = 0;
+    LaneCounts lc;
+    lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
+#pragma unroll 1
+    for (uint64_t u = 0; u < n_units; ++u) {
+        issue();   // unit u + kStages - 1 goes into the stage that unit u - 1 used; every lane is past it (__syncwarp below)
+        const int st = (int)(u % kStages);
+        mbar_wait(&W.full[st], (uint32_t)((u / kStages) & 1));
+        const int lane_cells = (int)a.n_samples - (int)(chunk * kChunk) - lane * 16;
+        count_chunk(W.stage[st], lane_cells, W.ws.hist, lc);
+        __syncwarp();
+        if (++chunk == nchunk) {
+            site_finish(W.ws, s_lut, a, site, warp_global, lc);
+            lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
+            chunk = 0;
+            site += total_warps;
+        }
+    }
+}
+
+// ======================================================================================================
 // Synthetic pileup generator: one thread writes one 16-cell vector of each plane.
 // ======================================================================================================
 __global__ void __launch_bounds__(256) bv_synth_kernel(const bv_synth_model* __restrict__ model, uint64_t site0,
@@ -128,11 +203,11 @@ struct bv_ctx {
     double* d_logfact = nullptr;
     bv_synth_model* d_model = nullptr;
     uint32_t* d_bin_spill = nullptr;
-    double* d_lml_spill = nullptr;
     bool has_model = false;
     uint64_t pitch_cap = 0;
     bv_slot* slots = nullptr;
     uint64_t launches = 0;
+    bool use_ldg_kernel = false;
 };
 
 static char g_err[512] = "";
@@ -171,7 +246,6 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->lut = ctx->d_lut;
     a->logfact = ctx->d_logfact;
     a->bin_spill = ctx->d_bin_spill;
-    a->lml_spill = ctx->d_lml_spill;
     a->pitch = t->pitch;
     a->n_sites = t->n_sites;
     a->n_samples = t->n_samples;
@@ -183,13 +257,25 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     return BV_OK;
 }
 
+static size_t tma_smem_bytes() { return bv::kLutBytes + (size_t)bv::kTmaWarpsPerCta * sizeof(bv::TmaWarpScratch); }
+
 static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream) {
     if (a.n_sites == 0) return BV_OK;
-    const size_t smem = bv::kLutBytes + (size_t)bv::kWarpsPerCta * sizeof(bv::WarpScratch);
-    uint32_t grid = (a.n_sites + bv::kWarpsPerCta - 1) / bv::kWarpsPerCta;
-    const uint32_t max_grid = (uint32_t)ctx->num_sms * 2u;
-    if (grid > max_grid) grid = max_grid;
-    bv::bv_site_kernel<<<grid, bv::kWarpsPerCta * 32, smem, stream>>>(a);
+    if (a.n_samples == 0) {   // no cells: every record is all-zero
+        BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
+        return BV_OK;
+    }
+    if (ctx->use_ldg_kernel) {   // kept only for A/B measurements (BV_KERNEL=ldg)
+        const size_t smem = bv::kLutBytes + (size_t)bv::kWarpsPerCta * sizeof(bv::WarpScratch);
+        uint32_t grid = (a.n_sites + bv::kWarpsPerCta - 1) / bv::kWarpsPerCta;
+        const uint32_t max_grid = (uint32_t)ctx->num_sms * 2u;
+        if (grid > max_grid) grid = max_grid;
+        bv::bv_site_kernel<<<grid, bv::kWarpsPerCta * 32, smem, stream>>>(a);
+    } else {
+        uint32_t grid = (a.n_sites + bv::kTmaWarpsPerCta - 1) / bv::kTmaWarpsPerCta;
+        if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+        bv::bv_site_kernel_tma<<<grid, bv::kTmaWarpsPerCta * 32, tma_smem_bytes(), stream>>>(a);
+    }
     BV_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return BV_OK;
@@ -258,12 +344,19 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
                          cudaGetErrorString(cudaGetLastError()));
             break;
         }
+        if (cudaFuncSetAttribute(bv::bv_site_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()) != cudaSuccess) {
+            rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute(tma) failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        {
+            const char* k = getenv("BV_KERNEL");
+            ctx->use_ldg_kernel = (k && strcmp(k, "ldg") == 0);
+        }
         rc = upload_tables(ctx);
         if (rc != BV_OK) break;
         {   // per-warp overflow scratch of the EM (only touched by sites with very many distinct bins)
             const size_t warps = (size_t)ctx->num_sms * 2 * bv::kWarpsPerCta;
-            cudaError_t ce = cudaMalloc(&ctx->d_bin_spill, warps * (bv::kMaxBins - bv::kSmemBins) * sizeof(uint32_t));
-            if (ce == cudaSuccess) ce = cudaMalloc(&ctx->d_lml_spill, warps * bv::kMaxBins * sizeof(double));
+            cudaError_t ce = cudaMalloc(&ctx->d_bin_spill, warps * bv::kMaxBins * sizeof(uint32_t));
             if (ce != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(ce)); break; }
         }
         ctx->pitch_cap = ((uint64_t)params->max_samples + 15) / 16 * 16;
@@ -300,7 +393,7 @@ void bv_destroy(bv_ctx* ctx) {
         delete[] ctx->slots;
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model);
-    cudaFree(ctx->d_bin_spill); cudaFree(ctx->d_lml_spill);
+    cudaFree(ctx->d_bin_spill);
     delete ctx;
 }
 

@@ -16,8 +16,15 @@
 
 namespace bv {
 
+// The kernel's hot loop is instruction-cache sensitive (ncu: `no_inst` was the top stall when the kernel was
+// ~6600 SASS instructions).  libdevice log/exp/log10 are 40-90 instructions each and get inlined at every call
+// site, so the rarely executed numerics (QUAL, Fisher) call them through these out-of-line wrappers.
+__device__ __noinline__ double nlog(double x) { return log(x); }
+__device__ __noinline__ double nexp(double x) { return exp(x); }
+__device__ __noinline__ double nlog10(double x) { return log10(x); }
+
 // ---- kf_lgamma (AS245), kfunc.c:39-52 ------------------------------------------------------------
-__device__ __forceinline__ double lgamma_as245(double z) {
+__device__ __noinline__ double lgamma_as245(double z) {
     double x = 0;
     x += 0.1659470187408462e-06 / (z + 7);
     x += 0.9934937113930748e-05 / (z + 6);
@@ -28,7 +35,7 @@ __device__ __forceinline__ double lgamma_as245(double z) {
     x -= 1259.139216722289 / (z + 1);
     x += 676.5203681218835 / z;
     x += 0.9999999999995183;
-    return log(x) - 5.58106146679532777 - z + (z - 0.5) * log(z + 6.5);
+    return nlog(x) - 5.58106146679532777 - z + (z - 0.5) * nlog(z + 6.5);
 }
 
 // ---- kf_gammaq(s, z), kfunc.c:103-143 --------------------------------------------------------------
@@ -40,7 +47,7 @@ __device__ __noinline__ double gammaq(double s, double z) {
             sum += x;
             if (x / sum < 1e-14) break;
         }
-        return 1. - exp(s * log(z) - z - lgamma_as245(s + 1.) + log(sum));
+        return 1. - nexp(s * nlog(z) - z - lgamma_as245(s + 1.) + nlog(sum));
     }
     const double tiny = 1e-290;
     double f = 1. + z - s, C = f, D = 0.;
@@ -55,14 +62,14 @@ __device__ __noinline__ double gammaq(double s, double z) {
         f *= d;
         if (fabs(d - 1.) < 1e-14) break;
     }
-    return exp(s * log(z) - z - lgamma_as245(s) - log(f));
+    return nexp(s * nlog(z) - z - lgamma_as245(s) - nlog(f));
 }
 
 // ---- QUAL rule, src/basetype.cpp:188-194 (chi2_test = kf_gammaq(dof/2, chi/2), algorithm.h:44-46) ----
-__device__ __forceinline__ double qual_from_chi(double chi) {
+__device__ __noinline__ double qual_from_chi(double chi) {
     double p = gammaq(0.5, chi / 2.0);
     if (isnan(p)) p = 1.0;
-    double q = (p != 0.0) ? -10 * log10(p) : 10000.0;
+    double q = (p != 0.0) ? -10 * nlog10(p) : 10000.0;
     if (q == 0.0) q = 0.0;  // scrubs -0.0
     return q;
 }
@@ -80,12 +87,12 @@ __device__ __forceinline__ double lbinom_tab(const double* __restrict__ logfact,
     return __ldg(logfact + n) - __ldg(logfact + k) - __ldg(logfact + (n - k));
 }
 
-__device__ __forceinline__ double hypergeo_tab(const double* __restrict__ lf, int n11, int n1_, int n_1, int n) {
-    return exp(lbinom_tab(lf, n1_, n11) + lbinom_tab(lf, n - n1_, n_1 - n11) - lbinom_tab(lf, n, n_1));
+__device__ __noinline__ double hypergeo_tab(const double* __restrict__ lf, int n11, int n1_, int n_1, int n) {
+    return nexp(lbinom_tab(lf, n1_, n11) + lbinom_tab(lf, n - n1_, n_1 - n11) - lbinom_tab(lf, n, n_1));
 }
 
 // kfunc.c:220-243 with only n11 moving
-__device__ __forceinline__ double hg_move(const double* __restrict__ lf, HgState& st, int n11) {
+__device__ __noinline__ double hg_move(const double* __restrict__ lf, HgState& st, int n11) {
     int n22 = n11 + st.n - st.n1_ - st.n_1;
     if ((n11 % 11) && n22) {
         if (n11 == st.n11 + 1) {
@@ -135,17 +142,17 @@ __device__ __noinline__ double fisher_two_sided(const double* __restrict__ lf, i
 }
 
 // src/basetype.cpp:277-283
-__device__ __forceinline__ double fs_from_table(const double* __restrict__ lf, int rf, int rr, int af, int ar) {
+__device__ __noinline__ double fs_from_table(const double* __restrict__ lf, int rf, int rr, int af, int ar) {
     const double p = fisher_two_sided(lf, rf, rr, af, ar);
     if (p == 1.0) return 0.0;   // -10*log10(1) = -0.0, scrubbed to +0.0 by the reference's `fs == 0` branch
-    double fs = -10 * log10(p);
+    double fs = -10 * nlog10(p);
     if (isinf(fs)) fs = 10000;
     else if (fs == 0) fs = 0.0;
     return fs;
 }
 
 // ---- warp reductions ------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __noinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
