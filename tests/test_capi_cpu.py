@@ -1,0 +1,87 @@
+"""CPU (-m "not gpu"): the C-ABI library builds for sm_100a, loads, and exports every symbol include/basevar_b200.h
+declares; entry points that need a device fail loudly (no CPU fallback); the host twin of the synthetic generator."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import basevar_b200 as bv
+from basevar_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "basevar_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(bv_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree(built_lib):
+    assert header_symbols() == sorted(capi.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = C.CDLL(built_lib)
+    for name in header_symbols():
+        assert hasattr(lib, name), f"{name} is declared in include/basevar_b200.h but not exported"
+    assert capi.load_library().bv_version() == 1
+
+
+def test_struct_layouts_match_the_header(built_lib):
+    assert capi.SITE_OUT_DTYPE.itemsize == 128
+    assert C.sizeof(capi.BvParams) == 36 and C.sizeof(capi.BvTile) == 56
+    assert C.sizeof(capi.BvSynthModel) == 32 + 4 * (96 + 1024 + 256)
+    offs = {n: capi.SITE_OUT_DTYPE.fields[n][1] for n in capi.SITE_OUT_DTYPE.names}
+    assert offs == {"depth": 0, "depth_other": 16, "reserved0": 20, "fwd": 24, "rev": 40, "n_alt": 56, "alt": 57,
+                    "n_active": 61, "flags": 62, "em_calls": 63, "af": 64, "qual": 96, "chi2": 104, "fs_cvg": 112,
+                    "fs_vcf": 120}
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bv.BvError, match="no CUDA device|CUDA"):
+        bv.BaseTypeEngine(device=0, max_samples=16, max_sites=16, n_slots=1)
+    lib = capi.load_library()
+    ctx = C.c_void_p()
+    assert lib.bv_create(0, None, C.byref(ctx)) == -1          # BV_ERR_ARG
+    prm = capi.make_params(max_samples=16)
+    assert lib.bv_create(0, C.byref(prm), C.byref(ctx)) == -2  # BV_ERR_CUDA
+    assert b"no CPU fallback" in lib.bv_last_error(None)
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under basevar_b200/ or include/ may reference it."""
+    for d in ("basevar_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, d)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert "oracle" not in txt.lower(), f"{dirpath}/{f} mentions the oracle"
+
+
+def test_cli_min_af_clamp():
+    # std::min(float(100)/n_bam, min_af) in float, widened to double later (src/basetype_caller.cpp:122,506)
+    assert bv.cli_min_af(0.01, 1000) == float(np.float32(0.01)) == 0.009999999776482582
+    assert bv.cli_min_af(0.01, 100000) == float(np.float32(100.0) / np.float32(100000)) == 0.0010000000474974513
+    assert bv.cli_min_af(0.05, 100) == 0.05000000074505806
+
+
+def test_synth_host_twin_is_deterministic_and_tileable(built_lib):
+    m = bv.synth.config_model("C2")
+    b, q, s, mq, r = bv.synth_fill_host(m, 100, 64, 1000, with_mapq=True)
+    b2, q2, s2, _, r2 = bv.synth_fill_host(m, 132, 32, 1000)
+    assert np.array_equal(b[32:], b2) and np.array_equal(q[32:], q2) and np.array_equal(s[32:], s2) and np.array_equal(r[32:], r2)
+    assert b.shape == (64, 1008) and (b[:, 1000:] == capi.BASE_N).all() and (s[:, 1000:] == capi.STRAND_NONE).all()
+    cov = (b[:, :1000] < 5).mean()
+    assert 0.08 < cov < 0.12
+    covered = b[:, :1000] < 5
+    assert (q[:, :1000][covered] >= 20).all() and (q[:, :1000][covered] <= 40).all() and (q[:, :1000][~covered] == 0).all()
+    assert set(np.unique(s[:, :1000][covered])) <= {0, 1} and (s[:, :1000][~covered] == 2).all()
+    assert set(np.unique(r)) <= {65, 67, 71, 84}
+    assert (mq[:, :1000][covered] >= 10).all()
