@@ -18,124 +18,126 @@
 
 namespace bv {
 
-constexpr int kWarpsPerCta = 16;
-constexpr int kLutBytes = 4 * kQStride * (int)sizeof(double);
+// ======================================================================================================
+// Site kernel (the product path): persistent CTAs, one warp per site, per-warp TMA ring.  See bv_site_kernel.cuh.
+// ======================================================================================================
+static_assert(sizeof(CtaShared) + (size_t)kWarps * sizeof(WarpSmem) <= 232448, "shared memory of the site kernel exceeds 227 KB");
 
-// ======================================================================================================
-// Site kernel: persistent CTAs, one warp per site, 128-bit streaming loads software-pipelined one vector
-// ahead (a row of <= 1024 samples is fully in flight before the first cell is counted).
-// ======================================================================================================
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) bv_site_kernel(const SiteKernelArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double* s_lut = reinterpret_cast<double*>(smem);
+__global__ void __launch_bounds__(kWarps * 32, 1) bv_site_kernel(const __grid_constant__ SiteKernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    CtaShared& cs = *reinterpret_cast<CtaShared*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem + kLutBytes)[warp];
+    WarpSmem& W = reinterpret_cast<WarpSmem*>(smem_raw + sizeof(CtaShared))[warp];
 
-    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) s_lut[i] = a.lut[i];
-    for (int i = lane; i < kHistWords; i += 32) ws.hist[i] = 0;
-    __syncthreads();
-
-    const uint32_t total_warps = gridDim.x * kWarpsPerCta;
-    const uint32_t warp_global = blockIdx.x * kWarpsPerCta + warp;
-    const int nvec = (int)((a.n_samples + 15u) >> 4);   // 16-cell vectors per row (last one may be partial)
-    const int niter = (nvec + 31) >> 5;                 // warp iterations per row
-    for (uint32_t site = warp_global; site < a.n_sites; site += total_warps) {
-        LaneCounts lc;
-        lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
-        const size_t row = (size_t)site * a.pitch;
-        const uint4* pb = reinterpret_cast<const uint4*>(a.base + row);
-        const uint4* pq = reinterpret_cast<const uint4*>(a.qual + row);
-        const uint4* ps = reinterpret_cast<const uint4*>(a.strand + row);
-        // every lane runs the same number of iterations (count_word ends in a full-warp barrier); lanes past the end
-        // of the row carry an all-'N' vector
-        const uint4 kAllN = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
-        int v = lane;
-        uint4 b0 = kAllN, q0 = kAllN, s0 = kAllN;
-        if (v < nvec) { b0 = ld_stream(pb + v); q0 = ld_stream(pq + v); s0 = ld_stream(ps + v); }
-        for (int it = 0; it < niter; ++it) {
-            const int vn = v + 32;
-            uint4 b1 = kAllN, q1 = kAllN, s1 = kAllN;
-            if (vn < nvec) { b1 = ld_stream(pb + vn); q1 = ld_stream(pq + vn); s1 = ld_stream(ps + vn); }
-            count_vec(b0, q0, s0, (int)a.n_samples - 16 * v, ws.hist, lc);
-            b0 = b1; q0 = q1; s0 = s1;
-            v = vn;
-        }
-        site_finish(ws, s_lut, a, site, warp_global, lc);
-    }
-}
-
-// ======================================================================================================
-// Site kernel, TMA-staged (the product path): persistent CTAs, one warp per site, per-warp mbarrier ring.
-// ======================================================================================================
-constexpr int kTmaWarpsPerCta = 20;
-
-struct __align__(128) TmaWarpScratch {
-    Stage stage[kStages];
-    WarpScratch ws;
-    uint64_t full[kStages];
-};
-
-__global__ void __launch_bounds__(kTmaWarpsPerCta * 32, 1) bv_site_kernel_tma(const SiteKernelArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_tma[];
-    double* s_lut = reinterpret_cast<double*>(smem_tma);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TmaWarpScratch& W = reinterpret_cast<TmaWarpScratch*>(smem_tma + kLutBytes)[warp];
-
-    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) s_lut[i] = a.lut[i];
-    for (int i = lane; i < kHistWords; i += 32) W.ws.hist[i] = 0;
+    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) cs.lut[i] = a.lut[i];
+    if (threadIdx.x == 0) cs.a = a;
+    for (int i = lane; i < kHistWords; i += 32) W.hist[i] = 0;
+    if (lane < 12) W.nr_cnt[lane] = 0;
     if (lane == 0) {
+        W.flag_word = 0;
+        W.p2_phase = 0;
         for (int s = 0; s < kStages; ++s) mbar_init(&W.full[s], 1);
+        mbar_init(&W.p2bar[0], 1);
+        mbar_init(&W.p2bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const uint32_t total_warps = gridDim.x * kTmaWarpsPerCta;
-    const uint32_t warp_global = blockIdx.x * kTmaWarpsPerCta + warp;
-    const uint32_t row_bytes = (a.n_samples + 15u) & ~15u;               // bytes of a row that hold cells
-    const uint32_t nchunk = (row_bytes + kChunk - 1) / kChunk;           // >= 1 when n_samples > 0
-    if (warp_global >= a.n_sites || nchunk == 0) return;
-    const uint32_t my_sites = (a.n_sites - warp_global + total_warps - 1) / total_warps;
-    const uint64_t n_units = (uint64_t)my_sites * nchunk;
+    const uint32_t total_warps = gridDim.x * kWarps;
+    const uint32_t warp_global = blockIdx.x * kWarps + warp;
+    const uint32_t N = a.n_samples;
+    const uint32_t row_bytes = (N + 15u) & ~15u;                         // bytes of a row that hold cells
+    const uint32_t nchunk = (row_bytes + kChunk - 1) / kChunk;           // >= 1 (n_samples > 0)
+    if (warp_global >= a.n_sites) return;
 
-    // producer state (lane 0): next unit to issue
-    uint64_t pu = 0;
-    uint32_t p_site = warp_global, p_chunk = 0;
+    // ---- producer cursor: lane 0 issues the bulk copies of the unit kStages-1 ahead of the one being scanned ----
+    uint32_t p_site = warp_global, p_chunk = 0, p_stage = 0;
     auto issue = [&]() {
-        if (pu < n_units) {
+        if (p_site < a.n_sites) {
             if (lane == 0) {
-                const int st = (int)(pu % kStages);
                 const uint32_t off = p_chunk * kChunk;
                 const uint32_t bytes = min((uint32_t)kChunk, row_bytes - off);
                 const size_t g = (size_t)p_site * a.pitch + off;
-                mbar_expect_tx(&W.full[st], 3 * bytes);
-                bulk_g2s(W.stage[st].base, a.base + g, bytes, &W.full[st]);
-                bulk_g2s(W.stage[st].qual, a.qual + g, bytes, &W.full[st]);
-                bulk_g2s(W.stage[st].strand, a.strand + g, bytes, &W.full[st]);
+                mbar_expect_tx(&W.full[p_stage], 2 * bytes);
+                bulk_g2s(W.stage[p_stage].base, a.base + g, bytes, &W.full[p_stage]);
+                bulk_g2s(W.stage[p_stage].strand, a.strand + g, bytes, &W.full[p_stage]);
             }
-            ++pu;
+            p_stage = (p_stage + 1 == kStages) ? 0 : p_stage + 1;
             if (++p_chunk == nchunk) { p_chunk = 0; p_site += total_warps; }
         }
     };
 #pragma unroll 1
     for (int s = 0; s < kStages - 1; ++s) issue();
 
-    uint32_t site = warp_global, chunk = 0;
-    LaneCounts lc;
-    lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
+    uint32_t c_stage = 0, phases = 0;
+    uint32_t ref_raw = a.ref_base[warp_global];
+    const uint32_t one_active = (1.0 >= a.min_af) ? 1u : 0u;   // a site whose reads all agree has that allele active
 #pragma unroll 1
-    for (uint64_t u = 0; u < n_units; ++u) {
-        issue();   // unit u + kStages - 1 goes into the stage that unit u - 1 used; every lane is past it (__syncwarp below)
-        const int st = (int)(u % kStages);
-        mbar_wait(&W.full[st], (uint32_t)((u / kStages) & 1));
-        const int lane_cells = (int)a.n_samples - (int)(chunk * kChunk) - lane * 16;
-        count_chunk(W.stage[st], lane_cells, W.ws.hist, lc);
-        __syncwarp();
-        if (++chunk == nchunk) {
-            site_finish(W.ws, s_lut, a, site, warp_global, lc);
-            lc.qmin = 0xffffffffu; lc.qmax = 0; lc.flags = 0;
-            chunk = 0;
-            site += total_warps;
+    for (uint32_t site = warp_global; site < a.n_sites; site += total_warps) {
+        // reference base of this site (prefetched one site ahead), toupper (src/basetype.cpp:171)
+        const uint32_t next_site = site + total_warps;
+        const uint32_t ref_next = next_site < a.n_sites ? (uint32_t)__ldg(a.ref_base + next_site) : 0u;
+        uint32_t rc = ref_raw;
+        if (rc >= 'a' && rc <= 'z') rc -= 32;
+        const int ref_code = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
+        const uint32_t refw = ref_code >= 0 ? (uint32_t)ref_code * 0x01010101u : 0x08080808u;
+
+        // ---- pass 1 ----
+        ScanAcc A;
+        A.nref = 0; A.nrev = 0; A.nonref = 0; A.bad = 0;
+#pragma unroll 1
+        for (uint32_t chunk = 0; chunk < nchunk; ++chunk) {
+            issue();   // the unit kStages-1 ahead goes into the stage the previous unit used; every lane is past it
+            mbar_wait(&W.full[c_stage], (phases >> c_stage) & 1u);
+            phases ^= 1u << c_stage;
+            const int lane_cells = (int)N - (int)(chunk * kChunk) - lane * 16;
+            if (lane_cells > 0) {
+                const uint8_t* cellp = W.stage[c_stage].base + lane * 16;
+                uint4 vb = *reinterpret_cast<const uint4*>(cellp);
+                const uint4 vs = *reinterpret_cast<const uint4*>(cellp + kChunk);
+                if (lane_cells < 16) mask_tail(vb, lane_cells);
+                const uint32_t nr0 = scan_word(vb.x, vs.x, refw, A);
+                const uint32_t nr1 = scan_word(vb.y, vs.y, refw, A);
+                const uint32_t nr2 = scan_word(vb.z, vs.z, refw, A);
+                const uint32_t nr3 = scan_word(vb.w, vs.w, refw, A);
+                if (nr0 | nr1 | nr2 | nr3) {
+                    // counted cells that are not the reference base (sequencing errors, ALT alleles): one by one
+                    uint32_t t = (nr0 >> 7) | (nr1 >> 6) | (nr2 >> 5) | (nr3 >> 4);   // bit (8*byte + word)
+                    A.nonref |= t;
+                    do {
+                        int top;
+                        asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+                        t ^= 1u << top;
+                        const int cell = ((top & 3) << 2) | (top >> 3);
+                        const uint32_t b = cellp[cell];
+                        const uint32_t s = cellp[cell + kChunk];
+                        atomicAdd(&W.nr_cnt[2u * b + (s & 1u)], 1u);
+                    } while (t);
+                }
+            }
+            __syncwarp();
+            c_stage = (c_stage + 1 == kStages) ? 0 : c_stage + 1;
         }
+
+        // ---- finish ----
+        const uint32_t fl = __reduce_or_sync(kFull, A.nonref | (A.bad ? 0x80000000u : 0u));
+        const uint32_t n_ref = __reduce_add_sync(kFull, A.nref) >> 7;
+        const uint32_t n_rev = __reduce_add_sync(kFull, A.nrev) >> 7;
+        if (fl == 0) {
+            // Every counted cell holds the reference base (or nothing is covered): depth[REF] = n_ref, one active
+            // allele == REF, the EM's answer is f = 1 (src/algorithm.h:210-255 with a single column), no ALT,
+            // QUAL / FS / chi2 = 0.  Lanes compose the 32 words of the record.
+            const uint32_t n_active = (n_ref > 0) ? one_active : 0u;
+            uint32_t w = 0;
+            if (lane == ref_code) w = n_ref;                      // depth[REF]
+            if (lane == ref_code + 6) w = n_ref - n_rev;          // fwd[REF]
+            if (lane == ref_code + 10) w = n_rev;                 // rev[REF]
+            if (lane == 15) w = (n_active << 8) | (n_active << 24);   // n_active | flags 0 | em_calls
+            reinterpret_cast<uint32_t*>(a.out + site)[lane] = w;
+        } else {
+            site_slow(&W, &cs, site, warp_global, n_ref, n_rev, fl >> 31, ref_code);
+        }
+        ref_raw = ref_next;
     }
 }
 
@@ -203,11 +205,11 @@ struct bv_ctx {
     double* d_logfact = nullptr;
     bv_synth_model* d_model = nullptr;
     uint32_t* d_bin_spill = nullptr;
+    double* d_lml_spill = nullptr;
     bool has_model = false;
     uint64_t pitch_cap = 0;
     bv_slot* slots = nullptr;
     uint64_t launches = 0;
-    bool use_ldg_kernel = false;
 };
 
 static char g_err[512] = "";
@@ -246,6 +248,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->lut = ctx->d_lut;
     a->logfact = ctx->d_logfact;
     a->bin_spill = ctx->d_bin_spill;
+    a->lml_spill = ctx->d_lml_spill;
     a->pitch = t->pitch;
     a->n_sites = t->n_sites;
     a->n_samples = t->n_samples;
@@ -257,7 +260,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     return BV_OK;
 }
 
-static size_t tma_smem_bytes() { return bv::kLutBytes + (size_t)bv::kTmaWarpsPerCta * sizeof(bv::TmaWarpScratch); }
+static size_t site_smem_bytes() { return sizeof(bv::CtaShared) + (size_t)bv::kWarps * sizeof(bv::WarpSmem); }
 
 static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream) {
     if (a.n_sites == 0) return BV_OK;
@@ -265,17 +268,10 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
         BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
         return BV_OK;
     }
-    if (ctx->use_ldg_kernel) {   // kept only for A/B measurements (BV_KERNEL=ldg)
-        const size_t smem = bv::kLutBytes + (size_t)bv::kWarpsPerCta * sizeof(bv::WarpScratch);
-        uint32_t grid = (a.n_sites + bv::kWarpsPerCta - 1) / bv::kWarpsPerCta;
-        const uint32_t max_grid = (uint32_t)ctx->num_sms * 2u;
-        if (grid > max_grid) grid = max_grid;
-        bv::bv_site_kernel<<<grid, bv::kWarpsPerCta * 32, smem, stream>>>(a);
-    } else {
-        uint32_t grid = (a.n_sites + bv::kTmaWarpsPerCta - 1) / bv::kTmaWarpsPerCta;
-        if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
-        bv::bv_site_kernel_tma<<<grid, bv::kTmaWarpsPerCta * 32, tma_smem_bytes(), stream>>>(a);
-    }
+    // persistent: one CTA per SM, each warp strides over the sites
+    uint32_t grid = (a.n_sites + bv::kWarps - 1) / bv::kWarps;
+    if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+    bv::bv_site_kernel<<<grid, bv::kWarps * 32, site_smem_bytes(), stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return BV_OK;
@@ -338,25 +334,17 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
         ctx->num_sms = prop.multiProcessorCount;
-        const size_t smem = bv::kLutBytes + (size_t)bv::kWarpsPerCta * sizeof(bv::WarpScratch);
-        if (cudaFuncSetAttribute(bv::bv_site_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        if (cudaFuncSetAttribute(bv::bv_site_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)site_smem_bytes()) != cudaSuccess) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
                          cudaGetErrorString(cudaGetLastError()));
             break;
         }
-        if (cudaFuncSetAttribute(bv::bv_site_kernel_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()) != cudaSuccess) {
-            rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute(tma) failed: %s", cudaGetErrorString(cudaGetLastError()));
-            break;
-        }
-        {
-            const char* k = getenv("BV_KERNEL");
-            ctx->use_ldg_kernel = (k && strcmp(k, "ldg") == 0);
-        }
         rc = upload_tables(ctx);
         if (rc != BV_OK) break;
         {   // per-warp overflow scratch of the EM (only touched by sites with very many distinct bins)
-            const size_t warps = (size_t)ctx->num_sms * 2 * bv::kWarpsPerCta;
+            const size_t warps = (size_t)ctx->num_sms * bv::kWarps;
             cudaError_t ce = cudaMalloc(&ctx->d_bin_spill, warps * bv::kMaxBins * sizeof(uint32_t));
+            if (ce == cudaSuccess) ce = cudaMalloc(&ctx->d_lml_spill, warps * bv::kMaxBins * sizeof(double));
             if (ce != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(ce)); break; }
         }
         ctx->pitch_cap = ((uint64_t)params->max_samples + 15) / 16 * 16;
@@ -394,6 +382,7 @@ void bv_destroy(bv_ctx* ctx) {
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model);
     cudaFree(ctx->d_bin_spill);
+    cudaFree(ctx->d_lml_spill);
     delete ctx;
 }
 

@@ -1,26 +1,30 @@
 // bv_site_kernel.cuh -- the per-site statistical core of `basevar basetype` as one fused sm_100a kernel.
 //
-// One warp owns one genomic site at a time (sites are the embarrassingly parallel axis, samples the
-// reduction axis).  For its site the warp
-//   1. streams the three u8 planes of the site row (base, qual, strand) with 128-bit loads and counts every
-//      read into a warp-private shared-memory histogram hist[strand 0..1][base 0..4][phred 0..95]
-//                                                            (BaseType::BaseType, src/basetype.cpp:45-71;
-//                                                             strand_bias counting, src/basetype.cpp:252-274)
-//   2. sweeps the touched phred range once: per-base depths and the 2x4 strand table by warp reductions
-//   3. decides the active alleles (depth/total >= min_af).  With ONE active allele the reference's EM has a
-//      closed form (AF == 1.0 exactly) and nothing else is computed.  Otherwise the non-empty (base, phred)
-//      bins are compacted and EM + LRT backward elimination run on the bins: all reads of one bin are
-//      exchangeable in e_step/m_step (src/algorithm.h:148-198), so a bin of c reads contributes c * (per-read
-//      term); lanes own bins, allele sums are warp-shuffle reductions
-//                                                            (EM, src/algorithm.h:210-255;
-//                                                             _f / lrt, src/basetype.cpp:105-199)
-//   4. QUAL (chi2 survival via kf_gammaq) and the two Fisher strand-bias tests
-//                                                            (src/basetype.cpp:180-194, :244-295)
-//   5. writes the fixed 128-byte bv_site_out record with one coalesced store.
+// One warp owns one genomic site at a time (sites are the embarrassingly parallel axis, samples the reduction
+// axis).  Persistent CTAs; every warp streams its own sequence of site rows through a private ring of
+// TMA-filled shared-memory stages (cp.async.bulk + mbarrier, SASS UBLKCP / SYNCS).
 //
-// The only FP64 work that scales with the number of samples is gone: the sample axis is byte loads and
-// integer shared-memory atomics; FP64 work is O(bins) per site.  Per-read likelihood values (1-eps,
-// eps/3) come from a host-computed table (glibc exp), so they are bit-identical with the reference.
+//   pass 1 (every site, every cell)   base + strand planes only.  SIMD-in-register byte arithmetic: cells that
+//        hold the reference base are counted with dp4a, 16 cells per lane per step, no per-cell work and no atomics;
+//        the (rare) counted cells that are NOT the reference base are counted one by one into ten shared-memory
+//        counters.  Result: per-base depths and the 2x4 strand table, bit-exact
+//                                                            (BaseType::BaseType, src/basetype.cpp:45-71;
+//                                                             strand_bias counting, src/basetype.cpp:252-274).
+//   fast finish   a site whose counted cells all equal the reference base has a closed-form record (one active
+//        allele == REF, no ALT, FS 0): 32 lanes compose the 128-byte record in registers and store it coalesced.
+//   pass 2 (only sites whose result depends on base qualities: >= 2 active alleles, or a single active allele that
+//        is not REF)   the row's base + qual chunks are fetched again (L2 / HBM) and the covered cells are
+//        histogrammed by (base, phred); the non-empty bins are compacted and EM + LRT backward elimination run on
+//        the bins: all reads of one bin are exchangeable in e_step/m_step (src/algorithm.h:148-198), so a bin of c
+//        reads contributes c * (per-read term); lanes own bins, allele sums are warp-shuffle reductions
+//                                                            (EM, src/algorithm.h:210-255;
+//                                                             _f / lrt, src/basetype.cpp:105-199).
+//   QUAL (chi2 survival via kf_gammaq) and the two Fisher strand-bias tests
+//                                                            (src/basetype.cpp:180-194, :244-295).
+//
+// The qual plane is therefore read only where the reference's outputs depend on it; everywhere else the sample
+// axis costs two byte loads and ~3 integer instructions per cell.  Per-read likelihood values (1-eps, eps/3) come
+// from a host-computed table (glibc exp), so they are bit-identical with the reference.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,15 +34,22 @@
 
 namespace bv {
 
-constexpr int kQStride = 128;                // phred slots per histogram row (0..93 used; 7-bit index never overflows)
-constexpr int kHistRows = 10;                // (strand 0..1) x (A,C,G,T,other)
-constexpr int kHistWords = kHistRows * kQStride;
+#ifndef BV_WARPS
+#define BV_WARPS 28
+#endif
+constexpr int kWarps = BV_WARPS;             // warps per CTA, one CTA per SM
+constexpr int kChunk = 512;                  // cells per stage and plane: one 16-cell vector per lane
+constexpr int kStages = 3;                   // ring depth per warp
+constexpr int kQStride = 128;                // phred slots per LUT row
+constexpr int kQSlots = 96;                  // phred slots per histogram row (0..93 valid; larger values clamp to 95)
+constexpr int kHistWords = 5 * kQSlots;      // (A,C,G,T,other) x phred
 constexpr int kSmemBins = 160;               // compact bins kept in shared memory; more spill to global scratch
-constexpr int kMaxBins = 5 * kQStride;       // upper bound on distinct (base, phred) bins
+constexpr int kMaxBins = kHistWords;         // upper bound on distinct (base, phred) bins
 constexpr int kLutOneMinusEps = 0;           // lut[0][q] = 1 - eps(q)
 constexpr int kLutEpsThird = 1;              // lut[1][q] = eps(q) / 3
 constexpr int kLutLogMatch = 2;              // lut[2][q] = log(1 - eps(q))   (glibc)
 constexpr int kLutLogMis = 3;                // lut[3][q] = log(eps(q) / 3)   (glibc)
+constexpr uint32_t kFull = 0xffffffffu;
 
 struct SiteKernelArgs {
     const uint8_t* base;
@@ -49,6 +60,7 @@ struct SiteKernelArgs {
     const double* lut;       // [4][kQStride]
     const double* logfact;   // [max_samples + 2], lgamma(k+1) from glibc
     uint32_t* bin_spill;     // [total warps][kMaxBins] global copy of the compact bins (used when > kSmemBins)
+    double* lml_spill;       // [total warps][kMaxBins] per-bin EM state for the same case
     uint64_t pitch;
     uint32_t n_sites;
     uint32_t n_samples;
@@ -59,11 +71,37 @@ struct SiteKernelArgs {
     int abs_mode;
 };
 
-// Per-warp shared-memory working set.
-struct __align__(16) WarpScratch {
-    uint32_t hist[kHistWords];   // dense histogram, all-zero between sites
-    uint32_t bins[kSmemBins];    // compact non-empty (base, phred) bins: (base << 29) | (phred << 22) | count
-    bv_site_out rec;             // record staging for one coalesced 128-byte store
+// ---- shared memory ---------------------------------------------------------------------------------------------------
+struct __align__(128) Stage {      // pass 1: one chunk of the base and strand planes of one site row
+    uint8_t base[kChunk];
+    uint8_t strand[kChunk];
+};
+struct __align__(128) P2Buf {      // pass 2: one chunk of the base and qual planes
+    uint8_t base[kChunk];
+    uint8_t qual[kChunk];
+};
+
+struct __align__(128) WarpSmem {
+    Stage stage[kStages];
+    P2Buf p2[2];
+    uint32_t hist[kHistWords];   // (base, phred) histogram of pass 2, all-zero between sites; the EM's per-bin state
+                                 // (one double per compact bin) overlays it once the bins are compacted
+    uint32_t bins[kSmemBins];    // compact non-empty bins: (base << 29) | (phred << 22) | count
+    uint32_t nr_cnt[12];         // pass 1: counted cells that are not the reference base, [2*base + strand]
+    double emf[4];               // EM: allele frequencies in / out
+    double res_f[4];             // LRT: frequencies of the accepted model
+    double res_chi;              // LRT: last chi_sqrt_value
+    uint32_t flag_word;          // BV_FLAG_* raised inside out-of-line code
+    uint32_t p2_phase;           // mbarrier phase bits of p2bar[]
+    uint64_t full[kStages];
+    uint64_t p2bar[2];
+    alignas(16) bv_site_out rec; // record staging for one coalesced 128-byte store (slow path)
+};
+
+struct __align__(128) CtaShared {
+    double lut[4 * kQStride];
+    SiteKernelArgs a;            // kernel parameters for out-of-line device functions (a reference to the
+                                 // __global__ parameter itself would force a local-memory copy)
 };
 
 __device__ __forceinline__ uint32_t pack_bin(uint32_t b, uint32_t q, uint32_t count) {
@@ -73,80 +111,7 @@ __device__ __forceinline__ uint32_t bin_base(uint32_t p) { return p >> 29; }
 __device__ __forceinline__ uint32_t bin_qual(uint32_t p) { return (p >> 22) & 0x7fu; }
 __device__ __forceinline__ uint32_t bin_count(uint32_t p) { return p & 0x3fffffu; }
 
-// streaming loads: read once, do not pollute L1
-__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
-// Per-lane state of one site row.
-struct LaneCounts {
-    uint32_t qmin, qmax, flags;
-};
-
-// Count the 4 cells of one 32-bit word of each plane.  Histogram slot of a read: (base << 8) | (strand << 7) | phred.
-__device__ __forceinline__ void count_word(uint32_t wb, uint32_t wq, uint32_t ws, uint32_t* hist, LaneCounts& lc) {
-    // bit 7 of each byte of `m` is set iff the base code is < 5 (A,C,G,T,other): the cell is counted
-    uint32_t m = ~((((wb | 0x80808080u) - 0x05050505u) | wb)) & 0x80808080u;
-    if (m) {
-        // rare input errors, checked per word: a counted cell with phred > 93 or a strand symbol other than +/-
-        const uint32_t bytes = (m >> 7) * 0xffu;
-        const uint32_t badq = ((wq + 0x22222222u) | wq) & m, bads = ws & 0xfefefefeu & bytes;
-        if (badq | bads) lc.flags |= (badq ? BV_FLAG_BAD_QUAL : 0u) | (bads ? BV_FLAG_BAD_STRAND : 0u);
-        const uint32_t sq = (wq & 0x7f7f7f7fu) | ((ws & 0x01010101u) << 7);   // per byte: strand << 7 | phred
-        do {
-            int top;                         // bit 7 of the highest counted cell
-            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(m));
-            const int sh = top - 7;
-            m ^= 1u << top;
-            const uint32_t b = (wb >> sh) & 0xffu;
-            const uint32_t x = (sq >> sh) & 0xffu;
-            atomicAdd(&hist[(b << 8) | x], 1u);
-            const uint32_t q = x & 0x7fu;
-            lc.qmin = min(lc.qmin, q);
-            lc.qmax = max(lc.qmax, q);
-        } while (m);
-    }
-    // Lanes leave the cell loop after different trip counts; without an explicit barrier the warp stays split
-    // into fragments for the rest of the row (measured: 6.5 active lanes per streaming load).
-    __syncwarp();
-}
-
-// valid = number of real cells in this 16-cell vector (>= 16 for all but the row's last vector): padding cells
-// are turned into 'N'
-__device__ __forceinline__ void mask_tail(uint4& vb, int valid) {
-    uint32_t w[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int left = valid - 4 * k;
-        const uint32_t keep = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
-        w[k] = (w[k] & keep) | (0x05050505u & ~keep);
-    }
-    vb = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-__device__ __forceinline__ void count_vec(uint4 vb, const uint4& vq, const uint4& vs, int valid, uint32_t* hist,
-                                          LaneCounts& lc) {
-    if (valid < 16) mask_tail(vb, valid);
-    count_word(vb.x, vq.x, vs.x, hist, lc);
-    count_word(vb.y, vq.y, vs.y, hist, lc);
-    count_word(vb.z, vq.z, vs.z, hist, lc);
-    count_word(vb.w, vq.w, vs.w, hist, lc);
-}
-
-// =====================================================================================================================
-// TMA-staged streaming (sm_100a): every warp owns a private ring of kStages stage buffers in shared memory.  One stage
-// holds one chunk (<= kChunk cells) of the three planes of one site row.  Lane 0 issues the three bulk copies
-// (cp.async.bulk, SASS UBLKCP) of the chunk kStages-1 units ahead and arms the stage's mbarrier with the byte count;
-// all lanes wait on the mbarrier phase, then read the chunk from shared memory.  No register staging, no LDG in the
-// hot loop, and the next rows are in flight while EM/Fisher of the current site run.
-// =====================================================================================================================
-constexpr int kChunk = 512;     // cells per stage and plane: one 16-cell vector per lane
-constexpr int kStages = 3;
-
+// ---- TMA bulk copies + mbarrier (sm_90+; SASS UBLKCP / SYNCS) -----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -172,63 +137,129 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// One stage: three planes of one chunk.
-struct __align__(128) Stage {
-    uint8_t base[kChunk];
-    uint8_t qual[kChunk];
-    uint8_t strand[kChunk];
+// valid = number of real cells in this 16-cell vector (>= 16 for all but the row's last vector): padding cells
+// are turned into 'N'
+__device__ __forceinline__ void mask_tail(uint4& vb, int valid) {
+    uint32_t w[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int left = valid - 4 * k;
+        const uint32_t keep = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+        w[k] = (w[k] & keep) | (0x05050505u & ~keep);
+    }
+    vb = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// =====================================================================================================================
+// Pass 1: SIMD-in-register scan of 4 cells (one 32-bit word of the base plane and of the strand plane).
+// Every mask has its information in bit 7 of each byte.
+// =====================================================================================================================
+struct ScanAcc {
+    uint32_t nref;     // 128 * (# cells holding the reference base)
+    uint32_t nrev;     // 128 * (# of those on the '-' strand)
+    uint32_t nonref;   // != 0: the row has counted cells that are not the reference base
+    uint32_t bad;      // != 0: a counted cell has a strand code other than +/-
 };
 
-// Count one chunk that sits in shared memory.  `cells` = real cells of this chunk that belong to this lane's 16-cell
-// vector and beyond (<= 0: the lane has nothing).  The cell loop is warp-uniform: its trip count is the warp maximum of
-// the per-lane counted cells and lanes that run out are predicated off, so the warp never splits (a divergent loop
-// left the warp in fragments for the rest of the row: 6.5 active lanes per load, measured with ncu).
-__device__ __forceinline__ void count_chunk(const Stage& st, int lane_cells, uint32_t* hist, LaneCounts& lc) {
+__device__ __forceinline__ uint32_t scan_word(uint32_t wb, uint32_t ws, uint32_t refw, ScanAcc& A) {
+    // counted: base code < 5 (A,C,G,T,other); bytes >= 0x80 are never counted
+    const uint32_t m = ~(((wb | 0x80808080u) - 0x05050505u) | wb) & 0x80808080u;
+    // equal to the reference base (refw = code * 0x01010101, or 0x08080808 when REF is not A/C/G/T)
+    const uint32_t x = (wb ^ refw) & 0x7f7f7f7fu;
+    const uint32_t eq = ~((x + 0x7f7f7f7fu) | wb) & 0x80808080u;
+    // strand code >= 2 in a counted cell: the reference throws (src/basetype.cpp:271-273)
+    A.bad |= (((ws & 0x7f7f7f7fu) + 0x7e7e7e7eu) | ws) & m;
+    A.nref = __dp4a(eq, 0x01010101u, A.nref);
+    A.nrev = __dp4a(eq, ws, A.nrev);
+    return m & ~eq;
+}
+
+// =====================================================================================================================
+// Pass 2: (base, phred) histogram of the covered cells of one row.  Out of line; runs on the sites whose result depends
+// on base qualities.  Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
+// =====================================================================================================================
+__device__ __noinline__ uint32_t build_hist(WarpSmem* Wp, const CtaShared* cs, uint32_t site) {
+    WarpSmem& W = *Wp;
     const int lane = threadIdx.x & 31;
-    uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
-    if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(st.base + lane * 16);
-    if (lane_cells < 16) mask_tail(vb, lane_cells);
-    // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
-    const uint32_t n0 = (((vb.x | 0x80808080u) - 0x05050505u) | vb.x) & 0x80808080u;
-    const uint32_t n1 = (((vb.y | 0x80808080u) - 0x05050505u) | vb.y) & 0x80808080u;
-    const uint32_t n2 = (((vb.z | 0x80808080u) - 0x05050505u) | vb.z) & 0x80808080u;
-    const uint32_t n3 = (((vb.w | 0x80808080u) - 0x05050505u) | vb.w) & 0x80808080u;
-    uint32_t t = ((n0 >> 7) | (n1 >> 6) | (n2 >> 5) | (n3 >> 4)) ^ 0x0f0f0f0fu;
-    const int n = (int)__reduce_max_sync(0xffffffffu, (uint32_t)__popc(t));
-    const uint8_t* cellp = st.base + lane * 16;
-#pragma unroll 1
-    for (int i = 0; i < n; ++i) {
-        const bool on = t != 0u;
-        int top;
-        asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
-        t &= ~(1u << (top & 31));
-        const int cell = ((top & 3) << 2) | ((top >> 3) & 3);   // word k = top & 7 (0..3), byte j = top >> 3
-        if (on) {
-            const uint32_t b = cellp[cell];
-            const uint32_t q = cellp[cell + kChunk] & 0x7fu;     // rows have 128 slots: no overflow whatever the byte
-            const uint32_t s = cellp[cell + 2 * kChunk];
-            if (s > BV_STRAND_REV) lc.flags |= BV_FLAG_BAD_STRAND;
-            atomicAdd(&hist[(b << 8) | ((s & 1u) << 7) | q], 1u);
-            lc.qmin = min(lc.qmin, q);
-            lc.qmax = max(lc.qmax, q);
-        }
+    const uint32_t N = cs->a.n_samples;
+    const uint32_t row_bytes = (N + 15u) & ~15u;
+    const uint32_t nchunk = (row_bytes + kChunk - 1) / kChunk;
+    const size_t row = (size_t)site * cs->a.pitch;
+    const uint8_t* gb = cs->a.base + row;
+    const uint8_t* gq = cs->a.qual + row;
+    uint32_t phase = W.p2_phase;
+    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
+    if (lane == 0) {
+        const uint32_t bytes = min((uint32_t)kChunk, row_bytes);
+        mbar_expect_tx(&W.p2bar[0], 2 * bytes);
+        bulk_g2s(W.p2[0].base, gb, bytes, &W.p2bar[0]);
+        bulk_g2s(W.p2[0].qual, gq, bytes, &W.p2bar[0]);
     }
+#pragma unroll 1
+    for (uint32_t c = 0; c < nchunk; ++c) {
+        const uint32_t buf = c & 1u;
+        if (c + 1 < nchunk && lane == 0) {   // chunk c+1 goes where chunk c-1 was (all lanes are past it: __syncwarp below)
+            const uint32_t off = (c + 1) * kChunk;
+            const uint32_t bytes = min((uint32_t)kChunk, row_bytes - off);
+            mbar_expect_tx(&W.p2bar[buf ^ 1u], 2 * bytes);
+            bulk_g2s(W.p2[buf ^ 1u].base, gb + off, bytes, &W.p2bar[buf ^ 1u]);
+            bulk_g2s(W.p2[buf ^ 1u].qual, gq + off, bytes, &W.p2bar[buf ^ 1u]);
+        }
+        mbar_wait(&W.p2bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        const int lane_cells = (int)N - (int)(c * kChunk) - lane * 16;
+        const uint8_t* cellp = W.p2[buf].base + lane * 16;
+        uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
+        if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(cellp);
+        if (lane_cells < 16) mask_tail(vb, lane_cells);
+        // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
+        const uint32_t n0 = (((vb.x | 0x80808080u) - 0x05050505u) | vb.x) & 0x80808080u;
+        const uint32_t n1 = (((vb.y | 0x80808080u) - 0x05050505u) | vb.y) & 0x80808080u;
+        const uint32_t n2 = (((vb.z | 0x80808080u) - 0x05050505u) | vb.z) & 0x80808080u;
+        const uint32_t n3 = (((vb.w | 0x80808080u) - 0x05050505u) | vb.w) & 0x80808080u;
+        uint32_t t = ((n0 >> 7) | (n1 >> 6) | (n2 >> 5) | (n3 >> 4)) ^ 0x0f0f0f0fu;
+        // warp-uniform trip count, lanes that run out are predicated off: the warp never splits
+        const int n = (int)__reduce_max_sync(kFull, (uint32_t)__popc(t));
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const bool on = t != 0u;
+            int top;
+            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+            t &= ~(1u << (top & 31));
+            const int cell = ((top & 3) << 2) | ((top >> 3) & 3);   // word k = top & 3, byte j = top >> 3
+            if (on) {
+                const uint32_t b = cellp[cell];
+                uint32_t q = cellp[cell + kChunk];
+                if (q > BV_QUAL_MAX) { flags |= BV_FLAG_BAD_QUAL; q = min(q, (uint32_t)(kQSlots - 1)); }
+                atomicAdd(&W.hist[b * kQSlots + q], 1u);
+                qmin = min(qmin, q);
+                qmax = max(qmax, q);
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) W.p2_phase = phase;
+    qmin = __reduce_min_sync(kFull, qmin);
+    qmax = __reduce_max_sync(kFull, qmax);
+    flags = __reduce_or_sync(kFull, flags);
+    return qmin | (qmax << 8) | (flags << 16);
 }
 
 // ---- EM on compact bins (src/algorithm.h:210-255) ----------------------------------------------------------------
 // bins: nb packed (base, phred, count) entries; lml: nb doubles of scratch (log marginal likelihood per bin).
-// subset: bit j set => allele j in the candidate combination.  f: initial frequencies in (NOT renormalised,
+// subset: bit j set => allele j in the candidate combination.  W.emf: initial frequencies in (NOT renormalised,
 // src/basetype.cpp:93-103), estimated frequencies out.  Returns the sum of log marginal likelihoods under the
 // second-to-last frequency vector, exactly what _f() sums (src/basetype.cpp:119-120).
-struct Freq4 {
-    double v0, v1, v2, v3;
-};
-
-__device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb, const double* s_lut, int subset,
-                                       double total, Freq4& f, const SiteKernelArgs& a, uint32_t& flags) {
+__device__ __noinline__ double em_bins(WarpSmem* Wp, const CtaShared* cs, const uint32_t* bins, double* lml, int nb,
+                                       int subset, double total) {
+    WarpSmem& W = *Wp;
+    const double* s_lut = cs->lut;
     const int lane = threadIdx.x & 31;
-    double f0 = f.v0, f1 = f.v1, f2 = f.v2, f3 = f.v3;
-    int it = a.em_max_iter;
+    const int abs_mode = cs->a.abs_mode;
+    const double em_eps = cs->a.em_eps;
+    double f0 = W.emf[0], f1 = W.emf[1], f2 = W.emf[2], f3 = W.emf[3];
+    __syncwarp();
+    int it = cs->a.em_max_iter;
     bool first = true;
     for (;;) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0, delta = 0;
@@ -249,7 +280,7 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb
             const double llh = log(m);
             if (!first) {
                 const double diff = llh - lml[i];
-                if (a.abs_mode == BV_EM_ABS_INT_TRUNC) {
+                if (abs_mode == BV_EM_ABS_INT_TRUNC) {
                     // (double)abs((int)diff): non-zero iff |diff| >= 1; NaN/inf convert to INT_MIN whose
                     // "abs" stays negative and ends the loop (results are NaN by then)
                     if (fabs(diff) >= 1.0 && fabs(diff) < 2147483648.0) big = true;
@@ -259,7 +290,7 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb
             }
             lml[i] = llh;
             // m_step (algorithm.h:184-198): column sums of the posteriors; c equal reads add c * post
-                    if (subset & 1) s0 += cd * (l0 / m);
+            if (subset & 1) s0 += cd * (l0 / m);
             if (subset & 2) s1 += cd * (l1 / m);
             if (subset & 4) s2 += cd * (l2 / m);
             if (subset & 8) s3 += cd * (l3 / m);
@@ -270,25 +301,25 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb
         if (subset & 8) f3 = warp_sum(s3) / total;
         if (first) { first = false; continue; }
         bool more;
-        if (a.abs_mode == BV_EM_ABS_INT_TRUNC) more = __any_sync(0xffffffffu, big);
-        else more = !(warp_sum(delta) < a.em_eps);
+        if (abs_mode == BV_EM_ABS_INT_TRUNC) more = __any_sync(kFull, big);
+        else more = !(warp_sum(delta) < em_eps);
         --it;
-        if (it == 0) flags |= BV_FLAG_EM_MAXITER;
+        if (it == 0 && lane == 0) W.flag_word |= BV_FLAG_EM_MAXITER;
         if (!more || it == 0) break;
     }
     double ll = 0;
 #pragma unroll 1
     for (int i = lane; i < nb; i += 32) ll += (double)bin_count(bins[i]) * lml[i];
-    f.v0 = f0; f.v1 = f1; f.v2 = f2; f.v3 = f3;
+    if (lane == 0) { W.emf[0] = f0; W.emf[1] = f1; W.emf[2] = f2; W.emf[3] = f3; }
+    __syncwarp();
     return warp_sum(ll);
 }
 
 // Log-likelihood of the single-allele model {b} (an EM whose answer is closed form):
 // after the first m_step f_b == 1.0 exactly (every posterior is x/x), so every later marginal is L_b itself and
 // the reported log marginal is log(1-eps) or log(eps/3) -- both tabulated on the host with glibc.  A bin of base b
-// with phred 0 has L_b == 0: the reference then divides 0/0 and everything becomes NaN.
-__device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, const double* s_lut, int b_allele,
-                                                bool& is_nan) {
+// with phred 0 has L_b == 0: the reference then divides 0/0 and everything becomes NaN (returned as NaN).
+__device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, const double* s_lut, int b_allele) {
     const int lane = threadIdx.x & 31;
     double ll = 0;
     bool bad = false;
@@ -300,8 +331,9 @@ __device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, co
         if (match && q == 0) bad = true;
         ll += (double)bin_count(p) * s_lut[(match ? kLutLogMatch : kLutLogMis) * kQStride + q];
     }
-    is_nan = __any_sync(0xffffffffu, bad);
-    return warp_sum(ll);
+    ll = warp_sum(ll);
+    if (__any_sync(kFull, bad)) ll = __longlong_as_double(0x7ff8000000000000ll);
+    return ll;
 }
 
 __device__ __forceinline__ double sel4(int j, double v0, double v1, double v2, double v3) {
@@ -330,25 +362,20 @@ __device__ __forceinline__ bool is_active(uint32_t dep, uint32_t total, double d
     return (double)dep / dtot >= min_af;
 }
 
-// State of the LRT of one site (warp-uniform).
-struct LrtState {
-    Freq4 fa;          // frequencies of the accepted model
-    double chi;        // last chi_sqrt_value
-    uint32_t act;      // bit b set => base b active
-    int n_act;
-    uint32_t em_calls;
-    uint32_t flags;
-};
-
 // ---- sites with >= 2 active alleles: compact the bins, EM on the full set, backward elimination -----------------------
-// (src/basetype.cpp:144-168).  Out of line: ~25 % of sites at N=1000/0.1x, ~2 % at N=10,000.
-__device__ __noinline__ void lrt_multi(WarpScratch& ws, const double* s_lut, const SiteKernelArgs& a, uint32_t warp_global,
-                                       uint32_t qmin, uint32_t qmax, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3,
-                                       double dtot, LrtState& st) {
+// (src/basetype.cpp:144-168).  In: the row's histogram in W.hist, phred range, depths, active set.  Out: W.res_f /
+// W.res_chi and the return value act | n_act << 4 | em_calls << 8.
+__device__ __noinline__ uint32_t lrt_multi(WarpSmem* Wp, const CtaShared* cs, uint32_t warp_global, uint32_t qmin,
+                                           uint32_t qmax, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3,
+                                           uint32_t total, uint32_t act) {
+    WarpSmem& W = *Wp;
+    const double* s_lut = cs->lut;
     const int lane = threadIdx.x & 31;
-    // sweep 2: histogram back to zero while the non-empty (base, phred) bins are compacted, in (base, phred) order
+    const double dtot = (double)total;
+    const double lrt_threshold = cs->a.lrt_threshold;
+    // histogram back to zero while the non-empty (base, phred) bins are compacted, in (base, phred) order
     int nb = 0;
-    uint32_t* gbins = a.bin_spill + (size_t)warp_global * kMaxBins;
+    uint32_t* gbins = cs->a.bin_spill + (size_t)warp_global * kMaxBins;
 #pragma unroll 1
     for (int b = 0; b < 5; ++b) {
 #pragma unroll 1
@@ -356,15 +383,14 @@ __device__ __noinline__ void lrt_multi(WarpScratch& ws, const double* s_lut, con
             const uint32_t q = q0 + lane;
             uint32_t v = 0;
             if (q <= qmax) {
-                v = ws.hist[(2 * b) * kQStride + q] + ws.hist[(2 * b + 1) * kQStride + q];
-                ws.hist[(2 * b) * kQStride + q] = 0;
-                ws.hist[(2 * b + 1) * kQStride + q] = 0;
+                v = W.hist[b * kQSlots + q];
+                W.hist[b * kQSlots + q] = 0;
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, v != 0);
+            const uint32_t bal = __ballot_sync(kFull, v != 0);
             if (v) {
                 const int pos = nb + __popc(bal & ((1u << lane) - 1u));
                 const uint32_t p = pack_bin(b, q, v);
-                if (pos < kSmemBins) ws.bins[pos] = p;
+                if (pos < kSmemBins) W.bins[pos] = p;
                 gbins[pos] = p;
             }
             nb += __popc(bal);
@@ -373,39 +399,47 @@ __device__ __noinline__ void lrt_multi(WarpScratch& ws, const double* s_lut, con
     __syncwarp();
     // bins live in shared memory unless there are more than kSmemBins of them (then the global copy is used);
     // the EM's per-bin state overlays the (now all-zero) histogram
-    const uint32_t* bins = nb <= kSmemBins ? ws.bins : gbins;
-    double* lml = reinterpret_cast<double*>(ws.hist);
+    const bool in_smem = nb <= kSmemBins;
+    const uint32_t* bins = in_smem ? W.bins : gbins;
+    double* lml = in_smem ? reinterpret_cast<double*>(W.hist) : cs->a.lml_spill + (size_t)warp_global * kMaxBins;
 
     const double i0 = (double)d0 / dtot, i1 = (double)d1 / dtot, i2 = (double)d2 / dtot, i3 = (double)d3 / dtot;
-    uint32_t act = st.act;
-    int n_act = st.n_act;
-    Freq4 fa = {(act & 1) ? i0 : 0.0, (act & 2) ? i1 : 0.0, (act & 4) ? i2 : 0.0, (act & 8) ? i3 : 0.0};
-    uint32_t flags = st.flags;
+    int n_act = __popc(act);
+    double fa0, fa1, fa2, fa3;
+    uint32_t flags = 0;
     double chi = 0.0;
-    double lr_alt = em_bins(bins, lml, nb, s_lut, (int)act, dtot, fa, a, flags);
+    if (lane == 0) {
+        W.emf[0] = (act & 1) ? i0 : 0.0; W.emf[1] = (act & 2) ? i1 : 0.0;
+        W.emf[2] = (act & 4) ? i2 : 0.0; W.emf[3] = (act & 8) ? i3 : 0.0;
+    }
+    __syncwarp();
+    double lr_alt = em_bins(Wp, cs, bins, lml, nb, (int)act, dtot);
+    fa0 = W.emf[0]; fa1 = W.emf[1]; fa2 = W.emf[2]; fa3 = W.emf[3];
     uint32_t em_calls = 1;
 #pragma unroll 1
     for (int n = n_act - 1; n > 0; --n) {
         // the n-subsets of the n+1 active bases in the lexicographic order of
         // src/external/combinations.h:19-84: the i-th subset drops the (n-i)-th active base
         double best_chi = 0, best_lr = 0;
-        Freq4 best_f = {0, 0, 0, 0};
+        double bf0 = 0, bf1 = 0, bf2 = 0, bf3 = 0;
         uint32_t best_set = 0;
 #pragma unroll 1
         for (int i = 0; i <= n; ++i) {
             const uint32_t sub = act & ~(1u << nth_set_bit(act, n - i));
-            Freq4 g = {(sub & 1) ? i0 : 0.0, (sub & 2) ? i1 : 0.0, (sub & 4) ? i2 : 0.0, (sub & 8) ? i3 : 0.0};
-            if (g.v0 + g.v1 + g.v2 + g.v3 == 0) flags |= BV_FLAG_ZERO_SUBSET;   // the reference throws (basetype.cpp:113)
+            double g0 = (sub & 1) ? i0 : 0.0, g1 = (sub & 2) ? i1 : 0.0, g2 = (sub & 4) ? i2 : 0.0, g3 = (sub & 8) ? i3 : 0.0;
+            if (g0 + g1 + g2 + g3 == 0) flags |= BV_FLAG_ZERO_SUBSET;   // the reference throws (basetype.cpp:113)
             double lr;
             if (n == 1) {
                 const int single = __ffs(sub) - 1;
-                bool bad;
-                lr = single_allele_ll(bins, nb, s_lut, single, bad);
-                double v = 1.0;
-                if (bad) { lr = __longlong_as_double(0x7ff8000000000000ll); v = lr; }
-                g.v0 = single == 0 ? v : 0.0; g.v1 = single == 1 ? v : 0.0; g.v2 = single == 2 ? v : 0.0; g.v3 = single == 3 ? v : 0.0;
+                lr = single_allele_ll(bins, nb, s_lut, single);
+                const double v = (lr != lr) ? lr : 1.0;
+                g0 = single == 0 ? v : 0.0; g1 = single == 1 ? v : 0.0; g2 = single == 2 ? v : 0.0; g3 = single == 3 ? v : 0.0;
             } else {
-                lr = em_bins(bins, lml, nb, s_lut, (int)sub, dtot, g, a, flags);
+                __syncwarp();
+                if (lane == 0) { W.emf[0] = g0; W.emf[1] = g1; W.emf[2] = g2; W.emf[3] = g3; }
+                __syncwarp();
+                lr = em_bins(Wp, cs, bins, lml, nb, (int)sub, dtot);
+                g0 = W.emf[0]; g1 = W.emf[1]; g2 = W.emf[2]; g3 = W.emf[3];
             }
             if (em_calls < 255) ++em_calls;
             const double c = 2 * (lr_alt - lr);
@@ -416,110 +450,118 @@ __device__ __noinline__ void lrt_multi(WarpScratch& ws, const double* s_lut, con
             const double tie_tol = 1e-11 * (fabs(lr_alt) + fabs(lr));
             if (i > 0 && fabs(c - best_chi) <= tie_tol) flags |= BV_FLAG_LRT_TIE;
             if (i == 0 || c < best_chi - tie_tol) {
-                best_chi = c; best_lr = lr; best_set = sub; best_f = g;
+                best_chi = c; best_lr = lr; best_set = sub; bf0 = g0; bf1 = g1; bf2 = g2; bf3 = g3;
             }
         }
         lr_alt = best_lr;
         chi = best_chi;
-        if (fabs(chi - a.lrt_threshold) < 1e-9 * a.lrt_threshold) flags |= BV_FLAG_NEAR_LRT;
-        if (chi < a.lrt_threshold) {
-            act = best_set; n_act = n; fa = best_f;
+        if (fabs(chi - lrt_threshold) < 1e-9 * lrt_threshold) flags |= BV_FLAG_NEAR_LRT;
+        if (chi < lrt_threshold) {
+            act = best_set; n_act = n; fa0 = bf0; fa1 = bf1; fa2 = bf2; fa3 = bf3;
         } else {
             break;
         }
     }
     // the EM state overlaid the histogram: back to all-zero for the next site
     __syncwarp();
+    if (in_smem) {
 #pragma unroll 1
-    for (int i = lane; i < 2 * nb; i += 32) ws.hist[i] = 0;
-    st.fa = fa; st.chi = chi; st.act = act; st.n_act = n_act; st.em_calls = em_calls; st.flags = flags;
+        for (int i = lane; i < 2 * nb; i += 32) W.hist[i] = 0;
+    }
+    if (lane == 0) {
+        W.res_f[0] = fa0; W.res_f[1] = fa1; W.res_f[2] = fa2; W.res_f[3] = fa3;
+        W.res_chi = chi;
+        W.flag_word |= flags;
+    }
+    __syncwarp();
+    return act | ((uint32_t)n_act << 4) | (em_calls << 8);
 }
 
-// ---- the warp-per-site core: everything after the row has been histogrammed ----------------------------------------
-__device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut, const SiteKernelArgs& a,
-                                            uint32_t site, uint32_t warp_global, LaneCounts& lc) {
+// ---- slow finish: the row has non-reference reads (or REF is not A/C/G/T, or a bad strand code) -------------------------
+// n_ref / n_rev: reads holding the reference base (all / '-' strand) from pass 1; the other counted cells are in
+// W.nr_cnt.  Everything here is warp-uniform.
+__device__ __noinline__ void site_slow(WarpSmem* Wp, const CtaShared* cs, uint32_t site, uint32_t warp_global,
+                                       uint32_t n_ref, uint32_t n_rev, uint32_t bad_strand, int ref_code) {
+    WarpSmem& W = *Wp;
     const int lane = threadIdx.x & 31;
-    LrtState st;
-    st.flags = __reduce_or_sync(0xffffffffu, lc.flags);
-    const uint32_t qmin = __reduce_min_sync(0xffffffffu, lc.qmin);
-    const uint32_t qmax = __reduce_max_sync(0xffffffffu, lc.qmax);
-    if (qmin <= qmax && qmax > BV_QUAL_MAX) st.flags |= BV_FLAG_BAD_QUAL;   // phred 94..127 (>= 128 wraps modulo 128)
+    const double min_af = cs->a.min_af;
+    // ---- depths and strand table ----
+    const uint4 c0 = *reinterpret_cast<const uint4*>(&W.nr_cnt[0]);
+    const uint4 c1 = *reinterpret_cast<const uint4*>(&W.nr_cnt[4]);
+    const uint2 c2 = *reinterpret_cast<const uint2*>(&W.nr_cnt[8]);
     __syncwarp();
-
-    // ---- sweep 1: depths and strand table from the touched phred range ----
-    // row 2*base + strand ('+' = 0, '-' = 1).  A counted cell whose strand is neither sets BV_FLAG_BAD_STRAND and is
-    // counted by the low bit of its code: the reference throws on such a site (src/basetype.cpp:271-273), so only its
-    // depths and flags are specified.
-    uint32_t f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
-    if (qmin <= qmax) {
-#pragma unroll 1
-        for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
-            f0 += ws.hist[0 * kQStride + q]; r0 += ws.hist[1 * kQStride + q];
-            f1 += ws.hist[2 * kQStride + q]; r1 += ws.hist[3 * kQStride + q];
-            f2 += ws.hist[4 * kQStride + q]; r2 += ws.hist[5 * kQStride + q];
-            f3 += ws.hist[6 * kQStride + q]; r3 += ws.hist[7 * kQStride + q];
-            f4 += ws.hist[8 * kQStride + q]; r4 += ws.hist[9 * kQStride + q];
-        }
-        f0 = __reduce_add_sync(0xffffffffu, f0); f1 = __reduce_add_sync(0xffffffffu, f1);
-        f2 = __reduce_add_sync(0xffffffffu, f2); f3 = __reduce_add_sync(0xffffffffu, f3);
-        r0 = __reduce_add_sync(0xffffffffu, r0); r1 = __reduce_add_sync(0xffffffffu, r1);
-        r2 = __reduce_add_sync(0xffffffffu, r2); r3 = __reduce_add_sync(0xffffffffu, r3);
-        f4 = __reduce_add_sync(0xffffffffu, f4 + r4);
+    if (lane < 12) W.nr_cnt[lane] = 0;
+    if (lane == 0) W.flag_word = bad_strand ? BV_FLAG_BAD_STRAND : 0u;
+    uint32_t f0 = c0.x, r0 = c0.y, f1 = c0.z, r1 = c0.w, f2 = c1.x, r2 = c1.y, f3 = c1.z, r3 = c1.w;
+    const uint32_t other = c2.x + c2.y;
+    {
+        const uint32_t rf = n_ref - n_rev;
+        if (ref_code == 0) { f0 += rf; r0 += n_rev; }
+        if (ref_code == 1) { f1 += rf; r1 += n_rev; }
+        if (ref_code == 2) { f2 += rf; r2 += n_rev; }
+        if (ref_code == 3) { f3 += rf; r3 += n_rev; }
     }
-    const uint32_t d0 = f0 + r0, d1 = f1 + r1, d2 = f2 + r2, d3 = f3 + r3, other = f4;
+    const uint32_t d0 = f0 + r0, d1 = f1 + r1, d2 = f2 + r2, d3 = f3 + r3;
     const uint32_t total = d0 + d1 + d2 + d3 + other;
     const double dtot = (double)total;
 
-    // ---- reference base ----
-    int ref_char = a.ref_base[site];
-    if (ref_char >= 'a' && ref_char <= 'z') ref_char -= 32;  // toupper (src/basetype.cpp:171)
-    const int ref_code = ref_char == 'A' ? 0 : ref_char == 'C' ? 1 : ref_char == 'G' ? 2 : ref_char == 'T' ? 3 : -1;
-
     // ---- lrt (src/basetype.cpp:130-199): active set ----
-    st.act = 0;
+    uint32_t act = 0;
     if (total > 0) {
-        st.act |= is_active(d0, total, dtot, a.min_af) ? 1u : 0u;
-        st.act |= is_active(d1, total, dtot, a.min_af) ? 2u : 0u;
-        st.act |= is_active(d2, total, dtot, a.min_af) ? 4u : 0u;
-        st.act |= is_active(d3, total, dtot, a.min_af) ? 8u : 0u;
+        act |= is_active(d0, total, dtot, min_af) ? 1u : 0u;
+        act |= is_active(d1, total, dtot, min_af) ? 2u : 0u;
+        act |= is_active(d2, total, dtot, min_af) ? 4u : 0u;
+        act |= is_active(d3, total, dtot, min_af) ? 8u : 0u;
     }
-    st.n_act = __popc(st.act);
-    st.fa.v0 = st.fa.v1 = st.fa.v2 = st.fa.v3 = 0.0;
-    st.chi = 0.0;
-    st.em_calls = 0;
+    int n_act = __popc(act);
+    double fa0 = 0.0, fa1 = 0.0, fa2 = 0.0, fa3 = 0.0, chi = 0.0;
+    uint32_t em_calls = 0;
+    const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
+    __syncwarp();
 
-    if (st.n_act >= 2) {
-        lrt_multi(ws, s_lut, a, warp_global, qmin, qmax, d0, d1, d2, d3, dtot, st);
-    } else {
-        if (st.n_act == 1) {
+    if (n_act >= 2 || (n_act == 1 && (act & ~ref_bit))) {
+        // the result depends on base qualities: histogram the row by (base, phred)
+        const uint32_t h = build_hist(Wp, cs, site);
+        const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
+        if (lane == 0) W.flag_word |= h >> 16;
+        __syncwarp();
+        if (n_act >= 2) {
+            const uint32_t r = lrt_multi(Wp, cs, warp_global, qmin, qmax, d0, d1, d2, d3, total, act);
+            act = r & 0xfu; n_act = (int)((r >> 4) & 0xfu); em_calls = r >> 8;
+            fa0 = W.res_f[0]; fa1 = W.res_f[1]; fa2 = W.res_f[2]; fa3 = W.res_f[3];
+            chi = W.res_chi;
+        } else {
             // One active allele: the reference still runs one EM; its answer is closed form (see single_allele_ll):
             // AF == 1.0 exactly, or NaN when a phred-0 read of that base exists.
-            const int b = __ffs(st.act) - 1;
-            bool bad = false;
-            if (qmin == 0) bad = (ws.hist[(2 * b) * kQStride] + ws.hist[(2 * b + 1) * kQStride]) != 0;
+            const int b = __ffs(act) - 1;
+            const bool bad = qmin == 0 && W.hist[b * kQSlots] != 0;
             const double v = bad ? __longlong_as_double(0x7ff8000000000000ll) : 1.0;
-            st.fa.v0 = b == 0 ? v : 0.0; st.fa.v1 = b == 1 ? v : 0.0; st.fa.v2 = b == 2 ? v : 0.0; st.fa.v3 = b == 3 ? v : 0.0;
-            st.em_calls = 1;
-        }
-        __syncwarp();
-        if (qmin <= qmax) {   // sweep 2: histogram back to zero
+            fa0 = b == 0 ? v : 0.0; fa1 = b == 1 ? v : 0.0; fa2 = b == 2 ? v : 0.0; fa3 = b == 3 ? v : 0.0;
+            em_calls = 1;
+            __syncwarp();
+            if (qmin <= qmax) {   // histogram back to zero
 #pragma unroll 1
-            for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
+                for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
 #pragma unroll
-                for (int r = 0; r < kHistRows; ++r) ws.hist[r * kQStride + q] = 0;
+                    for (int r = 0; r < 5; ++r) W.hist[r * kQSlots + q] = 0;
+                }
             }
         }
+    } else if (n_act == 1) {
+        em_calls = 1;   // the single active allele is REF: AF is not reported
     }
+    __syncwarp();
+    uint32_t flags = W.flag_word;
 
     // ---- ALT / QUAL (src/basetype.cpp:170-196) ----
-    const uint32_t alt_set = (ref_code >= 0) ? (st.act & ~(1u << ref_code)) : st.act;
+    const uint32_t alt_set = act & ~ref_bit;
     const int n_alt = __popc(alt_set);
     double qual = 0.0;
     if (n_alt) {
-        const int first_act = __ffs(st.act) - 1;
+        const int first_act = __ffs(act) - 1;
         const double r = (double)sel4u(first_act, d0, d1, d2, d3) / dtot;
-        if (st.n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; st.flags |= BV_FLAG_MONO_QUAL; }
-        else qual = qual_from_chi(st.chi);
+        if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
+        else qual = qual_from_chi(chi);
     }
 
     // ---- strand bias (src/basetype.cpp:244-295): CVG row = ref vs all non-ref ACGT; VCF row = ref vs ALT ----
@@ -529,19 +571,18 @@ __device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut
         const int rr = ref_code < 0 ? 0 : (int)sel4u(ref_code, r0, r1, r2, r3);
         const int af_ = (int)(f0 + f1 + f2 + f3) - rf, ar = (int)(r0 + r1 + r2 + r3) - rr;
         // a table with an empty row or column has a single possible outcome: p == 1, FS == 0 (kfunc.c:256)
-        if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(a.logfact, rf, rr, af_, ar);
+        if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(cs->a.logfact, rf, rr, af_, ar);
         if (n_alt) {
             const int vf = (int)(((alt_set & 1) ? f0 : 0u) + ((alt_set & 2) ? f1 : 0u) + ((alt_set & 4) ? f2 : 0u) + ((alt_set & 8) ? f3 : 0u));
             const int vr = (int)(((alt_set & 1) ? r0 : 0u) + ((alt_set & 2) ? r1 : 0u) + ((alt_set & 4) ? r2 : 0u) + ((alt_set & 8) ? r3 : 0u));
             if (vf == af_ && vr == ar) fs_vcf = fs_cvg;   // same 2x2 table
-            else fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
+            else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(cs->a.logfact, rf, rr, vf, vr);
         }
     }
 
     // ---- record ----
-    __syncwarp();
     if (lane == 0) {
-        bv_site_out& r = ws.rec;
+        bv_site_out& r = W.rec;
         r.depth[0] = d0; r.depth[1] = d1; r.depth[2] = d2; r.depth[3] = d3;
         r.depth_other = other;
         r.reserved0 = 0;
@@ -549,27 +590,26 @@ __device__ __forceinline__ void site_finish(WarpScratch& ws, const double* s_lut
         r.rev[0] = r0; r.rev[1] = r1; r.rev[2] = r2; r.rev[3] = r3;
         // ALT alleles in ACGT order of the active set (src/basetype.cpp:172-177)
         uint32_t alts = 0;
-        double af[4] = {0.0, 0.0, 0.0, 0.0};
         int k = 0;
-        if (alt_set & 1) { af[k] = st.fa.v0; alts |= 0u << (8 * k); ++k; }
-        if (alt_set & 2) { af[k] = st.fa.v1; alts |= 1u << (8 * k); ++k; }
-        if (alt_set & 4) { af[k] = st.fa.v2; alts |= 2u << (8 * k); ++k; }
-        if (alt_set & 8) { af[k] = st.fa.v3; alts |= 3u << (8 * k); ++k; }
+        r.af[0] = 0.0; r.af[1] = 0.0; r.af[2] = 0.0; r.af[3] = 0.0;
+        if (alt_set & 1) { r.af[k] = fa0; alts |= 0u << (8 * k); ++k; }
+        if (alt_set & 2) { r.af[k] = fa1; alts |= 1u << (8 * k); ++k; }
+        if (alt_set & 4) { r.af[k] = fa2; alts |= 2u << (8 * k); ++k; }
+        if (alt_set & 8) { r.af[k] = fa3; alts |= 3u << (8 * k); ++k; }
         r.n_alt = (uint8_t)n_alt;
         r.alt[0] = (uint8_t)alts; r.alt[1] = (uint8_t)(alts >> 8); r.alt[2] = (uint8_t)(alts >> 16); r.alt[3] = (uint8_t)(alts >> 24);
-        r.af[0] = af[0]; r.af[1] = af[1]; r.af[2] = af[2]; r.af[3] = af[3];
-        r.n_active = (uint8_t)st.n_act;
-        r.flags = (uint8_t)st.flags;
-        r.em_calls = (uint8_t)st.em_calls;
+        r.n_active = (uint8_t)n_act;
+        r.flags = (uint8_t)flags;
+        r.em_calls = (uint8_t)(em_calls > 255u ? 255u : em_calls);
         r.qual = qual;
-        r.chi2 = st.chi;
+        r.chi2 = chi;
         r.fs_cvg = fs_cvg;
         r.fs_vcf = fs_vcf;
     }
     __syncwarp();
     if (lane < 8) {
-        const uint4* src = reinterpret_cast<const uint4*>(&ws.rec);
-        uint4* dst = reinterpret_cast<uint4*>(a.out + site);
+        const uint4* src = reinterpret_cast<const uint4*>(&W.rec);
+        uint4* dst = reinterpret_cast<uint4*>(cs->a.out + site);
         dst[lane] = src[lane];
     }
     __syncwarp();
