@@ -24,15 +24,25 @@ namespace bv {
 static_assert(sizeof(CtaShared) + (size_t)kWarps * sizeof(WarpSmem) <= 232448, "shared memory of the site kernel exceeds 227 KB");
 
 __global__ void __launch_bounds__(kWarps * 32, 1) bv_site_kernel(const __grid_constant__ SiteKernelArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    CtaShared& cs = *reinterpret_cast<CtaShared*>(smem_raw);
+    CtaShared& cs = cta_shared();
+    WarpSmem& W = warp_smem();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem& W = reinterpret_cast<WarpSmem*>(smem_raw + sizeof(CtaShared))[warp];
 
     for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) cs.lut[i] = a.lut[i];
-    if (threadIdx.x == 0) cs.a = a;
+    if (threadIdx.x == 0) {
+        cs.a = a;
+        // byte masks of the row's last 16-cell vector when N is not a multiple of 16
+        const int valid = (int)(a.n_samples & 15u);
+        for (int k = 0; k < 4; ++k) {
+            const int left = valid == 0 ? 4 : valid - 4 * k;
+            cs.tail_keep[k] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+        }
+        cs.tail_lane = valid == 0 ? 32u : (((a.n_samples - 1u) % kChunk) >> 4);
+    }
     for (int i = lane; i < kHistWords; i += 32) W.hist[i] = 0;
     if (lane < 12) W.nr_cnt[lane] = 0;
+    const uint32_t total_warps = gridDim.x * kWarps;
+    const uint32_t warp_global = blockIdx.x * kWarps + warp;
     if (lane == 0) {
         W.flag_word = 0;
         W.p2_phase = 0;
@@ -42,103 +52,32 @@ __global__ void __launch_bounds__(kWarps * 32, 1) bv_site_kernel(const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-
-    const uint32_t total_warps = gridDim.x * kWarps;
-    const uint32_t warp_global = blockIdx.x * kWarps + warp;
-    const uint32_t N = a.n_samples;
-    const uint32_t row_bytes = (N + 15u) & ~15u;                         // bytes of a row that hold cells
-    const uint32_t nchunk = (row_bytes + kChunk - 1) / kChunk;           // >= 1 (n_samples > 0)
     if (warp_global >= a.n_sites) return;
 
-    // ---- producer cursor: lane 0 issues the bulk copies of the unit kStages-1 ahead of the one being scanned ----
-    uint32_t p_site = warp_global, p_chunk = 0, p_stage = 0;
-    auto issue = [&]() {
-        if (p_site < a.n_sites) {
+    // ---- prologue of the ring: the first kStages-1 units of this warp's site sequence ----
+    {
+        const uint32_t row_bytes = (a.n_samples + 15u) & ~15u;
+        uint32_t p_site = warp_global, p_off = 0, p_slot = 0;
+        for (int s = 0; s < kStages - 1 && p_site < a.n_sites; ++s) {
             if (lane == 0) {
-                const uint32_t off = p_chunk * kChunk;
-                const uint32_t bytes = min((uint32_t)kChunk, row_bytes - off);
-                const size_t g = (size_t)p_site * a.pitch + off;
-                mbar_expect_tx(&W.full[p_stage], 2 * bytes);
-                bulk_g2s(W.stage[p_stage].base, a.base + g, bytes, &W.full[p_stage]);
-                bulk_g2s(W.stage[p_stage].strand, a.strand + g, bytes, &W.full[p_stage]);
+                const uint32_t bytes = min((uint32_t)kChunk, row_bytes - p_off);
+                const size_t g = (size_t)p_site * a.pitch + p_off;
+                mbar_expect_tx(&W.full[p_slot], 2 * bytes);
+                bulk_g2s(W.stage[p_slot].base, a.base + g, bytes, &W.full[p_slot]);
+                bulk_g2s(W.stage[p_slot].strand, a.strand + g, bytes, &W.full[p_slot]);
             }
-            p_stage = (p_stage + 1 == kStages) ? 0 : p_stage + 1;
-            if (++p_chunk == nchunk) { p_chunk = 0; p_site += total_warps; }
+            ++p_slot;
+            p_off += kChunk;
+            if (p_off >= row_bytes) { p_off = 0; p_site += total_warps; }
         }
-    };
-#pragma unroll 1
-    for (int s = 0; s < kStages - 1; ++s) issue();
-
-    uint32_t c_stage = 0, phases = 0;
-    uint32_t ref_raw = a.ref_base[warp_global];
-    const uint32_t one_active = (1.0 >= a.min_af) ? 1u : 0u;   // a site whose reads all agree has that allele active
-#pragma unroll 1
-    for (uint32_t site = warp_global; site < a.n_sites; site += total_warps) {
-        // reference base of this site (prefetched one site ahead), toupper (src/basetype.cpp:171)
-        const uint32_t next_site = site + total_warps;
-        const uint32_t ref_next = next_site < a.n_sites ? (uint32_t)__ldg(a.ref_base + next_site) : 0u;
-        uint32_t rc = ref_raw;
-        if (rc >= 'a' && rc <= 'z') rc -= 32;
-        const int ref_code = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
-        const uint32_t refw = ref_code >= 0 ? (uint32_t)ref_code * 0x01010101u : 0x08080808u;
-
-        // ---- pass 1 ----
-        ScanAcc A;
-        A.nref = 0; A.nrev = 0; A.nonref = 0; A.bad = 0;
-#pragma unroll 1
-        for (uint32_t chunk = 0; chunk < nchunk; ++chunk) {
-            issue();   // the unit kStages-1 ahead goes into the stage the previous unit used; every lane is past it
-            mbar_wait(&W.full[c_stage], (phases >> c_stage) & 1u);
-            phases ^= 1u << c_stage;
-            const int lane_cells = (int)N - (int)(chunk * kChunk) - lane * 16;
-            if (lane_cells > 0) {
-                const uint8_t* cellp = W.stage[c_stage].base + lane * 16;
-                uint4 vb = *reinterpret_cast<const uint4*>(cellp);
-                const uint4 vs = *reinterpret_cast<const uint4*>(cellp + kChunk);
-                if (lane_cells < 16) mask_tail(vb, lane_cells);
-                const uint32_t nr0 = scan_word(vb.x, vs.x, refw, A);
-                const uint32_t nr1 = scan_word(vb.y, vs.y, refw, A);
-                const uint32_t nr2 = scan_word(vb.z, vs.z, refw, A);
-                const uint32_t nr3 = scan_word(vb.w, vs.w, refw, A);
-                if (nr0 | nr1 | nr2 | nr3) {
-                    // counted cells that are not the reference base (sequencing errors, ALT alleles): one by one
-                    uint32_t t = (nr0 >> 7) | (nr1 >> 6) | (nr2 >> 5) | (nr3 >> 4);   // bit (8*byte + word)
-                    A.nonref |= t;
-                    do {
-                        int top;
-                        asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
-                        t ^= 1u << top;
-                        const int cell = ((top & 3) << 2) | (top >> 3);
-                        const uint32_t b = cellp[cell];
-                        const uint32_t s = cellp[cell + kChunk];
-                        atomicAdd(&W.nr_cnt[2u * b + (s & 1u)], 1u);
-                    } while (t);
-                }
-            }
-            __syncwarp();
-            c_stage = (c_stage + 1 == kStages) ? 0 : c_stage + 1;
+        if (lane == 0) {
+            W.sv_p_site = p_site; W.sv_p_off = p_off; W.sv_p_slot = p_slot % kStages;
+            W.sv_c_slot = 0; W.sv_c_par = 0; W.sv_site = warp_global; W.sv_ref_raw = a.ref_base[warp_global];
         }
-
-        // ---- finish ----
-        const uint32_t fl = __reduce_or_sync(kFull, A.nonref | (A.bad ? 0x80000000u : 0u));
-        const uint32_t n_ref = __reduce_add_sync(kFull, A.nref) >> 7;
-        const uint32_t n_rev = __reduce_add_sync(kFull, A.nrev) >> 7;
-        if (fl == 0) {
-            // Every counted cell holds the reference base (or nothing is covered): depth[REF] = n_ref, one active
-            // allele == REF, the EM's answer is f = 1 (src/algorithm.h:210-255 with a single column), no ALT,
-            // QUAL / FS / chi2 = 0.  Lanes compose the 32 words of the record.
-            const uint32_t n_active = (n_ref > 0) ? one_active : 0u;
-            uint32_t w = 0;
-            if (lane == ref_code) w = n_ref;                      // depth[REF]
-            if (lane == ref_code + 6) w = n_ref - n_rev;          // fwd[REF]
-            if (lane == ref_code + 10) w = n_rev;                 // rev[REF]
-            if (lane == 15) w = (n_active << 8) | (n_active << 24);   // n_active | flags 0 | em_calls
-            reinterpret_cast<uint32_t*>(a.out + site)[lane] = w;
-        } else {
-            site_slow(&W, &cs, site, warp_global, n_ref, n_rev, fl >> 31, ref_code);
-        }
-        ref_raw = ref_next;
+        __syncwarp();
     }
+    // ---- stream; leave the call-free loop only for the sites that need the slow path ----
+    while (stream_sites()) site_slow();
 }
 
 // ======================================================================================================

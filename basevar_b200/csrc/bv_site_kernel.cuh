@@ -90,9 +90,14 @@ struct __align__(128) WarpSmem {
     uint32_t nr_cnt[12];         // pass 1: counted cells that are not the reference base, [2*base + strand]
     double emf[4];               // EM: allele frequencies in / out
     double res_f[4];             // LRT: frequencies of the accepted model
+    double best_f[4];            // LRT: frequencies of the best candidate subset of the current round
     double res_chi;              // LRT: last chi_sqrt_value
     uint32_t flag_word;          // BV_FLAG_* raised inside out-of-line code
     uint32_t p2_phase;           // mbarrier phase bits of p2bar[]
+    // state of the streaming loop while the warp is away in the slow path (see stream_sites)
+    uint32_t sv_p_site, sv_p_off, sv_p_slot, sv_c_slot, sv_c_par, sv_site, sv_ref_raw;
+    // the slow site handed from stream_sites to site_slow
+    uint32_t slow_site, slow_n_ref, slow_n_rev, slow_bad, slow_ref_code;
     uint64_t full[kStages];
     uint64_t p2bar[2];
     alignas(16) bv_site_out rec; // record staging for one coalesced 128-byte store (slow path)
@@ -100,9 +105,20 @@ struct __align__(128) WarpSmem {
 
 struct __align__(128) CtaShared {
     double lut[4 * kQStride];
+    uint32_t tail_keep[4];       // byte masks of the row's last, partial 16-cell vector (all ones when N % 16 == 0)
+    uint32_t tail_lane;          // lane that holds that vector in the row's last chunk (32: none)
+    uint32_t pad_[3];
     SiteKernelArgs a;            // kernel parameters for out-of-line device functions (a reference to the
                                  // __global__ parameter itself would force a local-memory copy)
 };
+
+// The kernel's dynamic shared memory: CtaShared, then one WarpSmem per warp.  Device functions reach it through these
+// accessors (not through pointer arguments) so that the compiler knows the address space and emits LDS/STS/ATOMS.
+extern __shared__ __align__(128) unsigned char bv_smem_raw[];
+__device__ __forceinline__ CtaShared& cta_shared() { return *reinterpret_cast<CtaShared*>(bv_smem_raw); }
+__device__ __forceinline__ WarpSmem& warp_smem() {
+    return reinterpret_cast<WarpSmem*>(bv_smem_raw + sizeof(CtaShared))[threadIdx.x >> 5];
+}
 
 __device__ __forceinline__ uint32_t pack_bin(uint32_t b, uint32_t q, uint32_t count) {
     return (b << 29) | (q << 22) | count;
@@ -178,15 +194,16 @@ __device__ __forceinline__ uint32_t scan_word(uint32_t wb, uint32_t ws, uint32_t
 // Pass 2: (base, phred) histogram of the covered cells of one row.  Out of line; runs on the sites whose result depends
 // on base qualities.  Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
 // =====================================================================================================================
-__device__ __noinline__ uint32_t build_hist(WarpSmem* Wp, const CtaShared* cs, uint32_t site) {
-    WarpSmem& W = *Wp;
+__device__ __noinline__ uint32_t build_hist(uint32_t site) {
+    WarpSmem& W = warp_smem();
+    const CtaShared& cs = cta_shared();
     const int lane = threadIdx.x & 31;
-    const uint32_t N = cs->a.n_samples;
+    const uint32_t N = cs.a.n_samples;
     const uint32_t row_bytes = (N + 15u) & ~15u;
     const uint32_t nchunk = (row_bytes + kChunk - 1) / kChunk;
-    const size_t row = (size_t)site * cs->a.pitch;
-    const uint8_t* gb = cs->a.base + row;
-    const uint8_t* gq = cs->a.qual + row;
+    const size_t row = (size_t)site * cs.a.pitch;
+    const uint8_t* gb = cs.a.base + row;
+    const uint8_t* gq = cs.a.qual + row;
     uint32_t phase = W.p2_phase;
     uint32_t qmin = 0xffu, qmax = 0, flags = 0;
     if (lane == 0) {
@@ -250,16 +267,15 @@ __device__ __noinline__ uint32_t build_hist(WarpSmem* Wp, const CtaShared* cs, u
 // subset: bit j set => allele j in the candidate combination.  W.emf: initial frequencies in (NOT renormalised,
 // src/basetype.cpp:93-103), estimated frequencies out.  Returns the sum of log marginal likelihoods under the
 // second-to-last frequency vector, exactly what _f() sums (src/basetype.cpp:119-120).
-__device__ __noinline__ double em_bins(WarpSmem* Wp, const CtaShared* cs, const uint32_t* bins, double* lml, int nb,
-                                       int subset, double total) {
-    WarpSmem& W = *Wp;
-    const double* s_lut = cs->lut;
+__device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb, int subset, double total) {
+    WarpSmem& W = warp_smem();
+    const CtaShared& cs = cta_shared();
+    const double* s_lut = cs.lut;
     const int lane = threadIdx.x & 31;
-    const int abs_mode = cs->a.abs_mode;
-    const double em_eps = cs->a.em_eps;
+    const int abs_mode = cs.a.abs_mode;
     double f0 = W.emf[0], f1 = W.emf[1], f2 = W.emf[2], f3 = W.emf[3];
     __syncwarp();
-    int it = cs->a.em_max_iter;
+    int it = cs.a.em_max_iter;
     bool first = true;
     for (;;) {
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0, delta = 0;
@@ -302,7 +318,7 @@ __device__ __noinline__ double em_bins(WarpSmem* Wp, const CtaShared* cs, const 
         if (first) { first = false; continue; }
         bool more;
         if (abs_mode == BV_EM_ABS_INT_TRUNC) more = __any_sync(kFull, big);
-        else more = !(warp_sum(delta) < em_eps);
+        else more = !(warp_sum(delta) < cs.a.em_eps);
         --it;
         if (it == 0 && lane == 0) W.flag_word |= BV_FLAG_EM_MAXITER;
         if (!more || it == 0) break;
@@ -319,7 +335,8 @@ __device__ __noinline__ double em_bins(WarpSmem* Wp, const CtaShared* cs, const 
 // after the first m_step f_b == 1.0 exactly (every posterior is x/x), so every later marginal is L_b itself and
 // the reported log marginal is log(1-eps) or log(eps/3) -- both tabulated on the host with glibc.  A bin of base b
 // with phred 0 has L_b == 0: the reference then divides 0/0 and everything becomes NaN (returned as NaN).
-__device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, const double* s_lut, int b_allele) {
+__device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, int b_allele) {
+    const double* s_lut = cta_shared().lut;
     const int lane = threadIdx.x & 31;
     double ll = 0;
     bool bad = false;
@@ -336,9 +353,6 @@ __device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, co
     return ll;
 }
 
-__device__ __forceinline__ double sel4(int j, double v0, double v1, double v2, double v3) {
-    return j == 0 ? v0 : j == 1 ? v1 : j == 2 ? v2 : v3;
-}
 __device__ __forceinline__ uint32_t sel4u(int j, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
     return j == 0 ? v0 : j == 1 ? v1 : j == 2 ? v2 : v3;
 }
@@ -363,21 +377,21 @@ __device__ __forceinline__ bool is_active(uint32_t dep, uint32_t total, double d
 }
 
 // ---- sites with >= 2 active alleles: compact the bins, EM on the full set, backward elimination -----------------------
-// (src/basetype.cpp:144-168).  In: the row's histogram in W.hist, phred range, depths, active set.  Out: W.res_f /
-// W.res_chi and the return value act | n_act << 4 | em_calls << 8.
-__device__ __noinline__ uint32_t lrt_multi(WarpSmem* Wp, const CtaShared* cs, uint32_t warp_global, uint32_t qmin,
-                                           uint32_t qmax, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3,
-                                           uint32_t total, uint32_t act) {
-    WarpSmem& W = *Wp;
-    const double* s_lut = cs->lut;
+// (src/basetype.cpp:144-168).  In: the row's histogram in W.hist, phred range, depths in W.rec.depth[] (already final),
+// active set.  Out: W.res_f / W.res_chi and the return value act | n_act << 4 | em_calls << 8.  The warp-uniform
+// model state lives in shared memory (W.emf / W.best_f / W.res_f), not in registers that would have to survive the
+// calls into em_bins.
+__device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_t act) {
+    WarpSmem& W = warp_smem();
+    const CtaShared& cs = cta_shared();
     const int lane = threadIdx.x & 31;
-    const double dtot = (double)total;
-    const double lrt_threshold = cs->a.lrt_threshold;
+    const uint32_t warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
     // histogram back to zero while the non-empty (base, phred) bins are compacted, in (base, phred) order
     int nb = 0;
-    uint32_t* gbins = cs->a.bin_spill + (size_t)warp_global * kMaxBins;
+    uint32_t* gbins = cs.a.bin_spill + (size_t)warp_global * kMaxBins;
 #pragma unroll 1
     for (int b = 0; b < 5; ++b) {
+        if (b < 4 ? W.rec.depth[b] == 0 : W.rec.depth_other == 0) continue;
 #pragma unroll 1
         for (uint32_t q0 = qmin; q0 <= qmax; q0 += 32) {
             const uint32_t q = q0 + lane;
@@ -401,45 +415,40 @@ __device__ __noinline__ uint32_t lrt_multi(WarpSmem* Wp, const CtaShared* cs, ui
     // the EM's per-bin state overlays the (now all-zero) histogram
     const bool in_smem = nb <= kSmemBins;
     const uint32_t* bins = in_smem ? W.bins : gbins;
-    double* lml = in_smem ? reinterpret_cast<double*>(W.hist) : cs->a.lml_spill + (size_t)warp_global * kMaxBins;
+    double* lml = in_smem ? reinterpret_cast<double*>(W.hist) : cs.a.lml_spill + (size_t)warp_global * kMaxBins;
 
-    const double i0 = (double)d0 / dtot, i1 = (double)d1 / dtot, i2 = (double)d2 / dtot, i3 = (double)d3 / dtot;
+    const double dtot = (double)(W.rec.depth[0] + W.rec.depth[1] + W.rec.depth[2] + W.rec.depth[3] + W.rec.depth_other);
     int n_act = __popc(act);
-    double fa0, fa1, fa2, fa3;
     uint32_t flags = 0;
     double chi = 0.0;
-    if (lane == 0) {
-        W.emf[0] = (act & 1) ? i0 : 0.0; W.emf[1] = (act & 2) ? i1 : 0.0;
-        W.emf[2] = (act & 4) ? i2 : 0.0; W.emf[3] = (act & 8) ? i3 : 0.0;
-    }
+    // initial frequencies of a subset: depth/total for its members, 0 elsewhere (src/basetype.cpp:93-103)
+    if (lane < 4) W.emf[lane] = (act >> lane & 1u) ? (double)W.rec.depth[lane] / dtot : 0.0;
     __syncwarp();
-    double lr_alt = em_bins(Wp, cs, bins, lml, nb, (int)act, dtot);
-    fa0 = W.emf[0]; fa1 = W.emf[1]; fa2 = W.emf[2]; fa3 = W.emf[3];
+    double lr_alt = em_bins(bins, lml, nb, (int)act, dtot);
+    if (lane < 4) W.res_f[lane] = W.emf[lane];
     uint32_t em_calls = 1;
 #pragma unroll 1
     for (int n = n_act - 1; n > 0; --n) {
         // the n-subsets of the n+1 active bases in the lexicographic order of
         // src/external/combinations.h:19-84: the i-th subset drops the (n-i)-th active base
         double best_chi = 0, best_lr = 0;
-        double bf0 = 0, bf1 = 0, bf2 = 0, bf3 = 0;
         uint32_t best_set = 0;
 #pragma unroll 1
         for (int i = 0; i <= n; ++i) {
             const uint32_t sub = act & ~(1u << nth_set_bit(act, n - i));
-            double g0 = (sub & 1) ? i0 : 0.0, g1 = (sub & 2) ? i1 : 0.0, g2 = (sub & 4) ? i2 : 0.0, g3 = (sub & 8) ? i3 : 0.0;
-            if (g0 + g1 + g2 + g3 == 0) flags |= BV_FLAG_ZERO_SUBSET;   // the reference throws (basetype.cpp:113)
+            __syncwarp();
+            if (lane < 4) W.emf[lane] = (sub >> lane & 1u) ? (double)W.rec.depth[lane] / dtot : 0.0;
+            __syncwarp();
+            if (W.emf[0] + W.emf[1] + W.emf[2] + W.emf[3] == 0) flags |= BV_FLAG_ZERO_SUBSET;   // the reference throws (basetype.cpp:113)
             double lr;
             if (n == 1) {
                 const int single = __ffs(sub) - 1;
-                lr = single_allele_ll(bins, nb, s_lut, single);
+                lr = single_allele_ll(bins, nb, single);
                 const double v = (lr != lr) ? lr : 1.0;
-                g0 = single == 0 ? v : 0.0; g1 = single == 1 ? v : 0.0; g2 = single == 2 ? v : 0.0; g3 = single == 3 ? v : 0.0;
+                if (lane < 4) W.emf[lane] = lane == single ? v : 0.0;
+                __syncwarp();
             } else {
-                __syncwarp();
-                if (lane == 0) { W.emf[0] = g0; W.emf[1] = g1; W.emf[2] = g2; W.emf[3] = g3; }
-                __syncwarp();
-                lr = em_bins(Wp, cs, bins, lml, nb, (int)sub, dtot);
-                g0 = W.emf[0]; g1 = W.emf[1]; g2 = W.emf[2]; g3 = W.emf[3];
+                lr = em_bins(bins, lml, nb, (int)sub, dtot);
             }
             if (em_calls < 255) ++em_calls;
             const double c = 2 * (lr_alt - lr);
@@ -450,14 +459,18 @@ __device__ __noinline__ uint32_t lrt_multi(WarpSmem* Wp, const CtaShared* cs, ui
             const double tie_tol = 1e-11 * (fabs(lr_alt) + fabs(lr));
             if (i > 0 && fabs(c - best_chi) <= tie_tol) flags |= BV_FLAG_LRT_TIE;
             if (i == 0 || c < best_chi - tie_tol) {
-                best_chi = c; best_lr = lr; best_set = sub; bf0 = g0; bf1 = g1; bf2 = g2; bf3 = g3;
+                best_chi = c; best_lr = lr; best_set = sub;
+                if (lane < 4) W.best_f[lane] = W.emf[lane];
             }
         }
         lr_alt = best_lr;
         chi = best_chi;
+        const double lrt_threshold = cs.a.lrt_threshold;
         if (fabs(chi - lrt_threshold) < 1e-9 * lrt_threshold) flags |= BV_FLAG_NEAR_LRT;
         if (chi < lrt_threshold) {
-            act = best_set; n_act = n; fa0 = bf0; fa1 = bf1; fa2 = bf2; fa3 = bf3;
+            act = best_set; n_act = n;
+            __syncwarp();
+            if (lane < 4) W.res_f[lane] = W.best_f[lane];
         } else {
             break;
         }
@@ -469,7 +482,6 @@ __device__ __noinline__ uint32_t lrt_multi(WarpSmem* Wp, const CtaShared* cs, ui
         for (int i = lane; i < 2 * nb; i += 32) W.hist[i] = 0;
     }
     if (lane == 0) {
-        W.res_f[0] = fa0; W.res_f[1] = fa1; W.res_f[2] = fa2; W.res_f[3] = fa3;
         W.res_chi = chi;
         W.flag_word |= flags;
     }
@@ -478,32 +490,43 @@ __device__ __noinline__ uint32_t lrt_multi(WarpSmem* Wp, const CtaShared* cs, ui
 }
 
 // ---- slow finish: the row has non-reference reads (or REF is not A/C/G/T, or a bad strand code) -------------------------
-// n_ref / n_rev: reads holding the reference base (all / '-' strand) from pass 1; the other counted cells are in
-// W.nr_cnt.  Everything here is warp-uniform.
-__device__ __noinline__ void site_slow(WarpSmem* Wp, const CtaShared* cs, uint32_t site, uint32_t warp_global,
-                                       uint32_t n_ref, uint32_t n_rev, uint32_t bad_strand, int ref_code) {
-    WarpSmem& W = *Wp;
+// In (W.slow_*): the site, reads holding the reference base (all / '-' strand) from pass 1, REF code; the other counted
+// cells are in W.nr_cnt.  Everything here is warp-uniform.
+__device__ __noinline__ void site_slow() {
+    WarpSmem& W = warp_smem();
+    const CtaShared& cs = cta_shared();
     const int lane = threadIdx.x & 31;
-    const double min_af = cs->a.min_af;
+    const uint32_t site = W.slow_site;
+    const int ref_code = (int)W.slow_ref_code;
+    const double min_af = cs.a.min_af;
     // ---- depths and strand table ----
     const uint4 c0 = *reinterpret_cast<const uint4*>(&W.nr_cnt[0]);
     const uint4 c1 = *reinterpret_cast<const uint4*>(&W.nr_cnt[4]);
     const uint2 c2 = *reinterpret_cast<const uint2*>(&W.nr_cnt[8]);
-    __syncwarp();
-    if (lane < 12) W.nr_cnt[lane] = 0;
-    if (lane == 0) W.flag_word = bad_strand ? BV_FLAG_BAD_STRAND : 0u;
     uint32_t f0 = c0.x, r0 = c0.y, f1 = c0.z, r1 = c0.w, f2 = c1.x, r2 = c1.y, f3 = c1.z, r3 = c1.w;
     const uint32_t other = c2.x + c2.y;
     {
-        const uint32_t rf = n_ref - n_rev;
+        const uint32_t n_rev = W.slow_n_rev, rf = W.slow_n_ref - n_rev;
         if (ref_code == 0) { f0 += rf; r0 += n_rev; }
         if (ref_code == 1) { f1 += rf; r1 += n_rev; }
         if (ref_code == 2) { f2 += rf; r2 += n_rev; }
         if (ref_code == 3) { f3 += rf; r3 += n_rev; }
     }
+    const uint32_t bad_strand = W.slow_bad;
+    __syncwarp();
+    if (lane < 12) W.nr_cnt[lane] = 0;
     const uint32_t d0 = f0 + r0, d1 = f1 + r1, d2 = f2 + r2, d3 = f3 + r3;
     const uint32_t total = d0 + d1 + d2 + d3 + other;
     const double dtot = (double)total;
+    if (lane == 0) {
+        W.flag_word = bad_strand ? BV_FLAG_BAD_STRAND : 0u;
+        bv_site_out& r = W.rec;
+        r.depth[0] = d0; r.depth[1] = d1; r.depth[2] = d2; r.depth[3] = d3;
+        r.depth_other = other;
+        r.reserved0 = 0;
+        r.fwd[0] = f0; r.fwd[1] = f1; r.fwd[2] = f2; r.fwd[3] = f3;
+        r.rev[0] = r0; r.rev[1] = r1; r.rev[2] = r2; r.rev[3] = r3;
+    }
 
     // ---- lrt (src/basetype.cpp:130-199): active set ----
     uint32_t act = 0;
@@ -514,21 +537,20 @@ __device__ __noinline__ void site_slow(WarpSmem* Wp, const CtaShared* cs, uint32
         act |= is_active(d3, total, dtot, min_af) ? 8u : 0u;
     }
     int n_act = __popc(act);
-    double fa0 = 0.0, fa1 = 0.0, fa2 = 0.0, fa3 = 0.0, chi = 0.0;
+    double chi = 0.0;
     uint32_t em_calls = 0;
     const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
     __syncwarp();
 
     if (n_act >= 2 || (n_act == 1 && (act & ~ref_bit))) {
         // the result depends on base qualities: histogram the row by (base, phred)
-        const uint32_t h = build_hist(Wp, cs, site);
+        const uint32_t h = build_hist(site);
         const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
         if (lane == 0) W.flag_word |= h >> 16;
         __syncwarp();
         if (n_act >= 2) {
-            const uint32_t r = lrt_multi(Wp, cs, warp_global, qmin, qmax, d0, d1, d2, d3, total, act);
+            const uint32_t r = lrt_multi(qmin, qmax, act);
             act = r & 0xfu; n_act = (int)((r >> 4) & 0xfu); em_calls = r >> 8;
-            fa0 = W.res_f[0]; fa1 = W.res_f[1]; fa2 = W.res_f[2]; fa3 = W.res_f[3];
             chi = W.res_chi;
         } else {
             // One active allele: the reference still runs one EM; its answer is closed form (see single_allele_ll):
@@ -536,9 +558,9 @@ __device__ __noinline__ void site_slow(WarpSmem* Wp, const CtaShared* cs, uint32
             const int b = __ffs(act) - 1;
             const bool bad = qmin == 0 && W.hist[b * kQSlots] != 0;
             const double v = bad ? __longlong_as_double(0x7ff8000000000000ll) : 1.0;
-            fa0 = b == 0 ? v : 0.0; fa1 = b == 1 ? v : 0.0; fa2 = b == 2 ? v : 0.0; fa3 = b == 3 ? v : 0.0;
-            em_calls = 1;
             __syncwarp();
+            if (lane < 4) W.res_f[lane] = lane == b ? v : 0.0;
+            em_calls = 1;
             if (qmin <= qmax) {   // histogram back to zero
 #pragma unroll 1
                 for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
@@ -547,8 +569,9 @@ __device__ __noinline__ void site_slow(WarpSmem* Wp, const CtaShared* cs, uint32
                 }
             }
         }
-    } else if (n_act == 1) {
-        em_calls = 1;   // the single active allele is REF: AF is not reported
+    } else {
+        if (lane < 4) W.res_f[lane] = 0.0;
+        if (n_act == 1) em_calls = 1;   // the single active allele is REF: AF is not reported
     }
     __syncwarp();
     uint32_t flags = W.flag_word;
@@ -571,31 +594,27 @@ __device__ __noinline__ void site_slow(WarpSmem* Wp, const CtaShared* cs, uint32
         const int rr = ref_code < 0 ? 0 : (int)sel4u(ref_code, r0, r1, r2, r3);
         const int af_ = (int)(f0 + f1 + f2 + f3) - rf, ar = (int)(r0 + r1 + r2 + r3) - rr;
         // a table with an empty row or column has a single possible outcome: p == 1, FS == 0 (kfunc.c:256)
-        if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(cs->a.logfact, rf, rr, af_, ar);
+        if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(cs.a.logfact, rf, rr, af_, ar);
         if (n_alt) {
             const int vf = (int)(((alt_set & 1) ? f0 : 0u) + ((alt_set & 2) ? f1 : 0u) + ((alt_set & 4) ? f2 : 0u) + ((alt_set & 8) ? f3 : 0u));
             const int vr = (int)(((alt_set & 1) ? r0 : 0u) + ((alt_set & 2) ? r1 : 0u) + ((alt_set & 4) ? r2 : 0u) + ((alt_set & 8) ? r3 : 0u));
             if (vf == af_ && vr == ar) fs_vcf = fs_cvg;   // same 2x2 table
-            else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(cs->a.logfact, rf, rr, vf, vr);
+            else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(cs.a.logfact, rf, rr, vf, vr);
         }
     }
 
     // ---- record ----
     if (lane == 0) {
         bv_site_out& r = W.rec;
-        r.depth[0] = d0; r.depth[1] = d1; r.depth[2] = d2; r.depth[3] = d3;
-        r.depth_other = other;
-        r.reserved0 = 0;
-        r.fwd[0] = f0; r.fwd[1] = f1; r.fwd[2] = f2; r.fwd[3] = f3;
-        r.rev[0] = r0; r.rev[1] = r1; r.rev[2] = r2; r.rev[3] = r3;
         // ALT alleles in ACGT order of the active set (src/basetype.cpp:172-177)
         uint32_t alts = 0;
         int k = 0;
+        double af[4] = {W.res_f[0], W.res_f[1], W.res_f[2], W.res_f[3]};
         r.af[0] = 0.0; r.af[1] = 0.0; r.af[2] = 0.0; r.af[3] = 0.0;
-        if (alt_set & 1) { r.af[k] = fa0; alts |= 0u << (8 * k); ++k; }
-        if (alt_set & 2) { r.af[k] = fa1; alts |= 1u << (8 * k); ++k; }
-        if (alt_set & 4) { r.af[k] = fa2; alts |= 2u << (8 * k); ++k; }
-        if (alt_set & 8) { r.af[k] = fa3; alts |= 3u << (8 * k); ++k; }
+        if (alt_set & 1) { r.af[k] = af[0]; alts |= 0u << (8 * k); ++k; }
+        if (alt_set & 2) { r.af[k] = af[1]; alts |= 1u << (8 * k); ++k; }
+        if (alt_set & 4) { r.af[k] = af[2]; alts |= 2u << (8 * k); ++k; }
+        if (alt_set & 8) { r.af[k] = af[3]; alts |= 3u << (8 * k); ++k; }
         r.n_alt = (uint8_t)n_alt;
         r.alt[0] = (uint8_t)alts; r.alt[1] = (uint8_t)(alts >> 8); r.alt[2] = (uint8_t)(alts >> 16); r.alt[3] = (uint8_t)(alts >> 24);
         r.n_active = (uint8_t)n_act;
@@ -609,10 +628,142 @@ __device__ __noinline__ void site_slow(WarpSmem* Wp, const CtaShared* cs, uint32
     __syncwarp();
     if (lane < 8) {
         const uint4* src = reinterpret_cast<const uint4*>(&W.rec);
-        uint4* dst = reinterpret_cast<uint4*>(cs->a.out + site);
+        uint4* dst = reinterpret_cast<uint4*>(cs.a.out + site);
         dst[lane] = src[lane];
     }
     __syncwarp();
+}
+
+// =====================================================================================================================
+// The streaming loop.  Call-free on purpose: with a call inside, the ABI makes the compiler keep the loop-carried state
+// in local memory for the whole loop (measured: 4.9 GB of spill traffic per 1e9 cells).  It runs from the state saved
+// in W.sv_* until it meets a site for the slow path, saves its state, describes the site in W.slow_* and returns 1;
+// returns 0 when the warp's sites are exhausted.
+// =====================================================================================================================
+__device__ __noinline__ uint32_t stream_sites() {
+    WarpSmem& W = warp_smem();
+    const CtaShared& cs = cta_shared();
+    const int lane = threadIdx.x & 31;
+    const uint32_t N = cs.a.n_samples, n_sites = cs.a.n_sites;
+    const uint64_t pitch = cs.a.pitch;
+    const uint8_t* const g_base = cs.a.base;
+    const uint8_t* const g_strand = cs.a.strand;
+    const uint8_t* const g_ref = cs.a.ref_base;
+    uint32_t* const g_out = reinterpret_cast<uint32_t*>(cs.a.out);
+    const uint32_t row_bytes = (N + 15u) & ~15u;   // bytes of a row that hold cells
+    const uint32_t total_warps = gridDim.x * kWarps;
+    const uint32_t one_active = (1.0 >= cs.a.min_af) ? 1u : 0u;   // a site whose reads all agree has that allele active
+    const uint32_t tail_lane = cs.tail_lane;
+    const uint32_t sW = smem_u32(&W);
+    const uint32_t s_full0 = smem_u32(&W.full[0]);
+
+    uint32_t p_site = W.sv_p_site, p_off = W.sv_p_off, p_slot = W.sv_p_slot;      // producer cursor (lane 0 issues)
+    uint32_t c_slot = W.sv_c_slot, c_par = W.sv_c_par, site = W.sv_site, ref_raw = W.sv_ref_raw;
+
+#pragma unroll 1
+    for (; site < n_sites; site += total_warps) {
+        // reference base of this site (fetched one site ahead), toupper (src/basetype.cpp:171)
+        const uint32_t next_site = site + total_warps;
+        const uint32_t ref_next = next_site < n_sites ? (uint32_t)__ldg(g_ref + next_site) : 0u;
+        uint32_t rc = ref_raw;
+        if (rc >= 'a' && rc <= 'z') rc -= 32;
+        const int ref_code = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
+        const uint32_t refw = ref_code >= 0 ? (uint32_t)ref_code * 0x01010101u : 0x08080808u;
+
+        // ---- pass 1 ----
+        ScanAcc A;
+        A.nref = 0; A.nrev = 0; A.nonref = 0; A.bad = 0;
+#pragma unroll 1
+        for (uint32_t c_off = 0; c_off < row_bytes; c_off += kChunk) {
+            // the unit kStages-1 ahead goes into the slot the previous unit used; every lane is past it (__syncwarp)
+            if (p_site < n_sites) {
+                if (lane == 0) {
+                    const uint32_t bytes = min((uint32_t)kChunk, row_bytes - p_off);
+                    const size_t g = (size_t)p_site * pitch + p_off;
+                    const uint32_t bar = s_full0 + 8u * p_slot, dst = sW + (uint32_t)sizeof(Stage) * p_slot;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(g_base + g), "r"(bytes), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst + (uint32_t)kChunk), "l"(g_strand + g), "r"(bytes), "r"(bar) : "memory");
+                }
+                p_slot = (p_slot + 1 == kStages) ? 0 : p_slot + 1;
+                p_off += kChunk;
+                if (p_off >= row_bytes) { p_off = 0; p_site += total_warps; }
+            }
+            {   // wait for this unit's bytes
+                const uint32_t bar = s_full0 + 8u * c_slot;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "WAIT_%=:\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                    "@p bra DONE_%=;\n\t"
+                    "bra WAIT_%=;\n\t"
+                    "DONE_%=:\n\t"
+                    "}" ::"r"(bar), "r"(c_par) : "memory");
+            }
+            const int lane_cells = (int)N - (int)c_off - lane * 16;
+            if (lane_cells > 0) {
+                const uint8_t* cellp = W.stage[c_slot].base + lane * 16;
+                uint4 vb = *reinterpret_cast<const uint4*>(cellp);
+                const uint4 vs = *reinterpret_cast<const uint4*>(cellp + kChunk);
+                if (lane_cells < 16) {   // the row's last, partial vector: one lane, once per row
+                    const uint4 k = *reinterpret_cast<const uint4*>(cs.tail_keep);
+                    vb.x = (vb.x & k.x) | (0x05050505u & ~k.x); vb.y = (vb.y & k.y) | (0x05050505u & ~k.y);
+                    vb.z = (vb.z & k.z) | (0x05050505u & ~k.z); vb.w = (vb.w & k.w) | (0x05050505u & ~k.w);
+                }
+                const uint32_t nr0 = scan_word(vb.x, vs.x, refw, A);
+                const uint32_t nr1 = scan_word(vb.y, vs.y, refw, A);
+                const uint32_t nr2 = scan_word(vb.z, vs.z, refw, A);
+                const uint32_t nr3 = scan_word(vb.w, vs.w, refw, A);
+                if (nr0 | nr1 | nr2 | nr3) {
+                    // counted cells that are not the reference base (sequencing errors, ALT alleles): one by one
+                    uint32_t t = (nr0 >> 7) | (nr1 >> 6) | (nr2 >> 5) | (nr3 >> 4);   // bit (8*byte + word)
+                    A.nonref |= t;
+                    do {
+                        int top;
+                        asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+                        t ^= 1u << top;
+                        const int cell = ((top & 3) << 2) | (top >> 3);
+                        const uint32_t b = cellp[cell];
+                        const uint32_t s = cellp[cell + kChunk];
+                        atomicAdd(&W.nr_cnt[2u * b + (s & 1u)], 1u);
+                    } while (t);
+                }
+            }
+            __syncwarp();
+            if (++c_slot == kStages) { c_slot = 0; c_par ^= 1u; }
+        }
+        (void)tail_lane;
+
+        // ---- finish ----
+        const uint32_t fl = __reduce_or_sync(kFull, A.nonref | (A.bad ? 0x80000000u : 0u));
+        const uint32_t n_ref = __reduce_add_sync(kFull, A.nref) >> 7;
+        const uint32_t n_rev = __reduce_add_sync(kFull, A.nrev) >> 7;
+        if (fl != 0) {
+            if (lane == 0) {
+                W.sv_p_site = p_site; W.sv_p_off = p_off; W.sv_p_slot = p_slot; W.sv_c_slot = c_slot; W.sv_c_par = c_par;
+                W.sv_site = next_site; W.sv_ref_raw = ref_next;
+                W.slow_site = site; W.slow_n_ref = n_ref; W.slow_n_rev = n_rev; W.slow_bad = fl >> 31;
+                W.slow_ref_code = (uint32_t)ref_code;
+            }
+            __syncwarp();
+            return 1u;
+        }
+        // Every counted cell holds the reference base (or nothing is covered): depth[REF] = n_ref, one active
+        // allele == REF, the EM's answer is f = 1 (src/algorithm.h:210-255 with a single column), no ALT,
+        // QUAL / FS / chi2 = 0.  Lanes compose the 32 words of the record.
+        const uint32_t n_active = (n_ref > 0) ? one_active : 0u;
+        uint32_t w = 0;
+        if (lane == ref_code) w = n_ref;                          // depth[REF]
+        if (lane == ref_code + 6) w = n_ref - n_rev;              // fwd[REF]
+        if (lane == ref_code + 10) w = n_rev;                     // rev[REF]
+        if (lane == 15) w = (n_active << 8) | (n_active << 24);   // n_active | flags 0 | em_calls
+        g_out[(size_t)site * 32 + lane] = w;
+        ref_raw = ref_next;
+    }
+    return 0u;
 }
 
 }  // namespace bv
