@@ -20,7 +20,7 @@ BV_EM_ABS_INT_TRUNC, BV_EM_ABS_DOUBLE = 0, 1
 BASE_N, STRAND_NONE = 5, 2
 
 FLAG_BAD_STRAND, FLAG_BAD_QUAL, FLAG_ZERO_SUBSET, FLAG_MONO_QUAL = 0x01, 0x02, 0x04, 0x08
-FLAG_NEAR_LRT, FLAG_NEAR_MINAF, FLAG_EM_MAXITER, FLAG_LRT_TIE = 0x10, 0x20, 0x40, 0x80
+FLAG_NEAR_LRT, FLAG_LRT_BOUND, FLAG_EM_MAXITER, FLAG_LRT_TIE = 0x10, 0x20, 0x40, 0x80
 
 # struct bv_site_out, 128 bytes
 SITE_OUT_DTYPE = np.dtype(

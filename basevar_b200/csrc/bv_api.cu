@@ -37,7 +37,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) bv_site_kernel(const __grid_co
             const int left = valid == 0 ? 4 : valid - 4 * k;
             cs.tail_keep[k] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
         }
-        cs.tail_lane = valid == 0 ? 32u : (((a.n_samples - 1u) % kChunk) >> 4);
+    }
+    for (int q = threadIdx.x; q < kQSlots; q += blockDim.x) {
+        // per-read log-likelihood gain of calling the read's own base, fixed point 2^-20, rounded up (lrt_bound)
+        const double g = a.lut[kLutLogMatch * kQStride + q] - a.lut[kLutLogMis * kQStride + q];
+        cs.gfix[q] = (q >= 2 && q <= BV_QUAL_MAX) ? (uint32_t)ceil(g * 1048576.0) + 1u : 0x01000000u;
     }
     for (int i = lane; i < kHistWords; i += 32) W.hist[i] = 0;
     if (lane < 12) W.nr_cnt[lane] = 0;

@@ -141,9 +141,27 @@ __device__ __noinline__ double fisher_two_sided(const double* __restrict__ lf, i
     return two;
 }
 
+// A 2x2 table with a margin of 1 has two possible outcomes: the single read of that margin falls into the other
+// margin's first or second class, with probabilities k/n and 1 - k/n (k = the observed class's total).  kt_fisher_exact
+// (kfunc.c:245-313) then returns the observed probability when it is the smaller of the two and (clamped) 1 otherwise;
+// ties are exact (2k == n), far outside its 1e-8 comparison slack.  This is the table of every site with one
+// sequencing-error read, the most common reason to need the test at all.
+__device__ __forceinline__ bool fisher_margin1(int a, int b, int c, int d, double& p) {
+    int k;
+    if (c + d == 1) k = c ? a + c : b + d;
+    else if (a + b == 1) k = a ? a + c : b + d;
+    else if (a + c == 1) k = a ? a + b : c + d;
+    else if (b + d == 1) k = b ? a + b : c + d;
+    else return false;
+    const int n = a + b + c + d;
+    p = (2 * k >= n) ? 1.0 : (double)k / (double)n;
+    return true;
+}
+
 // src/basetype.cpp:277-283
 __device__ __noinline__ double fs_from_table(const double* __restrict__ lf, int rf, int rr, int af, int ar) {
-    const double p = fisher_two_sided(lf, rf, rr, af, ar);
+    double p;
+    if (!fisher_margin1(rf, rr, af, ar, p)) p = fisher_two_sided(lf, rf, rr, af, ar);
     if (p == 1.0) return 0.0;   // -10*log10(1) = -0.0, scrubbed to +0.0 by the reference's `fs == 0` branch
     double fs = -10 * nlog10(p);
     if (isinf(fs)) fs = 10000;

@@ -35,11 +35,12 @@
 namespace bv {
 
 #ifndef BV_WARPS
-#define BV_WARPS 28
+#define BV_WARPS 24
 #endif
 constexpr int kWarps = BV_WARPS;             // warps per CTA, one CTA per SM
-constexpr int kChunk = 512;                  // cells per stage and plane: one 16-cell vector per lane
-constexpr int kStages = 3;                   // ring depth per warp
+constexpr int kChunk = 1024;                 // pass 1: cells per stage and plane, two 16-cell vectors per lane
+constexpr int kStages = 2;                   // pass 1: ring depth per warp (one unit in flight while one is scanned)
+constexpr int kP2Chunk = 512;                // pass 2: cells per buffer and plane, one 16-cell vector per lane
 constexpr int kQStride = 128;                // phred slots per LUT row
 constexpr int kQSlots = 96;                  // phred slots per histogram row (0..93 valid; larger values clamp to 95)
 constexpr int kHistWords = 5 * kQSlots;      // (A,C,G,T,other) x phred
@@ -77,8 +78,8 @@ struct __align__(128) Stage {      // pass 1: one chunk of the base and strand p
     uint8_t strand[kChunk];
 };
 struct __align__(128) P2Buf {      // pass 2: one chunk of the base and qual planes
-    uint8_t base[kChunk];
-    uint8_t qual[kChunk];
+    uint8_t base[kP2Chunk];
+    uint8_t qual[kP2Chunk];
 };
 
 struct __align__(128) WarpSmem {
@@ -106,8 +107,9 @@ struct __align__(128) WarpSmem {
 struct __align__(128) CtaShared {
     double lut[4 * kQStride];
     uint32_t tail_keep[4];       // byte masks of the row's last, partial 16-cell vector (all ones when N % 16 == 0)
-    uint32_t tail_lane;          // lane that holds that vector in the row's last chunk (32: none)
-    uint32_t pad_[3];
+    uint32_t pad_[4];
+    uint32_t gfix[kQSlots];      // ceil(2^20 * (log(1-eps(q)) - log(eps(q)/3))): log-likelihood gain of calling a read's
+                                 // own base, fixed point, rounded up (see lrt_bound)
     SiteKernelArgs a;            // kernel parameters for out-of-line device functions (a reference to the
                                  // __global__ parameter itself would force a local-memory copy)
 };
@@ -191,23 +193,24 @@ __device__ __forceinline__ uint32_t scan_word(uint32_t wb, uint32_t ws, uint32_t
 }
 
 // =====================================================================================================================
-// Pass 2: (base, phred) histogram of the covered cells of one row.  Out of line; runs on the sites whose result depends
-// on base qualities.  Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
+// Pass 2: the row's base + qual chunks, fetched again (L2 / HBM) into the warp's two pass-2 buffers.  Out of line code;
+// runs on the sites whose result depends on base qualities.  f(cellp, vb, lane_cells): cellp points at this lane's 16
+// base cells in shared memory (quals at cellp + kP2Chunk), vb holds them with padding cells masked to 'N'.
 // =====================================================================================================================
-__device__ __noinline__ uint32_t build_hist(uint32_t site) {
+template <class F>
+__device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
     WarpSmem& W = warp_smem();
     const CtaShared& cs = cta_shared();
     const int lane = threadIdx.x & 31;
     const uint32_t N = cs.a.n_samples;
     const uint32_t row_bytes = (N + 15u) & ~15u;
-    const uint32_t nchunk = (row_bytes + kChunk - 1) / kChunk;
+    const uint32_t nchunk = (row_bytes + kP2Chunk - 1) / kP2Chunk;
     const size_t row = (size_t)site * cs.a.pitch;
     const uint8_t* gb = cs.a.base + row;
     const uint8_t* gq = cs.a.qual + row;
     uint32_t phase = W.p2_phase;
-    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
     if (lane == 0) {
-        const uint32_t bytes = min((uint32_t)kChunk, row_bytes);
+        const uint32_t bytes = min((uint32_t)kP2Chunk, row_bytes);
         mbar_expect_tx(&W.p2bar[0], 2 * bytes);
         bulk_g2s(W.p2[0].base, gb, bytes, &W.p2bar[0]);
         bulk_g2s(W.p2[0].qual, gq, bytes, &W.p2bar[0]);
@@ -216,19 +219,31 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site) {
     for (uint32_t c = 0; c < nchunk; ++c) {
         const uint32_t buf = c & 1u;
         if (c + 1 < nchunk && lane == 0) {   // chunk c+1 goes where chunk c-1 was (all lanes are past it: __syncwarp below)
-            const uint32_t off = (c + 1) * kChunk;
-            const uint32_t bytes = min((uint32_t)kChunk, row_bytes - off);
+            const uint32_t off = (c + 1) * kP2Chunk;
+            const uint32_t bytes = min((uint32_t)kP2Chunk, row_bytes - off);
             mbar_expect_tx(&W.p2bar[buf ^ 1u], 2 * bytes);
             bulk_g2s(W.p2[buf ^ 1u].base, gb + off, bytes, &W.p2bar[buf ^ 1u]);
             bulk_g2s(W.p2[buf ^ 1u].qual, gq + off, bytes, &W.p2bar[buf ^ 1u]);
         }
         mbar_wait(&W.p2bar[buf], (phase >> buf) & 1u);
         phase ^= 1u << buf;
-        const int lane_cells = (int)N - (int)(c * kChunk) - lane * 16;
+        const int lane_cells = (int)N - (int)(c * kP2Chunk) - lane * 16;
         const uint8_t* cellp = W.p2[buf].base + lane * 16;
         uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
         if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(cellp);
         if (lane_cells < 16) mask_tail(vb, lane_cells);
+        f(cellp, vb, lane_cells);
+        __syncwarp();
+    }
+    if (lane == 0) W.p2_phase = phase;
+}
+
+// (base, phred) histogram of the covered cells of one row into W.hist.
+// Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
+__device__ __noinline__ uint32_t build_hist(uint32_t site) {
+    WarpSmem& W = warp_smem();
+    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
+    for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int) {
         // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
         const uint32_t n0 = (((vb.x | 0x80808080u) - 0x05050505u) | vb.x) & 0x80808080u;
         const uint32_t n1 = (((vb.y | 0x80808080u) - 0x05050505u) | vb.y) & 0x80808080u;
@@ -246,20 +261,66 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site) {
             const int cell = ((top & 3) << 2) | ((top >> 3) & 3);   // word k = top & 3, byte j = top >> 3
             if (on) {
                 const uint32_t b = cellp[cell];
-                uint32_t q = cellp[cell + kChunk];
+                uint32_t q = cellp[cell + kP2Chunk];
                 if (q > BV_QUAL_MAX) { flags |= BV_FLAG_BAD_QUAL; q = min(q, (uint32_t)(kQSlots - 1)); }
                 atomicAdd(&W.hist[b * kQSlots + q], 1u);
                 qmin = min(qmin, q);
                 qmax = max(qmax, q);
             }
         }
-        __syncwarp();
-    }
-    if (lane == 0) W.p2_phase = phase;
+    });
     qmin = __reduce_min_sync(kFull, qmin);
     qmax = __reduce_max_sync(kFull, qmax);
     flags = __reduce_or_sync(kFull, flags);
     return qmin | (qmax << 8) | (flags << 16);
+}
+
+// ---- a bound that decides the LRT without running the EM ---------------------------------------------------------------
+// Site with exactly two active alleles, REF (r) and one other base (o) carried by a few reads -- the signature of
+// sequencing errors.  With L_ij the per-read likelihoods (src/basetype.cpp:61-64) and g_i = log(1-eps_i) - log(eps_i/3):
+//   * every log-likelihood the EM can report for {r,o} is a sum of log(sum_j L_ij f_j) with sum_j f_j <= 1, hence
+//       LL{r,o} <= sum_i log(max_j L_ij) = LL{r} + sum_{reads of o} g_i        (all phred >= 2, so 1-eps > eps/3)
+//     where LL{r} = sum_{reads of r} log(1-eps_i) + sum_{other reads} log(eps_i/3) is the closed form of the
+//     single-allele model (see single_allele_ll);
+//   * LL{r} - LL{o} = sum_{reads of r} g_i - sum_{reads of o} g_i >= 0.56 * depth[r] - G,  G = sum_{reads of o} g_i.
+// So when 2G < 23.9 and depth[r] >= 22, the first LRT round (src/basetype.cpp:151-168) picks subset {r}
+// (chi_r < chi_o) with chi_r = 2 (LL{r,o} - LL{r}) <= 2G < 24 = LRT_THRESHOLD and drops o: the site ends with the
+// single active allele REF, no ALT, whatever the EM would have returned.  Margins (23.9 vs 24, G rounded up in fixed
+// point) dwarf the 1e-12 rounding noise of the reference's sums.
+// Returns G in 2^-20 units, or 0xffffffff when a counted read has phred < 2 or > 93 (bound not applicable).
+constexpr uint32_t kBoundLimit = 12530483u;   // floor(11.95 * 2^20)
+__device__ __noinline__ uint32_t lrt_bound(uint32_t site, uint32_t o_code) {
+    const CtaShared& cs = cta_shared();
+    const uint32_t ow = o_code * 0x01010101u;
+    uint32_t G = 0, bad = 0;
+    for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int lane_cells) {
+        uint4 vq = make_uint4(0x02020202u, 0x02020202u, 0x02020202u, 0x02020202u);
+        if (lane_cells > 0) vq = *reinterpret_cast<const uint4*>(cellp + kP2Chunk);
+        const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w}, wq[4] = {vq.x, vq.y, vq.z, vq.w};
+        uint32_t eo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t m = ~(((wb[k] | 0x80808080u) - 0x05050505u) | wb[k]) & 0x80808080u;   // counted
+            const uint32_t q7 = wq[k] & 0x7f7f7f7fu;
+            bad |= (~(q7 + 0x7e7e7e7eu) | (q7 + 0x22222222u) | wq[k]) & m;                        // phred < 2 or > 93
+            const uint32_t x = (wb[k] ^ ow) & 0x7f7f7f7fu;
+            eo[k] = ~((x + 0x7f7f7f7fu) | wb[k]) & 0x80808080u;                                   // base == o
+        }
+        if (eo[0] | eo[1] | eo[2] | eo[3]) {
+            uint32_t t = (eo[0] >> 7) | (eo[1] >> 6) | (eo[2] >> 5) | (eo[3] >> 4);   // bit (8*byte + word)
+            do {
+                int top;
+                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+                t ^= 1u << top;
+                const int cell = ((top & 3) << 2) | (top >> 3);
+                const uint32_t q = cellp[cell + kP2Chunk];
+                G += cs.gfix[min(q, (uint32_t)(kQSlots - 1))];
+            } while (t);
+        }
+    });
+    G = __reduce_add_sync(kFull, G);
+    bad = __reduce_or_sync(kFull, bad);
+    return bad ? 0xffffffffu : G;
 }
 
 // ---- EM on compact bins (src/algorithm.h:210-255) ----------------------------------------------------------------
@@ -373,7 +434,12 @@ __device__ __forceinline__ int nth_set_bit(uint32_t mask, int k) {
 __device__ __forceinline__ bool is_active(uint32_t dep, uint32_t total, double dtot, double min_af) {
     if (dep == 0) return 0.0 >= min_af;
     if (dep == total) return 1.0 >= min_af;
-    return (double)dep / dtot >= min_af;
+    // away from the boundary the product decides (one multiply instead of a division); within 1e-9 of it, the
+    // reference's own expression
+    const double thr = min_af * dtot, x = (double)dep;
+    if (x > thr * 1.000000001) return true;
+    if (x < thr * 0.999999999) return false;
+    return x / dtot >= min_af;
 }
 
 // ---- sites with >= 2 active alleles: compact the bins, EM on the full set, backward elimination -----------------------
@@ -542,7 +608,21 @@ __device__ __noinline__ void site_slow() {
     const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
     __syncwarp();
 
-    if (n_act >= 2 || (n_act == 1 && (act & ~ref_bit))) {
+    bool bounded = false;
+    if (n_act == 2 && (act & ref_bit)) {
+        // REF plus one minor allele: try to settle the LRT by the bound (see lrt_bound)
+        const int o_code = __ffs(act & ~ref_bit) - 1;
+        const uint32_t d_ref = sel4u(ref_code, d0, d1, d2, d3), d_o = sel4u(o_code, d0, d1, d2, d3);
+        if (d_ref >= 22 && d_o <= 4 && lrt_bound(site, (uint32_t)o_code) < kBoundLimit) {
+            bounded = true;
+            act = ref_bit; n_act = 1;
+            if (lane == 0) W.flag_word |= BV_FLAG_LRT_BOUND;
+            if (lane < 4) W.res_f[lane] = 0.0;
+        }
+    }
+    if (bounded) {
+        // nothing else to compute: single active allele REF
+    } else if (n_act >= 2 || (n_act == 1 && (act & ~ref_bit))) {
         // the result depends on base qualities: histogram the row by (base, phred)
         const uint32_t h = build_hist(site);
         const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
@@ -653,7 +733,6 @@ __device__ __noinline__ uint32_t stream_sites() {
     const uint32_t row_bytes = (N + 15u) & ~15u;   // bytes of a row that hold cells
     const uint32_t total_warps = gridDim.x * kWarps;
     const uint32_t one_active = (1.0 >= cs.a.min_af) ? 1u : 0u;   // a site whose reads all agree has that allele active
-    const uint32_t tail_lane = cs.tail_lane;
     const uint32_t sW = smem_u32(&W);
     const uint32_t s_full0 = smem_u32(&W.full[0]);
 
@@ -703,39 +782,41 @@ __device__ __noinline__ uint32_t stream_sites() {
                     "DONE_%=:\n\t"
                     "}" ::"r"(bar), "r"(c_par) : "memory");
             }
-            const int lane_cells = (int)N - (int)c_off - lane * 16;
-            if (lane_cells > 0) {
-                const uint8_t* cellp = W.stage[c_slot].base + lane * 16;
-                uint4 vb = *reinterpret_cast<const uint4*>(cellp);
-                const uint4 vs = *reinterpret_cast<const uint4*>(cellp + kChunk);
-                if (lane_cells < 16) {   // the row's last, partial vector: one lane, once per row
-                    const uint4 k = *reinterpret_cast<const uint4*>(cs.tail_keep);
-                    vb.x = (vb.x & k.x) | (0x05050505u & ~k.x); vb.y = (vb.y & k.y) | (0x05050505u & ~k.y);
-                    vb.z = (vb.z & k.z) | (0x05050505u & ~k.z); vb.w = (vb.w & k.w) | (0x05050505u & ~k.w);
-                }
-                const uint32_t nr0 = scan_word(vb.x, vs.x, refw, A);
-                const uint32_t nr1 = scan_word(vb.y, vs.y, refw, A);
-                const uint32_t nr2 = scan_word(vb.z, vs.z, refw, A);
-                const uint32_t nr3 = scan_word(vb.w, vs.w, refw, A);
-                if (nr0 | nr1 | nr2 | nr3) {
-                    // counted cells that are not the reference base (sequencing errors, ALT alleles): one by one
-                    uint32_t t = (nr0 >> 7) | (nr1 >> 6) | (nr2 >> 5) | (nr3 >> 4);   // bit (8*byte + word)
-                    A.nonref |= t;
-                    do {
-                        int top;
-                        asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
-                        t ^= 1u << top;
-                        const int cell = ((top & 3) << 2) | (top >> 3);
-                        const uint32_t b = cellp[cell];
-                        const uint32_t s = cellp[cell + kChunk];
-                        atomicAdd(&W.nr_cnt[2u * b + (s & 1u)], 1u);
-                    } while (t);
+#pragma unroll
+            for (int v = 0; v < kChunk / 512; ++v) {
+                const int lane_cells = (int)N - (int)c_off - v * 512 - lane * 16;
+                if (lane_cells > 0) {
+                    const uint8_t* cellp = W.stage[c_slot].base + v * 512 + lane * 16;
+                    uint4 vb = *reinterpret_cast<const uint4*>(cellp);
+                    const uint4 vs = *reinterpret_cast<const uint4*>(cellp + kChunk);
+                    if (lane_cells < 16) {   // the row's last, partial vector: one lane, once per row
+                        const uint4 k = *reinterpret_cast<const uint4*>(cs.tail_keep);
+                        vb.x = (vb.x & k.x) | (0x05050505u & ~k.x); vb.y = (vb.y & k.y) | (0x05050505u & ~k.y);
+                        vb.z = (vb.z & k.z) | (0x05050505u & ~k.z); vb.w = (vb.w & k.w) | (0x05050505u & ~k.w);
+                    }
+                    const uint32_t nr0 = scan_word(vb.x, vs.x, refw, A);
+                    const uint32_t nr1 = scan_word(vb.y, vs.y, refw, A);
+                    const uint32_t nr2 = scan_word(vb.z, vs.z, refw, A);
+                    const uint32_t nr3 = scan_word(vb.w, vs.w, refw, A);
+                    if (nr0 | nr1 | nr2 | nr3) {
+                        // counted cells that are not the reference base (sequencing errors, ALT alleles): one by one
+                        uint32_t t = (nr0 >> 7) | (nr1 >> 6) | (nr2 >> 5) | (nr3 >> 4);   // bit (8*byte + word)
+                        A.nonref |= t;
+                        do {
+                            int top;
+                            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+                            t ^= 1u << top;
+                            const int cell = ((top & 3) << 2) | (top >> 3);
+                            const uint32_t b = cellp[cell];
+                            const uint32_t s = cellp[cell + kChunk];
+                            atomicAdd(&W.nr_cnt[2u * b + (s & 1u)], 1u);
+                        } while (t);
+                    }
                 }
             }
             __syncwarp();
             if (++c_slot == kStages) { c_slot = 0; c_par ^= 1u; }
         }
-        (void)tail_lane;
 
         // ---- finish ----
         const uint32_t fl = __reduce_or_sync(kFull, A.nonref | (A.bad ? 0x80000000u : 0u));

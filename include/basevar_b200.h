@@ -67,11 +67,12 @@ extern "C" {
 
 /* ---- per-site flags --------------------------------------------------------------------------- */
 #define BV_FLAG_BAD_STRAND   0x01u /* counted cell whose strand is not +/-: reference throws (basetype.cpp:271) */
-#define BV_FLAG_BAD_QUAL     0x02u /* counted cell with phred > 93                                             */
+#define BV_FLAG_BAD_QUAL     0x02u /* counted cell with phred > 93, at a site whose result depends on qualities  */
 #define BV_FLAG_ZERO_SUBSET  0x04u /* a candidate subset has zero depth: reference throws (basetype.cpp:113)  */
 #define BV_FLAG_MONO_QUAL    0x08u /* QUAL came from the mono-allelic 5000 rule (basetype.cpp:182-185)        */
 #define BV_FLAG_NEAR_LRT     0x10u /* some LRT decision had |chi2 - threshold| < 1e-9*threshold (possible flip) */
-#define BV_FLAG_NEAR_MINAF   0x20u /* some depth/total is within 4 ulp of min_af (never flips: exact compare)  */
+#define BV_FLAG_LRT_BOUND    0x20u /* the LRT outcome (drop the minor allele) was proven by a bound, no EM ran:   */
+                                   /* chi2 and em_calls of the record are 0 (the reference exposes neither here)  */
 #define BV_FLAG_EM_MAXITER   0x40u /* an EM used all em_max_iter iterations                                   */
 #define BV_FLAG_LRT_TIE      0x80u /* two candidate subsets had equal chi2 (to rounding): first one kept       */
 
