@@ -13,76 +13,11 @@
 #include <new>
 
 #include "../../include/basevar_b200.h"
-#include "bv_site_kernel.cuh"
+#include "bv_count_kernel.cuh"
+#include "bv_finish_kernels.cuh"
 #include "bv_synth.cuh"
 
 namespace bv {
-
-// ======================================================================================================
-// Site kernel (the product path): persistent CTAs, one warp per site, per-warp TMA ring.  See bv_site_kernel.cuh.
-// ======================================================================================================
-static_assert(sizeof(CtaShared) + (size_t)kWarps * sizeof(WarpSmem) <= 232448, "shared memory of the site kernel exceeds 227 KB");
-
-__global__ void __launch_bounds__(kWarps * 32, 1) bv_site_kernel(const __grid_constant__ SiteKernelArgs a) {
-    CtaShared& cs = cta_shared();
-    WarpSmem& W = warp_smem();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) cs.lut[i] = a.lut[i];
-    if (threadIdx.x == 0) {
-        cs.a = a;
-        // byte masks of the row's last 16-cell vector when N is not a multiple of 16
-        const int valid = (int)(a.n_samples & 15u);
-        for (int k = 0; k < 4; ++k) {
-            const int left = valid == 0 ? 4 : valid - 4 * k;
-            cs.tail_keep[k] = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
-        }
-    }
-    for (int q = threadIdx.x; q < kQSlots; q += blockDim.x) {
-        // per-read log-likelihood gain of calling the read's own base, fixed point 2^-20, rounded up (lrt_bound)
-        const double g = a.lut[kLutLogMatch * kQStride + q] - a.lut[kLutLogMis * kQStride + q];
-        cs.gfix[q] = (q >= 2 && q <= BV_QUAL_MAX) ? (uint32_t)ceil(g * 1048576.0) + 1u : 0x01000000u;
-    }
-    for (int i = lane; i < kHistWords; i += 32) W.hist[i] = 0;
-    if (lane < 12) W.nr_cnt[lane] = 0;
-    const uint32_t total_warps = gridDim.x * kWarps;
-    const uint32_t warp_global = blockIdx.x * kWarps + warp;
-    if (lane == 0) {
-        W.flag_word = 0;
-        W.p2_phase = 0;
-        for (int s = 0; s < kStages; ++s) mbar_init(&W.full[s], 1);
-        mbar_init(&W.p2bar[0], 1);
-        mbar_init(&W.p2bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp_global >= a.n_sites) return;
-
-    // ---- prologue of the ring: the first kStages-1 units of this warp's site sequence ----
-    {
-        const uint32_t row_bytes = (a.n_samples + 15u) & ~15u;
-        uint32_t p_site = warp_global, p_off = 0, p_slot = 0;
-        for (int s = 0; s < kStages - 1 && p_site < a.n_sites; ++s) {
-            if (lane == 0) {
-                const uint32_t bytes = min((uint32_t)kChunk, row_bytes - p_off);
-                const size_t g = (size_t)p_site * a.pitch + p_off;
-                mbar_expect_tx(&W.full[p_slot], 2 * bytes);
-                bulk_g2s(W.stage[p_slot].base, a.base + g, bytes, &W.full[p_slot]);
-                bulk_g2s(W.stage[p_slot].strand, a.strand + g, bytes, &W.full[p_slot]);
-            }
-            ++p_slot;
-            p_off += kChunk;
-            if (p_off >= row_bytes) { p_off = 0; p_site += total_warps; }
-        }
-        if (lane == 0) {
-            W.sv_p_site = p_site; W.sv_p_off = p_off; W.sv_p_slot = p_slot % kStages;
-            W.sv_c_slot = 0; W.sv_c_par = 0; W.sv_site = warp_global; W.sv_ref_raw = a.ref_base[warp_global];
-        }
-        __syncwarp();
-    }
-    // ---- stream; leave the call-free loop only for the sites that need the slow path ----
-    while (stream_sites()) site_slow();
-}
 
 // ======================================================================================================
 // Synthetic pileup generator: one thread writes one 16-cell vector of each plane.
@@ -203,20 +138,27 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     return BV_OK;
 }
 
-static size_t site_smem_bytes() { return sizeof(bv::CtaShared) + (size_t)bv::kWarps * sizeof(bv::WarpSmem); }
-
+// The basetype core of one tile: K1 (counts, every cell), K2 (scalar finish, one thread per site), K3 (sites whose
+// result depends on base qualities).  Stream ordered; see csrc/bv_common.cuh.
 static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream) {
     if (a.n_sites == 0) return BV_OK;
     if (a.n_samples == 0) {   // no cells: every record is all-zero
         BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
         return BV_OK;
     }
-    // persistent: one CTA per SM, each warp strides over the sites
-    uint32_t grid = (a.n_sites + bv::kWarps - 1) / bv::kWarps;
+    // K1, persistent: one CTA per SM, each warp strides over the sites
+    uint32_t grid = (a.n_sites + bv::kCountWarps - 1) / bv::kCountWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
-    bv::bv_site_kernel<<<grid, bv::kWarps * 32, site_smem_bytes(), stream>>>(a);
+    bv::bv_count_kernel<<<grid, bv::kCountWarps * 32, bv::kCountSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
+    bv::bv_scalar_kernel<<<(a.n_sites + 255) / 256, 256, 0, stream>>>(a);
+    BV_CUDA(ctx, cudaGetLastError());
+    // K3, persistent: each warp strides over groups of 32 sites
+    grid = ((a.n_sites + 31) / 32 + bv::kQualWarps - 1) / bv::kQualWarps;
+    if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+    bv::bv_qual_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
+    BV_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
     return BV_OK;
 }
 
@@ -277,7 +219,8 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
         ctx->num_sms = prop.multiProcessorCount;
-        if (cudaFuncSetAttribute(bv::bv_site_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)site_smem_bytes()) != cudaSuccess) {
+        if (cudaFuncSetAttribute(bv::bv_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCountSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_qual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
                          cudaGetErrorString(cudaGetLastError()));
             break;
@@ -285,7 +228,7 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         rc = upload_tables(ctx);
         if (rc != BV_OK) break;
         {   // per-warp overflow scratch of the EM (only touched by sites with very many distinct bins)
-            const size_t warps = (size_t)ctx->num_sms * bv::kWarps;
+            const size_t warps = (size_t)ctx->num_sms * bv::kQualWarps;
             cudaError_t ce = cudaMalloc(&ctx->d_bin_spill, warps * bv::kMaxBins * sizeof(uint32_t));
             if (ce == cudaSuccess) ce = cudaMalloc(&ctx->d_lml_spill, warps * bv::kMaxBins * sizeof(double));
             if (ce != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(ce)); break; }

@@ -1,0 +1,127 @@
+// bv_common.cuh -- definitions shared by the kernels of the basetype core (sm_100a).
+//
+// The per-site statistical core of `basevar basetype` runs as three kernels, split by the KIND of work so that every
+// kernel is small and all of its warps execute the same code (one fused kernel was measured instruction-cache bound:
+// 59 % of its stall samples were "no instruction" with 24 warps per SM spread over 76 KB of code):
+//
+//   K1  bv_count_kernel   (bv_count_kernel.cuh)    every site, every cell: streams the base + strand planes through
+//        per-warp TMA rings and counts -- per-base depths and the 2x4 strand table.  Sites whose reads all equal REF get
+//        their final record here; the others get their counts and the state BV_STATE_SCALAR.
+//   K2  bv_scalar_kernel  (bv_finish_kernels.cuh)  one THREAD per site in state SCALAR: active alleles, strand-bias
+//        Fisher test; final record unless the result depends on base qualities (then state BV_STATE_QUAL).
+//   K3  bv_qual_kernel    (bv_finish_kernels.cuh)  one warp per site in state QUAL: fetches the row's base + qual
+//        planes, settles the LRT by a rigorous bound or runs EM + LRT on (base, phred) bins; QUAL, ALT-table Fisher.
+//
+// The state travels in the record's `reserved0` word (0 in every finished record).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/basevar_b200.h"
+
+namespace bv {
+
+constexpr int kQStride = 128;                // phred slots per LUT row
+constexpr int kQSlots = 96;                  // phred slots per histogram row (0..93 valid; larger values clamp to 95)
+constexpr int kHistWords = 5 * kQSlots;      // (A,C,G,T,other) x phred
+constexpr int kSmemBins = 160;               // compact bins kept in shared memory; more spill to global scratch
+constexpr int kMaxBins = kHistWords;         // upper bound on distinct (base, phred) bins
+constexpr int kLutOneMinusEps = 0;           // lut[0][q] = 1 - eps(q)
+constexpr int kLutEpsThird = 1;              // lut[1][q] = eps(q) / 3
+constexpr int kLutLogMatch = 2;              // lut[2][q] = log(1 - eps(q))   (glibc)
+constexpr int kLutLogMis = 3;                // lut[3][q] = log(eps(q) / 3)   (glibc)
+constexpr uint32_t kFull = 0xffffffffu;
+
+constexpr uint32_t kStateDone = 0;           // record is final
+constexpr uint32_t kStateScalar = 1;         // counts are final, K2 has to finish the record
+constexpr uint32_t kStateQual = 2;           // K3 has to finish the record (result depends on base qualities)
+
+// word indices of bv_site_out seen as 32 x u32
+constexpr int kWDepth = 0, kWOther = 4, kWState = 5, kWFwd = 6, kWRev = 10, kWAlt = 14, kWInfo = 15;
+
+struct SiteKernelArgs {
+    const uint8_t* base;
+    const uint8_t* qual;
+    const uint8_t* strand;
+    const uint8_t* ref_base;
+    bv_site_out* out;
+    const double* lut;       // [4][kQStride]
+    const double* logfact;   // [max_samples + 2], lgamma(k+1) from glibc
+    uint32_t* bin_spill;     // [K3 warps][kMaxBins] global copy of the compact bins (used when > kSmemBins)
+    double* lml_spill;       // [K3 warps][kMaxBins] per-bin EM state for the same case
+    uint64_t pitch;
+    uint32_t n_sites;
+    uint32_t n_samples;
+    double min_af;           // (double)(float)min_af
+    double em_eps;           // (double)(float)0.001
+    double lrt_threshold;
+    int em_max_iter;
+    int abs_mode;
+};
+
+// Dynamic shared memory of K1 and K3.  Device functions reach it through accessors (not through pointer arguments) so
+// that the compiler knows the address space and emits LDS/STS/ATOMS.
+extern __shared__ __align__(128) unsigned char bv_smem_raw[];
+
+// REF character -> base code 0..3, or -1 (toupper first: src/basetype.cpp:171)
+__device__ __forceinline__ int ref_code_of(uint32_t rc) {
+    if (rc >= 'a' && rc <= 'z') rc -= 32;
+    return rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
+}
+
+// ---- TMA bulk copies + mbarrier (sm_90+; SASS UBLKCP / SYNCS) -----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// valid = number of real cells in this 16-cell vector (>= 16 for all but the row's last vector): padding cells
+// are turned into 'N'
+__device__ __forceinline__ void mask_tail(uint4& vb, int valid) {
+    uint32_t w[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int left = valid - 4 * k;
+        const uint32_t keep = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : (0xffffffffu >> (8 * (4 - left))));
+        w[k] = (w[k] & keep) | (0x05050505u & ~keep);
+    }
+    vb = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// exact `(double)dep / (double)total >= min_af` (src/basetype.cpp:137) with the trivial cases short-cut
+__device__ __forceinline__ bool is_active(uint32_t dep, uint32_t total, double dtot, double min_af) {
+    if (dep == 0) return 0.0 >= min_af;
+    if (dep == total) return 1.0 >= min_af;
+    // away from the boundary the product decides (one multiply instead of a division); within 1e-9 of it, the
+    // reference's own expression
+    const double thr = min_af * dtot, x = (double)dep;
+    if (x > thr * 1.000000001) return true;
+    if (x < thr * 0.999999999) return false;
+    return x / dtot >= min_af;
+}
+
+__device__ __forceinline__ uint32_t sel4u(int j, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    return j == 0 ? v0 : j == 1 ? v1 : j == 2 ? v2 : v3;
+}
+
+}  // namespace bv

@@ -1,0 +1,616 @@
+// bv_finish_kernels.cuh -- K2 (scalar finish, one thread per site) and K3 (quality-dependent sites, one warp per site).
+// See bv_common.cuh for the three-kernel split of the basetype core.
+#pragma once
+#include "bv_common.cuh"
+#include "bv_math.cuh"
+
+namespace bv {
+
+// =====================================================================================================================
+// K2: one thread per site in state kStateScalar (the row has reads that differ from REF, or REF is not A/C/G/T, or a
+// bad strand code).  Everything here is a function of the nine counts K1 left in the record:
+//   * active alleles: depth/total >= min_af                                            (src/basetype.cpp:135-139)
+//   * strand bias of the CVG row, ref vs all non-ref ACGT: two-sided Fisher, FS         (src/basetype.cpp:244-295,
+//                                                                                        basetype_caller.cpp:1236-1245)
+// If exactly one allele is active and it is REF the record is final (the reference's single-column EM gives f = 1, no
+// ALT).  Otherwise the result depends on base qualities: state kStateQual, K3 finishes it.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) bv_scalar_kernel(const __grid_constant__ SiteKernelArgs a) {
+    const uint32_t site = blockIdx.x * blockDim.x + threadIdx.x;
+    if (site >= a.n_sites) return;
+    uint32_t* rec = reinterpret_cast<uint32_t*>(a.out + site);
+    if (rec[kWState] != kStateScalar) return;
+    const uint4 w0 = reinterpret_cast<const uint4*>(rec)[0];   // depth[4]
+    const uint4 w1 = reinterpret_cast<const uint4*>(rec)[1];   // other, state, fwd[0..1]
+    const uint4 w2 = reinterpret_cast<const uint4*>(rec)[2];   // fwd[2..3], rev[0..1]
+    const uint4 w3 = reinterpret_cast<const uint4*>(rec)[3];   // rev[2..3], alt word, info word
+    const uint32_t d0 = w0.x, d1 = w0.y, d2 = w0.z, d3 = w0.w, other = w1.x;
+    const uint32_t f0 = w1.z, f1 = w1.w, f2 = w2.x, f3 = w2.y, r0 = w2.z, r1 = w2.w, r2 = w3.x, r3 = w3.y;
+    const uint32_t flags = (w3.w >> 16) & 0xffu;
+    const int ref_code = ref_code_of(a.ref_base[site]);
+    const uint32_t total = d0 + d1 + d2 + d3 + other;
+    const double dtot = (double)total;
+
+    uint32_t act = 0;
+    if (total > 0) {
+        act |= is_active(d0, total, dtot, a.min_af) ? 1u : 0u;
+        act |= is_active(d1, total, dtot, a.min_af) ? 2u : 0u;
+        act |= is_active(d2, total, dtot, a.min_af) ? 4u : 0u;
+        act |= is_active(d3, total, dtot, a.min_af) ? 8u : 0u;
+    }
+    const uint32_t n_act = __popc(act);
+    const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
+    const bool need_qual = n_act >= 2 || (n_act == 1 && (act & ~ref_bit));
+
+    double fs_cvg = 0.0;
+    {
+        const int rf = ref_code < 0 ? 0 : (int)sel4u(ref_code, f0, f1, f2, f3);
+        const int rr = ref_code < 0 ? 0 : (int)sel4u(ref_code, r0, r1, r2, r3);
+        const int af_ = (int)(f0 + f1 + f2 + f3) - rf, ar = (int)(r0 + r1 + r2 + r3) - rr;
+        // a table with an empty row or column has a single possible outcome: p == 1, FS == 0 (kfunc.c:256)
+        if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(a.logfact, rf, rr, af_, ar);
+    }
+    // n_active | flags | em_calls (a single active allele costs the reference one EM call)
+    const uint32_t em_calls = (!need_qual && n_act == 1) ? 1u : 0u;
+    rec[kWInfo] = (n_act << 8) | (flags << 16) | (em_calls << 24);
+    reinterpret_cast<double*>(rec)[14] = fs_cvg;
+    rec[kWState] = need_qual ? kStateQual : kStateDone;
+}
+
+// =====================================================================================================================
+// K3: one warp per site in state kStateQual.
+// =====================================================================================================================
+#ifndef BV_QUAL_WARPS
+#define BV_QUAL_WARPS 24
+#endif
+constexpr int kQualWarps = BV_QUAL_WARPS;
+constexpr int kP2Chunk = 512;                // cells per buffer and plane, one 16-cell vector per lane
+
+struct __align__(128) P2Buf {                // one chunk of the base and qual planes
+    uint8_t base[kP2Chunk];
+    uint8_t qual[kP2Chunk];
+};
+
+struct __align__(128) QualWarp {
+    P2Buf p2[2];
+    uint32_t hist[kHistWords];   // (base, phred) histogram, all-zero between sites; the EM's per-bin state (one double
+                                 // per compact bin) overlays it once the bins are compacted
+    uint32_t bins[kSmemBins];    // compact non-empty bins: (base << 29) | (phred << 22) | count
+    double emf[4];               // EM: allele frequencies in / out
+    double res_f[4];             // LRT: frequencies of the accepted model
+    double best_f[4];            // LRT: frequencies of the best candidate subset of the current round
+    double res_chi;              // LRT: last chi_sqrt_value
+    uint32_t flag_word;          // BV_FLAG_* raised inside out-of-line code
+    uint32_t p2_phase;           // mbarrier phase bits of p2bar[]
+    uint64_t p2bar[2];
+    alignas(16) bv_site_out rec; // the site's record: loaded from global, completed, stored back
+};
+
+struct __align__(128) QualCta {
+    double lut[4 * kQStride];
+    uint32_t gfix[kQSlots];      // ceil(2^20 * (log(1-eps(q)) - log(eps(q)/3))): log-likelihood gain of calling a read's
+                                 // own base, fixed point, rounded up (see lrt_bound)
+    SiteKernelArgs a;            // kernel parameters for out-of-line device functions (a reference to the
+                                 // __global__ parameter itself would force a local-memory copy)
+};
+constexpr size_t kQualSmemBytes = sizeof(QualCta) + (size_t)kQualWarps * sizeof(QualWarp);
+static_assert(kQualSmemBytes <= 232448, "shared memory of the qual kernel exceeds 227 KB");
+
+// K3's dynamic shared memory: QualCta, then one QualWarp per warp.
+__device__ __forceinline__ QualCta& cta_shared() { return *reinterpret_cast<QualCta*>(bv_smem_raw); }
+__device__ __forceinline__ QualWarp& warp_smem() {
+    return reinterpret_cast<QualWarp*>(bv_smem_raw + sizeof(QualCta))[threadIdx.x >> 5];
+}
+
+__device__ __forceinline__ uint32_t pack_bin(uint32_t b, uint32_t q, uint32_t count) {
+    return (b << 29) | (q << 22) | count;
+}
+__device__ __forceinline__ uint32_t bin_base(uint32_t p) { return p >> 29; }
+__device__ __forceinline__ uint32_t bin_qual(uint32_t p) { return (p >> 22) & 0x7fu; }
+__device__ __forceinline__ uint32_t bin_count(uint32_t p) { return p & 0x3fffffu; }
+
+// ---- the row's base + qual chunks, fetched (L2 / HBM) into the warp's two buffers ---------------------------------------
+// f(cellp, vb, lane_cells): cellp points at this lane's 16 base cells in shared memory (quals at cellp + kP2Chunk), vb
+// holds them with padding cells masked to 'N'.
+template <class F>
+__device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    const int lane = threadIdx.x & 31;
+    const uint32_t N = cs.a.n_samples;
+    const uint32_t row_bytes = (N + 15u) & ~15u;
+    const uint32_t nchunk = (row_bytes + kP2Chunk - 1) / kP2Chunk;
+    const size_t row = (size_t)site * cs.a.pitch;
+    const uint8_t* gb = cs.a.base + row;
+    const uint8_t* gq = cs.a.qual + row;
+    const uint32_t s_buf0 = smem_u32(&W.p2[0]), s_bar0 = smem_u32(&W.p2bar[0]);
+    uint32_t phase = W.p2_phase;
+    if (lane == 0) {
+        const uint32_t bytes = min((uint32_t)kP2Chunk, row_bytes);
+        mbar_expect_tx(s_bar0, 2 * bytes);
+        bulk_g2s(s_buf0, gb, bytes, s_bar0);
+        bulk_g2s(s_buf0 + kP2Chunk, gq, bytes, s_bar0);
+    }
+#pragma unroll 1
+    for (uint32_t c = 0; c < nchunk; ++c) {
+        const uint32_t buf = c & 1u;
+        if (c + 1 < nchunk && lane == 0) {   // chunk c+1 goes where chunk c-1 was (all lanes are past it: __syncwarp below)
+            const uint32_t off = (c + 1) * kP2Chunk;
+            const uint32_t bytes = min((uint32_t)kP2Chunk, row_bytes - off);
+            const uint32_t bar = s_bar0 + 8u * (buf ^ 1u), dst = s_buf0 + (uint32_t)sizeof(P2Buf) * (buf ^ 1u);
+            mbar_expect_tx(bar, 2 * bytes);
+            bulk_g2s(dst, gb + off, bytes, bar);
+            bulk_g2s(dst + kP2Chunk, gq + off, bytes, bar);
+        }
+        mbar_wait(s_bar0 + 8u * buf, (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        const int lane_cells = (int)N - (int)(c * kP2Chunk) - lane * 16;
+        const uint8_t* cellp = W.p2[buf].base + lane * 16;
+        uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
+        if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(cellp);
+        if (lane_cells < 16) mask_tail(vb, lane_cells);
+        f(cellp, vb, lane_cells);
+        __syncwarp();
+    }
+    if (lane == 0) W.p2_phase = phase;
+}
+
+// (base, phred) histogram of the covered cells of one row into W.hist
+// (BaseType::BaseType, src/basetype.cpp:45-71: one likelihood row per counted read, a function of base and phred only).
+// Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
+__device__ __noinline__ uint32_t build_hist(uint32_t site) {
+    QualWarp& W = warp_smem();
+    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
+    for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int) {
+        // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
+        const uint32_t n0 = (((vb.x | 0x80808080u) - 0x05050505u) | vb.x) & 0x80808080u;
+        const uint32_t n1 = (((vb.y | 0x80808080u) - 0x05050505u) | vb.y) & 0x80808080u;
+        const uint32_t n2 = (((vb.z | 0x80808080u) - 0x05050505u) | vb.z) & 0x80808080u;
+        const uint32_t n3 = (((vb.w | 0x80808080u) - 0x05050505u) | vb.w) & 0x80808080u;
+        uint32_t t = ((n0 >> 7) | (n1 >> 6) | (n2 >> 5) | (n3 >> 4)) ^ 0x0f0f0f0fu;
+        // warp-uniform trip count, lanes that run out are predicated off: the warp never splits
+        const int n = (int)__reduce_max_sync(kFull, (uint32_t)__popc(t));
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const bool on = t != 0u;
+            int top;
+            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+            t &= ~(1u << (top & 31));
+            const int cell = ((top & 3) << 2) | ((top >> 3) & 3);   // word k = top & 3, byte j = top >> 3
+            if (on) {
+                const uint32_t b = cellp[cell];
+                uint32_t q = cellp[cell + kP2Chunk];
+                if (q > BV_QUAL_MAX) { flags |= BV_FLAG_BAD_QUAL; q = min(q, (uint32_t)(kQSlots - 1)); }
+                atomicAdd(&W.hist[b * kQSlots + q], 1u);
+                qmin = min(qmin, q);
+                qmax = max(qmax, q);
+            }
+        }
+    });
+    qmin = __reduce_min_sync(kFull, qmin);
+    qmax = __reduce_max_sync(kFull, qmax);
+    flags = __reduce_or_sync(kFull, flags);
+    return qmin | (qmax << 8) | (flags << 16);
+}
+
+// ---- a bound that decides the LRT without running the EM ---------------------------------------------------------------
+// Site with exactly two active alleles, REF (r) and one other base (o) carried by a few reads -- the signature of
+// sequencing errors.  With L_ij the per-read likelihoods (src/basetype.cpp:61-64) and g_i = log(1-eps_i) - log(eps_i/3):
+//   * every log-likelihood the EM can report for {r,o} is a sum of log(sum_j L_ij f_j) with sum_j f_j <= 1, hence
+//       LL{r,o} <= sum_i log(max_j L_ij) = LL{r} + sum_{reads of o} g_i        (all phred >= 2, so 1-eps > eps/3)
+//     where LL{r} = sum_{reads of r} log(1-eps_i) + sum_{other reads} log(eps_i/3) is the closed form of the
+//     single-allele model (see single_allele_ll);
+//   * LL{r} - LL{o} = sum_{reads of r} g_i - sum_{reads of o} g_i >= 0.56 * depth[r] - G,  G = sum_{reads of o} g_i.
+// So when 2G < 23.9 and depth[r] >= 22, the first LRT round (src/basetype.cpp:151-168) picks subset {r}
+// (chi_r < chi_o) with chi_r = 2 (LL{r,o} - LL{r}) <= 2G < 24 = LRT_THRESHOLD and drops o: the site ends with the
+// single active allele REF, no ALT, whatever the EM would have returned.  Margins (23.9 vs 24, G rounded up in fixed
+// point) dwarf the 1e-12 rounding noise of the reference's sums.
+// Returns G in 2^-20 units, or 0xffffffff when a counted read has phred < 2 or > 93 (bound not applicable).
+constexpr uint32_t kBoundLimit = 12530483u;   // floor(11.95 * 2^20)
+__device__ __noinline__ uint32_t lrt_bound(uint32_t site, uint32_t o_code) {
+    const QualCta& cs = cta_shared();
+    const uint32_t ow = o_code * 0x01010101u;
+    uint32_t G = 0, bad = 0;
+    for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int lane_cells) {
+        uint4 vq = make_uint4(0x02020202u, 0x02020202u, 0x02020202u, 0x02020202u);
+        if (lane_cells > 0) vq = *reinterpret_cast<const uint4*>(cellp + kP2Chunk);
+        const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w}, wq[4] = {vq.x, vq.y, vq.z, vq.w};
+        uint32_t eo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t m = ~(((wb[k] | 0x80808080u) - 0x05050505u) | wb[k]) & 0x80808080u;   // counted
+            const uint32_t q7 = wq[k] & 0x7f7f7f7fu;
+            bad |= (~(q7 + 0x7e7e7e7eu) | (q7 + 0x22222222u) | wq[k]) & m;                        // phred < 2 or > 93
+            const uint32_t x = (wb[k] ^ ow) & 0x7f7f7f7fu;
+            eo[k] = ~((x + 0x7f7f7f7fu) | wb[k]) & 0x80808080u;                                   // base == o
+        }
+        if (eo[0] | eo[1] | eo[2] | eo[3]) {
+            uint32_t t = (eo[0] >> 7) | (eo[1] >> 6) | (eo[2] >> 5) | (eo[3] >> 4);   // bit (8*byte + word)
+            do {
+                int top;
+                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+                t ^= 1u << top;
+                const int cell = ((top & 3) << 2) | (top >> 3);
+                const uint32_t q = cellp[cell + kP2Chunk];
+                G += cs.gfix[min(q, (uint32_t)(kQSlots - 1))];
+            } while (t);
+        }
+    });
+    G = __reduce_add_sync(kFull, G);
+    bad = __reduce_or_sync(kFull, bad);
+    return bad ? 0xffffffffu : G;
+}
+
+// ---- EM on compact bins (src/algorithm.h:210-255) ----------------------------------------------------------------
+// bins: nb packed (base, phred, count) entries; lml: nb doubles of scratch (log marginal likelihood per bin).
+// subset: bit j set => allele j in the candidate combination.  W.emf: initial frequencies in (NOT renormalised,
+// src/basetype.cpp:93-103), estimated frequencies out.  Returns the sum of log marginal likelihoods under the
+// second-to-last frequency vector, exactly what _f() sums (src/basetype.cpp:119-120).
+__device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb, int subset, double total) {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    const double* s_lut = cs.lut;
+    const int lane = threadIdx.x & 31;
+    const int abs_mode = cs.a.abs_mode;
+    double f0 = W.emf[0], f1 = W.emf[1], f2 = W.emf[2], f3 = W.emf[3];
+    __syncwarp();
+    int it = cs.a.em_max_iter;
+    bool first = true;
+    for (;;) {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, delta = 0;
+        bool big = false;
+#pragma unroll 1
+        for (int i = lane; i < nb; i += 32) {
+            const uint32_t p = bins[i];
+            const uint32_t b = bin_base(p), q = bin_qual(p);
+            const double cd = (double)bin_count(p);
+            const double ome = s_lut[kLutOneMinusEps * kQStride + q], e3 = s_lut[kLutEpsThird * kQStride + q];
+            // e_step (algorithm.h:160-172): lik*freq summed in A,C,G,T order; alleles outside the subset have
+            // freq 0 and add an exact +0.0, so they are skipped
+            double l0 = 0, l1 = 0, l2 = 0, l3 = 0, m = 0;
+            if (subset & 1) { l0 = (b == 0 ? ome : e3) * f0; m += l0; }
+            if (subset & 2) { l1 = (b == 1 ? ome : e3) * f1; m += l1; }
+            if (subset & 4) { l2 = (b == 2 ? ome : e3) * f2; m += l2; }
+            if (subset & 8) { l3 = (b == 3 ? ome : e3) * f3; m += l3; }
+            const double llh = log(m);
+            if (!first) {
+                const double diff = llh - lml[i];
+                if (abs_mode == BV_EM_ABS_INT_TRUNC) {
+                    // (double)abs((int)diff): non-zero iff |diff| >= 1; NaN/inf convert to INT_MIN whose
+                    // "abs" stays negative and ends the loop (results are NaN by then)
+                    if (fabs(diff) >= 1.0 && fabs(diff) < 2147483648.0) big = true;
+                } else {
+                    delta += cd * fabs(diff);
+                }
+            }
+            lml[i] = llh;
+            // m_step (algorithm.h:184-198): column sums of the posteriors; c equal reads add c * post
+            if (subset & 1) s0 += cd * (l0 / m);
+            if (subset & 2) s1 += cd * (l1 / m);
+            if (subset & 4) s2 += cd * (l2 / m);
+            if (subset & 8) s3 += cd * (l3 / m);
+        }
+        if (subset & 1) f0 = warp_sum(s0) / total;
+        if (subset & 2) f1 = warp_sum(s1) / total;
+        if (subset & 4) f2 = warp_sum(s2) / total;
+        if (subset & 8) f3 = warp_sum(s3) / total;
+        if (first) { first = false; continue; }
+        bool more;
+        if (abs_mode == BV_EM_ABS_INT_TRUNC) more = __any_sync(kFull, big);
+        else more = !(warp_sum(delta) < cs.a.em_eps);
+        --it;
+        if (it == 0 && lane == 0) W.flag_word |= BV_FLAG_EM_MAXITER;
+        if (!more || it == 0) break;
+    }
+    double ll = 0;
+#pragma unroll 1
+    for (int i = lane; i < nb; i += 32) ll += (double)bin_count(bins[i]) * lml[i];
+    if (lane == 0) { W.emf[0] = f0; W.emf[1] = f1; W.emf[2] = f2; W.emf[3] = f3; }
+    __syncwarp();
+    return warp_sum(ll);
+}
+
+// Log-likelihood of the single-allele model {b} (an EM whose answer is closed form):
+// after the first m_step f_b == 1.0 exactly (every posterior is x/x), so every later marginal is L_b itself and
+// the reported log marginal is log(1-eps) or log(eps/3) -- both tabulated on the host with glibc.  A bin of base b
+// with phred 0 has L_b == 0: the reference then divides 0/0 and everything becomes NaN (returned as NaN).
+__device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, int b_allele) {
+    const double* s_lut = cta_shared().lut;
+    const int lane = threadIdx.x & 31;
+    double ll = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int i = lane; i < nb; i += 32) {
+        const uint32_t p = bins[i];
+        const uint32_t b = bin_base(p), q = bin_qual(p);
+        const bool match = ((int)b == b_allele);
+        if (match && q == 0) bad = true;
+        ll += (double)bin_count(p) * s_lut[(match ? kLutLogMatch : kLutLogMis) * kQStride + q];
+    }
+    ll = warp_sum(ll);
+    if (__any_sync(kFull, bad)) ll = __longlong_as_double(0x7ff8000000000000ll);
+    return ll;
+}
+
+// position of the k-th (k >= 0) set bit of a 4-bit mask
+__device__ __forceinline__ int nth_set_bit(uint32_t mask, int k) {
+    int pos = -1;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (mask & (1u << b)) {
+            if (k == 0 && pos < 0) pos = b;
+            --k;
+        }
+    }
+    return pos;
+}
+
+// ---- sites with >= 2 active alleles: compact the bins, EM on the full set, backward elimination -----------------------
+// (src/basetype.cpp:144-168).  In: the row's histogram in W.hist, phred range, depths in W.rec.depth[], active set.
+// Out: W.res_f / W.res_chi and the return value act | n_act << 4 | em_calls << 8.  The warp-uniform model state lives
+// in shared memory (W.emf / W.best_f / W.res_f), not in registers that would have to survive the calls into em_bins.
+__device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_t act) {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = blockIdx.x * kQualWarps + (threadIdx.x >> 5);
+    // histogram back to zero while the non-empty (base, phred) bins are compacted, in (base, phred) order
+    int nb = 0;
+    uint32_t* gbins = cs.a.bin_spill + (size_t)warp_global * kMaxBins;
+#pragma unroll 1
+    for (int b = 0; b < 5; ++b) {
+        if (b < 4 ? W.rec.depth[b] == 0 : W.rec.depth_other == 0) continue;
+#pragma unroll 1
+        for (uint32_t q0 = qmin; q0 <= qmax; q0 += 32) {
+            const uint32_t q = q0 + lane;
+            uint32_t v = 0;
+            if (q <= qmax) {
+                v = W.hist[b * kQSlots + q];
+                W.hist[b * kQSlots + q] = 0;
+            }
+            const uint32_t bal = __ballot_sync(kFull, v != 0);
+            if (v) {
+                const int pos = nb + __popc(bal & ((1u << lane) - 1u));
+                const uint32_t p = pack_bin(b, q, v);
+                if (pos < kSmemBins) W.bins[pos] = p;
+                gbins[pos] = p;
+            }
+            nb += __popc(bal);
+        }
+    }
+    __syncwarp();
+    // bins live in shared memory unless there are more than kSmemBins of them (then the global copy is used);
+    // the EM's per-bin state overlays the (now all-zero) histogram
+    const bool in_smem = nb <= kSmemBins;
+    const uint32_t* bins = in_smem ? W.bins : gbins;
+    double* lml = in_smem ? reinterpret_cast<double*>(W.hist) : cs.a.lml_spill + (size_t)warp_global * kMaxBins;
+
+    const double dtot = (double)(W.rec.depth[0] + W.rec.depth[1] + W.rec.depth[2] + W.rec.depth[3] + W.rec.depth_other);
+    int n_act = __popc(act);
+    uint32_t flags = 0;
+    double chi = 0.0;
+    // initial frequencies of a subset: depth/total for its members, 0 elsewhere (src/basetype.cpp:93-103)
+    if (lane < 4) W.emf[lane] = (act >> lane & 1u) ? (double)W.rec.depth[lane] / dtot : 0.0;
+    __syncwarp();
+    double lr_alt = em_bins(bins, lml, nb, (int)act, dtot);
+    if (lane < 4) W.res_f[lane] = W.emf[lane];
+    uint32_t em_calls = 1;
+#pragma unroll 1
+    for (int n = n_act - 1; n > 0; --n) {
+        // the n-subsets of the n+1 active bases in the lexicographic order of
+        // src/external/combinations.h:19-84: the i-th subset drops the (n-i)-th active base
+        double best_chi = 0, best_lr = 0;
+        uint32_t best_set = 0;
+#pragma unroll 1
+        for (int i = 0; i <= n; ++i) {
+            const uint32_t sub = act & ~(1u << nth_set_bit(act, n - i));
+            __syncwarp();
+            if (lane < 4) W.emf[lane] = (sub >> lane & 1u) ? (double)W.rec.depth[lane] / dtot : 0.0;
+            __syncwarp();
+            if (W.emf[0] + W.emf[1] + W.emf[2] + W.emf[3] == 0) flags |= BV_FLAG_ZERO_SUBSET;   // the reference throws (basetype.cpp:113)
+            double lr;
+            if (n == 1) {
+                const int single = __ffs(sub) - 1;
+                lr = single_allele_ll(bins, nb, single);
+                const double v = (lr != lr) ? lr : 1.0;
+                if (lane < 4) W.emf[lane] = lane == single ? v : 0.0;
+                __syncwarp();
+            } else {
+                lr = em_bins(bins, lml, nb, (int)sub, dtot);
+            }
+            if (em_calls < 255) ++em_calls;
+            const double c = 2 * (lr_alt - lr);
+            // std::min_element keeps the FIRST minimum (algorithm.h:24-27).  Alleles with identical read
+            // multisets have equal likelihood; the reference's pick between them hangs on the rounding noise
+            // of its read-order sums.  Values that agree to rounding noise are treated as the tie they are:
+            // the earlier subset stays and the site is flagged.
+            const double tie_tol = 1e-11 * (fabs(lr_alt) + fabs(lr));
+            if (i > 0 && fabs(c - best_chi) <= tie_tol) flags |= BV_FLAG_LRT_TIE;
+            if (i == 0 || c < best_chi - tie_tol) {
+                best_chi = c; best_lr = lr; best_set = sub;
+                if (lane < 4) W.best_f[lane] = W.emf[lane];
+            }
+        }
+        lr_alt = best_lr;
+        chi = best_chi;
+        const double lrt_threshold = cs.a.lrt_threshold;
+        if (fabs(chi - lrt_threshold) < 1e-9 * lrt_threshold) flags |= BV_FLAG_NEAR_LRT;
+        if (chi < lrt_threshold) {
+            act = best_set; n_act = n;
+            __syncwarp();
+            if (lane < 4) W.res_f[lane] = W.best_f[lane];
+        } else {
+            break;
+        }
+    }
+    // the EM state overlaid the histogram: back to all-zero for the next site
+    __syncwarp();
+    if (in_smem) {
+#pragma unroll 1
+        for (int i = lane; i < 2 * nb; i += 32) W.hist[i] = 0;
+    }
+    if (lane == 0) {
+        W.res_chi = chi;
+        W.flag_word |= flags;
+    }
+    __syncwarp();
+    return act | ((uint32_t)n_act << 4) | (em_calls << 8);
+}
+
+// ---- one site in state kStateQual ------------------------------------------------------------------------------------------
+// Everything here is warp-uniform.  The record (counts, FS of the CVG row, flags) comes from K1 / K2.
+__device__ __noinline__ void qual_site(uint32_t site) {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    const int lane = threadIdx.x & 31;
+    if (lane < 8) reinterpret_cast<uint4*>(&W.rec)[lane] = reinterpret_cast<const uint4*>(cs.a.out + site)[lane];
+    const int ref_code = ref_code_of(cs.a.ref_base[site]);
+    __syncwarp();
+    const uint32_t d0 = W.rec.depth[0], d1 = W.rec.depth[1], d2 = W.rec.depth[2], d3 = W.rec.depth[3];
+    const uint32_t total = d0 + d1 + d2 + d3 + W.rec.depth_other;
+    const double dtot = (double)total;
+    const double min_af = cs.a.min_af;
+    if (lane == 0) W.flag_word = W.rec.flags;
+
+    // ---- lrt (src/basetype.cpp:130-199): active set (total > 0 here) ----
+    uint32_t act = 0;
+    act |= is_active(d0, total, dtot, min_af) ? 1u : 0u;
+    act |= is_active(d1, total, dtot, min_af) ? 2u : 0u;
+    act |= is_active(d2, total, dtot, min_af) ? 4u : 0u;
+    act |= is_active(d3, total, dtot, min_af) ? 8u : 0u;
+    int n_act = __popc(act);
+    double chi = 0.0;
+    uint32_t em_calls = 0;
+    const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
+    __syncwarp();
+
+    bool bounded = false;
+    if (n_act == 2 && (act & ref_bit)) {
+        // REF plus one minor allele: try to settle the LRT by the bound (see lrt_bound)
+        const int o_code = __ffs(act & ~ref_bit) - 1;
+        const uint32_t d_ref = sel4u(ref_code, d0, d1, d2, d3), d_o = sel4u(o_code, d0, d1, d2, d3);
+        if (d_ref >= 22 && d_o <= 4 && lrt_bound(site, (uint32_t)o_code) < kBoundLimit) {
+            bounded = true;
+            act = ref_bit; n_act = 1;
+            if (lane == 0) W.flag_word |= BV_FLAG_LRT_BOUND;
+            if (lane < 4) W.res_f[lane] = 0.0;
+        }
+    }
+    if (!bounded) {
+        // histogram the row by (base, phred)
+        const uint32_t h = build_hist(site);
+        const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
+        if (lane == 0) W.flag_word |= h >> 16;
+        __syncwarp();
+        if (n_act >= 2) {
+            const uint32_t r = lrt_multi(qmin, qmax, act);
+            act = r & 0xfu; n_act = (int)((r >> 4) & 0xfu); em_calls = r >> 8;
+            chi = W.res_chi;
+        } else {
+            // One active allele: the reference still runs one EM; its answer is closed form (see single_allele_ll):
+            // AF == 1.0 exactly, or NaN when a phred-0 read of that base exists.
+            const int b = __ffs(act) - 1;
+            const bool bad = qmin == 0 && W.hist[b * kQSlots] != 0;
+            const double v = bad ? __longlong_as_double(0x7ff8000000000000ll) : 1.0;
+            __syncwarp();
+            if (lane < 4) W.res_f[lane] = lane == b ? v : 0.0;
+            em_calls = 1;
+            if (qmin <= qmax) {   // histogram back to zero
+#pragma unroll 1
+                for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) W.hist[r * kQSlots + q] = 0;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    uint32_t flags = W.flag_word;
+
+    // ---- ALT / QUAL (src/basetype.cpp:170-196) ----
+    const uint32_t alt_set = act & ~ref_bit;
+    const int n_alt = __popc(alt_set);
+    double qual = 0.0, fs_vcf = 0.0;
+    if (n_alt) {
+        const int first_act = __ffs(act) - 1;
+        const double r = (double)sel4u(first_act, d0, d1, d2, d3) / dtot;
+        if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
+        else qual = qual_from_chi(chi);
+        // strand bias of the VCF row: ref vs the called ALT alleles (src/basetype.cpp:244-295, basetype_caller.cpp:1164)
+        const uint32_t* f = W.rec.fwd;
+        const uint32_t* rv = W.rec.rev;
+        const int rf = ref_code < 0 ? 0 : (int)f[ref_code], rr = ref_code < 0 ? 0 : (int)rv[ref_code];
+        const int af_ = (int)(f[0] + f[1] + f[2] + f[3]) - rf, ar = (int)(rv[0] + rv[1] + rv[2] + rv[3]) - rr;
+        const int vf = (int)(((alt_set & 1) ? f[0] : 0u) + ((alt_set & 2) ? f[1] : 0u) + ((alt_set & 4) ? f[2] : 0u) + ((alt_set & 8) ? f[3] : 0u));
+        const int vr = (int)(((alt_set & 1) ? rv[0] : 0u) + ((alt_set & 2) ? rv[1] : 0u) + ((alt_set & 4) ? rv[2] : 0u) + ((alt_set & 8) ? rv[3] : 0u));
+        if (vf == af_ && vr == ar) fs_vcf = W.rec.fs_cvg;   // same 2x2 table as the CVG row
+        else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(cs.a.logfact, rf, rr, vf, vr);
+    }
+
+    // ---- record ----
+    __syncwarp();
+    if (lane == 0) {
+        bv_site_out& r = W.rec;
+        r.reserved0 = kStateDone;
+        // ALT alleles in ACGT order of the active set (src/basetype.cpp:172-177)
+        uint32_t alts = 0;
+        int k = 0;
+        const double af[4] = {W.res_f[0], W.res_f[1], W.res_f[2], W.res_f[3]};
+        r.af[0] = 0.0; r.af[1] = 0.0; r.af[2] = 0.0; r.af[3] = 0.0;
+        if (alt_set & 1) { r.af[k] = af[0]; alts |= 0u << (8 * k); ++k; }
+        if (alt_set & 2) { r.af[k] = af[1]; alts |= 1u << (8 * k); ++k; }
+        if (alt_set & 4) { r.af[k] = af[2]; alts |= 2u << (8 * k); ++k; }
+        if (alt_set & 8) { r.af[k] = af[3]; alts |= 3u << (8 * k); ++k; }
+        r.n_alt = (uint8_t)n_alt;
+        r.alt[0] = (uint8_t)alts; r.alt[1] = (uint8_t)(alts >> 8); r.alt[2] = (uint8_t)(alts >> 16); r.alt[3] = (uint8_t)(alts >> 24);
+        r.n_active = (uint8_t)n_act;
+        r.flags = (uint8_t)flags;
+        r.em_calls = (uint8_t)(em_calls > 255u ? 255u : em_calls);
+        r.qual = qual;
+        r.chi2 = chi;
+        r.fs_vcf = fs_vcf;
+    }
+    __syncwarp();
+    if (lane < 8) reinterpret_cast<uint4*>(cs.a.out + site)[lane] = reinterpret_cast<const uint4*>(&W.rec)[lane];
+    __syncwarp();
+}
+
+// Persistent warps; warp w looks at the groups of 32 consecutive sites w, w + W, ...: one coalesced look at the 32
+// state words, then the sites in state kStateQual one after the other.
+__global__ void __launch_bounds__(kQualWarps * 32, 1) bv_qual_kernel(const __grid_constant__ SiteKernelArgs a) {
+    QualCta& cs = cta_shared();
+    QualWarp& W = warp_smem();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) cs.lut[i] = a.lut[i];
+    for (int q = threadIdx.x; q < kQSlots; q += blockDim.x) {
+        // per-read log-likelihood gain of calling the read's own base, fixed point 2^-20, rounded up (lrt_bound)
+        const double g = a.lut[kLutLogMatch * kQStride + q] - a.lut[kLutLogMis * kQStride + q];
+        cs.gfix[q] = (q >= 2 && q <= BV_QUAL_MAX) ? (uint32_t)ceil(g * 1048576.0) + 1u : 0x01000000u;
+    }
+    if (threadIdx.x == 0) cs.a = a;
+    for (int i = lane; i < kHistWords; i += 32) W.hist[i] = 0;
+    if (lane == 0) {
+        W.flag_word = 0;
+        W.p2_phase = 0;
+        mbar_init(&W.p2bar[0], 1);
+        mbar_init(&W.p2bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t total_warps = gridDim.x * kQualWarps;
+    const uint32_t n_groups = (a.n_sites + 31u) >> 5;
+    const uint32_t* g_out = reinterpret_cast<const uint32_t*>(a.out);
+#pragma unroll 1
+    for (uint32_t g = blockIdx.x * kQualWarps + warp; g < n_groups; g += total_warps) {
+        const uint32_t s = g * 32u + lane;
+        const uint32_t st = s < a.n_sites ? g_out[(size_t)s * 32 + kWState] : kStateDone;
+        uint32_t todo = __ballot_sync(kFull, st == kStateQual);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            qual_site(g * 32u + (uint32_t)l);
+        }
+    }
+}
+
+}  // namespace bv

@@ -1,10 +1,13 @@
 #!/usr/bin/env bash
-# Tuning builds of the CUDA library: tools/build_variants.sh "28 24 20" -> basevar_b200/variants/libbv_w<N>.so
+# Tuning builds of the CUDA library.  Each argument word is name:DEF[,DEF...]:
+#   tools/build_variants.sh "c24:BV_COUNT_WARPS=24 c32s2:BV_COUNT_WARPS=32,BV_COUNT_STAGES=2"
+# -> basevar_b200/variants/libbv_<name>.so
 set -e
 cd "$(dirname "$0")/../basevar_b200"
 mkdir -p variants
-for w in $1; do
+for v in $1; do
+  name=${v%%:*}; defs=$(echo "${v#*:}" | sed 's/,/ -D/g; s/^/-D/')
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -shared \
-       -DBV_WARPS=$w ${BV_EXTRA_FLAGS:-} -o variants/libbv_w$w.so csrc/bv_api.cu
+       $defs -o "variants/libbv_$name.so" csrc/bv_api.cu
 done
-ls -la variants
+ls variants
