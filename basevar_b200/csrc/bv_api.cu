@@ -64,8 +64,19 @@ __global__ void __launch_bounds__(256) bv_synth_kernel(const bv_synth_model* __r
 // ======================================================================================================
 // Context
 // ======================================================================================================
+// Scratch of one in-flight tile: work lists and counters (K1 -> K2 -> K3 -> K4) and the EM kernel's spill space.
+// Kernels of different tiles may overlap, so every slot (and the device-resident path) owns one.
+struct bv_scratch {
+    uint32_t* d_lists = nullptr;      // 3 x cap site indices
+    uint32_t* d_counters = nullptr;   // 8 x u32
+    uint32_t* d_bin_spill = nullptr;
+    double* d_lml_spill = nullptr;
+    uint32_t cap = 0;
+};
+
 struct bv_slot {
     cudaStream_t stream = nullptr;
+    bv_scratch scratch;
     uint8_t* d_planes = nullptr;   // base | qual | strand, each max_sites * pitch_cap
     uint8_t* d_ref = nullptr;
     bv_site_out* d_out = nullptr;
@@ -82,8 +93,7 @@ struct bv_ctx {
     double* d_lut = nullptr;
     double* d_logfact = nullptr;
     bv_synth_model* d_model = nullptr;
-    uint32_t* d_bin_spill = nullptr;
-    double* d_lml_spill = nullptr;
+    bv_scratch dev_scratch;           // bv_tile_run_device
     bool has_model = false;
     uint64_t pitch_cap = 0;
     bv_slot* slots = nullptr;
@@ -111,7 +121,30 @@ static int set_err(bv_ctx* ctx, int code, const char* fmt, ...) {
                            __FILE__, __LINE__);                                                         \
     } while (0)
 
-static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, bv::SiteKernelArgs* a) {
+static void scratch_free(bv_scratch& sc) {
+    cudaFree(sc.d_lists); cudaFree(sc.d_counters); cudaFree(sc.d_bin_spill); cudaFree(sc.d_lml_spill);
+    sc = bv_scratch();
+}
+
+// make room for tiles of up to n_sites sites (grows only; cudaMalloc synchronises, so slots are sized at bv_create)
+static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
+    if (!sc.d_counters) {
+        const size_t warps = (size_t)ctx->num_sms * bv::kQualWarps;
+        BV_CUDA(ctx, cudaMalloc(&sc.d_counters, 8 * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_bin_spill, warps * bv::kMaxBins * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_lml_spill, warps * bv::kMaxBins * sizeof(double)));
+    }
+    if (n_sites > sc.cap) {
+        if (sc.d_lists) BV_CUDA(ctx, cudaFree(sc.d_lists));
+        sc.d_lists = nullptr;
+        sc.cap = 0;
+        BV_CUDA(ctx, cudaMalloc(&sc.d_lists, 3 * (size_t)n_sites * sizeof(uint32_t)));
+        sc.cap = n_sites;
+    }
+    return BV_OK;
+}
+
+static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, bv_scratch& sc, bv::SiteKernelArgs* a) {
     if (!t || !t->base || !t->qual || !t->strand || !t->ref_base || !d_out)
         return set_err(ctx, BV_ERR_ARG, "bv_tile: null pointer");
     if (t->pitch % 16 != 0 || t->pitch < t->n_samples)
@@ -125,8 +158,16 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->out = d_out;
     a->lut = ctx->d_lut;
     a->logfact = ctx->d_logfact;
-    a->bin_spill = ctx->d_bin_spill;
-    a->lml_spill = ctx->d_lml_spill;
+    {
+        int rc = scratch_reserve(ctx, sc, t->n_sites);
+        if (rc != BV_OK) return rc;
+    }
+    a->bin_spill = sc.d_bin_spill;
+    a->lml_spill = sc.d_lml_spill;
+    a->list_slow = sc.d_lists;
+    a->list_bound = sc.d_lists + sc.cap;
+    a->list_em = sc.d_lists + 2 * (size_t)sc.cap;
+    a->counters = sc.d_counters;
     a->pitch = t->pitch;
     a->n_sites = t->n_sites;
     a->n_samples = t->n_samples;
@@ -138,27 +179,34 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     return BV_OK;
 }
 
-// The basetype core of one tile: K1 (counts, every cell), K2 (scalar finish, one thread per site), K3 (sites whose
-// result depends on base qualities).  Stream ordered; see csrc/bv_common.cuh.
+// The basetype core of one tile: K1 (counts, every cell), K2 (scalar finish, one thread per site), K3 / K4 (sites whose
+// result depends on base qualities: likelihood-ratio bound, then EM + LRT).  Stream ordered; see csrc/bv_common.cuh.
 static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream) {
     if (a.n_sites == 0) return BV_OK;
     if (a.n_samples == 0) {   // no cells: every record is all-zero
         BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
         return BV_OK;
     }
+    BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), stream));
     // K1, persistent: one CTA per SM, each warp strides over the sites
     uint32_t grid = (a.n_sites + bv::kCountWarps - 1) / bv::kCountWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
     bv::bv_count_kernel<<<grid, bv::kCountWarps * 32, bv::kCountSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
-    bv::bv_scalar_kernel<<<(a.n_sites + 255) / 256, 256, 0, stream>>>(a);
+    grid = (a.n_sites + 255) / 256;   // grid-stride over K1's work list
+    if (grid > (uint32_t)ctx->num_sms * 8u) grid = (uint32_t)ctx->num_sms * 8u;
+    bv::bv_scalar_kernel<<<grid, 256, 0, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
-    // K3, persistent: each warp strides over groups of 32 sites
+    // K3 and K4, persistent: each warp strides over groups of 32 sites
+    grid = ((a.n_sites + 31) / 32 + bv::kBoundWarps - 1) / bv::kBoundWarps;
+    if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+    bv::bv_bound_kernel<<<grid, bv::kBoundWarps * 32, bv::kBoundSmemBytes, stream>>>(a);
+    BV_CUDA(ctx, cudaGetLastError());
     grid = ((a.n_sites + 31) / 32 + bv::kQualWarps - 1) / bv::kQualWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
-    bv::bv_qual_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
+    bv::bv_em_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 4;
     return BV_OK;
 }
 
@@ -220,19 +268,14 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
         ctx->num_sms = prop.multiProcessorCount;
         if (cudaFuncSetAttribute(bv::bv_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCountSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_qual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess) {
+            cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
                          cudaGetErrorString(cudaGetLastError()));
             break;
         }
         rc = upload_tables(ctx);
         if (rc != BV_OK) break;
-        {   // per-warp overflow scratch of the EM (only touched by sites with very many distinct bins)
-            const size_t warps = (size_t)ctx->num_sms * bv::kQualWarps;
-            cudaError_t ce = cudaMalloc(&ctx->d_bin_spill, warps * bv::kMaxBins * sizeof(uint32_t));
-            if (ce == cudaSuccess) ce = cudaMalloc(&ctx->d_lml_spill, warps * bv::kMaxBins * sizeof(double));
-            if (ce != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(ce)); break; }
-        }
         ctx->pitch_cap = ((uint64_t)params->max_samples + 15) / 16 * 16;
         if (params->n_slots > 0 && params->max_sites > 0) {
             ctx->slots = new (std::nothrow) bv_slot[params->n_slots];
@@ -246,6 +289,7 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_out, (size_t)params->max_sites * sizeof(bv_site_out));
                 if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_out, (size_t)params->max_sites * sizeof(bv_site_out), cudaHostAllocDefault);
                 if (ce != cudaSuccess) rc = set_err(nullptr, BV_ERR_CUDA, "slot allocation failed: %s", cudaGetErrorString(ce));
+                else rc = scratch_reserve(ctx, s.scratch, params->max_sites);
             }
         }
     } while (0);
@@ -262,13 +306,13 @@ void bv_destroy(bv_ctx* ctx) {
             bv_slot& s = ctx->slots[i];
             if (s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
             cudaFree(s.d_planes); cudaFree(s.d_ref); cudaFree(s.d_out);
+            scratch_free(s.scratch);
             if (s.h_out) cudaFreeHost(s.h_out);
         }
         delete[] ctx->slots;
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model);
-    cudaFree(ctx->d_bin_spill);
-    cudaFree(ctx->d_lml_spill);
+    scratch_free(ctx->dev_scratch);
     delete ctx;
 }
 
@@ -287,7 +331,7 @@ int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, voi
     if (tile && tile->location != BV_LOC_DEVICE) return set_err(ctx, BV_ERR_ARG, "bv_tile_run_device: tile must be device resident");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
     bv::SiteKernelArgs a;
-    int rc = fill_kernel_args(ctx, tile, d_out, &a);
+    int rc = fill_kernel_args(ctx, tile, d_out, ctx->dev_scratch, &a);
     if (rc != BV_OK) return rc;
     return launch_site_kernel(ctx, a, (cudaStream_t)stream);
 }
@@ -323,7 +367,7 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
         dev.location = BV_LOC_DEVICE;
     }
     bv::SiteKernelArgs a;
-    int rc = fill_kernel_args(ctx, &dev, s.d_out, &a);
+    int rc = fill_kernel_args(ctx, &dev, s.d_out, s.scratch, &a);
     if (rc != BV_OK) return rc;
     rc = launch_site_kernel(ctx, a, s.stream);
     if (rc != BV_OK) return rc;

@@ -9,10 +9,15 @@
 //        their final record here; the others get their counts and the state BV_STATE_SCALAR.
 //   K2  bv_scalar_kernel  (bv_finish_kernels.cuh)  one THREAD per site in state SCALAR: active alleles, strand-bias
 //        Fisher test; final record unless the result depends on base qualities (then state BV_STATE_QUAL).
-//   K3  bv_qual_kernel    (bv_finish_kernels.cuh)  one warp per site in state QUAL: fetches the row's base + qual
-//        planes, settles the LRT by a rigorous bound or runs EM + LRT on (base, phred) bins; QUAL, ALT-table Fisher.
+//   K3  bv_bound_kernel   (bv_finish_kernels.cuh)  one warp per site in state BOUND (REF plus one minor allele carried by
+//        a few reads -- sequencing errors): fetches the row's base + qual planes and settles the LRT by a rigorous bound
+//        on the likelihood ratio, without running the EM; what the bound cannot decide goes to state EM.
+//   K4  bv_em_kernel      (bv_finish_kernels.cuh)  one warp per site in state EM: (base, phred) histogram of the row,
+//        EM + LRT backward elimination on the bins, QUAL, ALT-table Fisher.
 //
-// The state travels in the record's `reserved0` word (0 in every finished record).
+// Work moves between the kernels through compact lists of site indices (appended with warp-aggregated atomics, so their
+// order varies from run to run; every site is independent, so the records do not).  The record's `reserved0` word
+// carries the site's state for inspection (0 in every finished record).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,7 +39,10 @@ constexpr uint32_t kFull = 0xffffffffu;
 
 constexpr uint32_t kStateDone = 0;           // record is final
 constexpr uint32_t kStateScalar = 1;         // counts are final, K2 has to finish the record
-constexpr uint32_t kStateQual = 2;           // K3 has to finish the record (result depends on base qualities)
+constexpr uint32_t kStateBound = 2;          // result depends on base qualities; K3 tries the likelihood-ratio bound
+constexpr uint32_t kStateEM = 3;             // result depends on base qualities; K4 runs EM + LRT
+
+constexpr int kCntSlow = 0, kCntBound = 1, kCntEm = 2, kCntEmNext = 3;   // SiteKernelArgs::counters
 
 // word indices of bv_site_out seen as 32 x u32
 constexpr int kWDepth = 0, kWOther = 4, kWState = 5, kWFwd = 6, kWRev = 10, kWAlt = 14, kWInfo = 15;
@@ -47,8 +55,12 @@ struct SiteKernelArgs {
     bv_site_out* out;
     const double* lut;       // [4][kQStride]
     const double* logfact;   // [max_samples + 2], lgamma(k+1) from glibc
-    uint32_t* bin_spill;     // [K3 warps][kMaxBins] global copy of the compact bins (used when > kSmemBins)
-    double* lml_spill;       // [K3 warps][kMaxBins] per-bin EM state for the same case
+    uint32_t* bin_spill;     // [K4 warps][kMaxBins] global copy of the compact bins (used when > kSmemBins)
+    double* lml_spill;       // [K4 warps][kMaxBins] per-bin EM state for the same case
+    uint32_t* list_slow;     // work lists (site indices), each with room for n_sites entries: K1 -> K2,
+    uint32_t* list_bound;    //   K2 -> K3,
+    uint32_t* list_em;       //   K2 and K3 -> K4
+    uint32_t* counters;      // [kCntSlow .. kCntEmNext], zeroed before K1
     uint64_t pitch;
     uint32_t n_sites;
     uint32_t n_samples;

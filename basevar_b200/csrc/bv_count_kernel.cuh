@@ -13,7 +13,7 @@
 //
 // A site whose counted cells all equal REF (the common case) has a closed-form record -- one active allele == REF, the
 // EM's answer is f = 1, no ALT, QUAL / FS = 0 -- which 32 lanes compose in registers and store coalesced.  Every other
-// site gets its counts and the state kStateScalar for K2.
+// site gets its counts and goes onto the work list of K2.
 #pragma once
 #include "bv_common.cuh"
 
@@ -28,6 +28,7 @@ namespace bv {
 constexpr int kCountWarps = BV_COUNT_WARPS;   // warps per CTA, one CTA per SM
 constexpr int kCountStages = BV_COUNT_STAGES; // ring depth per warp
 constexpr int kChunk = 1024;                  // cells per stage and plane: two 16-cell vectors per lane
+constexpr int kSlowBatch = 16;                // one atomicAdd on the list counter per this many sites
 
 struct __align__(128) Stage {                 // one chunk of the base and strand planes of one site row
     uint8_t base[kChunk];
@@ -38,6 +39,7 @@ struct __align__(128) CountWarp {
     Stage stage[kCountStages];
     uint32_t nr_cnt[12];                      // counted cells that are not the reference base, [2*base + strand]
     uint32_t pad_[4];
+    uint32_t slow_buf[kSlowBatch];            // sites for K2, appended to the global list one batch at a time
     uint64_t full[kCountStages];
 };
 
@@ -117,6 +119,16 @@ __global__ void __launch_bounds__(kCountWarps * 32, 1) bv_count_kernel(const __g
 #pragma unroll
     for (int s = 0; s < kCountStages - 1; ++s) issue();
 
+    uint32_t slow_n = 0;
+    auto flush_slow = [&]() {   // warp-uniform
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(a.counters + kCntSlow, slow_n);
+        pos = __shfl_sync(kFull, pos, 0);
+        if ((uint32_t)lane < slow_n) a.list_slow[pos + lane] = W.slow_buf[lane];
+        slow_n = 0;
+        __syncwarp();
+    };
+
     uint32_t c_slot = 0, c_par = 0;
     uint32_t ref_raw = a.ref_base[warp_global];
 #pragma unroll 1
@@ -192,12 +204,16 @@ __global__ void __launch_bounds__(kCountWarps * 32, 1) bv_count_kernel(const __g
             if (lane == kWOther) w = W.nr_cnt[8] + W.nr_cnt[9];
             if (lane == kWState) w = kStateScalar;
             if (lane == kWInfo) w = (fl >> 31) ? ((uint32_t)BV_FLAG_BAD_STRAND << 16) : 0u;
+            if (lane == 0) W.slow_buf[slow_n] = site;
+            ++slow_n;
             __syncwarp();
             if (lane < 12) W.nr_cnt[lane] = 0;
+            if (slow_n == kSlowBatch) flush_slow();
         }
         g_out[(size_t)site * 32 + lane] = w;
         ref_raw = ref_next;
     }
+    if (slow_n) flush_slow();
 }
 
 }  // namespace bv

@@ -7,19 +7,44 @@
 namespace bv {
 
 // =====================================================================================================================
-// K2: one thread per site in state kStateScalar (the row has reads that differ from REF, or REF is not A/C/G/T, or a
+// K2: one thread per site of K1's work list (the row has reads that differ from REF, or REF is not A/C/G/T, or a
 // bad strand code).  Everything here is a function of the nine counts K1 left in the record:
 //   * active alleles: depth/total >= min_af                                            (src/basetype.cpp:135-139)
 //   * strand bias of the CVG row, ref vs all non-ref ACGT: two-sided Fisher, FS         (src/basetype.cpp:244-295,
 //                                                                                        basetype_caller.cpp:1236-1245)
 // If exactly one allele is active and it is REF the record is final (the reference's single-column EM gives f = 1, no
-// ALT).  Otherwise the result depends on base qualities: state kStateQual, K3 finishes it.
+// ALT).  Otherwise the result depends on base qualities: state kStateBound when the site has the shape the bound of K3
+// can decide (REF with >= 22 reads plus one minor allele with <= 4; the minor allele's code travels in the alt word),
+// else state kStateEM.
 // =====================================================================================================================
+// append `site` to a work list for the lanes with `pred`; one atomicAdd per warp (all 32 lanes must call)
+__device__ __forceinline__ void list_append(uint32_t* list, uint32_t* counter, bool pred, uint32_t site) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t m = __ballot_sync(kFull, pred);
+    if (m == 0) return;
+    uint32_t pos = 0;
+    if (lane == __ffs(m) - 1) pos = atomicAdd(counter, (uint32_t)__popc(m));
+    pos = __shfl_sync(kFull, pos, __ffs(m) - 1);
+    if (pred) list[pos + __popc(m & ((1u << lane) - 1u))] = site;
+}
+
+__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site);
+
 __global__ void __launch_bounds__(256) bv_scalar_kernel(const __grid_constant__ SiteKernelArgs a) {
-    const uint32_t site = blockIdx.x * blockDim.x + threadIdx.x;
-    if (site >= a.n_sites) return;
+    const uint32_t n_slow = a.counters[kCntSlow];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n_slow; i += stride) {   // warp-uniform trips
+        const bool valid = i < n_slow;
+        const uint32_t site = valid ? a.list_slow[i] : 0u;
+        const uint32_t state = valid ? scalar_site(a, site) : kStateDone;
+        list_append(a.list_bound, a.counters + kCntBound, state == kStateBound, site);
+        list_append(a.list_em, a.counters + kCntEm, state == kStateEM, site);
+    }
+}
+
+// returns the site's new state
+__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site) {
     uint32_t* rec = reinterpret_cast<uint32_t*>(a.out + site);
-    if (rec[kWState] != kStateScalar) return;
     const uint4 w0 = reinterpret_cast<const uint4*>(rec)[0];   // depth[4]
     const uint4 w1 = reinterpret_cast<const uint4*>(rec)[1];   // other, state, fwd[0..1]
     const uint4 w2 = reinterpret_cast<const uint4*>(rec)[2];   // fwd[2..3], rev[0..1]
@@ -50,15 +75,187 @@ __global__ void __launch_bounds__(256) bv_scalar_kernel(const __grid_constant__ 
         // a table with an empty row or column has a single possible outcome: p == 1, FS == 0 (kfunc.c:256)
         if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(a.logfact, rf, rr, af_, ar);
     }
+    uint32_t state = need_qual ? kStateEM : kStateDone;
+    if (n_act == 2 && (act & ref_bit)) {
+        const int o_code = __ffs(act & ~ref_bit) - 1;
+        if (sel4u(ref_code, d0, d1, d2, d3) >= 22 && sel4u(o_code, d0, d1, d2, d3) <= 4) {
+            state = kStateBound;
+            rec[kWAlt] = (uint32_t)o_code;
+        }
+    }
     // n_active | flags | em_calls (a single active allele costs the reference one EM call)
     const uint32_t em_calls = (!need_qual && n_act == 1) ? 1u : 0u;
     rec[kWInfo] = (n_act << 8) | (flags << 16) | (em_calls << 24);
     reinterpret_cast<double*>(rec)[14] = fs_cvg;
-    rec[kWState] = need_qual ? kStateQual : kStateDone;
+    rec[kWState] = state;
+    return state;
 }
 
 // =====================================================================================================================
-// K3: one warp per site in state kStateQual.
+// K3: one warp per site of the bound list -- a bound that decides the LRT without running the EM.
+//
+// Site with exactly two active alleles, REF (r) and one other base (o) carried by a few reads: the signature of
+// sequencing errors.  With L_ij the per-read likelihoods (src/basetype.cpp:61-64) and g_i = log(1-eps_i) - log(eps_i/3):
+//   * every log-likelihood the EM can report for {r,o} is a sum of log(sum_j L_ij f_j) with sum_j f_j <= 1, hence
+//       LL{r,o} <= sum_i log(max_j L_ij) = LL{r} + sum_{reads of o} g_i        (all phred >= 2, so 1-eps > eps/3)
+//     where LL{r} = sum_{reads of r} log(1-eps_i) + sum_{other reads} log(eps_i/3) is the closed form of the
+//     single-allele model (see single_allele_ll);
+//   * LL{r} - LL{o} = sum_{reads of r} g_i - sum_{reads of o} g_i >= 0.56 * depth[r] - G,  G = sum_{reads of o} g_i.
+// So when 2G < 23.9 and depth[r] >= 22, the first LRT round (src/basetype.cpp:151-168) picks subset {r}
+// (chi_r < chi_o) with chi_r = 2 (LL{r,o} - LL{r}) <= 2G < 24 = LRT_THRESHOLD and drops o: the site ends with the
+// single active allele REF, no ALT, whatever the EM would have returned.  Margins (23.9 vs 24, G rounded up in fixed
+// point) dwarf the 1e-12 rounding noise of the reference's sums.  A counted read with phred < 2 or > 93 voids the
+// argument; such a site goes to the EM kernel like the ones whose G is too large.
+//
+// Light kernel, high occupancy: the row's base + qual planes come through two TMA-filled buffers per warp, the next
+// unit (also the next site's first one) in flight while the current one is scanned with SIMD byte arithmetic.
+// =====================================================================================================================
+#ifndef BV_BOUND_WARPS
+#define BV_BOUND_WARPS 32
+#endif
+constexpr int kBoundWarps = BV_BOUND_WARPS;
+constexpr int kBChunk = 1024;                 // cells per buffer and plane: two 16-cell vectors per lane
+constexpr uint32_t kBoundLimit = 12530483u;   // floor(11.95 * 2^20)
+
+struct __align__(128) BoundBuf {
+    uint8_t base[kBChunk];
+    uint8_t qual[kBChunk];
+};
+struct __align__(128) BoundWarp {
+    BoundBuf buf[2];
+    uint64_t bar[2];
+};
+struct __align__(128) BoundCta {
+    uint32_t gfix[kQSlots];      // ceil(2^20 * (log(1-eps(q)) - log(eps(q)/3))) + 1: g in fixed point, rounded up
+};
+constexpr size_t kBoundSmemBytes = sizeof(BoundCta) + (size_t)kBoundWarps * sizeof(BoundWarp);
+static_assert(kBoundSmemBytes <= 232448, "shared memory of the bound kernel exceeds 227 KB");
+
+__global__ void __launch_bounds__(kBoundWarps * 32, 1) bv_bound_kernel(const __grid_constant__ SiteKernelArgs a) {
+    BoundCta& cs = *reinterpret_cast<BoundCta*>(bv_smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    BoundWarp& W = reinterpret_cast<BoundWarp*>(bv_smem_raw + sizeof(BoundCta))[warp];
+    for (int q = threadIdx.x; q < kQSlots; q += blockDim.x) {
+        const double g = a.lut[kLutLogMatch * kQStride + q] - a.lut[kLutLogMis * kQStride + q];
+        cs.gfix[q] = (q >= 2 && q <= BV_QUAL_MAX) ? (uint32_t)ceil(g * 1048576.0) + 1u : 0x01000000u;
+    }
+    if (lane == 0) {
+        mbar_init(&W.bar[0], 1);
+        mbar_init(&W.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t N = a.n_samples;
+    const uint32_t row_bytes = (N + 15u) & ~15u;
+    const uint64_t pitch = a.pitch;
+    const uint32_t total_warps = gridDim.x * kBoundWarps;
+    const uint32_t n_bound = a.counters[kCntBound];
+    const uint32_t n_groups = (n_bound + 31u) >> 5;
+    uint32_t* const g_out = reinterpret_cast<uint32_t*>(a.out);
+    const uint32_t s_buf0 = smem_u32(&W.buf[0]), s_bar0 = smem_u32(&W.bar[0]);
+    uint32_t p_buf = 0, c_buf = 0, phase = 0;   // buffers alternate over the whole unit stream of this warp
+
+#pragma unroll 1
+    for (uint32_t g = blockIdx.x * kBoundWarps + warp; g < n_groups; g += total_warps) {
+        // 32 consecutive entries of the work list: lane l looks after entry l, the warp scans them one after the other
+        const bool valid = g * 32u + lane < n_bound;
+        const uint32_t my_site = valid ? a.list_bound[g * 32u + lane] : 0u;
+        const uint32_t todo = __ballot_sync(kFull, valid);
+        uint32_t my_o = 0, my_info = 0;
+        if (valid) {
+            my_o = g_out[(size_t)my_site * 32 + kWAlt] & 3u;
+            my_info = g_out[(size_t)my_site * 32 + kWInfo];
+        }
+        // producer cursor over the units (site, chunk) of this group: one unit ahead of the scan
+        uint32_t p_todo = todo, p_off = 0;
+        uint32_t p_site = __shfl_sync(kFull, my_site, __ffs(p_todo) - 1);
+        p_todo &= p_todo - 1u;
+        bool p_valid = true;
+        auto issue = [&]() {
+            if (p_valid) {
+                if (lane == 0) {
+                    const uint32_t bytes = min((uint32_t)kBChunk, row_bytes - p_off);
+                    const size_t gsrc = (size_t)p_site * pitch + p_off;
+                    const uint32_t bar = s_bar0 + 8u * p_buf, dst = s_buf0 + (uint32_t)sizeof(BoundBuf) * p_buf;
+                    mbar_expect_tx(bar, 2u * bytes);
+                    bulk_g2s(dst, a.base + gsrc, bytes, bar);
+                    bulk_g2s(dst + (uint32_t)kBChunk, a.qual + gsrc, bytes, bar);
+                }
+                p_buf ^= 1u;
+                p_off += kBChunk;
+                if (p_off >= row_bytes) {
+                    p_off = 0;
+                    // (warp-uniform branch: every lane takes part in the shuffle)
+                    if (p_todo) { p_site = __shfl_sync(kFull, my_site, __ffs(p_todo) - 1); p_todo &= p_todo - 1u; }
+                    else p_valid = false;
+                }
+            }
+        };
+        issue();
+        uint32_t c_todo = todo;
+#pragma unroll 1
+        while (c_todo) {
+            const int l = __ffs(c_todo) - 1;
+            c_todo &= c_todo - 1u;
+            const uint32_t ow = __shfl_sync(kFull, my_o, l) * 0x01010101u;
+            uint32_t G = 0, bad = 0;
+#pragma unroll 1
+            for (uint32_t c_off = 0; c_off < row_bytes; c_off += kBChunk) {
+                issue();   // goes into the buffer the previous unit used; every lane is past it (__syncwarp below)
+                mbar_wait(s_bar0 + 8u * c_buf, (phase >> c_buf) & 1u);
+                phase ^= 1u << c_buf;
+#pragma unroll
+                for (int v = 0; v < kBChunk / 512; ++v) {
+                    const int lane_cells = (int)N - (int)c_off - v * 512 - lane * 16;
+                    if (lane_cells > 0) {
+                        const uint8_t* cellp = W.buf[c_buf].base + v * 512 + lane * 16;
+                        uint4 vb = *reinterpret_cast<const uint4*>(cellp);
+                        const uint4 vq = *reinterpret_cast<const uint4*>(cellp + kBChunk);
+                        if (lane_cells < 16) mask_tail(vb, lane_cells);
+                        const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w}, wq[4] = {vq.x, vq.y, vq.z, vq.w};
+                        uint32_t eo[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t m = ~(((wb[k] | 0x80808080u) - 0x05050505u) | wb[k]) & 0x80808080u;   // counted
+                            const uint32_t q7 = wq[k] & 0x7f7f7f7fu;
+                            bad |= (~(q7 + 0x7e7e7e7eu) | (q7 + 0x22222222u) | wq[k]) & m;                        // phred < 2 or > 93
+                            const uint32_t x = (wb[k] ^ ow) & 0x7f7f7f7fu;
+                            eo[k] = ~((x + 0x7f7f7f7fu) | wb[k]) & 0x80808080u;                                   // base == o
+                        }
+                        if (eo[0] | eo[1] | eo[2] | eo[3]) {
+                            uint32_t t = (eo[0] >> 7) | (eo[1] >> 6) | (eo[2] >> 5) | (eo[3] >> 4);   // bit (8*byte + word)
+                            do {
+                                int top;
+                                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+                                t ^= 1u << top;
+                                const int cell = ((top & 3) << 2) | (top >> 3);
+                                const uint32_t q = cellp[cell + kBChunk];
+                                G += cs.gfix[min(q, (uint32_t)(kQSlots - 1))];
+                            } while (t);
+                        }
+                    }
+                }
+                __syncwarp();
+                c_buf ^= 1u;
+            }
+            G = __reduce_add_sync(kFull, G);
+            bad = __reduce_or_sync(kFull, bad);
+            const bool pass = bad == 0 && G < kBoundLimit;
+            if (lane == l) {
+                uint32_t* rec = g_out + (size_t)my_site * 32;
+                rec[kWAlt] = 0;
+                // pass: single active allele REF, no EM ran: n_active 1, em_calls 0
+                if (pass) rec[kWInfo] = (1u << 8) | (((my_info >> 16) & 0xffu) | BV_FLAG_LRT_BOUND) << 16;
+                rec[kWState] = pass ? kStateDone : kStateEM;
+                if (!pass) a.list_em[atomicAdd(a.counters + kCntEm, 1u)] = my_site;
+            }
+        }
+    }
+}
+
+// =====================================================================================================================
+// K4: one warp per site of the EM list.
 // =====================================================================================================================
 #ifndef BV_QUAL_WARPS
 #define BV_QUAL_WARPS 24
@@ -88,8 +285,6 @@ struct __align__(128) QualWarp {
 
 struct __align__(128) QualCta {
     double lut[4 * kQStride];
-    uint32_t gfix[kQSlots];      // ceil(2^20 * (log(1-eps(q)) - log(eps(q)/3))): log-likelihood gain of calling a read's
-                                 // own base, fixed point, rounded up (see lrt_bound)
     SiteKernelArgs a;            // kernel parameters for out-of-line device functions (a reference to the
                                  // __global__ parameter itself would force a local-memory copy)
 };
@@ -191,54 +386,6 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site) {
     qmax = __reduce_max_sync(kFull, qmax);
     flags = __reduce_or_sync(kFull, flags);
     return qmin | (qmax << 8) | (flags << 16);
-}
-
-// ---- a bound that decides the LRT without running the EM ---------------------------------------------------------------
-// Site with exactly two active alleles, REF (r) and one other base (o) carried by a few reads -- the signature of
-// sequencing errors.  With L_ij the per-read likelihoods (src/basetype.cpp:61-64) and g_i = log(1-eps_i) - log(eps_i/3):
-//   * every log-likelihood the EM can report for {r,o} is a sum of log(sum_j L_ij f_j) with sum_j f_j <= 1, hence
-//       LL{r,o} <= sum_i log(max_j L_ij) = LL{r} + sum_{reads of o} g_i        (all phred >= 2, so 1-eps > eps/3)
-//     where LL{r} = sum_{reads of r} log(1-eps_i) + sum_{other reads} log(eps_i/3) is the closed form of the
-//     single-allele model (see single_allele_ll);
-//   * LL{r} - LL{o} = sum_{reads of r} g_i - sum_{reads of o} g_i >= 0.56 * depth[r] - G,  G = sum_{reads of o} g_i.
-// So when 2G < 23.9 and depth[r] >= 22, the first LRT round (src/basetype.cpp:151-168) picks subset {r}
-// (chi_r < chi_o) with chi_r = 2 (LL{r,o} - LL{r}) <= 2G < 24 = LRT_THRESHOLD and drops o: the site ends with the
-// single active allele REF, no ALT, whatever the EM would have returned.  Margins (23.9 vs 24, G rounded up in fixed
-// point) dwarf the 1e-12 rounding noise of the reference's sums.
-// Returns G in 2^-20 units, or 0xffffffff when a counted read has phred < 2 or > 93 (bound not applicable).
-constexpr uint32_t kBoundLimit = 12530483u;   // floor(11.95 * 2^20)
-__device__ __noinline__ uint32_t lrt_bound(uint32_t site, uint32_t o_code) {
-    const QualCta& cs = cta_shared();
-    const uint32_t ow = o_code * 0x01010101u;
-    uint32_t G = 0, bad = 0;
-    for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int lane_cells) {
-        uint4 vq = make_uint4(0x02020202u, 0x02020202u, 0x02020202u, 0x02020202u);
-        if (lane_cells > 0) vq = *reinterpret_cast<const uint4*>(cellp + kP2Chunk);
-        const uint32_t wb[4] = {vb.x, vb.y, vb.z, vb.w}, wq[4] = {vq.x, vq.y, vq.z, vq.w};
-        uint32_t eo[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t m = ~(((wb[k] | 0x80808080u) - 0x05050505u) | wb[k]) & 0x80808080u;   // counted
-            const uint32_t q7 = wq[k] & 0x7f7f7f7fu;
-            bad |= (~(q7 + 0x7e7e7e7eu) | (q7 + 0x22222222u) | wq[k]) & m;                        // phred < 2 or > 93
-            const uint32_t x = (wb[k] ^ ow) & 0x7f7f7f7fu;
-            eo[k] = ~((x + 0x7f7f7f7fu) | wb[k]) & 0x80808080u;                                   // base == o
-        }
-        if (eo[0] | eo[1] | eo[2] | eo[3]) {
-            uint32_t t = (eo[0] >> 7) | (eo[1] >> 6) | (eo[2] >> 5) | (eo[3] >> 4);   // bit (8*byte + word)
-            do {
-                int top;
-                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
-                t ^= 1u << top;
-                const int cell = ((top & 3) << 2) | (top >> 3);
-                const uint32_t q = cellp[cell + kP2Chunk];
-                G += cs.gfix[min(q, (uint32_t)(kQSlots - 1))];
-            } while (t);
-        }
-    });
-    G = __reduce_add_sync(kFull, G);
-    bad = __reduce_or_sync(kFull, bad);
-    return bad ? 0xffffffffu : G;
 }
 
 // ---- EM on compact bins (src/algorithm.h:210-255) ----------------------------------------------------------------
@@ -457,7 +604,7 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
     return act | ((uint32_t)n_act << 4) | (em_calls << 8);
 }
 
-// ---- one site in state kStateQual ------------------------------------------------------------------------------------------
+// ---- one site in state kStateEM --------------------------------------------------------------------------------------------
 // Everything here is warp-uniform.  The record (counts, FS of the CVG row, flags) comes from K1 / K2.
 __device__ __noinline__ void qual_site(uint32_t site) {
     QualWarp& W = warp_smem();
@@ -484,19 +631,7 @@ __device__ __noinline__ void qual_site(uint32_t site) {
     const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
     __syncwarp();
 
-    bool bounded = false;
-    if (n_act == 2 && (act & ref_bit)) {
-        // REF plus one minor allele: try to settle the LRT by the bound (see lrt_bound)
-        const int o_code = __ffs(act & ~ref_bit) - 1;
-        const uint32_t d_ref = sel4u(ref_code, d0, d1, d2, d3), d_o = sel4u(o_code, d0, d1, d2, d3);
-        if (d_ref >= 22 && d_o <= 4 && lrt_bound(site, (uint32_t)o_code) < kBoundLimit) {
-            bounded = true;
-            act = ref_bit; n_act = 1;
-            if (lane == 0) W.flag_word |= BV_FLAG_LRT_BOUND;
-            if (lane < 4) W.res_f[lane] = 0.0;
-        }
-    }
-    if (!bounded) {
+    {
         // histogram the row by (base, phred)
         const uint32_t h = build_hist(site);
         const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
@@ -575,18 +710,12 @@ __device__ __noinline__ void qual_site(uint32_t site) {
     __syncwarp();
 }
 
-// Persistent warps; warp w looks at the groups of 32 consecutive sites w, w + W, ...: one coalesced look at the 32
-// state words, then the sites in state kStateQual one after the other.
-__global__ void __launch_bounds__(kQualWarps * 32, 1) bv_qual_kernel(const __grid_constant__ SiteKernelArgs a) {
+// Persistent warps with dynamic work distribution over the EM list.
+__global__ void __launch_bounds__(kQualWarps * 32, 1) bv_em_kernel(const __grid_constant__ SiteKernelArgs a) {
     QualCta& cs = cta_shared();
     QualWarp& W = warp_smem();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) cs.lut[i] = a.lut[i];
-    for (int q = threadIdx.x; q < kQSlots; q += blockDim.x) {
-        // per-read log-likelihood gain of calling the read's own base, fixed point 2^-20, rounded up (lrt_bound)
-        const double g = a.lut[kLutLogMatch * kQStride + q] - a.lut[kLutLogMis * kQStride + q];
-        cs.gfix[q] = (q >= 2 && q <= BV_QUAL_MAX) ? (uint32_t)ceil(g * 1048576.0) + 1u : 0x01000000u;
-    }
     if (threadIdx.x == 0) cs.a = a;
     for (int i = lane; i < kHistWords; i += 32) W.hist[i] = 0;
     if (lane == 0) {
@@ -597,19 +726,14 @@ __global__ void __launch_bounds__(kQualWarps * 32, 1) bv_qual_kernel(const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const uint32_t total_warps = gridDim.x * kQualWarps;
-    const uint32_t n_groups = (a.n_sites + 31u) >> 5;
-    const uint32_t* g_out = reinterpret_cast<const uint32_t*>(a.out);
-#pragma unroll 1
-    for (uint32_t g = blockIdx.x * kQualWarps + warp; g < n_groups; g += total_warps) {
-        const uint32_t s = g * 32u + lane;
-        const uint32_t st = s < a.n_sites ? g_out[(size_t)s * 32 + kWState] : kStateDone;
-        uint32_t todo = __ballot_sync(kFull, st == kStateQual);
-        while (todo) {
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            qual_site(g * 32u + (uint32_t)l);
-        }
+    // the EM list is final (K3 is done); warps take one site at a time: the cost per site varies by an order of magnitude
+    const uint32_t n_em = a.counters[kCntEm];
+    for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(a.counters + kCntEmNext, 1u);
+        i = __shfl_sync(kFull, i, 0);
+        if (i >= n_em) break;
+        qual_site(a.list_em[i]);
     }
 }
 

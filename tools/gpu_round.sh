@@ -15,6 +15,6 @@ timeout 300 python tools/run_kernel.py --config C5 --sites 200000 --launches 5 >
 timeout 300 env BV_KERNEL=ldg python tools/run_kernel.py --config C2 --sites 1000000 --launches 5 > "$O/run_kernel_C2_ldg.log" 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$O/launches.csv" \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > "$O/bench_under_ncu.log" 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:bv_.*_kernel -s 4 -c 3 -f -o "$O/prof_C2" \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:bv_.*_kernel -s 5 -c 4 -f -o "$O/prof_C2" \
     python tools/run_kernel.py --config C2 --sites 1000000 --launches 3 > "$O/ncu_full.log" 2>&1
 tail -3 "$O/pytest_gpu.log"; cat "$O/bench.json"; cat "$O/run_kernel_"*.log
