@@ -94,6 +94,9 @@ struct bv_ctx {
     double* d_logfact = nullptr;
     bv_synth_model* d_model = nullptr;
     bv_scratch dev_scratch;           // bv_tile_run_device
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
     bool has_model = false;
     uint64_t pitch_cap = 0;
     bv_slot* slots = nullptr;
@@ -188,24 +191,30 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
         return BV_OK;
     }
     BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), stream));
+    const bool prof = ctx->profiling;
+    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
     // K1, persistent: one CTA per SM, each warp strides over the sites
     uint32_t grid = (a.n_sites + bv::kCountWarps - 1) / bv::kCountWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
     bv::bv_count_kernel<<<grid, bv::kCountWarps * 32, bv::kCountSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
+    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
     grid = (a.n_sites + 255) / 256;   // grid-stride over K1's work list
     if (grid > (uint32_t)ctx->num_sms * 8u) grid = (uint32_t)ctx->num_sms * 8u;
     bv::bv_scalar_kernel<<<grid, 256, 0, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
+    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));
     // K3 and K4, persistent: each warp strides over groups of 32 sites
     grid = ((a.n_sites + 31) / 32 + bv::kBoundWarps - 1) / bv::kBoundWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
     bv::bv_bound_kernel<<<grid, bv::kBoundWarps * 32, bv::kBoundSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
+    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
     grid = ((a.n_sites + 31) / 32 + bv::kQualWarps - 1) / bv::kQualWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
     bv::bv_em_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
+    if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream)); ctx->ev_valid = true; }
     ctx->launches += 4;
     return BV_OK;
 }
@@ -217,6 +226,25 @@ int bv_version(void) { return BV_VERSION_MAJOR * 1000 + BV_VERSION_MINOR; }
 const char* bv_last_error(const bv_ctx* ctx) { return ctx ? ctx->err : g_err; }
 
 uint64_t bv_launch_count(const bv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int bv_set_profiling(bv_ctx* ctx, int on) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0])
+        for (int i = 0; i < 5; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+    ctx->profiling = on != 0;
+    ctx->ev_valid = false;
+    return BV_OK;
+}
+
+int bv_last_kernel_times(bv_ctx* ctx, float ms[4]) {
+    if (!ctx || !ms) return set_err(ctx, BV_ERR_ARG, "null argument");
+    if (!ctx->ev_valid) return set_err(ctx, BV_ERR_STATE, "no profiled tile yet (bv_set_profiling)");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    for (int i = 0; i < 4; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    return BV_OK;
+}
 
 static int upload_tables(bv_ctx* ctx) {
     // per-phred likelihood table: eps = exp((q) * MLN10TO10) with glibc exp, exactly the reference's expression
@@ -313,6 +341,7 @@ void bv_destroy(bv_ctx* ctx) {
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model);
     scratch_free(ctx->dev_scratch);
+    for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     delete ctx;
 }
 

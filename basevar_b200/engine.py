@@ -56,6 +56,17 @@ class BaseTypeEngine:
     def launch_count(self):
         return int(self.lib.bv_launch_count(self._ctx))
 
+    KERNEL_NAMES = ("bv_count_kernel", "bv_scalar_kernel", "bv_bound_kernel", "bv_em_kernel")
+
+    def set_profiling(self, on=True):
+        self._check(self.lib.bv_set_profiling(self._ctx, int(on)), "bv_set_profiling")
+
+    def last_kernel_times(self):
+        """Durations (ms) of the four kernels of the most recent tile (profiling must be on); waits for it."""
+        ms = (C.c_float * 4)()
+        self._check(self.lib.bv_last_kernel_times(self._ctx, ms), "bv_last_kernel_times")
+        return dict(zip(self.KERNEL_NAMES, (float(x) for x in ms)))
+
     # -- tiles from host memory --------------------------------------------------------------------
     def call_host(self, base, qual, strand, ref_base, n_samples, out=None):
         """Run planes [S][pitch] (numpy uint8, ideally pinned) through the slot pipeline.

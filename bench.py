@@ -5,11 +5,13 @@
 
 metric  : sample-sites/s of the BaseType core (likelihoods, EM, LRT, QUAL, strand-bias Fisher)
 workload: BASELINE.json configs[1] = synthetic 1,000 samples x 1 Mb at 0.1x ("C2"), per GPU.
-step    : one pass of the site kernel over the whole per-GPU workload (S sites x N samples).
-value   : whole-job sample-sites/s with the planes resident in HBM (kernel only, CUDA events, max over ranks).
+step    : one pass of the basetype core (kernels K1 count, K2 scalar, K3 bound, K4 EM) over the whole per-GPU workload
+          (S sites x N samples).
+value   : whole-job sample-sites/s with the planes resident in HBM (kernels only, CUDA events, max over ranks).
 e2e     : the same metric through the C ABI with HOST buffers: pinned planes -> bv_tile_submit (H2D, kernel, D2H
           of the 128-byte records) -> bv_tile_wait, tiles pipelined over 3 streams; copies inside the timed region.
-roofline: algorithmic bytes S*(3N+128) per launch / average launch time, against MEASURED_PEAKS.json hbm_gbs.
+roofline: algorithmic bytes S*(3N+128) per step / average step time (all four kernels), against MEASURED_PEAKS.json
+          hbm_gbs; the per-kernel durations are measured live with CUDA events between the kernels (bv_set_profiling).
 cpu_baseline: the UNMODIFIED reference (oracle/_ref/libbvref.so: BaseType ctor + lrt() + strand_bias) on the
           host cores, on a bounded prefix of the same workload (rank 0, N=1 only).
 Multi-GPU: sites are sharded by contiguous region, one process per GPU, no collective on the data path
@@ -38,6 +40,19 @@ def load_peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(config, n_samples, sites):
+    """DRAM bytes (read + write) of one step from the committed `ncu --set full` capture of this workload, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    e = t.get(config)
+    if not e or e.get("n_samples") != n_samples or e.get("sites") != sites:
+        return None
+    return e["dram_bytes_per_step"]
 
 
 class ClockSampler:
@@ -216,6 +231,16 @@ def main():
     total_ms_max = float(t.item())
     value = world * S * n_samples * args.steps / (total_ms_max * 1e-3)
 
+    # ---- per-kernel durations, live (CUDA events between the four kernels, recorded by the library) ------------
+    eng.set_profiling(True)
+    ksum = None
+    for _ in range(args.steps):
+        step()
+        t_k = eng.last_kernel_times()
+        ksum = t_k if ksum is None else {k: ksum[k] + v for k, v in t_k.items()}
+    eng.set_profiling(False)
+    kernel_ms = {k: v / args.steps for k, v in ksum.items()}
+
     # ---- end to end through the C ABI with host buffers --------------------------------------------------------
     h_planes = [torch.empty((S, pitch), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
     h_ref = torch.empty(S, dtype=torch.uint8, pin_memory=True)
@@ -262,8 +287,15 @@ def main():
                        "l2": "inputs (3 planes, %.2f GB) larger than L2; no flush needed" % (3 * S * pitch / 1e9),
                        "parallelism": f"region-sharded x{world}, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                         "kernel": "bv_site_kernel", "avg_launch_ms": avg_ms},
+                         "traffic": load_traffic(args.config, n_samples, S), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel": "the step's four kernels together (K1 bv_count_kernel dominates)", "avg_launch_ms": avg_ms,
+                         "kernel_ms": kernel_ms,
+                         # K1 alone moves 2 of the 3 planes (base + strand; the qual plane is read only where the result
+                         # depends on it): its own bytes / its own time
+                         "k1_bytes": S * (2 * n_samples + 128),
+                         "k1_achieved": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9,
+                         "k1_frac": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(3 * S * pitch + S), "d2h_bytes_per_step": int(S * 128),
                     "ms_per_step": 1e3 * float(t.item()), "tile_sites": tile_sites, "slots": 3, "records_match_device_path": same},
             "gpu_launches": int(launches + e2e_launches),

@@ -8,8 +8,8 @@
  *   ----------------------------------------------------------  ---------------------------------
  *   struct BatchInfo                    src/basetype.h:25-43     bv_tile (packed SoA planes)
  *   BaseType::BaseType(BatchInfo*,af)   src/basetype.h:105       bv_tile_submit / bv_tile_run_device
- *                                       src/basetype.cpp:22-72   (site histogram kernel stage)
- *   BaseType::lrt()                     src/basetype.h:117-118   same call (EM + LRT + QUAL stage)
+ *                                       src/basetype.cpp:22-72   (count kernel: depths, strand table)
+ *   BaseType::lrt()                     src/basetype.h:117-118   same call (scalar / bound / EM kernels)
  *                                       src/basetype.cpp:130-199
  *   EM / e_step / m_step                src/algorithm.h:148-255  same call
  *   chi2_test -> kf_gammaq              src/algorithm.h:44-46    same call
@@ -153,6 +153,10 @@ void        bv_destroy(bv_ctx* ctx);
 const char* bv_last_error(const bv_ctx* ctx);                  /* ctx may be NULL: last global error */
 int         bv_set_params(bv_ctx* ctx, const bv_params* params); /* change min_af / em mode; capacities fixed */
 uint64_t    bv_launch_count(const bv_ctx* ctx);                /* kernels launched by this context so far */
+/* Instrumentation: with profiling on, every tile records CUDA events between its kernels (K1 count, K2 scalar,
+ * K3 bound, K4 EM); bv_last_kernel_times() waits for the most recent tile and returns their durations in ms. */
+int         bv_set_profiling(bv_ctx* ctx, int on);
+int         bv_last_kernel_times(bv_ctx* ctx, float ms[4]);
 
 /* ---- tile pipeline (replaces: BatchInfo -> BaseType ctor -> lrt() -> strand_bias per site) ------ */
 /* Asynchronous.  Host tiles are copied H2D on the slot's stream (pinned memory makes the copy
