@@ -39,6 +39,32 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_LIB = os.path.join(HERE, "libbasevar_b200_host.so")
+HOST_SRC = [os.path.join(HERE, "host", "bv_host.cpp")]
+HOST_DEPS = HOST_SRC + [os.path.join(HERE, "host", "bv_host.hpp"), os.path.join(HERE, "..", "include", "basevar_b200.h")]
+ROOT = os.path.dirname(HERE)
+CPP_TESTS = {"test_host_cpu": [], "test_host_gpu": ["-ldl"]}
+
+
+def build_host(force=False):
+    """The C++ host layer (g++) over the C ABI, and its test programs under tests/cpp/bin/."""
+    build(force=False)
+    cxx = os.environ.get("CXX", "g++")
+    if force or not os.path.exists(HOST_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB) for d in HOST_DEPS + [LIB]):
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-o", HOST_LIB] + HOST_SRC +
+                              ["-L" + HERE, "-lbasevar_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    bindir = os.path.join(ROOT, "tests", "cpp", "bin")
+    os.makedirs(bindir, exist_ok=True)
+    for name, extra in CPP_TESTS.items():
+        src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
+        exe = os.path.join(bindir, name)
+        if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(HOST_LIB)):
+            subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-L" + HERE, "-lbasevar_b200_host",
+                                   "-lbasevar_b200", "-Wl,-rpath," + HERE, "-lpthread"] + extra)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host(force="--force" in sys.argv)
     print(LIB)

@@ -162,6 +162,7 @@ def main():
     args = ap.parse_args()
 
     import basevar_b200 as bv
+    from basevar_b200 import shard
     cfg = dict(bv.synth.CONFIGS[args.config])
     n_samples = cfg["n_samples"]
     rank = int(os.environ.get("RANK", "0"))
@@ -196,7 +197,7 @@ def main():
     ref = torch.empty(S, dtype=torch.uint8, device=dev)
     out = torch.empty(S * 128, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
-    eng.synth_fill_device(rank * S, S, n_samples, pitch, base.data_ptr(), qual.data_ptr(), strand.data_ptr(), 0,
+    eng.synth_fill_device(shard.rank_site_range(rank, world, S)[0], S, n_samples, pitch, base.data_ptr(), qual.data_ptr(), strand.data_ptr(), 0,
                           ref.data_ptr(), stream)
     torch.cuda.synchronize()
 
@@ -225,10 +226,7 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     launches = eng.launch_count - launches0
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = shard.max_over_ranks(total_ms, dev)
     value = world * S * n_samples * args.steps / (total_ms_max * 1e-3)
 
     # ---- per-kernel durations, live (CUDA events between the four kernels, recorded by the library) ------------
@@ -260,10 +258,8 @@ def main():
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
     e2e_launches = eng.launch_count - l0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * S * n_samples / float(t.item())
+    e2e_s_max = shard.max_over_ranks(e2e_s, dev)
+    e2e_value = world * S * n_samples / e2e_s_max
     clk = clocks.stop()
 
     # the e2e records must be the very records of the device-resident path
@@ -297,7 +293,7 @@ def main():
                          "k1_achieved": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9,
                          "k1_frac": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(3 * S * pitch + S), "d2h_bytes_per_step": int(S * 128),
-                    "ms_per_step": 1e3 * float(t.item()), "tile_sites": tile_sites, "slots": 3, "records_match_device_path": same},
+                    "ms_per_step": 1e3 * e2e_s_max, "tile_sites": tile_sites, "slots": 3, "records_match_device_path": same},
             "gpu_launches": int(launches + e2e_launches),
             "clocks": clk,
         }

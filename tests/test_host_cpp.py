@@ -1,0 +1,37 @@
+"""The C++ host layer (basevar_b200/host): compiled test programs, run from pytest.
+CPU: packer / encodings / error messages / BaseType getters / strand_bias / region sharding / no-fallback.
+GPU: BaseType + strand_bias mirror vs the oracle and the compiled reference, drop-in constructor, sharded region run."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "bin")
+
+
+@pytest.fixture(scope="module")
+def host_built(built_lib, oracle_lib):
+    from basevar_b200 import build
+    build.build_host()
+    return BIN
+
+
+def _run(exe, *args, env=None):
+    p = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and "ALL OK" in p.stdout, p.stdout[-4000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def test_host_layer_cpu(host_built):
+    import torch
+    env = dict(os.environ)
+    if torch.cuda.is_available():
+        env["BV_EXPECT_GPU"] = "1"
+    _run(os.path.join(host_built, "test_host_cpu"), env=env)
+
+
+@pytest.mark.gpu
+def test_host_layer_gpu(host_built):
+    out = _run(os.path.join(host_built, "test_host_gpu"), ROOT)
+    assert "region sharding" in out and "batch path" in out
