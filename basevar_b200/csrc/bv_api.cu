@@ -193,10 +193,19 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), stream));
     const bool prof = ctx->profiling;
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
-    // K1, persistent: one CTA per SM, each warp strides over the sites
-    uint32_t grid = (a.n_sites + bv::kCountWarps - 1) / bv::kCountWarps;
-    if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
-    bv::bv_count_kernel<<<grid, bv::kCountWarps * 32, bv::kCountSmemBytes, stream>>>(a);
+    // K1, persistent: one CTA per SM, each warp strides over the sites; kernel shape by row length
+    uint32_t grid;
+    if (a.n_samples > (uint32_t)bv::kLongRowSamples) {
+        grid = (a.n_sites + BV_COUNT_WARPS_LONG - 1) / BV_COUNT_WARPS_LONG;
+        if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+        bv::bv_count_kernel<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG><<<grid, BV_COUNT_WARPS_LONG * 32,
+            bv::count_smem_bytes<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>(), stream>>>(a);
+    } else {
+        grid = (a.n_sites + BV_COUNT_WARPS - 1) / BV_COUNT_WARPS;
+        if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+        bv::bv_count_kernel<BV_COUNT_WARPS, BV_COUNT_STAGES><<<grid, BV_COUNT_WARPS * 32,
+            bv::count_smem_bytes<BV_COUNT_WARPS, BV_COUNT_STAGES>(), stream>>>(a);
+    }
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
     grid = (a.n_sites + 255) / 256;   // grid-stride over K1's work list
@@ -295,7 +304,10 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
         ctx->num_sms = prop.multiProcessorCount;
-        if (cudaFuncSetAttribute(bv::bv_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCountSmemBytes) != cudaSuccess ||
+        if (cudaFuncSetAttribute(bv::bv_count_kernel<BV_COUNT_WARPS, BV_COUNT_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)bv::count_smem_bytes<BV_COUNT_WARPS, BV_COUNT_STAGES>()) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_count_kernel<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)bv::count_smem_bytes<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>()) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",

@@ -19,14 +19,23 @@
 
 namespace bv {
 
+// Two shapes of the kernel (warps per CTA x ring depth per warp), chosen by the row length at launch.  Measured on
+// B200 (profiles/r01o_k1_ring_shapes.txt): rows of <= 1,000 samples want many warps (per-site work is short, 32 warps
+// keep the issue slots 82 % busy), rows of 10,000 samples want deeper rings on fewer warps (0.66 ms vs 0.93 ms per
+// 10^9 cells).
 #ifndef BV_COUNT_WARPS
 #define BV_COUNT_WARPS 32
 #endif
 #ifndef BV_COUNT_STAGES
 #define BV_COUNT_STAGES 3
 #endif
-constexpr int kCountWarps = BV_COUNT_WARPS;   // warps per CTA, one CTA per SM
-constexpr int kCountStages = BV_COUNT_STAGES; // ring depth per warp
+#ifndef BV_COUNT_WARPS_LONG
+#define BV_COUNT_WARPS_LONG 16
+#endif
+#ifndef BV_COUNT_STAGES_LONG
+#define BV_COUNT_STAGES_LONG 4
+#endif
+constexpr int kLongRowSamples = 4096;         // rows longer than this use the *_LONG shape
 constexpr int kChunk = 1024;                  // cells per stage and plane: two 16-cell vectors per lane
 constexpr int kSlowBatch = 16;                // one atomicAdd on the list counter per this many sites
 
@@ -35,6 +44,7 @@ struct __align__(128) Stage {                 // one chunk of the base and stran
     uint8_t strand[kChunk];
 };
 
+template <int kCountStages>
 struct __align__(128) CountWarp {
     Stage stage[kCountStages];
     uint32_t nr_cnt[12];                      // counted cells that are not the reference base, [2*base + strand]
@@ -43,8 +53,10 @@ struct __align__(128) CountWarp {
     uint64_t full[kCountStages];
 };
 
-constexpr size_t kCountSmemBytes = (size_t)kCountWarps * sizeof(CountWarp);
-static_assert(kCountSmemBytes <= 232448, "shared memory of the count kernel exceeds 227 KB");
+template <int kCountWarps, int kCountStages>
+constexpr size_t count_smem_bytes() { return (size_t)kCountWarps * sizeof(CountWarp<kCountStages>); }
+static_assert(count_smem_bytes<BV_COUNT_WARPS, BV_COUNT_STAGES>() <= 232448, "shared memory of the count kernel exceeds 227 KB");
+static_assert(count_smem_bytes<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>() <= 232448, "shared memory of the count kernel exceeds 227 KB");
 
 struct ScanAcc {
     uint32_t nref;     // 128 * (# cells holding the reference base)
@@ -68,9 +80,10 @@ __device__ __forceinline__ uint32_t scan_word(uint32_t wb, uint32_t ws, uint32_t
     return m & ~eq;
 }
 
+template <int kCountWarps, int kCountStages>
 __global__ void __launch_bounds__(kCountWarps * 32, 1) bv_count_kernel(const __grid_constant__ SiteKernelArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    CountWarp& W = reinterpret_cast<CountWarp*>(bv_smem_raw)[warp];
+    CountWarp<kCountStages>& W = reinterpret_cast<CountWarp<kCountStages>*>(bv_smem_raw)[warp];
 
     if (lane < 12) W.nr_cnt[lane] = 0;
     if (lane == 0) {

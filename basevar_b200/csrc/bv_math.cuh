@@ -14,6 +14,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "bv_fisher_fast.h"
+
 namespace bv {
 
 // The kernel's hot loop is instruction-cache sensitive (ncu: `no_inst` was the top stall when the kernel was
@@ -87,6 +89,14 @@ __device__ __forceinline__ double lbinom_tab(const double* __restrict__ logfact,
     return __ldg(logfact + n) - __ldg(logfact + k) - __ldg(logfact + (n - k));
 }
 
+struct LogFactTab {   // lgamma(k+1), glibc values tabulated on the host
+    const double* lf;
+    __device__ __forceinline__ double operator()(int k) const { return __ldg(lf + k); }
+};
+struct ExpFn {
+    __device__ __forceinline__ double operator()(double x) const { return nexp(x); }
+};
+
 __device__ __noinline__ double hypergeo_tab(const double* __restrict__ lf, int n11, int n1_, int n_1, int n) {
     return nexp(lbinom_tab(lf, n1_, n11) + lbinom_tab(lf, n - n1_, n_1 - n11) - lbinom_tab(lf, n, n_1));
 }
@@ -122,6 +132,8 @@ __device__ __noinline__ double fisher_two_sided(const double* __restrict__ lf, i
     st.p = hypergeo_tab(lf, n11, n1_, n_1, n);
     double q = st.p;
     if (q == 0.0) return 0.0;
+    // wide supports (deep or dense pileups): bisection + short tail sums instead of a walk over the whole support
+    if (fisher_fast_applicable(lo, hi, q)) return fisher_two_sided_fast(LogFactTab{lf}, ExpFn{}, n11, n1_, n_1, n, lo, hi, q);
     double p, left, right;
     int i, j;
     p = hg_move(lf, st, lo);

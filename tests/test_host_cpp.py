@@ -31,6 +31,13 @@ def test_host_layer_cpu(host_built):
     _run(os.path.join(host_built, "test_host_cpu"), env=env)
 
 
+def test_fast_fisher_matches_the_reference_algorithm(host_built):
+    """csrc/bv_fisher_fast.h (O(log range) two-sided Fisher of the product, compiled for the host) vs the oracle's
+    restatement of kt_fisher_exact on 1.6e5 tables."""
+    out = _run(os.path.join(host_built, "test_fisher_fast"), ROOT)
+    assert "through the fast path" in out
+
+
 @pytest.mark.gpu
 def test_host_layer_gpu(host_built):
     out = _run(os.path.join(host_built, "test_host_gpu"), ROOT)
