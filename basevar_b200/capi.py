@@ -96,6 +96,7 @@ _SIGNATURES = [
     ("bv_last_error", C.c_char_p, [C.c_void_p]),
     ("bv_set_params", C.c_int, [C.c_void_p, C.POINTER(BvParams)]),
     ("bv_launch_count", C.c_uint64, [C.c_void_p]),
+    ("bv_h2d_bytes", C.c_uint64, [C.c_void_p]),
     ("bv_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("bv_last_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("bv_tile_submit", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvTile)]),

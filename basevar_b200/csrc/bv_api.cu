@@ -83,6 +83,8 @@ struct bv_slot {
     bv_site_out* h_out = nullptr;  // pinned
     uint32_t n_sites = 0;
     bool busy = false;
+    const uint8_t* qual_host = nullptr;   // this tile's qual plane is read in place from pinned host memory
+    size_t h2d_bytes = 0;                 // bytes uploaded for this tile by cudaMemcpyAsync
 };
 
 struct bv_ctx {
@@ -94,6 +96,8 @@ struct bv_ctx {
     double* d_logfact = nullptr;
     bv_synth_model* d_model = nullptr;
     bv_scratch dev_scratch;           // bv_tile_run_device
+    bool zero_copy_qual = true;       // BASEVAR_B200_ZERO_COPY_QUAL=0 uploads the whole qual plane instead
+    uint64_t h2d_bytes_total = 0;
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -172,6 +176,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->list_em = sc.d_lists + 2 * (size_t)sc.cap;
     a->counters = sc.d_counters;
     a->pitch = t->pitch;
+    a->qual_pitch = t->pitch;
     a->n_sites = t->n_sites;
     a->n_samples = t->n_samples;
     a->min_af = (double)ctx->prm.min_af;     // float -> double: src/basetype_caller.cpp:122,506
@@ -235,6 +240,7 @@ int bv_version(void) { return BV_VERSION_MAJOR * 1000 + BV_VERSION_MINOR; }
 const char* bv_last_error(const bv_ctx* ctx) { return ctx ? ctx->err : g_err; }
 
 uint64_t bv_launch_count(const bv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t bv_h2d_bytes(const bv_ctx* ctx) { return ctx ? ctx->h2d_bytes_total : 0; }
 
 int bv_set_profiling(bv_ctx* ctx, int on) {
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
@@ -314,6 +320,10 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
                          cudaGetErrorString(cudaGetLastError()));
             break;
         }
+        {
+            const char* z = getenv("BASEVAR_B200_ZERO_COPY_QUAL");
+            if (z && z[0] == '0') ctx->zero_copy_qual = false;
+        }
         rc = upload_tables(ctx);
         if (rc != BV_OK) break;
         ctx->pitch_cap = ((uint64_t)params->max_samples + 15) / 16 * 16;
@@ -385,6 +395,8 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
     if (s.busy) return set_err(ctx, BV_ERR_STATE, "slot %d is busy: call bv_tile_wait first", slot);
     if (tile->n_sites > ctx->prm.max_sites) return set_err(ctx, BV_ERR_ARG, "tile has %u sites > max_sites %u", tile->n_sites, ctx->prm.max_sites);
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    s.qual_host = nullptr;
+    s.h2d_bytes = 0;
     bv_tile dev = *tile;
     if (tile->location == BV_LOC_HOST) {
         if (!tile->base || !tile->qual || !tile->strand || !tile->ref_base) return set_err(ctx, BV_ERR_ARG, "bv_tile: null pointer");
@@ -395,7 +407,19 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
         const size_t plane = (size_t)ctx->prm.max_sites * ctx->pitch_cap;
         uint8_t* d[3] = {s.d_planes, s.d_planes + plane, s.d_planes + 2 * plane};
         const uint8_t* h[3] = {tile->base, tile->qual, tile->strand};
+        // The qual plane is read for the minority of rows whose result depends on base qualities (kernels K3 / K4).
+        // When it lives in pinned host memory the kernels fetch exactly those rows over PCIe themselves (zero copy),
+        // and the plane is not uploaded at all; pageable memory is copied like the other planes.
+        const uint8_t* qual_zero_copy = nullptr;
+        if (ctx->zero_copy_qual && tile->n_sites) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, tile->qual) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                qual_zero_copy = static_cast<const uint8_t*>(at.devicePointer);
+            else
+                cudaGetLastError();   // not registered: a sticky-free error on older runtimes
+        }
         for (int k = 0; k < 3 && tile->n_sites; ++k) {
+            if (k == 1 && qual_zero_copy) continue;
             if (dp == tile->pitch)
                 BV_CUDA(ctx, cudaMemcpyAsync(d[k], h[k], (size_t)tile->n_sites * dp, cudaMemcpyHostToDevice, s.stream));
             else
@@ -403,6 +427,8 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
         }
         if (tile->n_sites)
             BV_CUDA(ctx, cudaMemcpyAsync(s.d_ref, tile->ref_base, tile->n_sites, cudaMemcpyHostToDevice, s.stream));
+        s.qual_host = qual_zero_copy;
+        s.h2d_bytes = (size_t)tile->n_sites * dp * (qual_zero_copy ? 2 : 3) + tile->n_sites;
         dev.base = d[0]; dev.qual = d[1]; dev.strand = d[2]; dev.ref_base = s.d_ref;
         dev.pitch = dp;
         dev.location = BV_LOC_DEVICE;
@@ -410,12 +436,14 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
     bv::SiteKernelArgs a;
     int rc = fill_kernel_args(ctx, &dev, s.d_out, s.scratch, &a);
     if (rc != BV_OK) return rc;
+    if (tile->location == BV_LOC_HOST && s.qual_host) { a.qual = s.qual_host; a.qual_pitch = tile->pitch; }
     rc = launch_site_kernel(ctx, a, s.stream);
     if (rc != BV_OK) return rc;
     if (tile->n_sites)
         BV_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, (size_t)tile->n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
     s.n_sites = tile->n_sites;
     s.busy = true;
+    if (tile->location == BV_LOC_HOST) ctx->h2d_bytes_total += s.h2d_bytes;
     return BV_OK;
 }
 

@@ -61,7 +61,8 @@ struct SiteKernelArgs {
     uint32_t* list_bound;    //   K2 -> K3,
     uint32_t* list_em;       //   K2 and K3 -> K4
     uint32_t* counters;      // [kCntSlow .. kCntEmNext], zeroed before K1
-    uint64_t pitch;
+    uint64_t pitch;          // bytes between rows of the base and strand planes
+    uint64_t qual_pitch;     // bytes between rows of the qual plane (it may live in pinned host memory, see bv_tile_submit)
     uint32_t n_sites;
     uint32_t n_samples;
     double min_af;           // (double)(float)min_af

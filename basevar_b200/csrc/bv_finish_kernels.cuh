@@ -176,11 +176,10 @@ __global__ void __launch_bounds__(kBoundWarps * 32, 1) bv_bound_kernel(const __g
             if (p_valid) {
                 if (lane == 0) {
                     const uint32_t bytes = min((uint32_t)kBChunk, row_bytes - p_off);
-                    const size_t gsrc = (size_t)p_site * pitch + p_off;
                     const uint32_t bar = s_bar0 + 8u * p_buf, dst = s_buf0 + (uint32_t)sizeof(BoundBuf) * p_buf;
                     mbar_expect_tx(bar, 2u * bytes);
-                    bulk_g2s(dst, a.base + gsrc, bytes, bar);
-                    bulk_g2s(dst + (uint32_t)kBChunk, a.qual + gsrc, bytes, bar);
+                    bulk_g2s(dst, a.base + (size_t)p_site * pitch + p_off, bytes, bar);
+                    bulk_g2s(dst + (uint32_t)kBChunk, a.qual + (size_t)p_site * a.qual_pitch + p_off, bytes, bar);
                 }
                 p_buf ^= 1u;
                 p_off += kBChunk;
@@ -315,9 +314,8 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
     const uint32_t N = cs.a.n_samples;
     const uint32_t row_bytes = (N + 15u) & ~15u;
     const uint32_t nchunk = (row_bytes + kP2Chunk - 1) / kP2Chunk;
-    const size_t row = (size_t)site * cs.a.pitch;
-    const uint8_t* gb = cs.a.base + row;
-    const uint8_t* gq = cs.a.qual + row;
+    const uint8_t* gb = cs.a.base + (size_t)site * cs.a.pitch;
+    const uint8_t* gq = cs.a.qual + (size_t)site * cs.a.qual_pitch;
     const uint32_t s_buf0 = smem_u32(&W.p2[0]), s_bar0 = smem_u32(&W.p2bar[0]);
     uint32_t phase = W.p2_phase;
     if (lane == 0) {

@@ -56,6 +56,11 @@ class BaseTypeEngine:
     def launch_count(self):
         return int(self.lib.bv_launch_count(self._ctx))
 
+    @property
+    def h2d_bytes(self):
+        """Bytes uploaded by bv_tile_submit so far (host tiles)."""
+        return int(self.lib.bv_h2d_bytes(self._ctx))
+
     KERNEL_NAMES = ("bv_count_kernel", "bv_scalar_kernel", "bv_bound_kernel", "bv_em_kernel")
 
     def set_profiling(self, on=True):

@@ -153,14 +153,18 @@ void        bv_destroy(bv_ctx* ctx);
 const char* bv_last_error(const bv_ctx* ctx);                  /* ctx may be NULL: last global error */
 int         bv_set_params(bv_ctx* ctx, const bv_params* params); /* change min_af / em mode; capacities fixed */
 uint64_t    bv_launch_count(const bv_ctx* ctx);                /* kernels launched by this context so far */
+uint64_t    bv_h2d_bytes(const bv_ctx* ctx);                   /* bytes uploaded by bv_tile_submit so far (host tiles) */
 /* Instrumentation: with profiling on, every tile records CUDA events between its kernels (K1 count, K2 scalar,
  * K3 bound, K4 EM); bv_last_kernel_times() waits for the most recent tile and returns their durations in ms. */
 int         bv_set_profiling(bv_ctx* ctx, int on);
 int         bv_last_kernel_times(bv_ctx* ctx, float ms[4]);
 
 /* ---- tile pipeline (replaces: BatchInfo -> BaseType ctor -> lrt() -> strand_bias per site) ------ */
-/* Asynchronous.  Host tiles are copied H2D on the slot's stream (pinned memory makes the copy
- * truly asynchronous), the site kernel runs, and the records are copied back to pinned staging. */
+/* Asynchronous.  Host tiles are copied H2D on the slot's stream (pinned memory makes the copy truly
+ * asynchronous), the kernels run, and the records are copied back to pinned staging.  A qual plane in
+ * pinned memory (bv_host_alloc / cudaHostAlloc / cudaHostRegister) is not uploaded: the kernels read the
+ * rows they need (those whose result depends on base qualities, ~10 % at 0.1x) in place over PCIe.
+ * Host planes must stay valid and unchanged until bv_tile_wait() returns. */
 int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile);
 /* Blocks until the slot is done and copies n_sites records to `out` (host memory). */
 int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out);

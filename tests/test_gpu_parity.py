@@ -210,3 +210,27 @@ def test_golden_fixtures_from_the_compiled_reference(engine, path):
         assert len(ie) == 0, f"{os.path.basename(path)} mode {mode}: exact mismatch at {ie[:5]}: got {util.describe(got[ie[0]])} want {util.describe(want[ie[0]])}"
         assert len(fe) == 0, f"{os.path.basename(path)} mode {mode}: tolerance at {fe[:5]}: got {util.describe(got[fe[0]])} want {util.describe(want[fe[0]])}"
         assert len(flips) <= 2
+
+
+def test_pinned_host_planes_zero_copy_qual(engine):
+    """Planes in pinned host memory: the qual plane is not uploaded, K3 / K4 read the rows they need in place over PCIe.
+    Records must be byte-identical with the pageable-memory path (whole qual plane uploaded)."""
+    import torch
+    N, S = 1000, 9000
+    model = bv.synth.make_model(seed=4242, coverage=0.1, variant_frac=0.2, multi_frac=0.3)
+    b, q, s, _, r = bv.synth_fill_host(model, 0, S, N)
+    maf = bv.cli_min_af(0.01, N)
+    engine.set_params(min_af=maf, abs_mode=0)
+    before = engine.h2d_bytes
+    got_pageable = engine.call_host(b, q, s, r, N)
+    up_pageable = engine.h2d_bytes - before
+    pinned = [torch.from_numpy(x).pin_memory() for x in (b, q, s, r)]
+    pb, pq, ps, pr = (t.numpy() for t in pinned)
+    before = engine.h2d_bytes
+    got_pinned = engine.call_host(pb, pq, ps, pr, N)
+    up_pinned = engine.h2d_bytes - before
+    assert got_pinned.tobytes() == got_pageable.tobytes()
+    assert up_pageable == S * (3 * 1008 + 1) and up_pinned == S * (2 * 1008 + 1)
+    want = L.oracle_tile(b, q, s, r, N, maf, 0)
+    _check(got_pinned, want, "pinned / zero-copy qual", max_flips=2)
+    assert ((got_pinned["flags"] & capi.FLAG_LRT_BOUND) != 0).sum() > 100 and (got_pinned["em_calls"] >= 3).sum() > 50
