@@ -45,6 +45,13 @@ SITE_OUT_DTYPE = np.dtype(
 assert SITE_OUT_DTYPE.itemsize == 128
 
 
+# struct bv_call_out (16 bytes), struct bv_group_out (40 bytes)
+CALL_OUT_DTYPE = np.dtype([("site", "<u4"), ("mq_rank_sum", "<i4"), ("read_pos_rank_sum", "<i4"), ("base_q_rank_sum", "<i4")])
+GROUP_OUT_DTYPE = np.dtype([("n_alt", "u1"), ("alt", "u1", (4,)), ("flags", "u1"), ("reserved", "u1", (2,)), ("af", "<f8", (4,))])
+assert CALL_OUT_DTYPE.itemsize == 16 and GROUP_OUT_DTYPE.itemsize == 40
+GROUP_NONE = 255
+
+
 class BvParams(C.Structure):
     _fields_ = [
         ("min_af", C.c_float),
@@ -71,6 +78,10 @@ class BvTile(C.Structure):
         ("location", C.c_int32),
         ("reserved", C.c_int32),
     ]
+
+
+class BvTileAux(C.Structure):
+    _fields_ = [("mapq", C.c_void_p), ("rpr", C.c_void_p), ("rpr_pitch", C.c_uint64)]
 
 
 class BvSynthModel(C.Structure):
@@ -102,6 +113,13 @@ _SIGNATURES = [
     ("bv_tile_submit", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvTile)]),
     ("bv_tile_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("bv_tile_run_device", C.c_int, [C.c_void_p, C.POINTER(BvTile), C.c_void_p, C.c_void_p]),
+    ("bv_last_call_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    ("bv_set_groups", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    ("bv_tile_submit_calls", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvTile), C.POINTER(BvTileAux)]),
+    ("bv_tile_wait_calls", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]),
+    ("bv_tile_run_device_calls", C.c_int, [C.c_void_p, C.POINTER(BvTile), C.POINTER(BvTileAux)] + [C.c_void_p] * 5),
+    ("bv_synth_fill_rpr_device", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    ("bv_synth_fill_rpr_host", C.c_int, [C.POINTER(BvSynthModel), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]),
     ("bv_synth_set_model", C.c_int, [C.c_void_p, C.POINTER(BvSynthModel)]),
     ("bv_synth_fill_device", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64] + [C.c_void_p] * 6),
     ("bv_synth_fill_host", C.c_int, [C.POINTER(BvSynthModel), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64] + [C.c_void_p] * 5),

@@ -15,6 +15,7 @@
 #include "../../include/basevar_b200.h"
 #include "bv_count_kernel.cuh"
 #include "bv_finish_kernels.cuh"
+#include "bv_call_kernels.cuh"
 #include "bv_synth.cuh"
 
 namespace bv {
@@ -59,6 +60,28 @@ __global__ void __launch_bounds__(256) bv_synth_kernel(const bv_synth_model* __r
     }
 }
 
+__global__ void __launch_bounds__(256) bv_synth_rpr_kernel(const bv_synth_model* __restrict__ model, uint64_t site0,
+                                                          uint32_t n_sites, uint32_t n_samples, uint64_t rpr_pitch,
+                                                          uint16_t* rpr) {
+    const uint32_t vec_per_row = (uint32_t)(rpr_pitch >> 3);   // 8 cells (16 bytes) per thread
+    const uint64_t n_units = (uint64_t)n_sites * vec_per_row;
+    for (uint64_t u = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; u < n_units;
+         u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = (uint32_t)(u / vec_per_row);
+        const uint32_t v = (uint32_t)(u - (uint64_t)s * vec_per_row);
+        const SynthSite ss = synth_site(model, site0 + s);
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t i = v * 8 + 2 * k;
+            const uint32_t lo = i < n_samples ? synth_rpr(model, ss, i) : 0u;
+            const uint32_t hi = i + 1 < n_samples ? synth_rpr(model, ss, i + 1) : 0u;
+            w[k] = lo | (hi << 16);
+        }
+        *reinterpret_cast<uint4*>(rpr + (size_t)s * rpr_pitch + (size_t)v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 }  // namespace bv
 
 // ======================================================================================================
@@ -67,7 +90,7 @@ __global__ void __launch_bounds__(256) bv_synth_kernel(const bv_synth_model* __r
 // Scratch of one in-flight tile: work lists and counters (K1 -> K2 -> K3 -> K4) and the EM kernel's spill space.
 // Kernels of different tiles may overlap, so every slot (and the device-resident path) owns one.
 struct bv_scratch {
-    uint32_t* d_lists = nullptr;      // 3 x cap site indices
+    uint32_t* d_lists = nullptr;      // 4 x cap site indices
     uint32_t* d_counters = nullptr;   // 8 x u32
     uint32_t* d_bin_spill = nullptr;
     double* d_lml_spill = nullptr;
@@ -85,6 +108,12 @@ struct bv_slot {
     bool busy = false;
     const uint8_t* qual_host = nullptr;   // this tile's qual plane is read in place from pinned host memory
     size_t h2d_bytes = 0;                 // bytes uploaded for this tile by cudaMemcpyAsync
+    // called sites (bv_tile_submit_calls): the kernels write straight into pinned host memory
+    bv_call_out* h_calls = nullptr;       // [max_sites]
+    bv_group_out* h_groups = nullptr;     // [max_sites * n_groups], allocated by bv_set_groups
+    uint32_t* h_counters = nullptr;       // copy of the scratch counters (kCntCalled = number of calls)
+    uint8_t* d_aux = nullptr;             // mapq | rpr planes of pageable host tiles (allocated on first use)
+    bool with_calls = false;
 };
 
 struct bv_ctx {
@@ -105,6 +134,10 @@ struct bv_ctx {
     uint64_t pitch_cap = 0;
     bv_slot* slots = nullptr;
     uint64_t launches = 0;
+    uint8_t* d_group = nullptr;       // [round16(max_samples)] sample -> population group
+    uint32_t n_groups = 0;
+    cudaEvent_t ev_call[3] = {nullptr, nullptr, nullptr};
+    bool ev_call_valid = false;
 };
 
 static char g_err[512] = "";
@@ -145,7 +178,7 @@ static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
         if (sc.d_lists) BV_CUDA(ctx, cudaFree(sc.d_lists));
         sc.d_lists = nullptr;
         sc.cap = 0;
-        BV_CUDA(ctx, cudaMalloc(&sc.d_lists, 3 * (size_t)n_sites * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_lists, 4 * (size_t)n_sites * sizeof(uint32_t)));
         sc.cap = n_sites;
     }
     return BV_OK;
@@ -175,6 +208,9 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->list_bound = sc.d_lists + sc.cap;
     a->list_em = sc.d_lists + 2 * (size_t)sc.cap;
     a->counters = sc.d_counters;
+    a->list_called = nullptr;   // set_call_args() turns the called-site kernels on
+    a->mapq = nullptr; a->rpr = nullptr; a->aux_pitch = 0; a->rpr_pitch = 0;
+    a->sample_group = nullptr; a->calls = nullptr; a->groups = nullptr; a->n_groups = 0; a->pad0 = 0;
     a->pitch = t->pitch;
     a->qual_pitch = t->pitch;
     a->n_sites = t->n_sites;
@@ -184,6 +220,25 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->lrt_threshold = (double)ctx->prm.lrt_threshold;
     a->em_max_iter = ctx->prm.em_max_iter;
     a->abs_mode = ctx->prm.em_abs_mode;
+    return BV_OK;
+}
+
+// Called-site kernels on: K4 lists the called sites, K5 (rank sums) and K6 (population groups) follow.
+static int set_call_args(bv_ctx* ctx, const bv_tile* t, const bv_tile_aux* aux, bv_scratch& sc, bv_call_out* calls,
+                         bv_group_out* groups, bv::SiteKernelArgs* a) {
+    if (!aux || !aux->mapq || !aux->rpr || !calls) return set_err(ctx, BV_ERR_ARG, "bv_tile_aux: null pointer");
+    if (aux->rpr_pitch % 8 != 0 || aux->rpr_pitch < t->n_samples)
+        return set_err(ctx, BV_ERR_ARG, "bv_tile_aux: rpr_pitch %llu must be a multiple of 8 and >= n_samples %u",
+                       (unsigned long long)aux->rpr_pitch, t->n_samples);
+    if ((((uintptr_t)aux->mapq) | ((uintptr_t)aux->rpr)) & 15)
+        return set_err(ctx, BV_ERR_ARG, "bv_tile_aux: plane pointers must be 16-byte aligned");
+    if (ctx->n_groups && !groups) return set_err(ctx, BV_ERR_ARG, "population groups are set but the group output is null");
+    a->list_called = sc.d_lists + 3 * (size_t)sc.cap;
+    a->mapq = aux->mapq; a->rpr = aux->rpr;
+    a->aux_pitch = t->pitch; a->rpr_pitch = aux->rpr_pitch;
+    a->sample_group = ctx->d_group;
+    a->calls = calls; a->groups = groups;
+    a->n_groups = ctx->n_groups;
     return BV_OK;
 }
 
@@ -230,6 +285,25 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream)); ctx->ev_valid = true; }
     ctx->launches += 4;
+    if (a.list_called) {
+        // K5 / K6: the called sites (a few per mille of the tile at 0.1x); grids sized for the worst case, warps
+        // without work leave at once
+        if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev_call[0], stream));
+        grid = (a.n_sites + bv::kCallWarps - 1) / bv::kCallWarps;
+        if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+        bv::bv_ranksum_kernel<<<grid, bv::kCallWarps * 32, bv::kCallSmemBytes, stream>>>(a);
+        BV_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev_call[1], stream));
+        if (a.n_groups) {
+            grid = (a.n_sites + bv::kQualWarps - 1) / bv::kQualWarps;
+            if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+            bv::bv_group_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
+            BV_CUDA(ctx, cudaGetLastError());
+            ctx->launches += 1;
+        }
+        if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev_call[2], stream)); ctx->ev_call_valid = true; }
+    }
     return BV_OK;
 }
 
@@ -245,10 +319,22 @@ uint64_t bv_h2d_bytes(const bv_ctx* ctx) { return ctx ? ctx->h2d_bytes_total : 0
 int bv_set_profiling(bv_ctx* ctx, int on) {
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (on && !ctx->ev[0])
+    if (on && !ctx->ev[0]) {
         for (int i = 0; i < 5; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+        for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev_call[i]));
+    }
     ctx->profiling = on != 0;
     ctx->ev_valid = false;
+    ctx->ev_call_valid = false;
+    return BV_OK;
+}
+
+int bv_last_call_kernel_times(bv_ctx* ctx, float ms[2]) {
+    if (!ctx || !ms) return set_err(ctx, BV_ERR_ARG, "null argument");
+    if (!ctx->ev_call_valid) return set_err(ctx, BV_ERR_STATE, "no profiled tile with called-site kernels yet");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev_call[2]));
+    for (int i = 0; i < 2; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev_call[i], ctx->ev_call[i + 1]));
     return BV_OK;
 }
 
@@ -315,7 +401,9 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_count_kernel<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)bv::count_smem_bytes<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>()) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess) {
+            cudaFuncSetAttribute(bv::bv_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
                          cudaGetErrorString(cudaGetLastError()));
             break;
@@ -338,6 +426,8 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_ref, params->max_sites);
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_out, (size_t)params->max_sites * sizeof(bv_site_out));
                 if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_out, (size_t)params->max_sites * sizeof(bv_site_out), cudaHostAllocDefault);
+                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_calls, (size_t)params->max_sites * sizeof(bv_call_out), cudaHostAllocMapped);
+                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault);
                 if (ce != cudaSuccess) rc = set_err(nullptr, BV_ERR_CUDA, "slot allocation failed: %s", cudaGetErrorString(ce));
                 else rc = scratch_reserve(ctx, s.scratch, params->max_sites);
             }
@@ -358,12 +448,17 @@ void bv_destroy(bv_ctx* ctx) {
             cudaFree(s.d_planes); cudaFree(s.d_ref); cudaFree(s.d_out);
             scratch_free(s.scratch);
             if (s.h_out) cudaFreeHost(s.h_out);
+            if (s.h_calls) cudaFreeHost(s.h_calls);
+            if (s.h_groups) cudaFreeHost(s.h_groups);
+            if (s.h_counters) cudaFreeHost(s.h_counters);
+            cudaFree(s.d_aux);
         }
         delete[] ctx->slots;
     }
-    cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model);
+    cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model); cudaFree(ctx->d_group);
     scratch_free(ctx->dev_scratch);
     for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 3; ++i) if (ctx->ev_call[i]) cudaEventDestroy(ctx->ev_call[i]);
     delete ctx;
 }
 
@@ -387,7 +482,74 @@ int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, voi
     return launch_site_kernel(ctx, a, (cudaStream_t)stream);
 }
 
-int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
+int bv_tile_run_device_calls(bv_ctx* ctx, const bv_tile* tile, const bv_tile_aux* aux, bv_site_out* d_out,
+                             bv_call_out* d_calls, bv_group_out* d_groups, uint32_t* d_n_calls, void* stream) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (tile && tile->location != BV_LOC_DEVICE) return set_err(ctx, BV_ERR_ARG, "bv_tile_run_device_calls: tile must be device resident");
+    if (!d_n_calls) return set_err(ctx, BV_ERR_ARG, "bv_tile_run_device_calls: null d_n_calls");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    bv::SiteKernelArgs a;
+    int rc = fill_kernel_args(ctx, tile, d_out, ctx->dev_scratch, &a);
+    if (rc != BV_OK) return rc;
+    rc = set_call_args(ctx, tile, aux, ctx->dev_scratch, d_calls, d_groups, &a);
+    if (rc != BV_OK) return rc;
+    if (a.n_sites == 0 || a.n_samples == 0) {
+        BV_CUDA(ctx, cudaMemsetAsync(d_n_calls, 0, sizeof(uint32_t), (cudaStream_t)stream));
+        return launch_site_kernel(ctx, a, (cudaStream_t)stream);
+    }
+    rc = launch_site_kernel(ctx, a, (cudaStream_t)stream);
+    if (rc != BV_OK) return rc;
+    BV_CUDA(ctx, cudaMemcpyAsync(d_n_calls, a.counters + bv::kCntCalled, sizeof(uint32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return BV_OK;
+}
+
+int bv_set_groups(bv_ctx* ctx, const uint8_t* sample_group, uint32_t n_samples, uint32_t n_groups) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (n_groups > BV_MAX_GROUPS) return set_err(ctx, BV_ERR_ARG, "bv_set_groups: more than %d groups", BV_MAX_GROUPS);
+    if (n_groups && (!sample_group || n_samples > ctx->prm.max_samples))
+        return set_err(ctx, BV_ERR_ARG, "bv_set_groups: bad sample_group / n_samples");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; ctx->slots && i < ctx->prm.n_slots; ++i)
+        if (ctx->slots[i].busy) return set_err(ctx, BV_ERR_STATE, "bv_set_groups: slot %u is busy", i);
+    for (uint32_t i = 0; ctx->slots && i < ctx->prm.n_slots; ++i) {
+        bv_slot& s = ctx->slots[i];
+        if (s.h_groups) { BV_CUDA(ctx, cudaFreeHost(s.h_groups)); s.h_groups = nullptr; }
+        if (n_groups)
+            BV_CUDA(ctx, cudaHostAlloc(&s.h_groups, (size_t)ctx->prm.max_sites * n_groups * sizeof(bv_group_out), cudaHostAllocMapped));
+    }
+    ctx->n_groups = 0;
+    if (n_groups == 0) return BV_OK;
+    const size_t padded = ((size_t)ctx->prm.max_samples + 15) / 16 * 16;
+    if (!ctx->d_group) BV_CUDA(ctx, cudaMalloc(&ctx->d_group, padded));
+    uint8_t* tmp = (uint8_t*)malloc(padded);
+    if (!tmp) return set_err(ctx, BV_ERR_NOMEM, "out of host memory");
+    memset(tmp, BV_GROUP_NONE, padded);
+    for (uint32_t i = 0; i < n_samples; ++i) tmp[i] = sample_group[i] < n_groups ? sample_group[i] : (uint8_t)BV_GROUP_NONE;
+    cudaError_t e = cudaMemcpy(ctx->d_group, tmp, padded, cudaMemcpyHostToDevice);
+    free(tmp);
+    BV_CUDA(ctx, e);
+    ctx->n_groups = n_groups;
+    return BV_OK;
+}
+
+static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv_tile_aux* aux, bool with_calls);
+
+int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) { return tile_submit_impl(ctx, slot, tile, nullptr, false); }
+
+int bv_tile_submit_calls(bv_ctx* ctx, int slot, const bv_tile* tile, const bv_tile_aux* aux) {
+    if (!aux) return set_err(ctx, BV_ERR_ARG, "bv_tile_submit_calls: null aux");
+    return tile_submit_impl(ctx, slot, tile, aux, true);
+}
+
+// pinned (or otherwise device-accessible) host memory: the pointer the kernels can use, else null
+static const void* host_device_pointer(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    cudaGetLastError();   // not registered: a sticky-free error on older runtimes
+    return nullptr;
+}
+
+static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv_tile_aux* aux, bool with_calls) {
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
     if (!tile) return set_err(ctx, BV_ERR_ARG, "null tile");
@@ -411,13 +573,7 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
         // When it lives in pinned host memory the kernels fetch exactly those rows over PCIe themselves (zero copy),
         // and the plane is not uploaded at all; pageable memory is copied like the other planes.
         const uint8_t* qual_zero_copy = nullptr;
-        if (ctx->zero_copy_qual && tile->n_sites) {
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, tile->qual) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-                qual_zero_copy = static_cast<const uint8_t*>(at.devicePointer);
-            else
-                cudaGetLastError();   // not registered: a sticky-free error on older runtimes
-        }
+        if (ctx->zero_copy_qual && tile->n_sites) qual_zero_copy = static_cast<const uint8_t*>(host_device_pointer(tile->qual));
         for (int k = 0; k < 3 && tile->n_sites; ++k) {
             if (k == 1 && qual_zero_copy) continue;
             if (dp == tile->pitch)
@@ -437,10 +593,43 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile) {
     int rc = fill_kernel_args(ctx, &dev, s.d_out, s.scratch, &a);
     if (rc != BV_OK) return rc;
     if (tile->location == BV_LOC_HOST && s.qual_host) { a.qual = s.qual_host; a.qual_pitch = tile->pitch; }
+    if (with_calls) {
+        bv_tile_aux dev_aux = *aux;
+        if (tile->location == BV_LOC_HOST && tile->n_sites) {
+            // the aux planes are read for the called rows only: in place when pinned, else uploaded whole
+            const uint8_t* zm = static_cast<const uint8_t*>(host_device_pointer(aux->mapq));
+            const uint16_t* zr = static_cast<const uint16_t*>(host_device_pointer(aux->rpr));
+            if (aux->rpr_pitch % 8 != 0 || aux->rpr_pitch < tile->n_samples) return set_err(ctx, BV_ERR_ARG, "bv_tile_aux: bad rpr_pitch");
+            if (zm && zr) {
+                dev_aux.mapq = zm; dev_aux.rpr = zr;
+                rc = set_call_args(ctx, &dev, &dev_aux, s.scratch, s.h_calls, s.h_groups, &a);
+                a.aux_pitch = tile->pitch;
+            } else {
+                const size_t plane = (size_t)ctx->prm.max_sites * ctx->pitch_cap;
+                if (!s.d_aux) BV_CUDA(ctx, cudaMalloc(&s.d_aux, 3 * plane));
+                const uint64_t dp = dev.pitch;
+                BV_CUDA(ctx, cudaMemcpy2DAsync(s.d_aux, dp, aux->mapq, tile->pitch, dp, tile->n_sites, cudaMemcpyHostToDevice, s.stream));
+                BV_CUDA(ctx, cudaMemcpy2DAsync(s.d_aux + plane, 2 * dp, aux->rpr, 2 * aux->rpr_pitch, 2 * (size_t)tile->n_samples, tile->n_sites,
+                                               cudaMemcpyHostToDevice, s.stream));
+                s.h2d_bytes += (size_t)tile->n_sites * (dp + 2 * (size_t)tile->n_samples);
+                dev_aux.mapq = s.d_aux; dev_aux.rpr = reinterpret_cast<const uint16_t*>(s.d_aux + plane); dev_aux.rpr_pitch = dp;
+                rc = set_call_args(ctx, &dev, &dev_aux, s.scratch, s.h_calls, s.h_groups, &a);
+            }
+        } else {
+            rc = set_call_args(ctx, &dev, &dev_aux, s.scratch, s.h_calls, s.h_groups, &a);
+        }
+        if (rc != BV_OK) return rc;
+    }
     rc = launch_site_kernel(ctx, a, s.stream);
     if (rc != BV_OK) return rc;
     if (tile->n_sites)
         BV_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, (size_t)tile->n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
+    if (with_calls) {
+        s.h_counters[bv::kCntCalled] = 0;
+        if (tile->n_sites && tile->n_samples)
+            BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    }
+    s.with_calls = with_calls;
     s.n_sites = tile->n_sites;
     s.busy = true;
     if (tile->location == BV_LOC_HOST) ctx->h2d_bytes_total += s.h2d_bytes;
@@ -457,6 +646,50 @@ int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out) {
     s.busy = false;
     BV_CUDA(ctx, e);
     if (out && s.n_sites) memcpy(out, s.h_out, (size_t)s.n_sites * sizeof(bv_site_out));
+    return BV_OK;
+}
+
+int bv_tile_wait_calls(bv_ctx* ctx, int slot, bv_site_out* out, bv_call_out* calls, uint32_t max_calls,
+                       uint32_t* n_calls, bv_group_out* groups) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
+    if (!n_calls) return set_err(ctx, BV_ERR_ARG, "bv_tile_wait_calls: null n_calls");
+    bv_slot& s = ctx->slots[slot];
+    if (s.busy && !s.with_calls) return set_err(ctx, BV_ERR_STATE, "slot %d was submitted without called-site kernels", slot);
+    int rc = bv_tile_wait(ctx, slot, out);
+    if (rc != BV_OK) return rc;
+    const uint32_t n = s.h_counters[bv::kCntCalled];
+    *n_calls = n;
+    if (n > max_calls) return set_err(ctx, BV_ERR_ARG, "tile has %u called sites > max_calls %u", n, max_calls);
+    if (n && calls) memcpy(calls, s.h_calls, (size_t)n * sizeof(bv_call_out));
+    if (n && groups && ctx->n_groups && s.h_groups) memcpy(groups, s.h_groups, (size_t)n * ctx->n_groups * sizeof(bv_group_out));
+    return BV_OK;
+}
+
+int bv_synth_fill_rpr_device(bv_ctx* ctx, uint64_t site0, uint32_t n_sites, uint32_t n_samples, uint64_t rpr_pitch,
+                             uint16_t* d_rpr, void* stream) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (!ctx->has_model) return set_err(ctx, BV_ERR_STATE, "bv_synth_set_model was not called");
+    if (!d_rpr || rpr_pitch % 8 != 0 || rpr_pitch < n_samples) return set_err(ctx, BV_ERR_ARG, "bad rpr plane / pitch");
+    if (n_sites == 0) return BV_OK;
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t units = (uint64_t)n_sites * (rpr_pitch >> 3);
+    uint64_t blocks = (units + 255) / 256;
+    const uint64_t cap = (uint64_t)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    bv::bv_synth_rpr_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ctx->d_model, site0, n_sites, n_samples, rpr_pitch, d_rpr);
+    BV_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return BV_OK;
+}
+
+int bv_synth_fill_rpr_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
+                           uint64_t rpr_pitch, uint16_t* rpr) {
+    if (!model || !rpr || rpr_pitch < n_samples) return set_err(nullptr, BV_ERR_ARG, "bad argument");
+    for (uint32_t s = 0; s < n_sites; ++s) {
+        const bv::SynthSite ss = bv::synth_site(model, site0 + s);
+        for (uint64_t i = 0; i < rpr_pitch; ++i) rpr[(size_t)s * rpr_pitch + i] = i < n_samples ? bv::synth_rpr(model, ss, i) : 0;
+    }
     return BV_OK;
 }
 

@@ -43,6 +43,7 @@ constexpr uint32_t kStateBound = 2;          // result depends on base qualities
 constexpr uint32_t kStateEM = 3;             // result depends on base qualities; K4 runs EM + LRT
 
 constexpr int kCntSlow = 0, kCntBound = 1, kCntEm = 2, kCntEmNext = 3;   // SiteKernelArgs::counters
+constexpr int kCntCalled = 4, kCntGroupNext = 5;                          // called sites (K4 -> K5, K6)
 
 // word indices of bv_site_out seen as 32 x u32
 constexpr int kWDepth = 0, kWOther = 4, kWState = 5, kWFwd = 6, kWRev = 10, kWAlt = 14, kWInfo = 15;
@@ -60,7 +61,18 @@ struct SiteKernelArgs {
     uint32_t* list_slow;     // work lists (site indices), each with room for n_sites entries: K1 -> K2,
     uint32_t* list_bound;    //   K2 -> K3,
     uint32_t* list_em;       //   K2 and K3 -> K4
-    uint32_t* counters;      // [kCntSlow .. kCntEmNext], zeroed before K1
+    uint32_t* counters;      // [kCntSlow .. kCntGroupNext], zeroed before K1
+    // called sites (n_alt > 0): rank sums (K5) and population-group frequencies (K6); all null / 0 when not asked for
+    uint32_t* list_called;   // K4 -> K5, K6: site indices, room for n_sites entries
+    const uint8_t* mapq;     // [n_sites][aux_pitch]
+    const uint16_t* rpr;     // [n_sites][rpr_pitch] (elements)
+    uint64_t aux_pitch;
+    uint64_t rpr_pitch;
+    const uint8_t* sample_group;   // [round16(n_samples)] group index per sample, BV_GROUP_NONE padding
+    bv_call_out* calls;      // [n called sites], entry k belongs to list_called[k]
+    bv_group_out* groups;    // [n called sites][n_groups]
+    uint32_t n_groups;
+    uint32_t pad0;
     uint64_t pitch;          // bytes between rows of the base and strand planes
     uint64_t qual_pitch;     // bytes between rows of the qual plane (it may live in pinned host memory, see bv_tile_submit)
     uint32_t n_sites;

@@ -304,8 +304,8 @@ __device__ __forceinline__ uint32_t bin_qual(uint32_t p) { return (p >> 22) & 0x
 __device__ __forceinline__ uint32_t bin_count(uint32_t p) { return p & 0x3fffffu; }
 
 // ---- the row's base + qual chunks, fetched (L2 / HBM) into the warp's two buffers ---------------------------------------
-// f(cellp, vb, lane_cells): cellp points at this lane's 16 base cells in shared memory (quals at cellp + kP2Chunk), vb
-// holds them with padding cells masked to 'N'.
+// f(cellp, vb, lane_cells, cell0): cellp points at this lane's 16 base cells in shared memory (quals at cellp + kP2Chunk),
+// vb holds them with padding cells masked to 'N', cell0 is the sample index of the first of them.
 template <class F>
 __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
     QualWarp& W = warp_smem();
@@ -342,7 +342,7 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
         uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
         if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(cellp);
         if (lane_cells < 16) mask_tail(vb, lane_cells);
-        f(cellp, vb, lane_cells);
+        f(cellp, vb, lane_cells, c * kP2Chunk + lane * 16);
         __syncwarp();
     }
     if (lane == 0) W.p2_phase = phase;
@@ -351,15 +351,26 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
 // (base, phred) histogram of the covered cells of one row into W.hist
 // (BaseType::BaseType, src/basetype.cpp:45-71: one likelihood row per counted read, a function of base and phred only).
 // Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
-__device__ __noinline__ uint32_t build_hist(uint32_t site) {
+// grp != nullptr: only the samples of population group g are counted (__get_group_batchinfo,
+// src/basetype_caller.cpp:781-797); grp[] is padded with BV_GROUP_NONE to a multiple of 16 entries.
+__device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, uint32_t g) {
     QualWarp& W = warp_smem();
     uint32_t qmin = 0xffu, qmax = 0, flags = 0;
-    for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int) {
+    const uint32_t gw = g * 0x01010101u;
+    for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int lane_cells, uint32_t cell0) {
         // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
-        const uint32_t n0 = (((vb.x | 0x80808080u) - 0x05050505u) | vb.x) & 0x80808080u;
-        const uint32_t n1 = (((vb.y | 0x80808080u) - 0x05050505u) | vb.y) & 0x80808080u;
-        const uint32_t n2 = (((vb.z | 0x80808080u) - 0x05050505u) | vb.z) & 0x80808080u;
-        const uint32_t n3 = (((vb.w | 0x80808080u) - 0x05050505u) | vb.w) & 0x80808080u;
+        uint32_t n0 = (((vb.x | 0x80808080u) - 0x05050505u) | vb.x) & 0x80808080u;
+        uint32_t n1 = (((vb.y | 0x80808080u) - 0x05050505u) | vb.y) & 0x80808080u;
+        uint32_t n2 = (((vb.z | 0x80808080u) - 0x05050505u) | vb.z) & 0x80808080u;
+        uint32_t n3 = (((vb.w | 0x80808080u) - 0x05050505u) | vb.w) & 0x80808080u;
+        if (grp != nullptr && lane_cells > 0) {   // cells of other groups are not counted (byte != g  =>  bit 7 set)
+            const uint4 vg = __ldg(reinterpret_cast<const uint4*>(grp + cell0));
+            uint32_t x;
+            x = vg.x ^ gw; n0 |= (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+            x = vg.y ^ gw; n1 |= (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+            x = vg.z ^ gw; n2 |= (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+            x = vg.w ^ gw; n3 |= (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+        }
         uint32_t t = ((n0 >> 7) | (n1 >> 6) | (n2 >> 5) | (n3 >> 4)) ^ 0x0f0f0f0fu;
         // warp-uniform trip count, lanes that run out are predicated off: the warp never splits
         const int n = (int)__reduce_max_sync(kFull, (uint32_t)__popc(t));
@@ -477,11 +488,16 @@ __device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, in
     return ll;
 }
 
-// position of the k-th (k >= 0) set bit of a 4-bit mask
-__device__ __forceinline__ int nth_set_bit(uint32_t mask, int k) {
+// The k-th (k >= 0) active base of an ORDERED base list: `order` packs the list two bits per position (position 0 in
+// bits 0-1), `mask` says which alleles are active.  BaseType::lrt() passes A,C,G,T (kOrderACGT); the population-group
+// calls pass [REF, ALT...] (src/basetype_caller.cpp:750-753), and the order decides which subset wins a tie and which
+// base is dropped first (src/external/combinations.h:19-84).
+constexpr uint32_t kOrderACGT = 0xE4u;
+__device__ __forceinline__ int nth_active(uint32_t order, uint32_t mask, int k) {
     int pos = -1;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int p = 0; p < 4; ++p) {
+        const int b = (int)((order >> (2 * p)) & 3u);
         if (mask & (1u << b)) {
             if (k == 0 && pos < 0) pos = b;
             --k;
@@ -494,7 +510,7 @@ __device__ __forceinline__ int nth_set_bit(uint32_t mask, int k) {
 // (src/basetype.cpp:144-168).  In: the row's histogram in W.hist, phred range, depths in W.rec.depth[], active set.
 // Out: W.res_f / W.res_chi and the return value act | n_act << 4 | em_calls << 8.  The warp-uniform model state lives
 // in shared memory (W.emf / W.best_f / W.res_f), not in registers that would have to survive the calls into em_bins.
-__device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_t act) {
+__device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_t act, uint32_t order) {
     QualWarp& W = warp_smem();
     const QualCta& cs = cta_shared();
     const int lane = threadIdx.x & 31;
@@ -548,7 +564,7 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
         uint32_t best_set = 0;
 #pragma unroll 1
         for (int i = 0; i <= n; ++i) {
-            const uint32_t sub = act & ~(1u << nth_set_bit(act, n - i));
+            const uint32_t sub = act & ~(1u << nth_active(order, act, n - i));
             __syncwarp();
             if (lane < 4) W.emf[lane] = (sub >> lane & 1u) ? (double)W.rec.depth[lane] / dtot : 0.0;
             __syncwarp();
@@ -631,12 +647,12 @@ __device__ __noinline__ void qual_site(uint32_t site) {
 
     {
         // histogram the row by (base, phred)
-        const uint32_t h = build_hist(site);
+        const uint32_t h = build_hist(site, nullptr, 0);
         const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
         if (lane == 0) W.flag_word |= h >> 16;
         __syncwarp();
         if (n_act >= 2) {
-            const uint32_t r = lrt_multi(qmin, qmax, act);
+            const uint32_t r = lrt_multi(qmin, qmax, act, kOrderACGT);
             act = r & 0xfu; n_act = (int)((r >> 4) & 0xfu); em_calls = r >> 8;
             chi = W.res_chi;
         } else {
@@ -702,6 +718,8 @@ __device__ __noinline__ void qual_site(uint32_t site) {
         r.qual = qual;
         r.chi2 = chi;
         r.fs_vcf = fs_vcf;
+        // called sites go on to the rank-sum / population-group kernels (bv_call_kernels.cuh)
+        if (n_alt && cs.a.list_called) cs.a.list_called[atomicAdd(cs.a.counters + kCntCalled, 1u)] = site;
     }
     __syncwarp();
     if (lane < 8) reinterpret_cast<uint4*>(cs.a.out + site)[lane] = reinterpret_cast<const uint4*>(&W.rec)[lane];

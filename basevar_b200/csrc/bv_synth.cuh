@@ -77,4 +77,13 @@ BV_HD SynthCell synth_cell(const bv_synth_model* m, const SynthSite& s, uint64_t
     return c;
 }
 
+// read position rank of a cell (BatchInfo::base_pos_ranks): 1..35 for covered cells, 0 otherwise
+BV_HD uint16_t synth_rpr(const bv_synth_model* m, const SynthSite& s, uint64_t sample) {
+    const uint64_t k1 = mix64(s.h + (sample + 1) * 0xD1B54A32D192ED03ull);
+    if ((uint32_t)k1 >= m->cov_thr) return 0;
+    const uint64_t k2 = mix64(k1 ^ 0xA0761D6478BD642Full);
+    const uint64_t k3 = mix64(k2 + 0x632BE59BD9B4E019ull);
+    return (uint16_t)(1u + (uint32_t)((k3 >> 24) & 0xffff) % 35u);
+}
+
 }  // namespace bv

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import BvError, BvTile, SITE_OUT_DTYPE
+from .capi import BvError, BvTile, BvTileAux, CALL_OUT_DTYPE, GROUP_OUT_DTYPE, SITE_OUT_DTYPE
 
 
 def _ptr(a):
@@ -101,6 +101,64 @@ class BaseTypeEngine:
             self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data), "bv_tile_wait")
         return out
 
+    # -- called sites: rank sums + population groups ---------------------------------------------------
+    CALL_KERNEL_NAMES = ("bv_ranksum_kernel", "bv_group_kernel")
+
+    def last_call_kernel_times(self):
+        ms = (C.c_float * 2)()
+        self._check(self.lib.bv_last_call_kernel_times(self._ctx, ms), "bv_last_call_kernel_times")
+        return dict(zip(self.CALL_KERNEL_NAMES, (float(x) for x in ms)))
+
+    def set_groups(self, sample_group, n_groups):
+        """sample_group: uint8 [n_samples], group index or capi.GROUP_NONE; groups numbered in ascending-name order."""
+        self.n_groups = int(n_groups)
+        if n_groups:
+            sample_group = np.ascontiguousarray(sample_group, np.uint8)
+            self._check(self.lib.bv_set_groups(self._ctx, sample_group.ctypes.data, len(sample_group), n_groups), "bv_set_groups")
+        else:
+            self._check(self.lib.bv_set_groups(self._ctx, None, 0, 0), "bv_set_groups")
+
+    def call_host_calls(self, base, qual, strand, ref_base, mapq, rpr, n_samples):
+        """Like call_host, plus the called-site outputs.  mapq: uint8 [S][pitch]; rpr: uint16 [S][rpr_pitch].
+        Returns (records, calls sorted by GLOBAL site index, groups[n_calls][n_groups])."""
+        S, pitch = base.shape
+        assert mapq.shape == base.shape and mapq.dtype == np.uint8 and rpr.dtype == np.uint16 and rpr.shape[0] == S
+        rpr_pitch = rpr.shape[1]
+        G = getattr(self, "n_groups", 0)
+        out = np.zeros(S, dtype=SITE_OUT_DTYPE)
+        n_slots, step = self.params.n_slots, self.params.max_sites
+        assert n_slots >= 1 and step >= 1, "engine was created without slots"
+        calls, groups = [], []
+        tmp_calls = np.zeros(step, CALL_OUT_DTYPE)
+        tmp_groups = np.zeros((step, max(G, 1)), GROUP_OUT_DTYPE)
+        pending, slot = [], 0
+
+        def wait(ps, p0):
+            n = C.c_uint32(0)
+            self._check(self.lib.bv_tile_wait_calls(self._ctx, ps, out[p0:].ctypes.data, tmp_calls.ctypes.data, step, C.byref(n),
+                                                    tmp_groups.ctypes.data if G else None), "bv_tile_wait_calls")
+            c = tmp_calls[:n.value].copy()
+            c["site"] += p0
+            calls.append(c)
+            groups.append(tmp_groups.reshape(-1)[:n.value * G].reshape(n.value, G).copy() if G else np.zeros((n.value, 0), GROUP_OUT_DTYPE))
+
+        for s0 in range(0, max(S, 1), step):
+            ns = min(step, S - s0)
+            if len(pending) == n_slots:
+                wait(*pending.pop(0))
+            t = BvTile(base[s0:].ctypes.data, qual[s0:].ctypes.data, strand[s0:].ctypes.data, ref_base[s0:].ctypes.data, pitch, ns,
+                       n_samples, capi.BV_LOC_HOST, 0)
+            a = BvTileAux(mapq[s0:].ctypes.data, rpr[s0:].ctypes.data, rpr_pitch)
+            self._check(self.lib.bv_tile_submit_calls(self._ctx, slot, C.byref(t), C.byref(a)), "bv_tile_submit_calls")
+            pending.append((slot, s0))
+            slot = (slot + 1) % n_slots
+        for ps, p0 in pending:
+            wait(ps, p0)
+        calls = np.concatenate(calls) if calls else np.zeros(0, CALL_OUT_DTYPE)
+        groups = np.concatenate(groups) if groups else np.zeros((0, G), GROUP_OUT_DTYPE)
+        order = np.argsort(calls["site"], kind="stable")
+        return out, calls[order], groups[order]
+
     # -- device-resident tiles ---------------------------------------------------------------------
     def call_device(self, d_base, d_qual, d_strand, d_ref, n_sites, n_samples, pitch, d_out, stream=0):
         """All arguments are device pointers (ints); stream is a cudaStream_t handle (int).  Asynchronous."""
@@ -118,6 +176,17 @@ class BaseTypeEngine:
         self._check(self.lib.bv_synth_fill_device(self._ctx, site0, n_sites, n_samples, pitch, int(d_base), int(d_qual),
                                                   int(d_strand), int(d_mapq) if d_mapq else None, int(d_ref),
                                                   C.c_void_p(int(stream))), "bv_synth_fill_device")
+
+
+def synth_fill_rpr_host(model, site0, n_sites, n_samples):
+    """Read-position-rank plane (uint16 [n_sites][round8(n_samples)]) of the synthetic genome, host twin."""
+    lib = capi.load_library()
+    rp = (n_samples + 7) // 8 * 8
+    rpr = np.empty((n_sites, rp), np.uint16)
+    rc = lib.bv_synth_fill_rpr_host(C.byref(model), site0, n_sites, n_samples, rp, rpr.ctypes.data)
+    if rc != capi.BV_OK:
+        raise BvError(f"bv_synth_fill_rpr_host failed ({rc}): {lib.bv_last_error(None).decode()}")
+    return rpr
 
 
 def synth_fill_host(model, site0, n_sites, n_samples, pitch=None, with_mapq=False):

@@ -19,6 +19,10 @@
  *   getters get_alt_bases/get_lrt_af/   src/basetype.h:120-151   fields of bv_site_out
  *     get_var_qual/get_total_depth/get_base_depth
  *   per-site driver _basevar_caller     src/basetype_caller.cpp:667-765   caller loops over bv_site_out
+ *   ref_vs_alt_ranksumtest(...) x3      src/basetype.h:168-176   bv_tile_submit_calls (rank-sum kernel), bv_call_out
+ *     (MQRankSum/ReadPosRankSum/BaseQRankSum of the VCF row, src/basetype_caller.cpp:1151-1157)
+ *   __gb(): BaseType on one population  src/basetype_caller.cpp:767-797   bv_set_groups + bv_tile_submit_calls
+ *     group + lrt([REF, ALT...])        src/basetype_caller.cpp:747-760   (group kernel), bv_group_out
  *
  * Everything is `extern "C"`, plain pointers and sizes, POD structs; no exception crosses the
  * boundary.  Every entry point returns BV_OK (0) or a negative status; bv_last_error() gives text.
@@ -144,6 +148,40 @@ typedef struct bv_synth_model {
     uint32_t af_extra_thr[256]; /* same for ALT2/ALT3 of multi-allelic sites                              */
 } bv_synth_model;
 
+/* ---- called sites (n_alt > 0): the extra inputs and outputs of the VCF row ------------------------ */
+/* Planes the reference reads only at called sites (src/basetype_caller.cpp:1151-1157).  Same site-major layout as
+ * bv_tile; rows are fetched for the called sites only, so pinned host planes are read in place over PCIe. */
+typedef struct bv_tile_aux {
+    const uint8_t*  mapq;    /* [n_sites][pitch]      BatchInfo::mapqs, 0..255 (same pitch as the tile)             */
+    const uint16_t* rpr;     /* [n_sites][rpr_pitch]  BatchInfo::base_pos_ranks (read position rank), 0..65535      */
+    uint64_t rpr_pitch;      /* ELEMENTS between consecutive rows of `rpr`, multiple of 8, >= n_samples             */
+} bv_tile_aux;
+
+/* One per site with n_alt > 0, in NO particular order (`site` identifies the row).  16 bytes.
+ * Each rank sum is (int) ref_vs_alt_ranksumtest(upper REF, ALT string, first bases, values): the phred-scaled
+ * two-sided Wilcoxon p of REF reads vs reads of the called ALT alleles, 10000 when either class is empty or p == 0
+ * (src/basetype.cpp:201-242, src/algorithm.h:76-136), truncated to int as src/basetype_caller.cpp:1151-1157 does. */
+typedef struct bv_call_out {
+    uint32_t site;               /* row index inside the tile                        */
+    int32_t  mq_rank_sum;        /* values = mapqs                                   */
+    int32_t  read_pos_rank_sum;  /* values = base_pos_ranks                          */
+    int32_t  base_q_rank_sum;    /* values = align_base_quals                        */
+} bv_call_out;
+
+/* One per (called site, population group): BaseType over the group's samples + lrt([upper REF, ALT...])
+ * (src/basetype_caller.cpp:747-760,767-797).  n_alt == 0: the group reports no AF (no "<group>_AF=" entry,
+ * src/basetype_caller.cpp:1184-1194).  40 bytes. */
+typedef struct bv_group_out {
+    uint8_t n_alt;
+    uint8_t alt[4];          /* base codes, in the order of the group's BaseType::get_alt_bases()                  */
+    uint8_t flags;           /* BV_FLAG_* raised by the group's EM / LRT                                           */
+    uint8_t reserved[2];
+    double  af[4];           /* get_lrt_af(alt[i])                                                                 */
+} bv_group_out;
+
+#define BV_GROUP_NONE 255    /* sample belongs to no population group */
+#define BV_MAX_GROUPS 254
+
 typedef struct bv_ctx bv_ctx;
 
 /* ---- lifecycle --------------------------------------------------------------------------------- */
@@ -158,6 +196,7 @@ uint64_t    bv_h2d_bytes(const bv_ctx* ctx);                   /* bytes uploaded
  * K3 bound, K4 EM); bv_last_kernel_times() waits for the most recent tile and returns their durations in ms. */
 int         bv_set_profiling(bv_ctx* ctx, int on);
 int         bv_last_kernel_times(bv_ctx* ctx, float ms[4]);
+int         bv_last_call_kernel_times(bv_ctx* ctx, float ms[2]);   /* K5 rank sums, K6 population groups */
 
 /* ---- tile pipeline (replaces: BatchInfo -> BaseType ctor -> lrt() -> strand_bias per site) ------ */
 /* Asynchronous.  Host tiles are copied H2D on the slot's stream (pinned memory makes the copy truly
@@ -173,12 +212,35 @@ int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out);
  * `stream` is a cudaStream_t (NULL = the legacy default stream).  Stream ordered, returns at once. */
 int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, void* stream);
 
+/* ---- called sites: rank-sum INFO fields and population-group allele frequencies ----------------- */
+/* sample_group[i] = group index 0..n_groups-1 of sample i, or BV_GROUP_NONE.  The caller numbers the groups in the
+ * order the reference iterates them (std::map<std::string,...>: ascending group name, basetype_caller.cpp:756).
+ * n_groups == 0 turns the group kernel off.  Not allowed while a slot is busy. */
+int bv_set_groups(bv_ctx* ctx, const uint8_t* sample_group, uint32_t n_samples, uint32_t n_groups);
+/* bv_tile_submit + the kernels of the called sites.  `aux` planes live where the tile lives (host or device);
+ * pageable host planes are uploaded whole, pinned ones are read in place for the called rows only. */
+int bv_tile_submit_calls(bv_ctx* ctx, int slot, const bv_tile* tile, const bv_tile_aux* aux);
+/* Blocks; `out` receives n_sites records, `calls` up to max_calls entries, `groups` (may be NULL when no groups are
+ * set) n_groups entries per call, groups[k * n_groups + g] belonging to calls[k].  *n_calls = number of called sites
+ * of the tile; BV_ERR_ARG (nothing copied to calls/groups) when it exceeds max_calls. */
+int bv_tile_wait_calls(bv_ctx* ctx, int slot, bv_site_out* out, bv_call_out* calls, uint32_t max_calls,
+                       uint32_t* n_calls, bv_group_out* groups);
+/* Device-resident variant (tile, aux planes, d_out, d_calls [n_sites], d_groups [n_sites * n_groups] and d_n_calls
+ * are device pointers; d_groups may be NULL when no groups are set).  Stream ordered. */
+int bv_tile_run_device_calls(bv_ctx* ctx, const bv_tile* tile, const bv_tile_aux* aux, bv_site_out* d_out,
+                             bv_call_out* d_calls, bv_group_out* d_groups, uint32_t* d_n_calls, void* stream);
+
 /* ---- synthetic pileups --------------------------------------------------------------------------- */
 int bv_synth_set_model(bv_ctx* ctx, const bv_synth_model* model);
 /* Fill device planes for sites [site0, site0+n_sites) of the synthetic genome; mapq may be NULL. */
 int bv_synth_fill_device(bv_ctx* ctx, uint64_t site0, uint32_t n_sites, uint32_t n_samples, uint64_t pitch,
                          uint8_t* d_base, uint8_t* d_qual, uint8_t* d_strand, uint8_t* d_mapq,
                          uint8_t* d_ref_base, void* stream);
+/* Read-position-rank plane of the same synthetic genome (1 + draw % 35 for covered cells, 0 otherwise). */
+int bv_synth_fill_rpr_device(bv_ctx* ctx, uint64_t site0, uint32_t n_sites, uint32_t n_samples, uint64_t rpr_pitch,
+                             uint16_t* d_rpr, void* stream);
+int bv_synth_fill_rpr_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
+                           uint64_t rpr_pitch, uint16_t* rpr);
 /* Host twin of the generator (plain C loop, no CUDA): same bytes as bv_synth_fill_device. */
 int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
                        uint64_t pitch, uint8_t* base, uint8_t* qual, uint8_t* strand, uint8_t* mapq,

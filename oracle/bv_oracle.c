@@ -248,62 +248,27 @@ static int next_subset(int* idx, int k, int n) {
 }
 
 /* ------------------------------------------------------------------------------------------------
- * One site.
+ * BaseType::lrt(specific_bases), src/basetype.cpp:130-199: active set over the ORDERED candidate list `cand`
+ * (A,C,G,T for lrt(); [upper REF, ALT...] for the population-group calls, basetype_caller.cpp:750-753),
+ * full-model EM, backward elimination.  Returns the number of active bases left (0: nothing to report).
  * ------------------------------------------------------------------------------------------------ */
-int bvo_site(const uint8_t* base, const uint8_t* qual, const uint8_t* strand, uint32_t n_samples,
-             uint8_t ref_char, const bv_params* prm, bv_site_out* out) {
-    memset(out, 0, sizeof(*out));
+typedef struct {
+    int active[4];
+    double f_act[4];
+    double chi;
+    unsigned em_calls;
+} lrt_result;
+
+static int lrt_core(const double* lik, size_t d, const double* depth, int total, const int* cand, int n_cand,
+                    const bv_params* prm, unsigned* flags_io, lrt_result* res) {
     const double min_af = (double)prm->min_af; /* float -> double, basetype_caller.cpp:122,506 */
-
-    double* lik = (double*)malloc(sizeof(double) * 4 * (size_t)(n_samples ? n_samples : 1));
-    size_t d = 0;
-    double depth[4] = {0, 0, 0, 0};
-    unsigned flags = 0;
-    /* BaseType::BaseType, src/basetype.cpp:45-71 */
-    for (uint32_t i = 0; i < n_samples; ++i) {
-        uint8_t b = base[i];
-        if (b >= BV_BASE_N) continue; /* 'N' and indels are skipped, basetype.cpp:51 */
-        uint8_t q = qual[i];
-        if (q > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;
-        double eps = exp((double)q * kMLN10TO10);
-        if (b < 4) {
-            depth[b] += 1;
-            out->depth[b]++;
-            if (strand[i] == BV_STRAND_FWD) out->fwd[b]++;
-            else if (strand[i] == BV_STRAND_REV) out->rev[b]++;
-        } else {
-            out->depth_other++;
-        }
-        if (strand[i] != BV_STRAND_FWD && strand[i] != BV_STRAND_REV) flags |= BV_FLAG_BAD_STRAND;
-        for (int j = 0; j < 4; ++j) lik[4 * d + j] = (b == j) ? 1.0 - eps : eps / 3;
-        ++d;
-    }
-    const int total = (int)d;
-
-    /* strand_bias for the CVG row: ref vs all non-ref ACGT (basetype_caller.cpp:1236-1245) */
-    int up_ref = ref_char;
-    if (up_ref >= 'a' && up_ref <= 'z') up_ref -= 32; /* toupper, basetype.cpp:171 */
-    int ref_code = up_ref == 'A' ? 0 : up_ref == 'C' ? 1 : up_ref == 'G' ? 2 : up_ref == 'T' ? 3 : -1;
-    {
-        int rf = 0, rr = 0, af_ = 0, ar = 0;
-        for (int b = 0; b < 4; ++b) {
-            if (b == ref_code) { rf += out->fwd[b]; rr += out->rev[b]; }
-            else { af_ += out->fwd[b]; ar += out->rev[b]; }
-        }
-        out->fs_cvg = bvo_fs_from_table(rf, rr, af_, ar);
-    }
-
-    /* BaseType::lrt, src/basetype.cpp:130-199 */
+    unsigned flags = *flags_io;
     int active[4], n_active = 0;
     if (total > 0) {
-        for (int b = 0; b < 4; ++b)
-            if (depth[b] / total >= min_af) active[n_active++] = b;
+        for (int k = 0; k < n_cand; ++k)
+            if (depth[cand[k]] / total >= min_af) active[n_active++] = cand[k];
     }
-    if (total == 0 || n_active == 0) {
-        out->flags = (uint8_t)flags;
-        free(lik);
-        return 0;
-    }
+    if (total == 0 || n_active == 0) return 0;
 
     em_ws w;
     w.post = (double*)malloc(sizeof(double) * 4 * d);
@@ -361,6 +326,74 @@ int bvo_site(const uint8_t* base, const uint8_t* qual, const uint8_t* strand, ui
         }
     }
 
+    free(lml); free(w.post); free(w.marg);
+    for (int k = 0; k < n_active; ++k) res->active[k] = active[k];
+    memcpy(res->f_act, f_act, sizeof(f_act));
+    res->chi = chi;
+    res->em_calls = em_calls;
+    *flags_io = flags;
+    return n_active;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * One site.
+ * ------------------------------------------------------------------------------------------------ */
+int bvo_site(const uint8_t* base, const uint8_t* qual, const uint8_t* strand, uint32_t n_samples,
+             uint8_t ref_char, const bv_params* prm, bv_site_out* out) {
+    memset(out, 0, sizeof(*out));
+
+    double* lik = (double*)malloc(sizeof(double) * 4 * (size_t)(n_samples ? n_samples : 1));
+    size_t d = 0;
+    double depth[4] = {0, 0, 0, 0};
+    unsigned flags = 0;
+    /* BaseType::BaseType, src/basetype.cpp:45-71 */
+    for (uint32_t i = 0; i < n_samples; ++i) {
+        uint8_t b = base[i];
+        if (b >= BV_BASE_N) continue; /* 'N' and indels are skipped, basetype.cpp:51 */
+        uint8_t q = qual[i];
+        if (q > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;
+        double eps = exp((double)q * kMLN10TO10);
+        if (b < 4) {
+            depth[b] += 1;
+            out->depth[b]++;
+            if (strand[i] == BV_STRAND_FWD) out->fwd[b]++;
+            else if (strand[i] == BV_STRAND_REV) out->rev[b]++;
+        } else {
+            out->depth_other++;
+        }
+        if (strand[i] != BV_STRAND_FWD && strand[i] != BV_STRAND_REV) flags |= BV_FLAG_BAD_STRAND;
+        for (int j = 0; j < 4; ++j) lik[4 * d + j] = (b == j) ? 1.0 - eps : eps / 3;
+        ++d;
+    }
+    const int total = (int)d;
+
+    /* strand_bias for the CVG row: ref vs all non-ref ACGT (basetype_caller.cpp:1236-1245) */
+    int up_ref = ref_char;
+    if (up_ref >= 'a' && up_ref <= 'z') up_ref -= 32; /* toupper, basetype.cpp:171 */
+    int ref_code = up_ref == 'A' ? 0 : up_ref == 'C' ? 1 : up_ref == 'G' ? 2 : up_ref == 'T' ? 3 : -1;
+    {
+        int rf = 0, rr = 0, af_ = 0, ar = 0;
+        for (int b = 0; b < 4; ++b) {
+            if (b == ref_code) { rf += out->fwd[b]; rr += out->rev[b]; }
+            else { af_ += out->fwd[b]; ar += out->rev[b]; }
+        }
+        out->fs_cvg = bvo_fs_from_table(rf, rr, af_, ar);
+    }
+
+    /* BaseType::lrt, src/basetype.cpp:130-199 */
+    static const int kACGT[4] = {0, 1, 2, 3};
+    lrt_result res;
+    int n_active = lrt_core(lik, d, depth, total, kACGT, 4, prm, &flags, &res);
+    if (n_active == 0) {
+        out->flags = (uint8_t)flags;
+        free(lik);
+        return 0;
+    }
+    const int* active = res.active;
+    const double* f_act = res.f_act;
+    const double chi = res.chi;
+    const unsigned em_calls = res.em_calls;
+
     int n_alt = 0;
     for (int k = 0; k < n_active; ++k) {
         if (active[k] != ref_code) {
@@ -392,7 +425,7 @@ int bvo_site(const uint8_t* base, const uint8_t* qual, const uint8_t* strand, ui
         out->fs_vcf = bvo_fs_from_table(rf, rr, af_, ar);
     }
     out->flags = (uint8_t)flags;
-    free(lml); free(w.post); free(w.marg); free(lik);
+    free(lik);
     return 0;
 }
 
@@ -401,5 +434,144 @@ int bvo_tile(const uint8_t* base, const uint8_t* qual, const uint8_t* strand, co
     for (uint32_t s = 0; s < n_sites; ++s)
         bvo_site(base + (size_t)s * pitch, qual + (size_t)s * pitch, strand + (size_t)s * pitch, n_samples,
                  ref_base[s], prm, out + s);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Population group: __gb / __get_group_batchinfo (src/basetype_caller.cpp:767-797) = BaseType over the
+ * group's samples, then lrt([upper REF, ALT...]) (src/basetype_caller.cpp:747-760).
+ * order[]: the candidate base codes in list order (a REF that is not A/C/G/T is left out: it has no
+ * depth entry and can never be active).
+ * ------------------------------------------------------------------------------------------------ */
+int bvo_group_site(const uint8_t* base, const uint8_t* qual, uint32_t n_samples, const uint8_t* sample_group,
+                   uint32_t g, uint8_t ref_char, const uint8_t* order, int n_order, const bv_params* prm,
+                   bv_group_out* out) {
+    memset(out, 0, sizeof(*out));
+    double* lik = (double*)malloc(sizeof(double) * 4 * (size_t)(n_samples ? n_samples : 1));
+    size_t d = 0;
+    double depth[4] = {0, 0, 0, 0};
+    unsigned flags = 0;
+    for (uint32_t i = 0; i < n_samples; ++i) {
+        if (sample_group[i] != g) continue;
+        uint8_t b = base[i];
+        if (b >= BV_BASE_N) continue;
+        uint8_t q = qual[i];
+        if (q > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;
+        double eps = exp((double)q * kMLN10TO10);
+        if (b < 4) depth[b] += 1;
+        for (int j = 0; j < 4; ++j) lik[4 * d + j] = (b == j) ? 1.0 - eps : eps / 3;
+        ++d;
+    }
+    int up_ref = ref_char;
+    if (up_ref >= 'a' && up_ref <= 'z') up_ref -= 32;
+    int ref_code = up_ref == 'A' ? 0 : up_ref == 'C' ? 1 : up_ref == 'G' ? 2 : up_ref == 'T' ? 3 : -1;
+    int cand[4];
+    for (int k = 0; k < n_order && k < 4; ++k) cand[k] = order[k];
+    lrt_result res;
+    int n_active = lrt_core(lik, d, depth, (int)d, cand, n_order < 4 ? n_order : 4, prm, &flags, &res);
+    for (int k = 0; k < n_active; ++k) {
+        if (res.active[k] != ref_code) {
+            out->alt[out->n_alt] = (uint8_t)res.active[k];
+            out->af[out->n_alt] = res.f_act[res.active[k]];
+            out->n_alt++;
+        }
+    }
+    out->flags = (uint8_t)flags;
+    free(lik);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Rank sums: kf_erfc (htslib/kfunc.c:58-84), norm_dist / wilcoxon_ranksum_test (src/algorithm.h:48-50,
+ * 76-136), ref_vs_alt_ranksumtest (src/basetype.cpp:201-242), (int) at src/basetype_caller.cpp:1151-1157.
+ * ------------------------------------------------------------------------------------------------ */
+double bvo_erfc(double x) {
+    const double p0 = 220.2068679123761, p1 = 221.2135961699311, p2 = 112.0792914978709, p3 = 33.912866078383,
+                 p4 = 6.37396220353165, p5 = .7003830644436881, p6 = .03526249659989109;
+    const double q0 = 440.4137358247522, q1 = 793.8265125199484, q2 = 637.3336333788311, q3 = 296.5642487796737,
+                 q4 = 86.78073220294608, q5 = 16.06417757920695, q6 = 1.755667163182642, q7 = .08838834764831844;
+    double expntl, z, p;
+    z = fabs(x) * M_SQRT2;
+    if (z > 37.) return x > 0. ? 0. : 2.;
+    expntl = exp(z * z * -.5);
+    if (z < 10. / M_SQRT2)
+        p = expntl * ((((((p6 * z + p5) * z + p4) * z + p3) * z + p2) * z + p1) * z + p0) /
+            (((((((q7 * z + q6) * z + q5) * z + q4) * z + q3) * z + q2) * z + q1) * z + q0);
+    else
+        p = expntl / 2.506628274631001 / (z + 1. / (z + 2. / (z + 3. / (z + 4. / (z + .65)))));
+    return x > 0. ? 2. * p : 2. * (1. - p);
+}
+
+typedef struct { double v; size_t i; } rk_item;
+static int rk_desc(const void* a, const void* b) {
+    const rk_item *x = (const rk_item*)a, *y = (const rk_item*)b;
+    return x->v > y->v ? -1 : (x->v < y->v ? 1 : 0);
+}
+
+/* wilcoxon_ranksum_test: descending sort, average ranks for ties, normal approximation without tie correction */
+double bvo_wilcoxon(const double* s1, size_t n1, const double* s2, size_t n2) {
+    const size_t n = n1 + n2;
+    rk_item* it = (rk_item*)malloc(sizeof(rk_item) * (n ? n : 1));
+    double* rank = (double*)malloc(sizeof(double) * (n ? n : 1));
+    for (size_t i = 0; i < n1; ++i) { it[i].v = s1[i]; it[i].i = i; }
+    for (size_t i = 0; i < n2; ++i) { it[n1 + i].v = s2[i]; it[n1 + i].i = n1 + i; }
+    qsort(it, n, sizeof(rk_item), rk_desc);
+    for (size_t i = 0; i < n; ++i) rank[i] = (double)(i + 1);
+    double ranksum = 0.0, same_n = 1;
+    size_t i;
+    for (i = 0; i < n; ++i) {
+        if (i > 0 && it[i].v != it[i - 1].v) {
+            if (same_n > 1) {
+                double avg = ranksum / same_n;
+                for (size_t j = i - (size_t)same_n; j < i; ++j) rank[j] = avg;
+            }
+            same_n = 1;
+            ranksum = 0;
+        } else if (i > 0) {
+            same_n++;
+        }
+        ranksum += (double)(i + 1);
+    }
+    if (same_n > 1) {
+        double avg = ranksum / same_n;
+        for (size_t j = i - (size_t)same_n; j < i; ++j) rank[j] = avg;
+    }
+    double smp1 = 0.0;
+    for (size_t k = 0; k < n; ++k)
+        if (it[k].i < n1) smp1 += rank[k];
+    free(it); free(rank);
+    double e = (double)(n1 * (n1 + n2 + 1)) / 2.0;
+    double z = (smp1 - e) / sqrt((double)(n1 * n2 * (n1 + n2 + 1)) / 12.0);
+    return 2 * (bvo_erfc(fabs(z) / sqrt(2.0)) / 2.0);
+}
+
+/* one called site: the three INFO values from the packed planes; alt_mask bit b = base code b is a called ALT */
+int bvo_ranksums(const uint8_t* base, const uint8_t* qual, const uint8_t* mapq, const uint16_t* rpr, uint32_t n_samples,
+                 uint8_t ref_char, uint32_t alt_mask, int32_t out3[3]) {
+    int up_ref = ref_char;
+    if (up_ref >= 'a' && up_ref <= 'z') up_ref -= 32;
+    int ref_code = up_ref == 'A' ? 0 : up_ref == 'C' ? 1 : up_ref == 'G' ? 2 : up_ref == 'T' ? 3 : -1;
+    double* r = (double*)malloc(sizeof(double) * (n_samples ? n_samples : 1));
+    double* a = (double*)malloc(sizeof(double) * (n_samples ? n_samples : 1));
+    for (int t = 0; t < 3; ++t) {
+        size_t n1 = 0, n2 = 0;
+        for (uint32_t i = 0; i < n_samples; ++i) {
+            uint8_t b = base[i];
+            if (b > 3) continue; /* N, indels skipped; other characters match neither REF nor an ALT */
+            double v = t == 0 ? (double)mapq[i] : t == 1 ? (double)rpr[i] : (double)(qual[i] + 33);
+            if ((int)b == ref_code) r[n1++] = v;
+            else if (alt_mask >> b & 1u) a[n2++] = v;
+        }
+        double ph;
+        if (n1 > 0 && n2 > 0) {
+            double p = bvo_wilcoxon(r, n1, a, n2);
+            ph = -10 * log10(p);
+            if (isinf(ph)) ph = 10000;
+        } else {
+            ph = 10000;
+        }
+        out3[t] = cvt_trunc_x86(ph);
+    }
+    free(r); free(a);
     return 0;
 }

@@ -33,6 +33,10 @@ SITE_OUT_DTYPE = np.dtype(
     ]
 )
 assert SITE_OUT_DTYPE.itemsize == 128
+# struct bv_call_out (16 bytes) and struct bv_group_out (40 bytes)
+CALL_OUT_DTYPE = np.dtype([("site", "<u4"), ("mq_rank_sum", "<i4"), ("read_pos_rank_sum", "<i4"), ("base_q_rank_sum", "<i4")])
+GROUP_OUT_DTYPE = np.dtype([("n_alt", "u1"), ("alt", "u1", (4,)), ("flags", "u1"), ("reserved", "u1", (2,)), ("af", "<f8", (4,))])
+assert CALL_OUT_DTYPE.itemsize == 16 and GROUP_OUT_DTYPE.itemsize == 40
 
 
 class BvParams(C.Structure):
@@ -89,6 +93,16 @@ def load_oracle():
         lib.bvo_fs_from_table.argtypes = [C.c_int] * 4
         lib.bvo_sor_from_table.restype = C.c_double
         lib.bvo_sor_from_table.argtypes = [C.c_int] * 4
+        lib.bvo_erfc.restype = C.c_double
+        lib.bvo_erfc.argtypes = [C.c_double]
+        lib.bvo_wilcoxon.restype = C.c_double
+        lib.bvo_wilcoxon.argtypes = [C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double), C.c_size_t]
+        lib.bvo_ranksums.restype = C.c_int
+        lib.bvo_ranksums.argtypes = [C.POINTER(C.c_uint8)] * 3 + [C.POINTER(C.c_uint16), C.c_uint32, C.c_uint8, C.c_uint32,
+                                                                C.POINTER(C.c_int32)]
+        lib.bvo_group_site.restype = C.c_int
+        lib.bvo_group_site.argtypes = [C.POINTER(C.c_uint8)] * 2 + [C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32, C.c_uint8,
+                                                                  C.POINTER(C.c_uint8), C.c_int, C.POINTER(BvParams), C.c_void_p]
         _oracle = lib
     return _oracle
 
@@ -103,6 +117,58 @@ def oracle_tile(base, qual, strand, ref_base, n_samples, min_af=0.01, abs_mode=0
                       out.ctypes.data)
     assert rc == 0
     return out
+
+
+def _alt_mask(rec):
+    m = 0
+    for k in range(int(rec["n_alt"])):
+        m |= 1 << int(rec["alt"][k])
+    return m
+
+
+def _group_order(ref_char, rec):
+    """[upper REF, ALT...] as base codes (src/basetype_caller.cpp:750-753); a REF that is not A/C/G/T is left out."""
+    order = []
+    rc = "ACGT".find(chr(ref_char).upper())
+    if rc >= 0:
+        order.append(rc)
+    for k in range(int(rec["n_alt"])):
+        if int(rec["alt"][k]) not in order:
+            order.append(int(rec["alt"][k]))
+    return np.array(order, np.uint8)
+
+
+def oracle_calls(base, qual, mapq, rpr, ref_base, n_samples, recs, sample_group=None, n_groups=0, min_af=0.01, abs_mode=0,
+                 use_ref=False):
+    """Rank sums and population-group calls of the called sites (recs: SITE_OUT_DTYPE of the same planes), from the C
+    restatement or (use_ref) from the compiled reference.  Returns (calls sorted by site, groups[n_calls][n_groups])."""
+    lib = load_ref(bool(abs_mode)) if use_ref else load_oracle()
+    assert lib is not None
+    sites = np.nonzero(recs["n_alt"] > 0)[0]
+    calls = np.zeros(len(sites), CALL_OUT_DTYPE)
+    groups = np.zeros((len(sites), max(n_groups, 0)), GROUP_OUT_DTYPE)
+    prm = make_params(min_af, abs_mode)
+    u16p = C.POINTER(C.c_uint16)
+    rpr = np.ascontiguousarray(rpr, np.uint16)
+    for k, s in enumerate(sites):
+        out3 = (C.c_int32 * 3)()
+        row = lambda a: _u8p(np.ascontiguousarray(a[s]))
+        rr = np.ascontiguousarray(rpr[s])
+        fn = lib.bvref_ranksums if use_ref else lib.bvo_ranksums
+        rc = fn(row(base), row(qual), row(mapq), rr.ctypes.data_as(u16p), n_samples, int(ref_base[s]), _alt_mask(recs[s]), out3)
+        assert rc == 0
+        calls[k] = (s, out3[0], out3[1], out3[2])
+        for g in range(n_groups):
+            if use_ref:
+                alts = np.ascontiguousarray(recs[s]["alt"][:int(recs[s]["n_alt"])], np.uint8)
+                rc = lib.bvref_group_site(row(base), row(qual), n_samples, _u8p(sample_group), g, int(ref_base[s]), _u8p(alts),
+                                          len(alts), float(np.float32(min_af)), groups[k, g:g + 1].ctypes.data)
+            else:
+                order = _group_order(int(ref_base[s]), recs[s])
+                rc = lib.bvo_group_site(row(base), row(qual), n_samples, _u8p(sample_group), g, int(ref_base[s]), _u8p(order),
+                                        len(order), C.byref(prm), groups[k, g:g + 1].ctypes.data)
+            assert rc == 0
+    return calls, groups
 
 
 _ref = {}
@@ -128,6 +194,13 @@ def load_ref(dblabs=False):
             lib.bvref_fisher_fs.restype = C.c_double
             lib.bvref_fisher_fs.argtypes = [C.c_int] * 4
             lib.bvref_abs_mode.restype = C.c_int
+            lib.bvref_ranksums.restype = C.c_int
+            lib.bvref_ranksums.argtypes = [C.POINTER(C.c_uint8)] * 3 + [C.POINTER(C.c_uint16), C.c_uint32, C.c_uint8,
+                                                                      C.c_uint32, C.POINTER(C.c_int32)]
+            lib.bvref_group_site.restype = C.c_int
+            lib.bvref_group_site.argtypes = [C.POINTER(C.c_uint8)] * 2 + [C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32,
+                                                                        C.c_uint8, C.POINTER(C.c_uint8), C.c_int, C.c_float,
+                                                                        C.c_void_p]
             _ref[dblabs] = lib
     return _ref[dblabs]
 

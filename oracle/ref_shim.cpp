@@ -173,4 +173,65 @@ double bvref_fisher_fs(int ref_fwd, int ref_rev, int alt_fwd, int alt_rev) {
     return strand_bias('A', "C", bases, strands).fs;
 }
 
+// The three rank-sum INFO values of one called site, exactly as _out_vcf_line computes them
+// (src/basetype_caller.cpp:1151-1157): int = ref_vs_alt_ranksumtest(upper REF, ALT string, first bases, values).
+int bvref_ranksums(const uint8_t* base, const uint8_t* qual, const uint8_t* mapq, const uint16_t* rpr, uint32_t n_samples,
+                   uint8_t ref_char, uint32_t alt_mask, int32_t out3[3]) {
+    std::vector<char> first(n_samples), quals(n_samples);
+    std::vector<int> mapqs(n_samples), ranks(n_samples);
+    for (uint32_t i = 0; i < n_samples; ++i) {
+        uint8_t b = base[i] & 7;
+        first[i] = b == BV_BASE_INS ? '+' : b == BV_BASE_DEL ? '-' : kBaseChar[b];
+        quals[i] = (char)(qual[i] + 33);
+        mapqs[i] = mapq[i];
+        ranks[i] = rpr[i];
+    }
+    std::string alt_str;
+    for (int b = 0; b < 4; ++b) if (alt_mask >> b & 1u) alt_str.push_back(BASES[b]);
+    char upper_ref = (char)toupper((char)ref_char);
+    int mq = ref_vs_alt_ranksumtest(upper_ref, alt_str, first, mapqs);
+    int rp = ref_vs_alt_ranksumtest(upper_ref, alt_str, first, ranks);
+    int bq = ref_vs_alt_ranksumtest(upper_ref, alt_str, first, quals);
+    out3[0] = mq; out3[1] = rp; out3[2] = bq;
+    return 0;
+}
+
+// One population group of one called site: __gb (src/basetype_caller.cpp:767-797) restated with the reference's own
+// class -- BaseType over the group's BatchInfo, lrt([upper REF, ALT...]) (:747-760) -- and the ALT / AF read-out of
+// _out_vcf_line (:1184-1194).  alts[]: the site's ALT base codes in get_alt_bases() order.
+int bvref_group_site(const uint8_t* base, const uint8_t* qual, uint32_t n_samples, const uint8_t* sample_group,
+                     uint32_t g, uint8_t ref_char, const uint8_t* alts, int n_alts, float min_af, bv_group_out* out) {
+    std::memset(out, 0, sizeof(*out));
+    BatchInfo bi;
+    bi.ref_id = "chrS"; bi.ref_pos = 1; bi.ref_base.assign(1, (char)ref_char); bi.depth = 0;
+    for (uint32_t i = 0; i < n_samples; ++i) {
+        if (sample_group[i] != g) continue;
+        uint8_t b = base[i] & 7;
+        if (b == BV_BASE_INS) bi.align_bases.push_back("+A");
+        else if (b == BV_BASE_DEL) bi.align_bases.push_back("-A");
+        else bi.align_bases.push_back(std::string(1, kBaseChar[b]));
+        bi.align_base_quals.push_back((char)(qual[i] + 33));
+        bi.mapqs.push_back(0);
+        bi.map_strands.push_back('+');
+        bi.base_pos_ranks.push_back(0);
+    }
+    bi.n = bi.align_bases.size();
+    std::vector<char> basecombination;
+    basecombination.push_back((char)toupper((char)ref_char));
+    for (int k = 0; k < n_alts; ++k) basecombination.push_back(BASES[alts[k] & 3]);
+    try {
+        BaseType bt(&bi, (double)min_af);
+        bt.lrt(basecombination);
+        for (char b : bt.get_alt_bases()) {
+            if (out->n_alt >= 4) break;
+            out->alt[out->n_alt] = (uint8_t)base_code(b);
+            out->af[out->n_alt] = bt.get_lrt_af(b);
+            out->n_alt++;
+        }
+    } catch (const std::runtime_error&) {
+        out->flags |= BV_FLAG_ZERO_SUBSET;
+    }
+    return 0;
+}
+
 }  // extern "C"

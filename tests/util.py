@@ -97,3 +97,37 @@ def random_tile(rng, S, N, cov, qlo, qhi, nalt_max=3, other=0.0, indel=0.0, bad_
         strand[s, :N] = np.where(covd, st, 2)
     refc = np.array([65, 67, 71, 84], np.uint8)[ref]
     return base, qual, strand, refc
+
+
+def random_aux(rng, base, N, rpr_max=35, mapq_levels=(60, 60, 60, 37, 20, 0)):
+    """mapq (u8) and read-position-rank (u16) planes for a base plane; uncovered cells get 0 like the batchfile."""
+    S, pitch = base.shape
+    mapq = np.zeros((S, pitch), np.uint8)
+    rpr = np.zeros((S, (N + 7) // 8 * 8), np.uint16)
+    cov = base[:, :N] != 5
+    mapq[:, :N] = np.where(cov, rng.choice(np.array(mapq_levels, np.uint8), size=(S, N)), 0)
+    rpr[:, :N] = np.where(cov, rng.integers(1, rpr_max + 1, (S, N)), 0)
+    return mapq, rpr
+
+
+def random_groups(rng, N, n_groups, none_frac=0.1):
+    g = rng.integers(0, n_groups, N).astype(np.uint8)
+    g[rng.random(N) < none_frac] = 255
+    return g
+
+
+def compare_calls(got_calls, got_groups, want_calls, want_groups, rtol=RTOL):
+    """Called-site outputs: rank sums bit-exact; group ALT lists exact and AFs within rtol.  Both sorted by site."""
+    assert len(got_calls) == len(want_calls), (len(got_calls), len(want_calls))
+    bad = []
+    for f in ("site", "mq_rank_sum", "read_pos_rank_sum", "base_q_rank_sum"):
+        bad += [(f, int(i)) for i in np.nonzero(got_calls[f] != want_calls[f])[0]]
+    if want_groups.size:
+        assert got_groups.shape == want_groups.shape
+        same = (got_groups["n_alt"] == want_groups["n_alt"]) & (got_groups["alt"] == want_groups["alt"]).all(axis=-1)
+        bad += [("group_call", tuple(map(int, ix))) for ix in np.argwhere(~same)]
+        for k in range(4):
+            live = same & (got_groups["n_alt"] > k)
+            ok = close(got_groups["af"][..., k], want_groups["af"][..., k], rtol)
+            bad += [("group_af", tuple(map(int, ix))) for ix in np.argwhere(live & ~ok)]
+    return bad
