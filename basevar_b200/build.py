@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbasevar_b200.so")
 SOURCES = [os.path.join(CSRC, "bv_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("bv_common.cuh", "bv_count_kernel.cuh", "bv_finish_kernels.cuh", "bv_math.cuh", "bv_fisher_fast.h", "bv_synth.cuh")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("bv_common.cuh", "bv_count_kernel.cuh", "bv_finish_kernels.cuh", "bv_call_kernels.cuh", "bv_math.cuh",
+                                                  "bv_fisher_fast.h", "bv_synth.cuh")] + [
     os.path.join(HERE, "..", "include", "basevar_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -40,10 +41,12 @@ def build(force=False, verbose=False):
 
 
 HOST_LIB = os.path.join(HERE, "libbasevar_b200_host.so")
-HOST_SRC = [os.path.join(HERE, "host", "bv_host.cpp")]
-HOST_DEPS = HOST_SRC + [os.path.join(HERE, "host", "bv_host.hpp"), os.path.join(HERE, "..", "include", "basevar_b200.h")]
+HOST_SRC = [os.path.join(HERE, "host", "bv_host.cpp"), os.path.join(HERE, "host", "bv_caller.cpp")]
+HOST_DEPS = HOST_SRC + [os.path.join(HERE, "host", "bv_host.hpp"), os.path.join(HERE, "host", "bv_caller.hpp"),
+                        os.path.join(HERE, "..", "include", "basevar_b200.h")]
 ROOT = os.path.dirname(HERE)
-CPP_TESTS = {"test_host_cpu": [], "test_host_gpu": ["-ldl"], "test_fisher_fast": ["-ldl", "-lm"]}
+CPP_TESTS = {"test_host_cpu": [], "test_host_gpu": ["-ldl"], "test_fisher_fast": ["-ldl", "-lm"], "test_caller_cpu": [],
+             "test_caller_gpu": ["-lz"]}
 
 
 def build_host(force=False):
@@ -52,7 +55,7 @@ def build_host(force=False):
     cxx = os.environ.get("CXX", "g++")
     if force or not os.path.exists(HOST_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB) for d in HOST_DEPS + [LIB]):
         subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-fPIC", "-shared", "-o", HOST_LIB] + HOST_SRC +
-                              ["-L" + HERE, "-lbasevar_b200", "-Wl,-rpath,$ORIGIN", "-lpthread"])
+                              ["-L" + HERE, "-lbasevar_b200", "-Wl,-rpath,$ORIGIN", "-lpthread", "-lz"])
     bindir = os.path.join(ROOT, "tests", "cpp", "bin")
     os.makedirs(bindir, exist_ok=True)
     for name, extra in CPP_TESTS.items():

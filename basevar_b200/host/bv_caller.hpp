@@ -1,0 +1,123 @@
+// bv_caller.hpp -- the per-site driver of `basevar basetype` over the C ABI: batchfile rows in, VCF / CVG text out.
+//
+// Mirrors the reference's driver for the hot path (same argument meaning, same error texts, same output bytes):
+//
+//   reference (src/basetype_caller.{h,cpp})                      here (namespace bvhost)
+//   ----------------------------------------------------------   -------------------------------------------------------
+//   _basevar_caller(lines, group_smp_idx, min_af, n_sample,       BasevarCaller::call(lines)  (queues the position into the
+//                   vcf_hd, cvg_hd)               cpp:667-765      current tile) + finish()
+//   _out_cvg_line / __base_depth_and_indel        cpp:1211-1289   out_cvg_line(): text from the device record
+//   _out_vcf_line                                 cpp:1103-1209   out_vcf_line(): text from the record, the rank sums
+//                                                                 (K5) and the population-group calls (K6)
+//   __gb / __get_group_batchinfo                  cpp:767-797     bv_set_groups + K6 (sample -> group plane)
+//   _variant_calling_unit                         cpp:529-635     variant_calling_unit(): batchfiles (BGZF / gzip text)
+//                                                                 read with zlib, lock-step, one row per file
+//   vcf_header_define / cvg_header_define   basetype_utils.cpp:32-88   vcf_header_define() / cvg_header_define()
+//
+// What stays on the host is text: parsing the rows into the packed planes of a tile and formatting the records.
+// Likelihoods, EM, LRT, QUAL, Fisher, rank sums and group frequencies all come from the GPU through
+// include/basevar_b200.h; without a CUDA device the constructor throws.
+//
+// Positions are processed in tiles (CallerOptions::tile_sites) over n_slots in-flight slots: while the GPU works on a
+// tile the host parses the next one and formats the previous one.  Output order is input order.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "bv_host.hpp"
+
+namespace bvhost {
+
+using TextSink = std::function<void(const char* data, size_t len)>;
+
+struct CallerOptions {
+    int device = 0;
+    uint32_t tile_sites = 8192;
+    uint32_t n_slots = 2;
+    int em_abs_mode = BV_EM_ABS_INT_TRUNC;
+};
+
+// ---- number formatting of the reference's text outputs ---------------------------------------------------------------
+std::string to_string_f(double v);   // std::to_string(double): "%f"
+std::string tostring_g(double v);    // ngslib::tostring / join (src/utils.h:37-85): ostream << double, 6 significant digits;
+                                     // NaN prints "-nan" (x86 invalid-operation NaNs carry the sign bit)
+
+// ---- one position as the host keeps it next to the packed planes -------------------------------------------------------
+struct SiteMeta {
+    std::string ref_id;
+    std::string ref_base;     // column 3 verbatim (the reference prints the whole string)
+    uint32_t ref_pos = 0;
+    uint32_t depth = 0;       // sum of column 4 over the batchfiles
+    // cells whose align_bases string is not one of "A","C","G","T","N": (sample index, string) -- indels ("+ACG",
+    // "-AC") and other characters; needed for the Indels column of the CVG row and the AB field of the VCF row
+    std::vector<std::pair<uint32_t, std::string>> specials;
+    std::vector<std::pair<uint32_t, char>> odd_strands;   // strand characters other than '+', '-', '.'
+};
+
+// Row views of one site inside a tile (n_samples cells each).
+struct SiteCells {
+    const uint8_t* base;
+    const uint8_t* qual;
+    const uint8_t* strand;
+    uint32_t n_samples;
+};
+
+// _out_cvg_line (src/basetype_caller.cpp:1211-1260): "" when the site has no A/C/G/T read.
+std::string out_cvg_line(const SiteMeta& m, const SiteCells& c, const bv_site_out& rec);
+// _out_vcf_line (src/basetype_caller.cpp:1103-1209).  group_names in ascending order, groups[g] belongs to group_names[g].
+std::string out_vcf_line(const SiteMeta& m, const SiteCells& c, const bv_site_out& rec, const bv_call_out& call,
+                         const std::vector<std::string>& group_names, const bv_group_out* groups);
+
+std::string vcf_header_define(const std::vector<std::string>& contig_lines, const std::string& reference_line,
+                              const std::vector<std::string>& addition_info, const std::vector<std::string>& samples);
+std::string cvg_header_define();
+
+class BasevarCaller {
+public:
+    // n_sample, group_smp_idx, min_af: as _basevar_caller's arguments (min_af is the CLI's float widened to double,
+    // src/basetype_caller.cpp:122,506).  vcf / cvg receive the text the reference would bgzf_write to vcf_hd / cvg_hd.
+    BasevarCaller(size_t n_sample, const std::map<std::string, std::vector<size_t>>& group_smp_idx, double min_af,
+                  TextSink vcf, TextSink cvg, const CallerOptions& opt = CallerOptions());
+    ~BasevarCaller();
+    BasevarCaller(const BasevarCaller&) = delete;
+    BasevarCaller& operator=(const BasevarCaller&) = delete;
+
+    // One position: one row from each batchfile, in batchfile order (the smp_bf_line_vector of _basevar_caller).
+    // Throws std::runtime_error with the reference's messages on malformed rows.  Text may be emitted for earlier tiles.
+    void call(const std::vector<std::string>& smp_bf_line_vector);
+    // Drains the pipeline.  Returns true if any SNP row was written since construction (`has_data`, cpp:610).
+    bool finish();
+
+    uint64_t n_positions() const { return n_positions_; }   // positions with depth > 0 sent to the GPU
+    uint64_t n_snps() const { return n_snps_; }
+    uint64_t launch_count() const;
+
+private:
+    struct Tile;
+    void submit_current();
+    void drain(uint32_t slot);
+
+    size_t n_sample_;
+    std::vector<std::string> group_names_;
+    TextSink vcf_, cvg_;
+    CallerOptions opt_;
+    bv_ctx* ctx_ = nullptr;
+    std::vector<std::unique_ptr<Tile>> tiles_;
+    uint32_t cur_ = 0;
+    uint64_t n_positions_ = 0, n_snps_ = 0;
+};
+
+// _variant_calling_unit (src/basetype_caller.cpp:529-635): the batchfiles are read in lock step, one row from each per
+// position.  `region` ("chr", "chr:beg-end", or "" for everything) filters rows by coordinate (the reference asks the
+// tabix index for the same rows).  Returns has_data.
+bool variant_calling_unit(const std::vector<std::string>& batchfiles, const std::vector<std::string>& sample_ids,
+                          const std::map<std::string, std::vector<size_t>>& group_smp_idx, double min_af,
+                          const std::string& region, TextSink vcf, TextSink cvg, const CallerOptions& opt = CallerOptions());
+// "##SampleIDs=" headers of the batchfiles, concatenated (_get_sampleid_from_batchfiles, cpp:637-665)
+std::vector<std::string> get_sampleid_from_batchfiles(const std::vector<std::string>& batchfiles);
+
+}  // namespace bvhost

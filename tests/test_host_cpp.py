@@ -42,3 +42,20 @@ def test_fast_fisher_matches_the_reference_algorithm(host_built):
 def test_host_layer_gpu(host_built):
     out = _run(os.path.join(host_built, "test_host_gpu"), ROOT)
     assert "region sharding" in out and "batch path" in out
+
+
+def test_caller_text_side_cpu(host_built):
+    """basevar_b200/host/bv_caller: number formatting, CVG / VCF rows from hand-made records, headers, no-fallback."""
+    import torch
+    env = dict(os.environ)
+    if torch.cuda.is_available():
+        env["BV_EXPECT_GPU"] = "1"
+    _run(os.path.join(host_built, "test_caller_cpu"), env=env)
+
+
+@pytest.mark.gpu
+def test_caller_c1_end_to_end_gpu(host_built):
+    """BASELINE.json configs[0]: the reference's own batchfile rows -> our driver -> VCF / CVG text, byte-identical with
+    what the unmodified reference CLI wrote (tests/golden/c1, with and without --pop-group)."""
+    out = _run(os.path.join(host_built, "test_caller_gpu"), ROOT)
+    assert out.count("identical, CVG") >= 4 and "DIFFERENT" not in out and "error behaviour: ok" in out
