@@ -41,12 +41,13 @@ def build(force=False, verbose=False):
 
 
 HOST_LIB = os.path.join(HERE, "libbasevar_b200_host.so")
-HOST_SRC = [os.path.join(HERE, "host", "bv_host.cpp"), os.path.join(HERE, "host", "bv_caller.cpp")]
-HOST_DEPS = HOST_SRC + [os.path.join(HERE, "host", "bv_host.hpp"), os.path.join(HERE, "host", "bv_caller.hpp"),
-                        os.path.join(HERE, "..", "include", "basevar_b200.h")]
+HOST_SRC = [os.path.join(HERE, "host", f) for f in ("bv_host.cpp", "bv_caller.cpp", "bv_bam.cpp", "bv_pileup.cpp")]
+HOST_DEPS = HOST_SRC + [os.path.join(HERE, "host", f) for f in ("bv_host.hpp", "bv_caller.hpp", "bv_bam.hpp", "bv_pileup.hpp")] + [
+    os.path.join(HERE, "..", "include", "basevar_b200.h")]
+CLI = os.path.join(HERE, "bin", "basevar")   # `basevar basetype ...` over BAM files (host/bv_main.cpp)
 ROOT = os.path.dirname(HERE)
 CPP_TESTS = {"test_host_cpu": [], "test_host_gpu": ["-ldl"], "test_fisher_fast": ["-ldl", "-lm"], "test_caller_cpu": [],
-             "test_caller_gpu": ["-lz"]}
+             "test_caller_gpu": ["-lz"], "pileup_dump": ["-lz"]}
 
 
 def build_host(force=False):
@@ -64,6 +65,11 @@ def build_host(force=False):
         if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(HOST_LIB)):
             subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-o", exe, src, "-L" + HERE, "-lbasevar_b200_host",
                                    "-lbasevar_b200", "-Wl,-rpath," + HERE, "-lpthread"] + extra)
+    main_src = os.path.join(HERE, "host", "bv_main.cpp")
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    if force or not os.path.exists(CLI) or os.path.getmtime(CLI) < max(os.path.getmtime(main_src), os.path.getmtime(HOST_LIB)):
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-Wall", "-o", CLI, main_src, "-L" + HERE, "-lbasevar_b200_host",
+                               "-lbasevar_b200", "-Wl,-rpath," + HERE, "-Wl,-rpath,$ORIGIN/..", "-lpthread", "-lz"])
     return HOST_LIB
 
 

@@ -443,6 +443,31 @@ void BasevarCaller::call(const std::vector<std::string>& lines) {
     if (T.n_sites == opt_.tile_sites) submit_current();
 }
 
+TileRows BasevarCaller::begin_tile(uint32_t n_rows) {
+    if (n_rows == 0 || n_rows > opt_.tile_sites) throw std::invalid_argument("[ERROR] begin_tile: row count outside the tile");
+    if (!tiles_[cur_]->pending && tiles_[cur_]->n_sites) submit_current();   // rows queued through call() go first
+    Tile& T = *tiles_[cur_];
+    if (T.pending) drain(cur_);
+    const size_t cells = (size_t)n_rows * T.pitch;
+    memset(T.base, BV_BASE_N, cells); memset(T.qual, 0, cells); memset(T.strand, BV_STRAND_NONE, cells); memset(T.mapq, 0, cells);
+    memset(T.rpr, 0, (size_t)n_rows * T.rpr_pitch * sizeof(uint16_t));
+    for (uint32_t i = 0; i < n_rows; ++i) {
+        SiteMeta& m = T.meta[i];
+        m.specials.clear(); m.odd_strands.clear(); m.depth = 0;
+    }
+    T.n_sites = n_rows;
+    return TileRows{T.base, T.qual, T.strand, T.mapq, T.rpr, T.pitch, T.rpr_pitch, n_rows, T.meta.data()};
+}
+
+void BasevarCaller::commit_tile() {
+    Tile& T = *tiles_[cur_];
+    for (uint32_t i = 0; i < T.n_sites; ++i) {
+        T.ref[i] = T.meta[i].ref_base.empty() ? (uint8_t)'N' : (uint8_t)T.meta[i].ref_base[0];
+        if (T.meta[i].depth) ++n_positions_;
+    }
+    submit_current();
+}
+
 void BasevarCaller::submit_current() {
     Tile& T = *tiles_[cur_];
     if (T.n_sites == 0) return;
@@ -471,6 +496,7 @@ void BasevarCaller::drain(uint32_t slot) {
     for (uint32_t i = 0; i < T.n_sites; ++i) {
         const SiteCells c{T.base + (size_t)i * T.pitch, T.qual + (size_t)i * T.pitch, T.strand + (size_t)i * T.pitch, (uint32_t)n_sample_};
         const bv_site_out& rec = T.recs[i];
+        if (T.meta[i].depth == 0) continue;   // no sample covers the position: no row (cpp:717-718)
         if (rec.flags & BV_FLAG_ZERO_SUBSET)   // src/basetype.cpp:113-115
             throw std::runtime_error("[ERROR] The sum of frequence of active bases must always > 0. Check: " + T.meta[i].ref_id + ":" +
                                      std::to_string(T.meta[i].ref_pos));

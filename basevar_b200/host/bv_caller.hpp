@@ -72,6 +72,16 @@ std::string out_cvg_line(const SiteMeta& m, const SiteCells& c, const bv_site_ou
 std::string out_vcf_line(const SiteMeta& m, const SiteCells& c, const bv_site_out& rec, const bv_call_out& call,
                          const std::vector<std::string>& group_names, const bv_group_out* groups);
 
+// Direct row access for packers that fill a whole tile themselves (the BAM-driven packer, bv_pileup.hpp): the planes of the
+// current tile, pre-filled with uncovered cells (N ! 0 0 .), and one SiteMeta per row for the caller to fill.
+struct TileRows {
+    uint8_t *base, *qual, *strand, *mapq;
+    uint16_t* rpr;
+    uint64_t pitch, rpr_pitch;   // elements per row
+    uint32_t n_rows;
+    SiteMeta* meta;
+};
+
 std::string vcf_header_define(const std::vector<std::string>& contig_lines, const std::string& reference_line,
                               const std::vector<std::string>& addition_info, const std::vector<std::string>& samples);
 std::string cvg_header_define();
@@ -89,6 +99,11 @@ public:
     // One position: one row from each batchfile, in batchfile order (the smp_bf_line_vector of _basevar_caller).
     // Throws std::runtime_error with the reference's messages on malformed rows.  Text may be emitted for earlier tiles.
     void call(const std::vector<std::string>& smp_bf_line_vector);
+    // Tile path: begin_tile(n) hands out n (<= tile_sites) rows of a free tile; the packer fills cells and meta (ref_id,
+    // ref_pos, ref_base, depth, specials); commit_tile() sends them.  Rows whose depth stays 0 produce no output, as in
+    // _basevar_caller (cpp:717-718).  Text of earlier tiles may be emitted by begin_tile().
+    TileRows begin_tile(uint32_t n_rows);
+    void commit_tile();
     // Drains the pipeline.  Returns true if any SNP row was written since construction (`has_data`, cpp:610).
     bool finish();
 
