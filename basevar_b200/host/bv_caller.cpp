@@ -470,7 +470,7 @@ void BasevarCaller::commit_tile() {
 
 void BasevarCaller::submit_current() {
     Tile& T = *tiles_[cur_];
-    if (T.n_sites == 0) return;
+    if (T.pending || T.n_sites == 0) return;   // a pending tile still holds the rows it was submitted with
     bv_tile t;
     t.base = T.base; t.qual = T.qual; t.strand = T.strand; t.ref_base = T.ref;
     t.pitch = T.pitch; t.n_sites = T.n_sites; t.n_samples = (uint32_t)n_sample_;
