@@ -1,0 +1,46 @@
+"""-m gpu: every BASELINE.json configuration at its FULL size (C4: the shard one GPU of eight takes), streamed in tiles
+generated on the device (tools/full_configs.py): the size-independent properties -- depth conservation, fwd + rev ==
+depth, a checksum of checksums that does not depend on the tile size -- and random sites of the region against the CPU
+oracle through the host twin of the generator."""
+import pytest
+
+from tools import full_configs
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_ok(r):
+    print(r)
+    assert r["depth_conservation_violations"] == 0
+    assert r["strand_sum_violations"] == 0
+    assert r["tiling_invariant"], (r["checksum"], r["checksum_b"])
+    assert r["spot_exact_mismatches"] == 0 and r["spot_float_mismatches"] == 0 and r["spot_flips"] <= 2
+    assert r["variant_sites"] > 0 and r["covered_sites"] > 0.9 * r["sites"]
+
+
+def test_c2_full_size(built_lib, oracle_lib):
+    r = full_configs.run_config("C2", spot=2000)
+    assert r["sites"] == 1_000_000 and r["n_samples"] == 1_000
+    _assert_ok(r)
+
+
+def test_c3_full_size(built_lib, oracle_lib):
+    """10,000 samples x 10,000,000 sites = 1e11 sample-sites, about 300 GB of planes streamed through one GPU."""
+    r = full_configs.run_config("C3", spot=400)
+    assert r["sites"] == 10_000_000 and r["n_samples"] == 10_000
+    _assert_ok(r)
+
+
+def test_c4_one_shard_of_eight(built_lib, oracle_lib):
+    """100,000 samples x 64,000,000 sites over 8 GPUs: GPU 3's contiguous shard (8,000,000 sites = 8e11 sample-sites)."""
+    r = full_configs.run_config("C4", shard=(3, 8), spot=48)
+    assert r["sites"] == 8_000_000 and r["site_range"] == [24_000_000, 32_000_000] and r["n_samples"] == 100_000
+    _assert_ok(r)
+
+
+@pytest.mark.parametrize("abs_mode", [0, 1])
+def test_c5_full_size_both_abs_modes(built_lib, oracle_lib, abs_mode):
+    r = full_configs.run_config("C5", abs_mode=abs_mode, spot=600)
+    assert r["sites"] == 1_000_000 and r["n_samples"] == 2_000
+    _assert_ok(r)
+    assert r["variant_sites"] > 200_000
