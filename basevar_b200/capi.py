@@ -84,6 +84,28 @@ class BvTileAux(C.Structure):
     _fields_ = [("mapq", C.c_void_p), ("rpr", C.c_void_p), ("rpr_pitch", C.c_uint64)]
 
 
+class BvSparseTile(C.Structure):
+    _fields_ = [
+        ("cells", C.c_void_p),
+        ("cells_aux", C.c_void_p),
+        ("site_start", C.c_void_p),
+        ("ref_base", C.c_void_p),
+        ("out", C.c_void_p),
+        ("n_sites", C.c_uint32),
+        ("n_samples", C.c_uint32),
+    ]
+
+
+def cell_pack(sample, base, strand, phred):
+    """BV_CELL_PACK of include/basevar_b200.h (numpy arrays or ints)."""
+    return (np.asarray(sample, np.uint32) | (np.asarray(base, np.uint32) << 20) | (np.asarray(strand, np.uint32) << 23)
+            | (np.asarray(phred, np.uint32) << 25)).astype(np.uint32)
+
+
+def cell_aux_pack(mapq, rpr):
+    return (np.asarray(mapq, np.uint32) | (np.asarray(rpr, np.uint32) << 8)).astype(np.uint32)
+
+
 class BvSynthModel(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64),
@@ -123,6 +145,10 @@ _SIGNATURES = [
     ("bv_synth_set_model", C.c_int, [C.c_void_p, C.POINTER(BvSynthModel)]),
     ("bv_synth_fill_device", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64] + [C.c_void_p] * 6),
     ("bv_synth_fill_host", C.c_int, [C.POINTER(BvSynthModel), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64] + [C.c_void_p] * 5),
+    ("bv_tile_submit_sparse", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvSparseTile)]),
+    ("bv_tile_submit_sparse_calls", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvSparseTile)]),
+    ("bv_synth_fill_sparse_host", C.c_int, [C.POINTER(BvSynthModel), C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                            C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     ("bv_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     ("bv_host_free", C.c_int, [C.c_void_p]),
 ]

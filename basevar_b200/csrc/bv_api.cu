@@ -16,6 +16,7 @@
 #include "bv_count_kernel.cuh"
 #include "bv_finish_kernels.cuh"
 #include "bv_call_kernels.cuh"
+#include "bv_expand_kernel.cuh"
 #include "bv_synth.cuh"
 
 namespace bv {
@@ -114,6 +115,13 @@ struct bv_slot {
     uint32_t* h_counters = nullptr;       // copy of the scratch counters (kCntCalled = number of calls)
     uint8_t* d_aux = nullptr;             // mapq | rpr planes of pageable host tiles (allocated on first use)
     bool with_calls = false;
+    // sparse tiles (bv_tile_submit_sparse): the covered cells as uploaded, expanded into d_planes by K0
+    uint32_t* d_cells = nullptr;          // [cells_cap] cells, then [cells_cap] aux words
+    uint32_t* d_site_start = nullptr;     // [max_sites + 1]
+    uint64_t cells_cap = 0;
+    bool sparse = false;
+    bool out_direct = false;              // the D2H copy went straight into the caller's pinned buffer
+    bv_site_out* out_user = nullptr;      // bv_sparse_tile::out
 };
 
 struct bv_ctx {
@@ -244,13 +252,13 @@ static int set_call_args(bv_ctx* ctx, const bv_tile* t, const bv_tile_aux* aux, 
 
 // The basetype core of one tile: K1 (counts, every cell), K2 (scalar finish, one thread per site), K3 / K4 (sites whose
 // result depends on base qualities: likelihood-ratio bound, then EM + LRT).  Stream ordered; see csrc/bv_common.cuh.
-static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream) {
+static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream, bool counters_zeroed = false) {
     if (a.n_sites == 0) return BV_OK;
     if (a.n_samples == 0) {   // no cells: every record is all-zero
         BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
         return BV_OK;
     }
-    BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), stream));
+    if (!counters_zeroed) BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), stream));
     const bool prof = ctx->profiling;
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
     // K1, persistent: one CTA per SM, each warp strides over the sites; kernel shape by row length
@@ -452,6 +460,7 @@ void bv_destroy(bv_ctx* ctx) {
             if (s.h_groups) cudaFreeHost(s.h_groups);
             if (s.h_counters) cudaFreeHost(s.h_counters);
             cudaFree(s.d_aux);
+            cudaFree(s.d_cells); cudaFree(s.d_site_start);
         }
         delete[] ctx->slots;
     }
@@ -559,6 +568,7 @@ static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
     s.qual_host = nullptr;
     s.h2d_bytes = 0;
+    s.sparse = false; s.out_direct = false; s.out_user = nullptr;
     bv_tile dev = *tile;
     if (tile->location == BV_LOC_HOST) {
         if (!tile->base || !tile->qual || !tile->strand || !tile->ref_base) return set_err(ctx, BV_ERR_ARG, "bv_tile: null pointer");
@@ -636,6 +646,121 @@ static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv
     return BV_OK;
 }
 
+// Sparse host tile: upload the covered cells (4 bytes each), expand them into the slot's dense planes (K0), then the
+// same kernels as for a dense tile.  The qual plane -- and for the called-site kernels the mapq / rpr planes -- are
+// device resident here (there is no host plane to read in place).
+static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* t, bool with_calls) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
+    if (!t) return set_err(ctx, BV_ERR_ARG, "null tile");
+    bv_slot& s = ctx->slots[slot];
+    if (s.busy) return set_err(ctx, BV_ERR_STATE, "slot %d is busy: call bv_tile_wait first", slot);
+    if (t->n_sites > ctx->prm.max_sites) return set_err(ctx, BV_ERR_ARG, "tile has %u sites > max_sites %u", t->n_sites, ctx->prm.max_sites);
+    if (t->n_samples > ctx->prm.max_samples || t->n_samples > BV_CELL_MAX_SAMPLES)
+        return set_err(ctx, BV_ERR_ARG, "sparse tile: n_samples %u > max_samples %u or > %u", t->n_samples, ctx->prm.max_samples, BV_CELL_MAX_SAMPLES);
+    if (t->n_sites && (!t->site_start || !t->ref_base)) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: null pointer");
+    const uint64_t n_cells = t->n_sites ? t->site_start[t->n_sites] : 0;
+    if (t->n_sites && t->site_start[0] != 0) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: site_start[0] must be 0");
+    if (n_cells && (!t->cells || (with_calls && !t->cells_aux))) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: null cells");
+    if (n_cells > (uint64_t)t->n_sites * t->n_samples) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: more cells than sample-sites");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    s.qual_host = nullptr;
+    s.h2d_bytes = 0;
+    s.sparse = true; s.out_direct = false; s.out_user = t->out;
+    if (n_cells > s.cells_cap) {   // grows only; sized by the first tiles of a run
+        if (s.d_cells) BV_CUDA(ctx, cudaFree(s.d_cells));
+        s.d_cells = nullptr; s.cells_cap = 0;
+        const uint64_t cap = n_cells + n_cells / 4 + 1024;
+        BV_CUDA(ctx, cudaMalloc(&s.d_cells, 2 * cap * sizeof(uint32_t)));
+        s.cells_cap = cap;
+    }
+    if (!s.d_site_start) BV_CUDA(ctx, cudaMalloc(&s.d_site_start, ((size_t)ctx->prm.max_sites + 1) * sizeof(uint32_t)));
+    const uint64_t dp = ((uint64_t)t->n_samples + 15) / 16 * 16;
+    const size_t plane = (size_t)ctx->prm.max_sites * ctx->pitch_cap;
+    if (with_calls && !s.d_aux) BV_CUDA(ctx, cudaMalloc(&s.d_aux, 3 * plane));
+    bv_tile dev;
+    dev.base = s.d_planes; dev.qual = s.d_planes + plane; dev.strand = s.d_planes + 2 * plane; dev.ref_base = s.d_ref;
+    dev.pitch = dp; dev.n_sites = t->n_sites; dev.n_samples = t->n_samples; dev.location = BV_LOC_DEVICE; dev.reserved = 0;
+    bv::SiteKernelArgs a;
+    int rc = fill_kernel_args(ctx, &dev, s.d_out, s.scratch, &a);
+    if (rc != BV_OK) return rc;
+    if (with_calls) {
+        bv_tile_aux dev_aux;
+        dev_aux.mapq = s.d_aux; dev_aux.rpr = reinterpret_cast<const uint16_t*>(s.d_aux + plane); dev_aux.rpr_pitch = dp;
+        rc = set_call_args(ctx, &dev, &dev_aux, s.scratch, s.h_calls, s.h_groups, &a);
+        if (rc != BV_OK) return rc;
+    }
+    memset(s.h_counters, 0, 8 * sizeof(uint32_t));
+    if (t->n_sites && t->n_samples) {
+        if (n_cells) {
+            BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells, t->cells, n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            if (with_calls)
+                BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells + s.cells_cap, t->cells_aux, n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+        }
+        BV_CUDA(ctx, cudaMemcpyAsync(s.d_site_start, t->site_start, ((size_t)t->n_sites + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+        BV_CUDA(ctx, cudaMemcpyAsync(s.d_ref, t->ref_base, t->n_sites, cudaMemcpyHostToDevice, s.stream));
+        s.h2d_bytes = n_cells * sizeof(uint32_t) * (with_calls ? 2 : 1) + ((size_t)t->n_sites + 1) * sizeof(uint32_t) + t->n_sites;
+        BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), s.stream));
+        bv::ExpandArgs x;
+        x.cells = s.d_cells; x.cells_aux = with_calls ? s.d_cells + s.cells_cap : nullptr; x.site_start = s.d_site_start;
+        x.base = s.d_planes; x.qual = s.d_planes + plane; x.strand = s.d_planes + 2 * plane;
+        x.mapq = with_calls ? s.d_aux : nullptr;
+        x.rpr = with_calls ? reinterpret_cast<uint16_t*>(s.d_aux + plane) : nullptr;
+        x.counters = a.counters;
+        x.pitch = dp; x.rpr_pitch = dp; x.n_cells = n_cells; x.n_sites = t->n_sites; x.n_samples = t->n_samples;
+        uint32_t grid = (t->n_sites + bv::kExpandWarps - 1) / bv::kExpandWarps;
+        const uint32_t cap = (uint32_t)ctx->num_sms * 4u;   // 4 CTAs of 16 warps per SM: all 64 warp slots writing
+        if (grid > cap) grid = cap;
+        bv::bv_expand_kernel<<<grid, bv::kExpandWarps * 32, 0, s.stream>>>(x);
+        BV_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    rc = launch_site_kernel(ctx, a, s.stream, /*counters_zeroed=*/true);
+    if (rc != BV_OK) return rc;
+    if (t->n_sites) {
+        bv_site_out* dst = s.h_out;
+        if (t->out && host_device_pointer(t->out)) { dst = t->out; s.out_direct = true; }
+        BV_CUDA(ctx, cudaMemcpyAsync(dst, s.d_out, (size_t)t->n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
+        if (t->n_samples)
+            BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    }
+    s.with_calls = with_calls;
+    s.n_sites = t->n_sites;
+    s.busy = true;
+    ctx->h2d_bytes_total += s.h2d_bytes;
+    return BV_OK;
+}
+
+int bv_tile_submit_sparse(bv_ctx* ctx, int slot, const bv_sparse_tile* tile) { return tile_submit_sparse_impl(ctx, slot, tile, false); }
+int bv_tile_submit_sparse_calls(bv_ctx* ctx, int slot, const bv_sparse_tile* tile) { return tile_submit_sparse_impl(ctx, slot, tile, true); }
+
+int bv_synth_fill_sparse_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
+                              uint32_t* cells, uint32_t* cells_aux, uint64_t max_cells, uint32_t* site_start,
+                              uint8_t* ref_base, uint64_t* n_cells) {
+    if (!model || !n_cells) return set_err(nullptr, BV_ERR_ARG, "null argument");
+    if (n_samples > BV_CELL_MAX_SAMPLES) return set_err(nullptr, BV_ERR_ARG, "n_samples > %u", BV_CELL_MAX_SAMPLES);
+    uint64_t n = 0;
+    for (uint32_t s = 0; s < n_sites; ++s) {
+        const bv::SynthSite ss = bv::synth_site(model, site0 + s);
+        if (ref_base) ref_base[s] = "ACGT"[ss.ref];
+        if (site_start) site_start[s] = (uint32_t)n;
+        for (uint32_t i = 0; i < n_samples; ++i) {
+            const bv::SynthCell c = bv::synth_cell(model, ss, i);
+            if (c.base == BV_BASE_N) continue;   // the generator makes N only for uncovered cells
+            if (cells) {
+                if (n >= max_cells) return set_err(nullptr, BV_ERR_ARG, "more than max_cells cells");
+                cells[n] = BV_CELL_PACK(i, c.base, c.strand, c.qual);
+                if (cells_aux) cells_aux[n] = BV_CELL_AUX_PACK(c.mapq, bv::synth_rpr(model, ss, i));
+            }
+            ++n;
+        }
+        if (n > 0xffffffffull) return set_err(nullptr, BV_ERR_ARG, "more than 2^32 cells in one tile");
+    }
+    if (site_start) site_start[n_sites] = (uint32_t)n;
+    *n_cells = n;
+    return BV_OK;
+}
+
 int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out) {
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
@@ -645,7 +770,11 @@ int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out) {
     cudaError_t e = cudaStreamSynchronize(s.stream);
     s.busy = false;
     BV_CUDA(ctx, e);
-    if (out && s.n_sites) memcpy(out, s.h_out, (size_t)s.n_sites * sizeof(bv_site_out));
+    if (s.sparse && s.n_sites && s.h_counters[bv::kCntBadCell])
+        return set_err(ctx, BV_ERR_ARG, "sparse tile: cell with sample >= n_samples or site_start not ascending / beyond the cell count");
+    const bv_site_out* rec = s.out_direct ? s.out_user : s.h_out;
+    if (s.out_user && !s.out_direct && s.n_sites) memcpy(s.out_user, s.h_out, (size_t)s.n_sites * sizeof(bv_site_out));
+    if (out && out != rec && s.n_sites) memcpy(out, rec, (size_t)s.n_sites * sizeof(bv_site_out));
     return BV_OK;
 }
 

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import BvError, BvTile, BvTileAux, CALL_OUT_DTYPE, GROUP_OUT_DTYPE, SITE_OUT_DTYPE
+from .capi import BvError, BvSparseTile, BvTile, BvTileAux, CALL_OUT_DTYPE, GROUP_OUT_DTYPE, SITE_OUT_DTYPE
 
 
 def _ptr(a):
@@ -100,6 +100,77 @@ class BaseTypeEngine:
         for ps, p0 in pending:
             self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data), "bv_tile_wait")
         return out
+
+    # -- sparse tiles from host memory: only the covered cells cross PCIe ---------------------------------
+    def call_sparse(self, cells, site_start, ref_base, n_samples, out=None, out_pinned=False):
+        """cells: uint32 BV_CELL_PACK words grouped by site; site_start: uint32 [S + 1] offsets into cells.
+
+        Tiles of max_sites sites go through the slot pipeline (upload of the cells, K0 expand, K1..K4, D2H of the
+        records).  With out_pinned=True `out` is pinned host memory and the D2H DMA writes the records in place."""
+        S = ref_base.shape[0]
+        assert cells.dtype == np.uint32 and site_start.dtype == np.uint32 and site_start.shape[0] == S + 1
+        if out is None:
+            out = np.zeros(S, dtype=SITE_OUT_DTYPE)
+        n_slots, step = self.params.n_slots, self.params.max_sites
+        assert n_slots >= 1 and step >= 1, "engine was created without slots"
+        pending, slot, keep = [], 0, {}
+        for s0 in range(0, max(S, 1), step):
+            ns = min(step, S - s0)
+            if len(pending) == n_slots:
+                ps, p0 = pending.pop(0)
+                self._check(self.lib.bv_tile_wait(self._ctx, ps, None if out_pinned else out[p0:].ctypes.data), "bv_tile_wait")
+            c0 = int(site_start[s0])
+            # per-tile offsets start at 0 (a packer writes them so; here they are rebased from the whole-run array)
+            st = site_start[s0:s0 + ns + 1] - np.uint32(c0) if c0 else site_start[s0:s0 + ns + 1]
+            keep[slot] = st
+            t = BvSparseTile(cells[c0:].ctypes.data if c0 < cells.shape[0] else cells.ctypes.data, None, st.ctypes.data,
+                             ref_base[s0:].ctypes.data, out[s0:].ctypes.data if out_pinned else None, ns, n_samples)
+            self._check(self.lib.bv_tile_submit_sparse(self._ctx, slot, C.byref(t)), "bv_tile_submit_sparse")
+            pending.append((slot, s0))
+            slot = (slot + 1) % n_slots
+        for ps, p0 in pending:
+            self._check(self.lib.bv_tile_wait(self._ctx, ps, None if out_pinned else out[p0:].ctypes.data), "bv_tile_wait")
+        return out
+
+    def call_sparse_calls(self, cells, cells_aux, site_start, ref_base, n_samples):
+        """call_sparse plus the called-site outputs; returns what call_host_calls returns."""
+        S = ref_base.shape[0]
+        assert cells.dtype == np.uint32 and cells_aux.dtype == np.uint32 and site_start.dtype == np.uint32
+        G = getattr(self, "n_groups", 0)
+        out = np.zeros(S, dtype=SITE_OUT_DTYPE)
+        n_slots, step = self.params.n_slots, self.params.max_sites
+        calls, groups = [], []
+        tmp_calls = np.zeros(step, CALL_OUT_DTYPE)
+        tmp_groups = np.zeros((step, max(G, 1)), GROUP_OUT_DTYPE)
+        pending, slot, keep = [], 0, {}
+
+        def wait(ps, p0):
+            n = C.c_uint32(0)
+            self._check(self.lib.bv_tile_wait_calls(self._ctx, ps, out[p0:].ctypes.data, tmp_calls.ctypes.data, step, C.byref(n),
+                                                    tmp_groups.ctypes.data if G else None), "bv_tile_wait_calls")
+            c = tmp_calls[:n.value].copy()
+            c["site"] += p0
+            calls.append(c)
+            groups.append(tmp_groups.reshape(-1)[:n.value * G].reshape(n.value, G).copy() if G else np.zeros((n.value, 0), GROUP_OUT_DTYPE))
+
+        for s0 in range(0, max(S, 1), step):
+            ns = min(step, S - s0)
+            if len(pending) == n_slots:
+                wait(*pending.pop(0))
+            c0 = int(site_start[s0])
+            st = site_start[s0:s0 + ns + 1] - np.uint32(c0)
+            keep[slot] = st
+            off = min(c0, max(cells.shape[0] - 1, 0))
+            t = BvSparseTile(cells[off:].ctypes.data, cells_aux[off:].ctypes.data, st.ctypes.data, ref_base[s0:].ctypes.data, None, ns, n_samples)
+            self._check(self.lib.bv_tile_submit_sparse_calls(self._ctx, slot, C.byref(t)), "bv_tile_submit_sparse_calls")
+            pending.append((slot, s0))
+            slot = (slot + 1) % n_slots
+        for ps, p0 in pending:
+            wait(ps, p0)
+        calls = np.concatenate(calls) if calls else np.zeros(0, CALL_OUT_DTYPE)
+        groups = np.concatenate(groups) if groups else np.zeros((0, G), GROUP_OUT_DTYPE)
+        order = np.argsort(calls["site"], kind="stable")
+        return out, calls[order], groups[order]
 
     # -- called sites: rank sums + population groups ---------------------------------------------------
     CALL_KERNEL_NAMES = ("bv_ranksum_kernel", "bv_group_kernel")
@@ -204,3 +275,50 @@ def synth_fill_host(model, site0, n_sites, n_samples, pitch=None, with_mapq=Fals
     if rc != capi.BV_OK:
         raise BvError(f"bv_synth_fill_host failed ({rc}): {lib.bv_last_error(None).decode()}")
     return base, qual, strand, mapq, ref
+
+
+def dense_to_sparse(base, qual, strand, n_samples, mapq=None, rpr=None):
+    """Sparse form (cells, cells_aux | None, site_start) of dense planes: every cell that is not the uncovered triple
+    (BV_BASE_N, phred 0, BV_STRAND_NONE), in sample order within a site."""
+    b, q, s = base[:, :n_samples], qual[:, :n_samples], strand[:, :n_samples]
+    cov = (b != capi.BASE_N) | (q != 0) | (s != capi.STRAND_NONE)
+    if mapq is not None:
+        cov |= (mapq[:, :n_samples] != 0) | (rpr[:, :n_samples] != 0)
+    site, samp = np.nonzero(cov)
+    cells = capi.cell_pack(samp, b[site, samp], s[site, samp], q[site, samp])
+    aux = capi.cell_aux_pack(mapq[site, samp], rpr[site, samp]) if mapq is not None else None
+    site_start = np.zeros(base.shape[0] + 1, np.uint32)
+    np.cumsum(cov.sum(axis=1), out=site_start[1:])
+    return cells, aux, site_start
+
+
+def synth_fill_sparse_host(model, site0, n_sites, n_samples, with_aux=False, pinned=False):
+    """Host twin of the generator in sparse form.  Returns (cells, cells_aux | None, site_start, ref_base)."""
+    lib = capi.load_library()
+
+    def alloc(k, dt):
+        if pinned:
+            import torch
+            return torch.empty(max(k, 1), dtype={np.uint32: torch.int32, np.uint8: torch.uint8}[dt], pin_memory=True).numpy().view(dt)[:k]
+        return np.empty(k, dt)
+
+    site_start = alloc(n_sites + 1, np.uint32)
+    ref = alloc(n_sites, np.uint8)
+    total = n_sites * n_samples
+    # one pass with room for the expected number of cells + 6 sigma; a second, exact one if that was too small
+    exp = total * (model.cov_thr / 2.0 ** 32)
+    cap = int(min(total, exp + 6.0 * np.sqrt(exp + 1.0) + 64))
+    n = C.c_uint64(0)
+    for attempt in range(2):
+        cells = alloc(cap, np.uint32)
+        aux = alloc(cap, np.uint32) if with_aux else None
+        rc = lib.bv_synth_fill_sparse_host(C.byref(model), site0, n_sites, n_samples, cells.ctypes.data,
+                                           aux.ctypes.data if with_aux else None, cap, site_start.ctypes.data, ref.ctypes.data, C.byref(n))
+        if rc == capi.BV_OK:
+            return cells[:n.value], (aux[:n.value] if with_aux else None), site_start, ref
+        if attempt == 0:
+            rc2 = lib.bv_synth_fill_sparse_host(C.byref(model), site0, n_sites, n_samples, None, None, 0, None, None, C.byref(n))
+            if rc2 != capi.BV_OK:
+                break
+            cap = int(n.value)
+    raise BvError(f"bv_synth_fill_sparse_host failed ({rc}): {lib.bv_last_error(None).decode()}")

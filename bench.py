@@ -8,8 +8,9 @@ workload: BASELINE.json configs[1] = synthetic 1,000 samples x 1 Mb at 0.1x ("C2
 step    : one pass of the basetype core (kernels K1 count, K2 scalar, K3 bound, K4 EM) over the whole per-GPU workload
           (S sites x N samples).
 value   : whole-job sample-sites/s with the planes resident in HBM (kernels only, CUDA events, max over ranks).
-e2e     : the same metric through the C ABI with HOST buffers: pinned planes -> bv_tile_submit (H2D, kernel, D2H
-          of the 128-byte records) -> bv_tile_wait, tiles pipelined over 3 streams; copies inside the timed region.
+e2e     : the same metric through the C ABI with HOST buffers, copies inside the timed region, tiles pipelined over 3
+          streams: sparse tiles (pinned u32 cells of the covered reads -> bv_tile_submit_sparse: H2D, K0 expand, K1..K4,
+          D2H of the 128-byte records -> bv_tile_wait).  e2e_dense: the same through dense pinned planes (bv_tile_submit).
 roofline: algorithmic bytes S*(3N+128) per step / average step time (all four kernels), against MEASURED_PEAKS.json
           hbm_gbs; the per-kernel durations are measured live with CUDA events between the kernels (bv_set_profiling).
 cpu_baseline: the UNMODIFIED reference (oracle/_ref/libbvref.so: BaseType ctor + lrt() + strand_bias) on the
@@ -240,6 +241,29 @@ def main():
     kernel_ms = {k: v / args.steps for k, v in ksum.items()}
 
     # ---- end to end through the C ABI with host buffers --------------------------------------------------------
+    # (a) sparse tiles (the headline e2e): pinned host arrays of the covered cells (4 bytes each) -> bv_tile_submit_sparse
+    #     (H2D of the cells, K0 expand, K1..K4, D2H of the 128-byte records straight into a pinned buffer) -> bv_tile_wait
+    t_prep = time.perf_counter()
+    site0 = shard.rank_site_range(rank, world, S)[0]
+    cells, _, site_start, s_ref = bv.synth_fill_sparse_host(model, site0, S, n_samples, pinned=True)
+    t_prep = time.perf_counter() - t_prep
+    rec_sp = torch.empty(S * 128, dtype=torch.uint8, pin_memory=True).numpy().view(bv.SITE_OUT_DTYPE)
+    rec_sp[:] = 0
+    eng.call_sparse(cells, site_start, s_ref, n_samples, out=rec_sp, out_pinned=True)   # warm-up (sizes the cell buffers)
+    barrier()
+    l0 = eng.launch_count
+    up0 = eng.h2d_bytes
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        eng.call_sparse(cells, site_start, s_ref, n_samples, out=rec_sp, out_pinned=True)
+    torch.cuda.synchronize()
+    sp_s = (time.perf_counter() - t0) / args.e2e_steps
+    sp_launches = eng.launch_count - l0
+    sp_uploaded = (eng.h2d_bytes - up0) // args.e2e_steps
+    sp_s_max = shard.max_over_ranks(sp_s, dev)
+    sp_value = world * S * n_samples / sp_s_max
+
+    # (b) dense tiles: pinned planes -> bv_tile_submit (H2D of base + strand, qual rows read in place) -> bv_tile_wait
     h_planes = [torch.empty((S, pitch), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
     h_ref = torch.empty(S, dtype=torch.uint8, pin_memory=True)
     for h, d in zip(h_planes, (base, qual, strand)):
@@ -258,15 +282,16 @@ def main():
         eng.call_host(hb, hq, hs, hr, n_samples, out=rec)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-    e2e_launches = eng.launch_count - l0
+    e2e_launches = eng.launch_count - l0 + sp_launches
     uploaded = (eng.h2d_bytes - up0) // args.e2e_steps
     e2e_s_max = shard.max_over_ranks(e2e_s, dev)
     e2e_value = world * S * n_samples / e2e_s_max
     clk = clocks.stop()
 
-    # the e2e records must be the very records of the device-resident path
+    # the e2e records (both transports) must be the very records of the device-resident path
     dev_rec = out.cpu().numpy().view(bv.SITE_OUT_DTYPE)
     same = bool(dev_rec.tobytes() == rec.tobytes())
+    same_sp = bool(dev_rec.tobytes() == rec_sp.tobytes())
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -294,9 +319,15 @@ def main():
                          "k1_bytes": S * (2 * n_samples + 128),
                          "k1_achieved": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9,
                          "k1_frac": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9 / peak},
-            # h2d: bytes uploaded by cudaMemcpyAsync (base + strand planes, REF bases) plus the qual rows the kernels read
-            # in place from the pinned host plane (sites settled by the bound or by EM; bound failures read theirs twice)
-            "e2e": {"value": e2e_value, "unit": UNIT,
+            # e2e (headline): sparse host tiles.  h2d = 4 bytes per covered cell + the site offsets + REF bases
+            "e2e": {"value": sp_value, "unit": UNIT, "h2d_bytes_per_step": int(sp_uploaded), "d2h_bytes_per_step": int(S * 128),
+                    "ms_per_step": 1e3 * sp_s_max, "transport": "sparse tiles (bv_tile_submit_sparse): pinned u32 cells of the covered "
+                    "reads, expanded into the dense planes on the device (K0); records DMA'd into a pinned buffer",
+                    "cells_per_step": int(cells.shape[0]), "tile_sites": tile_sites, "slots": 3, "records_match_device_path": same_sp,
+                    "host_prep_s_untimed": t_prep},
+            # the dense-plane transport of the same workload.  h2d: bytes uploaded by cudaMemcpyAsync (base + strand planes,
+            # REF bases) plus the qual rows the kernels read in place from the pinned host plane
+            "e2e_dense": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(uploaded + pitch * int((((dev_rec["flags"] & 0x20) != 0) | (dev_rec["em_calls"] >= 3) | ((dev_rec["n_alt"] > 0) & (dev_rec["em_calls"] == 1))).sum())),
                     "uploaded_bytes_per_step": int(uploaded), "d2h_bytes_per_step": int(S * 128),
                     "ms_per_step": 1e3 * e2e_s_max, "tile_sites": tile_sites, "slots": 3, "records_match_device_path": same},

@@ -212,6 +212,47 @@ int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out);
  * `stream` is a cudaStream_t (NULL = the legacy default stream).  Stream ordered, returns at once. */
 int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, void* stream);
 
+/* ---- sparse host tiles: only the covered cells cross PCIe ------------------------------------------ */
+/* At the depths this caller is built for (< 1x) nine cells in ten are the constant "uncovered" triple
+ * (BV_BASE_N, phred 0, BV_STRAND_NONE) -- the `N ! 0 0 .` filler of the reference's batchfile rows
+ * (src/basetype_caller.cpp:1063-1075).  A sparse tile carries the covered cells only, 4 bytes each, grouped by
+ * site; the expand kernel (K0 bv_expand_kernel) writes the dense site-major planes in HBM and the same kernels
+ * run on them, so the records are byte-identical with those of the dense tile.  Pileup assembly produces this
+ * form naturally (one cell per aligned base of a read).
+ *
+ * cell = sample | base << 20 | strand << 23 | phred << 25   (sample < 2^20, base BV_BASE_*, strand BV_STRAND_*,
+ * phred 0..127).  Within a site every sample index may appear at most once (first-read-wins has already been
+ * applied by the packer); cells with sample >= n_samples, or offsets that are not ascending, make bv_tile_wait
+ * fail with BV_ERR_ARG. */
+#define BV_CELL_SAMPLE_BITS 20
+#define BV_CELL_MAX_SAMPLES (1u << BV_CELL_SAMPLE_BITS)
+#define BV_CELL_PACK(sample, base, strand, phred) \
+    ((uint32_t)(sample) | ((uint32_t)(base) << 20) | ((uint32_t)(strand) << 23) | ((uint32_t)(phred) << 25))
+/* aux word of a cell (called-site kernels): mapq | rpr << 8 */
+#define BV_CELL_AUX_PACK(mapq, rpr) ((uint32_t)(mapq) | ((uint32_t)(rpr) << 8))
+
+typedef struct bv_sparse_tile {
+    const uint32_t* cells;      /* [site_start[n_sites]] BV_CELL_PACK words, the cells of site 0 first            */
+    const uint32_t* cells_aux;  /* same indexing, BV_CELL_AUX_PACK words; only read by bv_tile_submit_sparse_calls */
+    const uint32_t* site_start; /* [n_sites + 1] ascending offsets into `cells`; site_start[0] == 0               */
+    const uint8_t*  ref_base;   /* [n_sites] as in bv_tile                                                        */
+    bv_site_out*    out;        /* optional: PINNED host memory for the n_sites records; the D2H DMA then writes  */
+                                /* them in place and bv_tile_wait's `out` may be NULL                             */
+    uint32_t n_sites;
+    uint32_t n_samples;
+} bv_sparse_tile;
+
+/* Asynchronous, like bv_tile_submit (host memory only; pinned memory makes the copies truly asynchronous). */
+int bv_tile_submit_sparse(bv_ctx* ctx, int slot, const bv_sparse_tile* tile);
+/* The same plus the called-site kernels; collect with bv_tile_wait_calls. */
+int bv_tile_submit_sparse_calls(bv_ctx* ctx, int slot, const bv_sparse_tile* tile);
+/* Host twin of the synthetic generator in sparse form: fills cells / cells_aux (may be NULL) / site_start / ref_base
+ * for sites [site0, site0 + n_sites); *n_cells receives the number of cells, BV_ERR_ARG if it exceeds max_cells
+ * (call with cells == NULL to count only). */
+int bv_synth_fill_sparse_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
+                              uint32_t* cells, uint32_t* cells_aux, uint64_t max_cells, uint32_t* site_start,
+                              uint8_t* ref_base, uint64_t* n_cells);
+
 /* ---- called sites: rank-sum INFO fields and population-group allele frequencies ----------------- */
 /* sample_group[i] = group index 0..n_groups-1 of sample i, or BV_GROUP_NONE.  The caller numbers the groups in the
  * order the reference iterates them (std::map<std::string,...>: ascending group name, basetype_caller.cpp:756).

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_struct_layouts_match_the_header(built_lib):
     assert capi.SITE_OUT_DTYPE.itemsize == 128
-    assert C.sizeof(capi.BvParams) == 36 and C.sizeof(capi.BvTile) == 56
+    assert C.sizeof(capi.BvParams) == 36 and C.sizeof(capi.BvTile) == 56 and C.sizeof(capi.BvSparseTile) == 48
     assert C.sizeof(capi.BvSynthModel) == 32 + 4 * (96 + 1024 + 256)
     offs = {n: capi.SITE_OUT_DTYPE.fields[n][1] for n in capi.SITE_OUT_DTYPE.names}
     assert offs == {"depth": 0, "depth_other": 16, "reserved0": 20, "fwd": 24, "rev": 40, "n_alt": 56, "alt": 57,
@@ -85,3 +85,20 @@ def test_synth_host_twin_is_deterministic_and_tileable(built_lib):
     assert set(np.unique(s[:, :1000][covered])) <= {0, 1} and (s[:, :1000][~covered] == 2).all()
     assert set(np.unique(r)) <= {65, 67, 71, 84}
     assert (mq[:, :1000][covered] >= 10).all()
+
+
+def test_sparse_host_twin_equals_the_dense_twin(built_lib):
+    """bv_synth_fill_sparse_host lists exactly the covered cells of bv_synth_fill_host, packed as BV_CELL_PACK."""
+    for cov, N, S in [(0.1, 1000, 200), (0.99326, 7, 300), (0.3, 1003, 50)]:
+        m = bv.synth.make_model(seed=5, coverage=cov, variant_frac=0.2, multi_frac=0.2)
+        b, q, s, mq, r = bv.synth_fill_host(m, 7, S, N, with_mapq=True)
+        rpr = bv.synth_fill_rpr_host(m, 7, S, N)
+        cells, aux, st, ref = bv.synth_fill_sparse_host(m, 7, S, N, with_aux=True)
+        c2, a2, st2 = bv.dense_to_sparse(b, q, s, N, mq, rpr)
+        assert np.array_equal(cells, c2) and np.array_equal(aux, a2) and np.array_equal(st, st2) and np.array_equal(ref, r)
+        # unpacking gives the planes back
+        site = np.repeat(np.arange(S), np.diff(st.astype(np.int64)))
+        samp = cells & ((1 << 20) - 1)
+        assert np.array_equal((cells >> 20) & 7, b[site, samp]) and np.array_equal((cells >> 23) & 3, s[site, samp])
+        assert np.array_equal(cells >> 25, q[site, samp]) and np.array_equal(aux & 255, mq[site, samp])
+        assert np.array_equal(aux >> 8, rpr[site, samp])

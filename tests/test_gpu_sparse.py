@@ -1,0 +1,141 @@
+"""-m gpu: sparse host tiles (bv_tile_submit_sparse, kernel K0 bv_expand_kernel) through the C ABI.
+
+The sparse tile is another transport of the same pileup, so the bar is stricter than parity: the records must be
+BYTE-identical with those of the dense tile (same kernels on the same planes), and they are checked against the CPU
+oracle as well.  Edge cases: empty tiles, sites without cells, a tile with no cell at all, every cell covered, junk
+characters / indels / bad strands (any cell that differs from the uncovered triple travels), cells in random order
+within a site, malformed input (sample out of range, descending offsets) -> BV_ERR_ARG."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import basevar_b200 as bv
+from basevar_b200 import capi
+from oracle import loader as L
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(built_lib):
+    eng = bv.BaseTypeEngine(device=0, max_samples=20000, max_sites=1024, n_slots=3, min_af=0.01)
+    yield eng
+    eng.close()
+
+
+def _both(engine, b, q, s, r, N, maf, abs_mode, label, shuffle=None):
+    engine.set_params(min_af=maf, abs_mode=abs_mode)
+    dense = engine.call_host(b, q, s, r, N)
+    cells, _, st = bv.dense_to_sparse(b, q, s, N)
+    if shuffle is not None:   # cell order within a site is free
+        for i in range(len(st) - 1):
+            shuffle.shuffle(cells[st[i]:st[i + 1]])
+    sparse = engine.call_sparse(cells, st, r, N)
+    assert sparse.tobytes() == dense.tobytes(), f"{label}: sparse and dense records differ"
+    want = L.oracle_tile(b, q, s, r, N, maf, abs_mode)
+    ie, fe, flips = util.compare_records(sparse, want)
+    assert len(ie) == 0 and len(fe) == 0, f"{label}: {len(ie)} exact / {len(fe)} float mismatches vs the oracle"
+    assert len(flips) <= 2
+    return sparse
+
+
+@pytest.mark.parametrize("abs_mode", [0, 1])
+@pytest.mark.parametrize(
+    "name,S,N,kw",
+    [
+        ("C2-like", 5000, 1000, dict(coverage=0.1, variant_frac=0.05)),
+        ("C1-like-N100", 3000, 100, dict(coverage=0.065, variant_frac=0.05)),
+        ("C3-like", 1100, 10000, dict(coverage=0.1, variant_frac=0.1)),
+        ("C5-like", 1100, 2000, dict(coverage=0.99326, variant_frac=0.5, multi_frac=0.5)),
+        ("odd-N", 2500, 1003, dict(coverage=0.3, variant_frac=0.3, multi_frac=0.5)),
+        ("tiny-N", 2500, 7, dict(coverage=0.8, variant_frac=0.5)),
+    ],
+)
+def test_sparse_equals_dense_and_oracle(engine, name, S, N, kw, abs_mode):
+    model = bv.synth.make_model(seed=4321 + N, **kw)
+    b, q, s, _, r = bv.synth_fill_host(model, 0, S, N)
+    got = _both(engine, b, q, s, r, N, bv.cli_min_af(0.01, N), abs_mode, name)
+    assert (got["n_alt"] > 0).sum() > 0
+
+
+def test_sparse_generator_twin(engine):
+    """bv_synth_fill_sparse_host == the dense host twin in sparse form, and runs to the same records."""
+    model = bv.synth.config_model("C2")
+    N, S = 1000, 3000
+    b, q, s, _, r = bv.synth_fill_host(model, 123456, S, N)
+    cells, _, st, ref = bv.synth_fill_sparse_host(model, 123456, S, N, pinned=True)
+    c2, _, st2 = bv.dense_to_sparse(b, q, s, N)
+    assert np.array_equal(cells, c2) and np.array_equal(st, st2) and np.array_equal(ref, r)
+    engine.set_params(min_af=bv.cli_min_af(0.01, N), abs_mode=0)
+    import torch
+    out = torch.empty(S * 128, dtype=torch.uint8, pin_memory=True).numpy().view(bv.SITE_OUT_DTYPE)
+    out[:] = 0
+    got = engine.call_sparse(cells, st, ref, N, out=out, out_pinned=True)     # records land by DMA in the pinned buffer
+    assert got.tobytes() == engine.call_host(b, q, s, r, N).tobytes()
+
+
+def test_sparse_fuzz_junk_and_random_cell_order(engine):
+    rng = np.random.default_rng(11)
+    for (S, N, cov, qlo, qhi, maf) in [(1500, 100, 0.5, 0, 40, 0.01), (1200, 1000, 0.1, 0, 93, 0.01), (600, 2000, 0.99, 2, 41, 0.01)]:
+        b, q, s, r = util.random_tile(rng, S, N, cov, qlo, qhi, other=0.01, indel=0.01, bad_strand=0.001)
+        _both(engine, b, q, s, r, N, maf, 0, f"fuzz N={N}", shuffle=rng)
+
+
+def test_sparse_edge_cases(engine):
+    engine.set_params(min_af=0.01, abs_mode=0)
+    N = 50
+    # no site at all
+    got = engine.call_sparse(np.zeros(0, np.uint32), np.zeros(1, np.uint32), np.zeros(0, np.uint8), N)
+    assert got.shape == (0,)
+    # sites without a single cell: all-zero records, like the dense path
+    S = 1500   # more than one tile
+    ref = np.full(S, ord("A"), np.uint8)
+    got = engine.call_sparse(np.zeros(0, np.uint32), np.zeros(S + 1, np.uint32), ref, N)
+    b = np.full((S, 64), 5, np.uint8); q = np.zeros((S, 64), np.uint8); s = np.full((S, 64), 2, np.uint8)
+    assert got.tobytes() == engine.call_host(b, q, s, ref, N).tobytes()
+    assert not got["depth"].any()
+    # every cell covered, one site empty in the middle
+    rng = np.random.default_rng(5)
+    b, q, s, r = util.random_tile(rng, 300, N, 1.0, 20, 40)
+    b[17, :] = 5; q[17, :] = 0; s[17, :] = 2
+    _both(engine, b, q, s, r, N, 0.01, 0, "full coverage")
+
+
+def test_sparse_malformed_input_is_an_error(engine):
+    engine.set_params(min_af=0.01, abs_mode=0)
+    N, S = 50, 10
+    ref = np.full(S, ord("C"), np.uint8)
+    cells = capi.cell_pack(np.arange(S) % N, 1, 0, 30)
+    st = np.arange(S + 1, dtype=np.uint32)
+    engine.call_sparse(cells, st, ref, N)                      # well formed
+    bad = cells.copy(); bad[3] = capi.cell_pack(N, 1, 0, 30)   # sample == n_samples
+    with pytest.raises(bv.BvError, match="sparse tile"):
+        engine.call_sparse(bad, st, ref, N)
+    st2 = st.copy(); st2[4], st2[5] = st[5], st[4]             # descending offsets
+    with pytest.raises(bv.BvError, match="sparse tile"):
+        engine.call_sparse(cells, st2, ref, N)
+    engine.call_sparse(cells, st, ref, N)                      # the slot is usable again
+
+
+@pytest.mark.parametrize("G", [0, 3])
+def test_sparse_calls_equal_dense_calls(built_lib, G):
+    """Called-site kernels on a sparse tile (mapq / rpr travel as the cells' aux words)."""
+    eng = bv.BaseTypeEngine(device=0, max_samples=2000, max_sites=512, n_slots=2, min_af=0.01)
+    try:
+        rng = np.random.default_rng(21 + G)
+        for (S, N, kw) in [(1500, 1000, dict(coverage=0.1, variant_frac=0.2)), (700, 2000, dict(coverage=0.99326, variant_frac=0.5, multi_frac=0.5))]:
+            model = bv.synth.make_model(seed=99 + N, **kw)
+            b, q, s, mapq, r = bv.synth_fill_host(model, 0, S, N, with_mapq=True)
+            rpr = bv.synth_fill_rpr_host(model, 0, S, N)
+            eng.set_params(min_af=bv.cli_min_af(0.01, N), abs_mode=0)
+            eng.set_groups(util.random_groups(rng, N, G) if G else None, G)
+            d_rec, d_calls, d_groups = eng.call_host_calls(b, q, s, r, mapq, rpr, N)
+            cells, aux, st, ref = bv.synth_fill_sparse_host(model, 0, S, N, with_aux=True)
+            s_rec, s_calls, s_groups = eng.call_sparse_calls(cells, aux, st, ref, N)
+            assert s_rec.tobytes() == d_rec.tobytes()
+            assert len(s_calls) > 0 and s_calls.tobytes() == d_calls.tobytes()
+            assert s_groups.tobytes() == d_groups.tobytes()
+    finally:
+        eng.close()
