@@ -13,7 +13,9 @@
 //        a few reads -- sequencing errors): fetches the row's base + qual planes and settles the LRT by a rigorous bound
 //        on the likelihood ratio, without running the EM; what the bound cannot decide goes to state EM.
 //   K4  bv_em_kernel      (bv_finish_kernels.cuh)  one warp per site in state EM: (base, phred) histogram of the row,
-//        EM + LRT backward elimination on the bins, QUAL, ALT-table Fisher.
+//        EM + LRT backward elimination on the bins.  QUAL (chi-square survival function) and the strand-bias Fisher test
+//        of the VCF row are scalar work that a warp would do 32 times over: the warp queues its sites with ALT alleles
+//        and finishes them 32 at a time, one THREAD per site.
 //
 // Work moves between the kernels through compact lists of site indices (appended with warp-aggregated atomics, so their
 // order varies from run to run; every site is independent, so the records do not).  The record's `reserved0` word
@@ -44,6 +46,7 @@ constexpr uint32_t kStateEM = 3;             // result depends on base qualities
 
 constexpr int kCntSlow = 0, kCntBound = 1, kCntEm = 2, kCntEmNext = 3;   // SiteKernelArgs::counters
 constexpr int kCntCalled = 4, kCntGroupNext = 5;                          // called sites (K4 -> K5, K6)
+constexpr int kCntBadCell = 6;                                            // malformed sparse input (K0, bv_expand_kernel.cuh)
 
 // word indices of bv_site_out seen as 32 x u32
 constexpr int kWDepth = 0, kWOther = 4, kWState = 5, kWFwd = 6, kWRev = 10, kWAlt = 14, kWInfo = 15;

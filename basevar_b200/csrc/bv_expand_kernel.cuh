@@ -15,7 +15,6 @@
 namespace bv {
 
 constexpr int kExpandWarps = 16;
-constexpr int kCntBadCell = 6;   // SiteKernelArgs::counters slot: malformed sparse input (sample out of range, bad offsets)
 
 struct ExpandArgs {
     const uint32_t* cells;

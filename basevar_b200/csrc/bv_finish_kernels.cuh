@@ -280,6 +280,8 @@ struct __align__(128) QualWarp {
     uint32_t p2_phase;           // mbarrier phase bits of p2bar[]
     uint64_t p2bar[2];
     alignas(16) bv_site_out rec; // the site's record: loaded from global, completed, stored back
+    uint32_t vcf_n;              // sites with ALT alleles waiting for their scalar finish (vcf_flush)
+    uint32_t vcf_site[32];
 };
 
 struct __align__(128) QualCta {
@@ -466,6 +468,119 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb
     return warp_sum(ll);
 }
 
+// ---- the same EM with the bins in registers ------------------------------------------------------------------------
+// Up to 32 * NS bins: lane l owns bins l, l + 32, ... (the order em_bins visits them in, so every sum is associated the
+// same way).  Each lane keeps its bins' likelihoods, counts and previous marginals in registers over all iterations and
+// works on its NS bins in one straight-line block, so that NS independent FP64 chains are in flight.  Two savings in
+// operation count, both inside the stated tolerance of the floating-point outputs (1e-9 here, 1e-6 in north_star):
+//   * the four posteriors of a read are l_j * (1/m) instead of l_j / m: one division per bin instead of one per allele;
+//   * as built (int abs(int), src/algorithm.h:245) the convergence sum is non-zero only when some log-marginal moved by
+//     at least 1, i.e. when a marginal changed by a factor e: decided exactly from the ratio of the marginals -- inside
+//     (1/2.5, 2.5) no logarithm is needed, otherwise the logarithms themselves decide -- so that `log` runs once per
+//     bin and EM call (for the reported log-likelihoods) instead of once per bin and iteration.
+template <int NS>
+__device__ __noinline__ double em_bins_reg(const uint32_t* bins, int nb, int subset, double total) {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    const double* s_lut = cs.lut;
+    const int lane = threadIdx.x & 31;
+    const bool int_mode = cs.a.abs_mode == BV_EM_ABS_INT_TRUNC;
+    double f0 = W.emf[0], f1 = W.emf[1], f2 = W.emf[2], f3 = W.emf[3];
+    __syncwarp();
+    double ome[NS], e3[NS], cd[NS], prev[NS];   // prev: marginal (int mode) or log marginal (double mode) of the last E-step
+    uint32_t bb[NS];
+    bool on[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int i = lane + 32 * k;
+        on[k] = i < nb;
+        const uint32_t p = on[k] ? bins[i] : pack_bin(4u, 0u, 0u);
+        const uint32_t q = bin_qual(p);
+        bb[k] = bin_base(p);
+        cd[k] = (double)bin_count(p);
+        ome[k] = s_lut[kLutOneMinusEps * kQStride + q];
+        e3[k] = s_lut[kLutEpsThird * kQStride + q];
+        prev[k] = 0.0;
+    }
+    int it = cs.a.em_max_iter;
+    bool first = true;
+    for (;;) {
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0, delta = 0;
+        bool big = false, unsure = false;
+        double mk[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            // e_step (algorithm.h:160-172): lik*freq summed in A,C,G,T order; alleles outside the subset add an exact +0.0
+            double l0 = 0, l1 = 0, l2 = 0, l3 = 0, m = 0;
+            if (subset & 1) { l0 = (bb[k] == 0 ? ome[k] : e3[k]) * f0; m += l0; }
+            if (subset & 2) { l1 = (bb[k] == 1 ? ome[k] : e3[k]) * f1; m += l1; }
+            if (subset & 4) { l2 = (bb[k] == 2 ? ome[k] : e3[k]) * f2; m += l2; }
+            if (subset & 8) { l3 = (bb[k] == 3 ? ome[k] : e3[k]) * f3; m += l3; }
+            mk[k] = m;
+            const double inv = 1.0 / m;
+            // m_step (algorithm.h:184-198): column sums of the posteriors; c equal reads add c * post
+            if (on[k]) {
+                if (subset & 1) s0 += cd[k] * (l0 * inv);
+                if (subset & 2) s1 += cd[k] * (l1 * inv);
+                if (subset & 4) s2 += cd[k] * (l2 * inv);
+                if (subset & 8) s3 += cd[k] * (l3 * inv);
+            }
+        }
+        if (int_mode) {
+            if (!first) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k)
+                    if (on[k] && !(mk[k] < 2.5 * prev[k] && prev[k] < 2.5 * mk[k])) unsure = true;   // also NaN / 0 / inf
+                if (__any_sync(kFull, unsure)) {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        // (double)abs((int)diff): non-zero iff |diff| >= 1; NaN/inf convert to INT_MIN whose "abs" stays
+                        // negative and ends the loop (results are NaN by then)
+                        const double diff = nlog(mk[k]) - nlog(prev[k]);
+                        if (on[k] && fabs(diff) >= 1.0 && fabs(diff) < 2147483648.0) big = true;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) prev[k] = mk[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const double llh = log(mk[k]);
+                if (!first && on[k]) delta += cd[k] * fabs(llh - prev[k]);
+                prev[k] = llh;
+            }
+        }
+        if (subset & 1) f0 = warp_sum(s0) / total;
+        if (subset & 2) f1 = warp_sum(s1) / total;
+        if (subset & 4) f2 = warp_sum(s2) / total;
+        if (subset & 8) f3 = warp_sum(s3) / total;
+        if (first) { first = false; continue; }
+        bool more;
+        if (int_mode) more = __any_sync(kFull, big);
+        else more = !(warp_sum(delta) < cs.a.em_eps);
+        --it;
+        if (it == 0 && lane == 0) W.flag_word |= BV_FLAG_EM_MAXITER;
+        if (!more || it == 0) break;
+    }
+    double ll = 0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const double lml = int_mode ? log(prev[k]) : prev[k];
+        if (on[k]) ll += cd[k] * lml;
+    }
+    if (lane == 0) { W.emf[0] = f0; W.emf[1] = f1; W.emf[2] = f2; W.emf[3] = f3; }
+    __syncwarp();
+    return warp_sum(ll);
+}
+
+// EM of one candidate subset: bins in registers when they fit (the usual case), else the loop over memory
+__device__ __forceinline__ double em_subset(const uint32_t* bins, double* lml, int nb, int subset, double total) {
+    if (nb <= 32) return em_bins_reg<1>(bins, nb, subset, total);
+    if (nb <= 96) return em_bins_reg<3>(bins, nb, subset, total);
+    return em_bins(bins, lml, nb, subset, total);
+}
+
 // Log-likelihood of the single-allele model {b} (an EM whose answer is closed form):
 // after the first m_step f_b == 1.0 exactly (every posterior is x/x), so every later marginal is L_b itself and
 // the reported log marginal is log(1-eps) or log(eps/3) -- both tabulated on the host with glibc.  A bin of base b
@@ -553,7 +668,7 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
     // initial frequencies of a subset: depth/total for its members, 0 elsewhere (src/basetype.cpp:93-103)
     if (lane < 4) W.emf[lane] = (act >> lane & 1u) ? (double)W.rec.depth[lane] / dtot : 0.0;
     __syncwarp();
-    double lr_alt = em_bins(bins, lml, nb, (int)act, dtot);
+    double lr_alt = em_subset(bins, lml, nb, (int)act, dtot);
     if (lane < 4) W.res_f[lane] = W.emf[lane];
     uint32_t em_calls = 1;
 #pragma unroll 1
@@ -577,7 +692,7 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
                 if (lane < 4) W.emf[lane] = lane == single ? v : 0.0;
                 __syncwarp();
             } else {
-                lr = em_bins(bins, lml, nb, (int)sub, dtot);
+                lr = em_subset(bins, lml, nb, (int)sub, dtot);
             }
             if (em_calls < 255) ++em_calls;
             const double c = 2 * (lr_alt - lr);
@@ -616,6 +731,43 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
     }
     __syncwarp();
     return act | ((uint32_t)n_act << 4) | (em_calls << 8);
+}
+
+// ---- scalar finish of the sites with ALT alleles, one THREAD per queued site ------------------------------------------------
+// QUAL = -10 log10 of the chi-square survival function of the last LRT statistic (src/basetype.cpp:188-194) unless the
+// mono-allelic rule already set it, and the strand bias of the VCF row, ref vs the called ALT alleles
+// (src/basetype.cpp:244-295, basetype_caller.cpp:1164).  Both are functions of a few numbers of the record; done inside
+// qual_site the whole warp would compute them 32 times over (34 % of K4's instructions on C5 before this queue).
+__device__ __noinline__ void vcf_flush() {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = W.vcf_n;
+    __syncwarp();
+    if (lane < n) {
+        const uint32_t site = W.vcf_site[lane];
+        bv_site_out* rec = cs.a.out + site;
+        const int ref_code = ref_code_of(cs.a.ref_base[site]);
+        if (!(rec->flags & BV_FLAG_MONO_QUAL)) rec->qual = qual_from_chi(rec->chi2);
+        uint32_t alt_set = 0;
+        for (int k = 0; k < (int)rec->n_alt; ++k) alt_set |= 1u << (rec->alt[k] & 3u);
+        const uint32_t f[4] = {rec->fwd[0], rec->fwd[1], rec->fwd[2], rec->fwd[3]};
+        const uint32_t rv[4] = {rec->rev[0], rec->rev[1], rec->rev[2], rec->rev[3]};
+        int rf = 0, rr = 0, vf = 0, vr = 0, af_ = 0, ar = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b == ref_code) { rf = (int)f[b]; rr = (int)rv[b]; }
+            else { af_ += (int)f[b]; ar += (int)rv[b]; }
+            if (alt_set >> b & 1u) { vf += (int)f[b]; vr += (int)rv[b]; }
+        }
+        double fs_vcf = 0.0;
+        if (vf == af_ && vr == ar) fs_vcf = rec->fs_cvg;   // same 2x2 table as the CVG row
+        else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(cs.a.logfact, rf, rr, vf, vr);
+        rec->fs_vcf = fs_vcf;
+    }
+    __syncwarp();
+    if (lane == 0) W.vcf_n = 0;
+    __syncwarp();
 }
 
 // ---- one site in state kStateEM --------------------------------------------------------------------------------------------
@@ -677,23 +829,16 @@ __device__ __noinline__ void qual_site(uint32_t site) {
     uint32_t flags = W.flag_word;
 
     // ---- ALT / QUAL (src/basetype.cpp:170-196) ----
+    // Here only the rule that needs no arithmetic (mono-allelic 5000); the chi-square survival function and the Fisher
+    // test of the VCF row are scalar, warp-uniform work: the site is queued and vcf_flush() does them one thread per site.
     const uint32_t alt_set = act & ~ref_bit;
     const int n_alt = __popc(alt_set);
-    double qual = 0.0, fs_vcf = 0.0;
+    double qual = 0.0;
+    const double fs_vcf = 0.0;
     if (n_alt) {
         const int first_act = __ffs(act) - 1;
         const double r = (double)sel4u(first_act, d0, d1, d2, d3) / dtot;
         if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
-        else qual = qual_from_chi(chi);
-        // strand bias of the VCF row: ref vs the called ALT alleles (src/basetype.cpp:244-295, basetype_caller.cpp:1164)
-        const uint32_t* f = W.rec.fwd;
-        const uint32_t* rv = W.rec.rev;
-        const int rf = ref_code < 0 ? 0 : (int)f[ref_code], rr = ref_code < 0 ? 0 : (int)rv[ref_code];
-        const int af_ = (int)(f[0] + f[1] + f[2] + f[3]) - rf, ar = (int)(rv[0] + rv[1] + rv[2] + rv[3]) - rr;
-        const int vf = (int)(((alt_set & 1) ? f[0] : 0u) + ((alt_set & 2) ? f[1] : 0u) + ((alt_set & 4) ? f[2] : 0u) + ((alt_set & 8) ? f[3] : 0u));
-        const int vr = (int)(((alt_set & 1) ? rv[0] : 0u) + ((alt_set & 2) ? rv[1] : 0u) + ((alt_set & 4) ? rv[2] : 0u) + ((alt_set & 8) ? rv[3] : 0u));
-        if (vf == af_ && vr == ar) fs_vcf = W.rec.fs_cvg;   // same 2x2 table as the CVG row
-        else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(cs.a.logfact, rf, rr, vf, vr);
     }
 
     // ---- record ----
@@ -720,10 +865,12 @@ __device__ __noinline__ void qual_site(uint32_t site) {
         r.fs_vcf = fs_vcf;
         // called sites go on to the rank-sum / population-group kernels (bv_call_kernels.cuh)
         if (n_alt && cs.a.list_called) cs.a.list_called[atomicAdd(cs.a.counters + kCntCalled, 1u)] = site;
+        if (n_alt) W.vcf_site[W.vcf_n++] = site;
     }
     __syncwarp();
     if (lane < 8) reinterpret_cast<uint4*>(cs.a.out + site)[lane] = reinterpret_cast<const uint4*>(&W.rec)[lane];
-    __syncwarp();
+    __syncwarp();   // also orders the record's stores before vcf_flush() reads them from other lanes
+    if (W.vcf_n == 32) vcf_flush();
 }
 
 // Persistent warps with dynamic work distribution over the EM list.
@@ -737,6 +884,7 @@ __global__ void __launch_bounds__(kQualWarps * 32, 1) bv_em_kernel(const __grid_
     if (lane == 0) {
         W.flag_word = 0;
         W.p2_phase = 0;
+        W.vcf_n = 0;
         mbar_init(&W.p2bar[0], 1);
         mbar_init(&W.p2bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -751,6 +899,7 @@ __global__ void __launch_bounds__(kQualWarps * 32, 1) bv_em_kernel(const __grid_
         if (i >= n_em) break;
         qual_site(a.list_em[i]);
     }
+    if (W.vcf_n) vcf_flush();
 }
 
 }  // namespace bv

@@ -65,7 +65,7 @@ BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_
                 left += p;
                 if (i == lo || p < 1e-18 * left) break;
                 // pmf(i-1) = pmf(i) * i * n22(i) / ((n1_-i+1) (n_1-i+1)),  n22(i) = i + n - n1_ - n_1   (kfunc.c:234-236)
-                p *= (double)i / (n1_ - i + 1) * (i + n - n1_ - n_1) / (n_1 - i + 1);
+                p *= ((double)i * (double)(i + n - n1_ - n_1)) / ((double)(n1_ - i + 1) * (double)(n_1 - i + 1));   // products < 2^53: exact
                 --i;
             }
         }
@@ -88,7 +88,7 @@ BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_
                 right += p;
                 if (i == hi || p < 1e-18 * right) break;
                 // pmf(i+1) = pmf(i) * (n1_-i) (n_1-i) / ((i+1) n22(i+1))                                  (kfunc.c:228-230)
-                p *= (double)(n1_ - i) / (i + 1) * (n_1 - i) / (i + 1 + n - n1_ - n_1);
+                p *= ((double)(n1_ - i) * (double)(n_1 - i)) / ((double)(i + 1) * (double)(i + 1 + n - n1_ - n_1));
                 ++i;
             }
         }
