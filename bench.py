@@ -157,7 +157,7 @@ def main():
     ap.add_argument("--sites", type=int, default=0, help="sites per GPU (default: the config's, capped to fit HBM)")
     ap.add_argument("--abs-mode", type=int, default=0, help="0 = as-built int abs() in EM, 1 = fabs")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--tile-sites", type=int, default=32768)
+    ap.add_argument("--tile-sites", type=int, default=131072, help="sites per host tile of the e2e legs (tools/e2e_sweep.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sites-per-core", type=int, default=40000)
     args = ap.parse_args()
