@@ -91,6 +91,56 @@ bv_tile TilePacker::tile() const {
     return t;
 }
 
+// ---- SparsePacker -----------------------------------------------------------------------------------------------------
+SparsePacker::SparsePacker(uint32_t n_samples, uint32_t max_sites, size_t reserve_cells) : n_samples_(n_samples), max_sites_(max_sites) {
+    if (n_samples > BV_CELL_MAX_SAMPLES) throw std::runtime_error("[ERROR] sparse tiles hold at most 2^20 samples");
+    site_start_ = reinterpret_cast<uint32_t*>(plane_alloc(((size_t)max_sites + 1) * sizeof(uint32_t), true));
+    ref_ = plane_alloc(max_sites ? max_sites : 1, true);
+    site_start_[0] = 0;
+    grow(reserve_cells ? reserve_cells : (size_t)max_sites * 16 + 1024);
+}
+
+SparsePacker::~SparsePacker() {
+    plane_free(reinterpret_cast<uint8_t*>(cells_), true); plane_free(reinterpret_cast<uint8_t*>(aux_), true);
+    plane_free(reinterpret_cast<uint8_t*>(site_start_), true); plane_free(ref_, true);
+}
+
+void SparsePacker::grow(size_t want) {
+    if (want <= cap_cells_) return;
+    size_t cap = cap_cells_ ? cap_cells_ : 1024;
+    while (cap < want) cap *= 2;
+    uint32_t* c = reinterpret_cast<uint32_t*>(plane_alloc(cap * sizeof(uint32_t), true));
+    uint32_t* a = reinterpret_cast<uint32_t*>(plane_alloc(cap * sizeof(uint32_t), true));
+    if (n_cells_) { memcpy(c, cells_, n_cells_ * sizeof(uint32_t)); memcpy(a, aux_, n_cells_ * sizeof(uint32_t)); }
+    plane_free(reinterpret_cast<uint8_t*>(cells_), true); plane_free(reinterpret_cast<uint8_t*>(aux_), true);
+    cells_ = c; aux_ = a; cap_cells_ = cap;
+}
+
+void SparsePacker::begin_site(char ref_base) {
+    if (n_sites_ >= max_sites_) throw std::runtime_error("[ERROR] SparsePacker is full");
+    ref_[n_sites_] = (uint8_t)ref_base;
+    ++n_sites_;
+    site_start_[n_sites_] = (uint32_t)n_cells_;
+}
+
+void SparsePacker::add_cell(uint32_t sample, uint8_t base, uint8_t strand, uint8_t phred, uint8_t mapq, uint16_t rpr) {
+    if (n_sites_ == 0) throw std::runtime_error("[ERROR] SparsePacker::add_cell before begin_site");
+    if (sample >= n_samples_) throw std::runtime_error("[ERROR] SparsePacker: sample index out of range");
+    if (n_cells_ >= 0xffffffffull) throw std::runtime_error("[ERROR] SparsePacker: more than 2^32 cells in one tile");
+    grow(n_cells_ + 1);
+    cells_[n_cells_] = BV_CELL_PACK(sample, base & 7u, strand & 3u, phred & 127u);
+    aux_[n_cells_] = BV_CELL_AUX_PACK(mapq, rpr);
+    ++n_cells_;
+    site_start_[n_sites_] = (uint32_t)n_cells_;
+}
+
+bv_sparse_tile SparsePacker::tile() const {
+    bv_sparse_tile t;
+    t.cells = cells_; t.cells_aux = aux_; t.site_start = site_start_; t.ref_base = ref_; t.out = nullptr;
+    t.n_sites = n_sites_; t.n_samples = n_samples_;
+    return t;
+}
+
 // ---- Context ----------------------------------------------------------------------------------------------------------
 Context::Context(int device, float min_af, uint32_t max_samples, uint32_t max_sites, uint32_t n_slots, int em_abs_mode)
     : n_slots_(n_slots) {
@@ -110,6 +160,13 @@ Context::~Context() { bv_destroy(ctx_); }
 void Context::submit(int slot, const bv_tile& tile) { check(bv_tile_submit(ctx_, slot, &tile), ctx_, "bv_tile_submit"); }
 void Context::wait(int slot, bv_site_out* out) { check(bv_tile_wait(ctx_, slot, out), ctx_, "bv_tile_wait"); }
 std::vector<bv_site_out> Context::run(const bv_tile& tile) {
+    std::vector<bv_site_out> out(tile.n_sites);
+    submit(0, tile);
+    wait(0, out.data());
+    return out;
+}
+void Context::submit(int slot, const bv_sparse_tile& tile) { check(bv_tile_submit_sparse(ctx_, slot, &tile), ctx_, "bv_tile_submit_sparse"); }
+std::vector<bv_site_out> Context::run(const bv_sparse_tile& tile) {
     std::vector<bv_site_out> out(tile.n_sites);
     submit(0, tile);
     wait(0, out.data());

@@ -103,6 +103,45 @@ private:
     uint8_t *base_ = nullptr, *qual_ = nullptr, *strand_ = nullptr, *mapq_ = nullptr, *ref_ = nullptr;
 };
 
+// ---- sparse packer: only the covered cells of a site travel (bv_sparse_tile) ----------------------------------------------
+// What a pileup produces at < 1x depth: one packed word per (sample, position) a read covers.  A sample whose entry is
+// the reference's filler for "no read here" (`N`, `!`, strand `.`; src/basetype_caller.cpp:1063-1075) adds nothing.
+class SparsePacker {
+public:
+    SparsePacker(uint32_t n_samples, uint32_t max_sites, size_t reserve_cells = 0);
+    ~SparsePacker();
+    SparsePacker(const SparsePacker&) = delete;
+    SparsePacker& operator=(const SparsePacker&) = delete;
+
+    void clear() { n_sites_ = 0; n_cells_ = 0; }
+    uint32_t n_sites() const { return n_sites_; }
+    size_t n_cells() const { return n_cells_; }
+
+    void begin_site(char ref_base);                                      // then add_cell() for its covered samples
+    void add_cell(uint32_t sample, uint8_t base, uint8_t strand, uint8_t phred, uint8_t mapq = 0, uint16_t rpr = 0);
+    template <class BI>
+    void add_site(const BI& bi) {   // the reference's per-site struct (any type with BatchInfo's members)
+        if (bi.n != n_samples_) throw std::runtime_error("[ERROR] BatchInfo::n does not match the tile's sample count");
+        begin_site(bi.ref_base.empty() ? 'N' : bi.ref_base[0]);
+        for (size_t i = 0; i < bi.n; ++i) {
+            const uint8_t b = encode_base(bi.align_bases[i]), st = encode_strand(bi.map_strands[i]);
+            const uint8_t q = (uint8_t)(bi.align_base_quals[i] - 33);
+            const int mq = bi.mapqs[i] > 255 ? 255 : bi.mapqs[i] < 0 ? 0 : bi.mapqs[i];
+            const int rp = bi.base_pos_ranks.empty() ? 0 : bi.base_pos_ranks[i];
+            if (b == BV_BASE_N && q == 0 && st == BV_STRAND_NONE && mq == 0 && rp == 0) continue;
+            add_cell((uint32_t)i, b, st, q, (uint8_t)mq, (uint16_t)(rp < 0 ? 0 : rp > 65535 ? 65535 : rp));
+        }
+    }
+    bv_sparse_tile tile() const;   // valid until the next clear() / add
+
+private:
+    void grow(size_t want);
+    uint32_t n_samples_, max_sites_, n_sites_ = 0;
+    size_t n_cells_ = 0, cap_cells_ = 0;
+    uint32_t *cells_ = nullptr, *aux_ = nullptr, *site_start_ = nullptr;   // pinned
+    uint8_t* ref_ = nullptr;
+};
+
 // ---- a context bound to one GPU ---------------------------------------------------------------------------------------
 class Context {
 public:
@@ -115,6 +154,8 @@ public:
     void submit(int slot, const bv_tile& tile);          // asynchronous; throws std::runtime_error on failure
     void wait(int slot, bv_site_out* out);               // blocks; `out` receives the tile's records
     std::vector<bv_site_out> run(const bv_tile& tile);   // submit + wait on slot 0
+    void submit(int slot, const bv_sparse_tile& tile);   // sparse transport of the same tile (kernel K0 expands it)
+    std::vector<bv_site_out> run(const bv_sparse_tile& tile);
     uint32_t n_slots() const { return n_slots_; }
     uint64_t launch_count() const;
     bv_ctx* raw() { return ctx_; }

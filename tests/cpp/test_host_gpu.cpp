@@ -128,6 +128,16 @@ int main(int argc, char** argv) {
         }
     }
     CHECK(n_var > 50);
+    {   // the same sites through the sparse transport: byte-identical records
+        SparsePacker sp((uint32_t)N, S);
+        for (int s = 0; s < S; ++s) sp.add_site(bis[s]);
+        CHECK(sp.n_sites() == (uint32_t)S && sp.n_cells() > 0 && sp.n_cells() < (size_t)S * N);
+        const uint64_t l0 = ctx.launch_count();
+        std::vector<bv_site_out> srecs = ctx.run(sp.tile());
+        CHECK(ctx.launch_count() - l0 == 5);   // K0 expand + K1..K4
+        CHECK(memcmp(srecs.data(), recs.data(), sizeof(bv_site_out) * S) == 0);
+        printf("sparse transport: %zu cells for %d x %zu sample-sites, records identical\n", sp.n_cells(), S, N);
+    }
     printf("batch path: %d sites, %d variant\n", S, n_var);
 
     // ---- drop-in constructor: BaseType bt(&bi, min_af); bt.lrt();  (src/basetype_caller.cpp:742-743) ----
