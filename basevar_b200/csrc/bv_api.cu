@@ -411,7 +411,8 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess) {
+            cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kExpandSmemBytes) != cudaSuccess) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
                          cudaGetErrorString(cudaGetLastError()));
             break;
@@ -709,9 +710,9 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
         x.counters = a.counters;
         x.pitch = dp; x.rpr_pitch = dp; x.n_cells = n_cells; x.n_sites = t->n_sites; x.n_samples = t->n_samples;
         uint32_t grid = (t->n_sites + bv::kExpandWarps - 1) / bv::kExpandWarps;
-        const uint32_t cap = (uint32_t)ctx->num_sms * 4u;   // 4 CTAs of 16 warps per SM: all 64 warp slots writing
+        const uint32_t cap = (uint32_t)ctx->num_sms * 2u;   // persistent: 2 CTAs of 16 warps per SM (96 KB of staging each)
         if (grid > cap) grid = cap;
-        bv::bv_expand_kernel<<<grid, bv::kExpandWarps * 32, 0, s.stream>>>(x);
+        bv::bv_expand_kernel<<<grid, bv::kExpandWarps * 32, bv::kExpandSmemBytes, s.stream>>>(x);
         BV_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }

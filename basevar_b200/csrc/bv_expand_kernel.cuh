@@ -3,11 +3,19 @@
 // A sparse tile (bv_sparse_tile, include/basevar_b200.h) carries only the covered cells of a pileup tile, one packed
 // u32 each, grouped by site.  This is what crosses PCIe: at 0.1x depth 0.4 bytes per sample-site instead of the 2-3
 // bytes of the dense planes.  K0 turns it back into the planes every other kernel reads (the layout BatchInfo is
-// replaced by, src/basetype.h:25-43): one warp per site writes the row's "uncovered" filler
-// (`N`, phred 0, strand none -- the reference's `N ! 0 0 .`, src/basetype_caller.cpp:1063-1075) with 16-byte stores and
-// then scatters the site's cells into it.  The scatter hits lines the same warp has just written, so it merges in L2
-// and every plane byte goes to DRAM once.
+// replaced by, src/basetype.h:25-43).  One warp per site:
 //
+//   staged path (rows up to kExStagedMaxPitch bytes): the row is built chunk by chunk in shared memory -- the
+//   "uncovered" filler (`N`, phred 0, strand none: the reference's `N ! 0 0 .`, src/basetype_caller.cpp:1063-1075)
+//   with 16-byte stores, then the site's cells scattered into it with byte stores -- and leaves as three TMA bulk stores
+//   (cp.async.bulk.global.shared::cta; SASS UBLKCP) from one of two buffers per warp, so that the next chunk is built
+//   while the previous one drains.  Every plane byte goes to HBM exactly once, in full lines, and no thread waits for a
+//   store; offsets (two sites ahead) and cells (one site ahead) are prefetched into registers.  Cells may come in any
+//   order within a site, so a row of k chunks scans the site's cells k times (they stay in L1): fine up to a few chunks;
+//   direct path (longer rows): filler and cells are written to global memory directly; the scatter hits lines the same
+//   warp has just written and merges in L2.
+//
+// The mapq / rpr planes of the called-site kernels (only with cells_aux) always take the direct path.
 // Bound: HBM writes, 3 bytes per sample-site (+3 with the called-site planes), reads 4 bytes per covered cell.
 #pragma once
 #include "bv_common.cuh"
@@ -15,6 +23,18 @@
 namespace bv {
 
 constexpr int kExpandWarps = 16;
+constexpr int kExChunk = 1024;                       // bytes (= samples) per staged chunk and plane
+constexpr uint32_t kExStagedMaxPitch = 16 * kExChunk;
+
+struct __align__(128) ExpandBuf {
+    uint8_t base[kExChunk];
+    uint8_t qual[kExChunk];
+    uint8_t strand[kExChunk];
+};
+struct __align__(128) ExpandWarp {
+    ExpandBuf buf[2];
+};
+constexpr size_t kExpandSmemBytes = (size_t)kExpandWarps * sizeof(ExpandWarp);   // 96 KB: two CTAs per SM
 
 struct ExpandArgs {
     const uint32_t* cells;
@@ -33,50 +53,136 @@ struct ExpandArgs {
     uint32_t n_samples;
 };
 
-__global__ void __launch_bounds__(kExpandWarps * 32) bv_expand_kernel(const ExpandArgs a) {
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const ExpandArgs a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
     const uint32_t n_warps = gridDim.x * kExpandWarps;
-    const uint32_t vecs = (uint32_t)(a.pitch >> 4);
+    ExpandWarp& W = reinterpret_cast<ExpandWarp*>(bv_smem_raw)[threadIdx.x >> 5];
+    const uint32_t pitch = (uint32_t)a.pitch;
+    const bool staged = a.pitch <= kExStagedMaxPitch;
     const uint4 fill_base = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);     // BV_BASE_N
     const uint4 fill_strand = make_uint4(0x02020202u, 0x02020202u, 0x02020202u, 0x02020202u);   // BV_STRAND_NONE
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     bool bad = false;
-    for (uint32_t s = warp; s < a.n_sites; s += n_warps) {
-        // the offsets first, so that the loads are in flight while the filler is written
-        const uint64_t beg = a.site_start[s], end = a.site_start[s + 1];
-        const size_t row = (size_t)s * a.pitch;
-        uint4* rb = reinterpret_cast<uint4*>(a.base + row);
-        uint4* rq = reinterpret_cast<uint4*>(a.qual + row);
-        uint4* rs = reinterpret_cast<uint4*>(a.strand + row);
-        for (uint32_t v = lane; v < vecs; v += 32) {
-            rb[v] = fill_base;
-            rq[v] = zero;
-            rs[v] = fill_strand;
+    uint32_t cur = 0;   // staging buffer of the next chunk
+
+    // Software pipeline over the warp's sites: the offsets are loaded two sites ahead and the first kExPre * 32 cells
+    // one site ahead, so that their DRAM latency (the cells have just arrived over PCIe) hides behind the site in hand.
+    constexpr int kExPre = 4;
+    auto load_offsets = [&](uint32_t site, uint64_t& b, uint64_t& e) {
+        b = 0; e = 0;
+        if (site < a.n_sites) { b = a.site_start[site]; e = a.site_start[site + 1]; }
+    };
+    auto load_cells = [&](uint64_t b, uint64_t e, uint32_t (&pre)[kExPre]) {
+        const bool ok = e >= b && e <= a.n_cells;
+#pragma unroll
+        for (int k = 0; k < kExPre; ++k) {
+            const uint64_t c = b + (uint32_t)(32 * k) + lane;
+            pre[k] = (ok && c < e) ? __ldg(a.cells + c) : 0xffffffffu;   // sample 2^20 - 1 with base 7: never a real cell
         }
-        if (a.mapq) {
+    };
+    uint32_t s = warp;
+    uint64_t beg, end, nbeg, nend;
+    uint32_t pre[kExPre], npre[kExPre];
+    load_offsets(s, beg, end);
+    load_offsets(s + n_warps, nbeg, nend);
+    load_cells(beg, end, pre);
+    while (s < a.n_sites) {
+        const uint32_t s_next = s + n_warps;
+        uint64_t n2beg, n2end;
+        load_offsets(s_next + n_warps, n2beg, n2end);
+        load_cells(nbeg, nend, npre);
+        const bool ok = end >= beg && end <= a.n_cells;   // warp-uniform
+        if (!ok) { bad = true; end = beg; }               // the row still gets its filler
+        const uint32_t n_here = (uint32_t)(end - beg);    // <= n_samples * ... fits: n_cells < 2^32
+        const size_t row = (size_t)s * a.pitch;
+
+        if (a.mapq) {   // called-site planes: direct path
             uint4* rm = reinterpret_cast<uint4*>(a.mapq + row);
-            for (uint32_t v = lane; v < vecs; v += 32) rm[v] = zero;
+            for (uint32_t v = lane; v < (pitch >> 4); v += 32) rm[v] = zero;
             uint4* rr = reinterpret_cast<uint4*>(a.rpr + (size_t)s * a.rpr_pitch);
             const uint32_t rvecs = (uint32_t)(a.rpr_pitch >> 3);
             for (uint32_t v = lane; v < rvecs; v += 32) rr[v] = zero;
-        }
-        if (end < beg || end > a.n_cells) { bad = true; continue; }   // warp-uniform
-        __syncwarp();   // orders the filler before the cell stores of other lanes
-        for (uint64_t c = beg + lane; c < end; c += 32) {
-            const uint32_t w = __ldg(a.cells + c);
-            const uint32_t i = w & (BV_CELL_MAX_SAMPLES - 1u);
-            if (i >= a.n_samples) { bad = true; continue; }
-            a.base[row + i] = (uint8_t)((w >> 20) & 7u);
-            a.strand[row + i] = (uint8_t)((w >> 23) & 3u);
-            a.qual[row + i] = (uint8_t)(w >> 25);
-            if (a.mapq) {
+            __syncwarp();   // orders the filler before the cell stores of other lanes
+            for (uint64_t c = beg + lane; c < end; c += 32) {
+                const uint32_t i = __ldg(a.cells + c) & (BV_CELL_MAX_SAMPLES - 1u);
+                if (i >= a.n_samples) continue;   // reported below
                 const uint32_t x = __ldg(a.cells_aux + c);
                 a.mapq[row + i] = (uint8_t)x;
                 a.rpr[(size_t)s * a.rpr_pitch + i] = (uint16_t)(x >> 8);
             }
         }
+
+        if (staged) {
+#pragma unroll 1
+            for (uint32_t off = 0; off < pitch; off += kExChunk) {
+                const uint32_t bytes = min((uint32_t)kExChunk, pitch - off);
+                ExpandBuf& B = W.buf[cur];
+                // the bulk stores issued from this buffer two chunks ago must have read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                for (uint32_t v = lane; v < (bytes >> 4); v += 32) {
+                    reinterpret_cast<uint4*>(B.base)[v] = fill_base;
+                    reinterpret_cast<uint4*>(B.qual)[v] = zero;
+                    reinterpret_cast<uint4*>(B.strand)[v] = fill_strand;
+                }
+                __syncwarp();   // filler before the cells of other lanes
+                auto put = [&](uint32_t w) {
+                    const uint32_t i = w & (BV_CELL_MAX_SAMPLES - 1u);
+                    if (i >= a.n_samples) { bad = true; return; }
+                    const uint32_t k = i - off;
+                    if (k < bytes) {   // (unsigned: also false for i < off)
+                        B.base[k] = (uint8_t)((w >> 20) & 7u);
+                        B.strand[k] = (uint8_t)((w >> 23) & 3u);
+                        B.qual[k] = (uint8_t)(w >> 25);
+                    }
+                };
+#pragma unroll
+                for (int k = 0; k < kExPre; ++k)
+                    if ((uint32_t)(32 * k) + lane < n_here) put(pre[k]);
+                for (uint64_t c = beg + (uint32_t)(32 * kExPre) + lane; c < end; c += 32) put(__ldg(a.cells + c));
+                // generic-proxy writes -> visible to the async proxy, then one lane hands the chunk to the TMA unit
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(a.base + row + off, smem_u32(B.base), bytes);
+                    bulk_s2g(a.qual + row + off, smem_u32(B.qual), bytes);
+                    bulk_s2g(a.strand + row + off, smem_u32(B.strand), bytes);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                cur ^= 1u;
+            }
+        } else {
+            uint4* rb = reinterpret_cast<uint4*>(a.base + row);
+            uint4* rq = reinterpret_cast<uint4*>(a.qual + row);
+            uint4* rs = reinterpret_cast<uint4*>(a.strand + row);
+            for (uint32_t v = lane; v < (pitch >> 4); v += 32) {
+                rb[v] = fill_base;
+                rq[v] = zero;
+                rs[v] = fill_strand;
+            }
+            __syncwarp();   // orders the filler before the cell stores of other lanes
+            auto put = [&](uint32_t w) {
+                const uint32_t i = w & (BV_CELL_MAX_SAMPLES - 1u);
+                if (i >= a.n_samples) { bad = true; return; }
+                a.base[row + i] = (uint8_t)((w >> 20) & 7u);
+                a.strand[row + i] = (uint8_t)((w >> 23) & 3u);
+                a.qual[row + i] = (uint8_t)(w >> 25);
+            };
+#pragma unroll
+            for (int k = 0; k < kExPre; ++k)
+                if ((uint32_t)(32 * k) + lane < n_here) put(pre[k]);
+            for (uint64_t c = beg + (uint32_t)(32 * kExPre) + lane; c < end; c += 32) put(__ldg(a.cells + c));
+        }
+        s = s_next; beg = nbeg; end = nend; nbeg = n2beg; nend = n2end;
+#pragma unroll
+        for (int k = 0; k < kExPre; ++k) pre[k] = npre[k];
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores are complete before the warp leaves
     if (__any_sync(kFull, bad) && lane == 0) atomicAdd(a.counters + kCntBadCell, 1u);
 }
 

@@ -47,7 +47,10 @@ def _both(engine, b, q, s, r, N, maf, abs_mode, label, shuffle=None):
     [
         ("C2-like", 5000, 1000, dict(coverage=0.1, variant_frac=0.05)),
         ("C1-like-N100", 3000, 100, dict(coverage=0.065, variant_frac=0.05)),
-        ("C3-like", 1100, 10000, dict(coverage=0.1, variant_frac=0.1)),
+        ("C3-like", 1100, 10000, dict(coverage=0.1, variant_frac=0.1)),            # 10 staged chunks per row
+        ("long-rows", 300, 20000, dict(coverage=0.05, variant_frac=0.2)),          # K0's direct path (pitch > 16 KB)
+        ("chunk-edge", 1500, 1024, dict(coverage=0.2, variant_frac=0.2)),          # row == one staged chunk
+        ("chunk-edge+1", 1500, 1025, dict(coverage=0.2, variant_frac=0.2)),        # a 16-byte second chunk
         ("C5-like", 1100, 2000, dict(coverage=0.99326, variant_frac=0.5, multi_frac=0.5)),
         ("odd-N", 2500, 1003, dict(coverage=0.3, variant_frac=0.3, multi_frac=0.5)),
         ("tiny-N", 2500, 7, dict(coverage=0.8, variant_frac=0.5)),
