@@ -703,6 +703,7 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
                 const int single = __ffs(sub) - 1;
                 lr = single_allele_ll(bins, nb, single);
                 const double v = (lr != lr) ? lr : 1.0;
+                __syncwarp();   // every lane has read W.emf above
                 if (lane < 4) W.emf[lane] = lane == single ? v : 0.0;
                 __syncwarp();
             } else {
