@@ -19,6 +19,10 @@
 #include "bv_expand_kernel.cuh"
 #include "bv_synth.cuh"
 
+#ifndef BV_SCALAR_CTAS_PER_SM
+#define BV_SCALAR_CTAS_PER_SM 8u
+#endif
+
 namespace bv {
 
 // ======================================================================================================
@@ -277,7 +281,7 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[1], stream));
     grid = (a.n_sites + 255) / 256;   // grid-stride over K1's work list
-    if (grid > (uint32_t)ctx->num_sms * 8u) grid = (uint32_t)ctx->num_sms * 8u;
+    if (grid > (uint32_t)ctx->num_sms * BV_SCALAR_CTAS_PER_SM) grid = (uint32_t)ctx->num_sms * BV_SCALAR_CTAS_PER_SM;
     bv::bv_scalar_kernel<<<grid, 256, 0, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[2], stream));

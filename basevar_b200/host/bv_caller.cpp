@@ -248,6 +248,19 @@ struct BasevarCaller::Tile {
     std::vector<bv_call_out> calls;
     std::vector<bv_group_out> groups;
     std::vector<int32_t> call_of_site;
+    // sparse transport of the tile in hand (pinned; filled by the packer through TileRows)
+    uint32_t *sp_cells = nullptr, *sp_aux = nullptr, *sp_start = nullptr;
+    size_t sp_cap = 0;
+    bool sparse_ready = false;
+
+    void reserve_cells(size_t n) {   // contents are not kept: called once per tile, before the cells are written
+        if (n <= sp_cap) return;
+        bv_host_free(sp_cells); bv_host_free(sp_aux);
+        sp_cells = sp_aux = nullptr; sp_cap = 0;
+        const size_t cap = n + n / 4 + 4096;
+        sp_cells = (uint32_t*)pinned(cap * sizeof(uint32_t)); sp_aux = (uint32_t*)pinned(cap * sizeof(uint32_t));
+        sp_cap = cap;
+    }
 
     Tile(uint32_t n_samples, uint32_t max_sites, size_t n_groups) {
         pitch = ((uint64_t)n_samples + 15) / 16 * 16;
@@ -255,6 +268,7 @@ struct BasevarCaller::Tile {
         const size_t plane = (size_t)max_sites * pitch;
         base = (uint8_t*)pinned(plane); qual = (uint8_t*)pinned(plane); strand = (uint8_t*)pinned(plane);
         mapq = (uint8_t*)pinned(plane); rpr = (uint16_t*)pinned(plane * 2); ref = (uint8_t*)pinned(max_sites);
+        sp_start = (uint32_t*)pinned(((size_t)max_sites + 1) * sizeof(uint32_t));
         meta.resize(max_sites);
         recs.resize(max_sites);
         calls.resize(max_sites);
@@ -263,6 +277,7 @@ struct BasevarCaller::Tile {
     }
     ~Tile() {
         bv_host_free(base); bv_host_free(qual); bv_host_free(strand); bv_host_free(mapq); bv_host_free(rpr); bv_host_free(ref);
+        bv_host_free(sp_start); bv_host_free(sp_cells); bv_host_free(sp_aux);
     }
 };
 
@@ -456,7 +471,18 @@ TileRows BasevarCaller::begin_tile(uint32_t n_rows) {
         m.specials.clear(); m.odd_strands.clear(); m.depth = 0;
     }
     T.n_sites = n_rows;
-    return TileRows{T.base, T.qual, T.strand, T.mapq, T.rpr, T.pitch, T.rpr_pitch, n_rows, T.meta.data()};
+    T.sparse_ready = false;
+    TileRows rows{T.base, T.qual, T.strand, T.mapq, T.rpr, T.pitch, T.rpr_pitch, n_rows, T.meta.data(), nullptr, nullptr, nullptr};
+    if (opt_.sparse_upload && n_sample_ <= BV_CELL_MAX_SAMPLES) {
+        Tile* tp = &T;
+        rows.site_start = T.sp_start;
+        rows.reserve_cells = [tp](size_t n, uint32_t** cells, uint32_t** aux) {
+            tp->reserve_cells(n);
+            *cells = tp->sp_cells; *aux = tp->sp_aux;
+        };
+        rows.sparse_ready = &T.sparse_ready;
+    }
+    return rows;
 }
 
 void BasevarCaller::commit_tile() {
@@ -471,6 +497,16 @@ void BasevarCaller::commit_tile() {
 void BasevarCaller::submit_current() {
     Tile& T = *tiles_[cur_];
     if (T.pending || T.n_sites == 0) return;   // a pending tile still holds the rows it was submitted with
+    if (T.sparse_ready) {   // the packer listed the covered cells: 8 bytes per read instead of 5 per sample-site
+        T.sparse_ready = false;
+        bv_sparse_tile st;
+        st.cells = T.sp_cells; st.cells_aux = T.sp_aux; st.site_start = T.sp_start; st.ref_base = T.ref; st.out = nullptr;
+        st.n_sites = T.n_sites; st.n_samples = (uint32_t)n_sample_;
+        check(bv_tile_submit_sparse_calls(ctx_, (int)cur_, &st), ctx_, "bv_tile_submit_sparse_calls");
+        T.pending = true;
+        cur_ = (cur_ + 1) % (uint32_t)tiles_.size();
+        return;
+    }
     bv_tile t;
     t.base = T.base; t.qual = T.qual; t.strand = T.strand; t.ref_base = T.ref;
     t.pitch = T.pitch; t.n_sites = T.n_sites; t.n_samples = (uint32_t)n_sample_;

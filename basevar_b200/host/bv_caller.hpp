@@ -39,6 +39,7 @@ struct CallerOptions {
     uint32_t tile_sites = 8192;
     uint32_t n_slots = 2;
     int em_abs_mode = BV_EM_ABS_INT_TRUNC;
+    bool sparse_upload = true;   // tiles whose packer lists its covered cells cross PCIe as bv_sparse_tile (see TileRows)
 };
 
 // ---- number formatting of the reference's text outputs ---------------------------------------------------------------
@@ -80,6 +81,14 @@ struct TileRows {
     uint64_t pitch, rpr_pitch;   // elements per row
     uint32_t n_rows;
     SiteMeta* meta;
+    // Sparse transport (bv_sparse_tile), offered when CallerOptions::sparse_upload is set and the sample count allows it
+    // (site_start != nullptr): a packer that knows its covered cells writes site_start[0 .. n_rows], asks reserve_cells(n)
+    // for the two arrays of n words, fills them with BV_CELL_PACK / BV_CELL_AUX_PACK words grouped by row, and sets
+    // *sparse_ready.  The tile then crosses PCIe as 8 bytes per covered cell instead of 5 bytes per sample-site.  The planes
+    // above are filled all the same: the text output reads them on the host.
+    uint32_t* site_start;
+    std::function<void(size_t n_cells, uint32_t** cells, uint32_t** aux)> reserve_cells;
+    bool* sparse_ready;
 };
 
 std::string vcf_header_define(const std::vector<std::string>& contig_lines, const std::string& reference_line,

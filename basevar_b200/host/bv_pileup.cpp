@@ -250,9 +250,14 @@ void BamPileup::scatter(uint32_t pos, uint32_t n, const std::string& ref_id, con
     std::vector<std::vector<uint32_t>> depth((size_t)T);
     std::vector<std::vector<Spec>> specs((size_t)T);
     const size_t block = 256;   // samples per work item: neighbouring columns stay with one thread
-    parallel_for((N + block - 1) / block, T, [&](size_t bi, int t) {
+    const size_t n_blocks = (N + block - 1) / block;
+    // sparse transport: cells per (sample block, row), so that the second pass below knows where each block writes
+    const bool sparse = rows.sparse_ready != nullptr && rows.site_start != nullptr && rows.reserve_cells;
+    std::vector<uint32_t> block_cnt(sparse ? n_blocks * (size_t)n : 0, 0);
+    parallel_for(n_blocks, T, [&](size_t bi, int t) {
         std::vector<uint32_t>& d = depth[(size_t)t];
         if (d.empty()) d.assign(n, 0);
+        uint32_t* bc = sparse ? block_cnt.data() + bi * (size_t)n : nullptr;
         for (size_t s = bi * block; s < std::min(N, (bi + 1) * block); ++s) {
             const std::vector<PileupCell>& cells = impl_->piles[s].cells;
             auto it = std::lower_bound(cells.begin(), cells.end(), off0, [](const PileupCell& c, uint32_t v) { return c.off < v; });
@@ -265,10 +270,41 @@ void BamPileup::scatter(uint32_t pos, uint32_t n, const std::string& ref_id, con
                 rows.mapq[at] = it->mapq;
                 rows.rpr[(size_t)row * rows.rpr_pitch + s] = it->rpr;
                 ++d[row];
+                if (bc) ++bc[row];
                 if (it->special >= 0) specs[(size_t)t].push_back(Spec{row, (uint32_t)s, it->special});
             }
         }
     });
+    if (sparse) {
+        // row offsets, then every block's write position inside its rows (exclusive prefix over the blocks)
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            rows.site_start[i] = (uint32_t)total;
+            for (size_t bi = 0; bi < n_blocks; ++bi) {
+                const uint32_t c = block_cnt[bi * (size_t)n + i];
+                block_cnt[bi * (size_t)n + i] = (uint32_t)total;
+                total += c;
+            }
+        }
+        rows.site_start[n] = (uint32_t)total;
+        if (total <= 0xffffffffull) {
+            uint32_t *sp_cells = nullptr, *sp_aux = nullptr;
+            rows.reserve_cells((size_t)total, &sp_cells, &sp_aux);
+            parallel_for(n_blocks, T, [&](size_t bi, int) {
+                uint32_t* at = block_cnt.data() + bi * (size_t)n;
+                for (size_t s = bi * block; s < std::min(N, (bi + 1) * block); ++s) {
+                    const std::vector<PileupCell>& cells = impl_->piles[s].cells;
+                    auto it = std::lower_bound(cells.begin(), cells.end(), off0, [](const PileupCell& c, uint32_t v) { return c.off < v; });
+                    for (; it != cells.end() && it->off < off0 + n; ++it) {
+                        const uint32_t k = at[it->off - off0]++;
+                        sp_cells[k] = BV_CELL_PACK((uint32_t)s, it->base, it->strand, it->qual);
+                        sp_aux[k] = BV_CELL_AUX_PACK(it->mapq, it->rpr);
+                    }
+                }
+            });
+            *rows.sparse_ready = true;
+        }
+    }
     for (uint32_t i = 0; i < n; ++i) {
         SiteMeta& m = rows.meta[i];
         m.ref_id = ref_id;
@@ -387,6 +423,7 @@ std::string BaseTypeRunner::usage() {
            "  --smart-rerun                Accepted and ignored.\n"
            "  --gpus=LIST                  Comma delimited CUDA devices to shard the regions over. [0]\n"
            "  --tile-sites=INT             Positions per GPU tile. [8192]\n"
+           "  --dense-upload               Upload the packed planes of a tile instead of its covered cells.\n"
            "  -h, --help                   Show this help message and exit.";
 }
 
@@ -404,6 +441,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
         {"output-vcf", required_argument, NULL, '1'},  {"output-cvg", required_argument, NULL, '2'},
         {"filename-has-samplename", no_argument, NULL, '3'}, {"smart-rerun", no_argument, NULL, '4'},
         {"gpus", required_argument, NULL, '5'},        {"tile-sites", required_argument, NULL, '6'},
+        {"dense-upload", no_argument, NULL, '7'},
         {"help", no_argument, NULL, 'h'},              {0, 0, 0, 0}};
     BaseTypeARGS a;
     optind = 1;
@@ -431,6 +469,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
                 break;
             }
             case '6': ss >> a.tile_sites; break;
+            case '7': a.dense_upload = true; break;
             case 'h': std::cout << usage() << std::endl; exit(1);
             default: std::cerr << "Unknown argument: " << (char)c << std::endl; exit(1);
         }
@@ -578,6 +617,7 @@ void BaseTypeRunner::run() {
                 opt.tile_sites = args_.tile_sites;
                 opt.n_slots = 2;
                 opt.em_abs_mode = args_.em_abs_mode;
+                opt.sparse_upload = !args_.dense_upload;
                 auto sink = [&out_mu, &next_to_write, si](std::string* buf, TextWriter* w) {
                     return [=, &out_mu, &next_to_write](const char* d, size_t n) {
                         std::lock_guard<std::mutex> g(out_mu);

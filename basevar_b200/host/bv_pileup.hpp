@@ -95,6 +95,7 @@ struct BaseTypeARGS {   // src/basetype_utils.h:74-96
     std::vector<int> devices;   // GPUs to shard the calling intervals over (empty: device 0)
     uint32_t tile_sites = 8192;
     int em_abs_mode = BV_EM_ABS_INT_TRUNC;
+    bool dense_upload = false;   // upload the packed planes instead of the covered cells (bv_tile instead of bv_sparse_tile)
 };
 
 class BaseTypeRunner {

@@ -106,8 +106,36 @@ int main(int argc, char** argv) {
                 memset(strand.data(), BV_STRAND_NONE, strand.size()); memset(mq.data(), 0, mq.size());
                 std::fill(rpr.begin(), rpr.end(), 0);
                 for (auto& m : meta) { m.specials.clear(); m.odd_strands.clear(); m.depth = 0; }
-                TileRows rows{base.data(), qual.data(), strand.data(), mq.data(), rpr.data(), pitch, pitch, n, meta.data()};
+                TileRows rows{base.data(), qual.data(), strand.data(), mq.data(), rpr.data(), pitch, pitch, n, meta.data(), nullptr, nullptr, nullptr};
+                // the sparse transport of the same tile: its cells, expanded, must give exactly the planes
+                std::vector<uint32_t> sp_start(n + 1), sp_cells, sp_aux;
+                bool sp_ready = false;
+                rows.site_start = sp_start.data();
+                rows.reserve_cells = [&](size_t k, uint32_t** c, uint32_t** a) { sp_cells.assign(k, 0); sp_aux.assign(k, 0); *c = sp_cells.data(); *a = sp_aux.data(); };
+                rows.sparse_ready = &sp_ready;
                 pile.scatter((uint32_t)p, n, ref_id, seq, rows);
+                {
+                    if (!sp_ready || sp_start[0] != 0 || sp_start[n] != sp_cells.size()) { fprintf(stderr, "sparse tile: not filled / bad offsets\n"); return 1; }
+                    std::vector<uint8_t> xb(n * pitch, BV_BASE_N), xq(n * pitch, 0), xs(n * pitch, BV_STRAND_NONE), xm(n * pitch, 0);
+                    std::vector<uint16_t> xr(n * pitch, 0);
+                    size_t covered = 0;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        if (sp_start[i + 1] < sp_start[i]) { fprintf(stderr, "sparse tile: offsets descend at row %u\n", i); return 1; }
+                        for (uint32_t k = sp_start[i]; k < sp_start[i + 1]; ++k) {
+                            const uint32_t w = sp_cells[k], smp = w & (BV_CELL_MAX_SAMPLES - 1u);
+                            const size_t at = (size_t)i * pitch + smp;
+                            if (smp >= N || xs[at] != BV_STRAND_NONE || xb[at] != BV_BASE_N) { fprintf(stderr, "sparse tile: bad or repeated sample %u at row %u\n", smp, i); return 1; }
+                            xb[at] = (uint8_t)((w >> 20) & 7u); xs[at] = (uint8_t)((w >> 23) & 3u); xq[at] = (uint8_t)(w >> 25);
+                            xm[at] = (uint8_t)sp_aux[k]; xr[at] = (uint16_t)(sp_aux[k] >> 8);
+                            ++covered;
+                        }
+                    }
+                    if (memcmp(xb.data(), base.data(), n * pitch) || memcmp(xq.data(), qual.data(), n * pitch) || memcmp(xs.data(), strand.data(), n * pitch) ||
+                        memcmp(xm.data(), mq.data(), n * pitch) || memcmp(xr.data(), rpr.data(), n * pitch * sizeof(uint16_t))) {
+                        fprintf(stderr, "sparse tile at %lu: expanded cells differ from the planes (%zu cells)\n", (unsigned long)p, covered);
+                        return 1;
+                    }
+                }
                 std::string out;
                 for (uint32_t i = 0; i < n; ++i) {
                     const SiteCells c{base.data() + i * pitch, qual.data() + i * pitch, strand.data() + i * pitch, (uint32_t)N};

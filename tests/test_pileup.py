@@ -131,8 +131,9 @@ def _meta(text):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag,tile,gz", [("syn", 8192, False), ("syng", 1000, True), ("syn", 129, False)])
-def test_command_end_to_end_on_synthetic_bams_gpu(host_built, syn, tmp_path, tag, tile, gz):
+@pytest.mark.parametrize("tag,tile,gz,dense", [("syn", 8192, False, False), ("syng", 1000, True, False), ("syn", 129, False, False),
+                                               ("syng", 8192, False, True), ("syn", 1000, False, True)])
+def test_command_end_to_end_on_synthetic_bams_gpu(host_built, syn, tmp_path, tag, tile, gz, dense):
     """`basevar basetype` over BAM files, no batchfiles: VCF and CVG equal what the unmodified reference command wrote
     (header lines apart from the two that hold file paths, and every row, byte for byte)."""
     vcf = tmp_path / ("out.vcf" + (".gz" if gz else ""))
@@ -141,6 +142,8 @@ def test_command_end_to_end_on_synthetic_bams_gpu(host_built, syn, tmp_path, tag
            "-t", "4", "--output-vcf", str(vcf), "--output-cvg", str(cvg), "--tile-sites", str(tile)]
     if tag == "syng":
         cmd += ["-G", os.path.join(FIX, "groups.info")]
+    if dense:   # the packed planes cross PCIe instead of the covered cells (the default): same text either way
+        cmd += ["--dense-upload"]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     rd = (lambda f: gzip.open(f, "rt").read()) if gz else (lambda f: open(f).read())
