@@ -93,7 +93,12 @@ class BvSparseTile(C.Structure):
         ("out", C.c_void_p),
         ("n_sites", C.c_uint32),
         ("n_samples", C.c_uint32),
+        ("format", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
+
+
+CELLS_U32, CELLS_U16 = 0, 1
 
 
 def cell_pack(sample, base, strand, phred):
@@ -147,6 +152,9 @@ _SIGNATURES = [
     ("bv_synth_fill_host", C.c_int, [C.POINTER(BvSynthModel), C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64] + [C.c_void_p] * 5),
     ("bv_tile_submit_sparse", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvSparseTile)]),
     ("bv_tile_submit_sparse_calls", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvSparseTile)]),
+    ("bv_sparse_encode16_bound", C.c_uint64, [C.c_uint64, C.c_uint32, C.c_uint32]),
+    ("bv_sparse_encode16", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                     C.POINTER(C.c_uint64)]),
     ("bv_synth_fill_sparse_host", C.c_int, [C.POINTER(BvSynthModel), C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                             C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     ("bv_host_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

@@ -416,7 +416,8 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kExpandSmemBytes) != cudaSuccess) {
+            cudaFuncSetAttribute(bv::bv_expand_kernel<BV_CELLS_U32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kExpandSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_expand_kernel<BV_CELLS_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kExpandSmemBytes) != cudaSuccess) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
                          cudaGetErrorString(cudaGetLastError()));
             break;
@@ -664,10 +665,14 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
     if (t->n_samples > ctx->prm.max_samples || t->n_samples > BV_CELL_MAX_SAMPLES)
         return set_err(ctx, BV_ERR_ARG, "sparse tile: n_samples %u > max_samples %u or > %u", t->n_samples, ctx->prm.max_samples, BV_CELL_MAX_SAMPLES);
     if (t->n_sites && (!t->site_start || !t->ref_base)) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: null pointer");
-    const uint64_t n_cells = t->n_sites ? t->site_start[t->n_sites] : 0;
+    if (t->format != BV_CELLS_U32 && t->format != BV_CELLS_U16) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: unknown format %u", t->format);
+    const bool u16 = t->format == BV_CELLS_U16;
+    const size_t word_bytes = u16 ? sizeof(uint16_t) : sizeof(uint32_t);
+    const uint64_t n_cells = t->n_sites ? t->site_start[t->n_sites] : 0;   // words of `format`
     if (t->n_sites && t->site_start[0] != 0) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: site_start[0] must be 0");
     if (n_cells && (!t->cells || (with_calls && !t->cells_aux))) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: null cells");
-    if (n_cells > (uint64_t)t->n_sites * t->n_samples) return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: more cells than sample-sites");
+    if (n_cells > (uint64_t)t->n_sites * ((uint64_t)t->n_samples + (u16 ? t->n_samples / BV_CELL16_GAP_SKIP + 2u : 0u)))
+        return set_err(ctx, BV_ERR_ARG, "bv_sparse_tile: more cells than sample-sites");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
     s.qual_host = nullptr;
     s.h2d_bytes = 0;
@@ -698,13 +703,13 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
     memset(s.h_counters, 0, 8 * sizeof(uint32_t));
     if (t->n_sites && t->n_samples) {
         if (n_cells) {
-            BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells, t->cells, n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells, t->cells, n_cells * word_bytes, cudaMemcpyHostToDevice, s.stream));
             if (with_calls)
                 BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells + s.cells_cap, t->cells_aux, n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
         }
         BV_CUDA(ctx, cudaMemcpyAsync(s.d_site_start, t->site_start, ((size_t)t->n_sites + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
         BV_CUDA(ctx, cudaMemcpyAsync(s.d_ref, t->ref_base, t->n_sites, cudaMemcpyHostToDevice, s.stream));
-        s.h2d_bytes = n_cells * sizeof(uint32_t) * (with_calls ? 2 : 1) + ((size_t)t->n_sites + 1) * sizeof(uint32_t) + t->n_sites;
+        s.h2d_bytes = n_cells * (word_bytes + (with_calls ? sizeof(uint32_t) : 0)) + ((size_t)t->n_sites + 1) * sizeof(uint32_t) + t->n_sites;
         BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), s.stream));
         bv::ExpandArgs x;
         x.cells = s.d_cells; x.cells_aux = with_calls ? s.d_cells + s.cells_cap : nullptr; x.site_start = s.d_site_start;
@@ -716,7 +721,8 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
         uint32_t grid = (t->n_sites + bv::kExpandWarps - 1) / bv::kExpandWarps;
         const uint32_t cap = (uint32_t)ctx->num_sms * 2u;   // persistent: 2 CTAs of 16 warps per SM (96 KB of staging each)
         if (grid > cap) grid = cap;
-        bv::bv_expand_kernel<<<grid, bv::kExpandWarps * 32, bv::kExpandSmemBytes, s.stream>>>(x);
+        if (u16) bv::bv_expand_kernel<BV_CELLS_U16><<<grid, bv::kExpandWarps * 32, bv::kExpandSmemBytes, s.stream>>>(x);
+        else bv::bv_expand_kernel<BV_CELLS_U32><<<grid, bv::kExpandWarps * 32, bv::kExpandSmemBytes, s.stream>>>(x);
         BV_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     }
@@ -738,6 +744,47 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
 
 int bv_tile_submit_sparse(bv_ctx* ctx, int slot, const bv_sparse_tile* tile) { return tile_submit_sparse_impl(ctx, slot, tile, false); }
 int bv_tile_submit_sparse_calls(bv_ctx* ctx, int slot, const bv_sparse_tile* tile) { return tile_submit_sparse_impl(ctx, slot, tile, true); }
+
+uint64_t bv_sparse_encode16_bound(uint64_t n_cells, uint32_t n_sites, uint32_t n_samples) {
+    return n_cells + (uint64_t)n_sites * (n_samples / BV_CELL16_GAP_SKIP + 1u);   // at most n_samples / 31 skips per site
+}
+
+int bv_sparse_encode16(const uint32_t* cells, const uint32_t* aux32, const uint32_t* site_start, uint32_t n_sites,
+                       uint16_t* words16, uint32_t* aux16, uint64_t max_words, uint32_t* start16, uint64_t* n_words) {
+    if (!site_start || !n_words || (n_sites && site_start[n_sites] && !cells)) return set_err(nullptr, BV_ERR_ARG, "null argument");
+    uint64_t n = 0;
+    for (uint32_t s = 0; s < n_sites; ++s) {
+        if (start16) start16[s] = (uint32_t)n;
+        if (site_start[s + 1] < site_start[s]) return set_err(nullptr, BV_ERR_ARG, "site_start does not ascend at site %u", s);
+        uint32_t next = 0;   // the sample index a gap of 0 would mean
+        for (uint32_t c = site_start[s]; c < site_start[s + 1]; ++c) {
+            const uint32_t w = cells[c], i = w & (BV_CELL_MAX_SAMPLES - 1u), strand = (w >> 23) & 3u;
+            if (i < next) return set_err(nullptr, BV_ERR_ARG, "site %u: cells do not ascend by sample (BV_CELLS_U16 needs them to)", s);
+            if (strand > BV_STRAND_REV) return set_err(nullptr, BV_ERR_ARG, "site %u, sample %u: strand code %u has no 16-bit form", s, i, strand);
+            uint32_t gap = i - next;
+            while (gap >= BV_CELL16_GAP_SKIP) {
+                if (words16) {
+                    if (n >= max_words) return set_err(nullptr, BV_ERR_ARG, "more than max_words words");
+                    words16[n] = (uint16_t)BV_CELL16_GAP_SKIP;
+                    if (aux16) aux16[n] = 0;
+                }
+                ++n;
+                gap -= BV_CELL16_GAP_SKIP;
+            }
+            if (words16) {
+                if (n >= max_words) return set_err(nullptr, BV_ERR_ARG, "more than max_words words");
+                words16[n] = BV_CELL16_PACK(gap, (w >> 20) & 7u, strand, w >> 25);
+                if (aux16) aux16[n] = aux32 ? aux32[c] : 0;
+            }
+            ++n;
+            next = i + 1;
+        }
+        if (n > 0xffffffffull) return set_err(nullptr, BV_ERR_ARG, "more than 2^32 words in one tile");
+    }
+    if (start16) start16[n_sites] = (uint32_t)n;
+    *n_words = n;
+    return BV_OK;
+}
 
 int bv_synth_fill_sparse_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
                               uint32_t* cells, uint32_t* cells_aux, uint64_t max_cells, uint32_t* site_start,

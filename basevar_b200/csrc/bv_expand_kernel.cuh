@@ -15,6 +15,10 @@
 //   direct path (longer rows): filler and cells are written to global memory directly; the scatter hits lines the same
 //   warp has just written and merges in L2.
 //
+// Two cell formats (include/basevar_b200.h): BV_CELLS_U32, one self-contained word per cell, any order within a site;
+// BV_CELLS_U16, two bytes per cell with the sample index delta-coded against the previous cell of the site (ascending
+// samples, "skip 31" words for longer gaps): the warp turns a batch of 32 words into sample indices with one inclusive
+// scan of the deltas.
 // The mapq / rpr planes of the called-site kernels (only with cells_aux) always take the direct path.
 // Bound: HBM writes, 3 bytes per sample-site (+3 with the called-site planes), reads 4 bytes per covered cell.
 #pragma once
@@ -37,7 +41,7 @@ struct __align__(128) ExpandWarp {
 constexpr size_t kExpandSmemBytes = (size_t)kExpandWarps * sizeof(ExpandWarp);   // 96 KB: two CTAs per SM
 
 struct ExpandArgs {
-    const uint32_t* cells;
+    const void* cells;           // u32 (BV_CELLS_U32) or u16 (BV_CELLS_U16) words
     const uint32_t* cells_aux;   // null: no mapq / rpr planes
     const uint32_t* site_start;  // [n_sites + 1]
     uint8_t* base;
@@ -57,6 +61,62 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 
+constexpr int kExPre = 4;   // words per lane prefetched one site ahead (the first 128 words of a site)
+
+template <int FMT>
+__device__ __forceinline__ uint32_t load_word(const void* cells, uint64_t c) {
+    if (FMT == BV_CELLS_U16) return __ldg(reinterpret_cast<const uint16_t*>(cells) + c);
+    return __ldg(reinterpret_cast<const uint32_t*>(cells) + c);
+}
+
+// Visits the cells of one site, 32 words per step: f(sample, base, strand, phred, word index) for the lanes that hold a
+// cell.  `upto` (BV_CELLS_U16 only; samples ascend): stops once every further cell has sample >= upto.
+// Returns false when a cell's sample index is >= n_samples (malformed input).
+template <int FMT, class F>
+__device__ __forceinline__ bool for_each_cell(const void* cells, uint64_t beg, uint64_t end, const uint32_t (&pre)[kExPre],
+                                              uint32_t lane, uint32_t n_samples, uint32_t upto, F&& f) {
+    bool good = true;
+    uint32_t next = 0;   // BV_CELLS_U16: the sample index a gap of 0 would mean (warp-uniform)
+    int k = 0;
+#pragma unroll 1
+    for (uint64_t c0 = beg; c0 < end; c0 += 32, ++k) {
+        const uint64_t c = c0 + lane;
+        const bool live = c < end;
+        uint32_t w = 0;
+        if (k < kExPre) {   // (warp-uniform) the prefetched words
+            w = k == 0 ? pre[0] : k == 1 ? pre[1] : k == 2 ? pre[2] : pre[3];
+        } else if (live) {
+            w = load_word<FMT>(cells, c);
+        }
+        if (FMT == BV_CELLS_U16) {
+            const uint32_t gap = w & 31u;
+            const bool is_cell = live && gap != BV_CELL16_GAP_SKIP;
+            const uint32_t inc = live ? (gap == BV_CELL16_GAP_SKIP ? BV_CELL16_GAP_SKIP : gap + 1u) : 0u;
+            uint32_t x = inc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFull, x, o);
+                if ((int)lane >= o) x += y;
+            }
+            const uint32_t sample = next + (x - inc) + gap;
+            next += __shfl_sync(kFull, x, 31);
+            if (is_cell) {
+                if (sample >= n_samples) good = false;
+                else f(sample, (w >> 5) & 7u, (w >> 8) & 1u, w >> 9, c);
+            }
+            if (next >= upto) break;   // warp-uniform
+        } else {
+            if (live) {
+                const uint32_t sample = w & (BV_CELL_MAX_SAMPLES - 1u);
+                if (sample >= n_samples) good = false;
+                else f(sample, (w >> 20) & 7u, (w >> 23) & 3u, w >> 25, c);
+            }
+        }
+    }
+    return good;
+}
+
+template <int FMT>
 __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const ExpandArgs a) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp = blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
@@ -70,9 +130,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
     bool bad = false;
     uint32_t cur = 0;   // staging buffer of the next chunk
 
-    // Software pipeline over the warp's sites: the offsets are loaded two sites ahead and the first kExPre * 32 cells
+    // Software pipeline over the warp's sites: the offsets are loaded two sites ahead and the first kExPre * 32 words
     // one site ahead, so that their DRAM latency (the cells have just arrived over PCIe) hides behind the site in hand.
-    constexpr int kExPre = 4;
     auto load_offsets = [&](uint32_t site, uint64_t& b, uint64_t& e) {
         b = 0; e = 0;
         if (site < a.n_sites) { b = a.site_start[site]; e = a.site_start[site + 1]; }
@@ -82,7 +141,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
 #pragma unroll
         for (int k = 0; k < kExPre; ++k) {
             const uint64_t c = b + (uint32_t)(32 * k) + lane;
-            pre[k] = (ok && c < e) ? __ldg(a.cells + c) : 0xffffffffu;   // sample 2^20 - 1 with base 7: never a real cell
+            pre[k] = (ok && c < e) ? load_word<FMT>(a.cells, c) : 0u;
         }
     };
     uint32_t s = warp;
@@ -98,7 +157,6 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
         load_cells(nbeg, nend, npre);
         const bool ok = end >= beg && end <= a.n_cells;   // warp-uniform
         if (!ok) { bad = true; end = beg; }               // the row still gets its filler
-        const uint32_t n_here = (uint32_t)(end - beg);    // <= n_samples * ... fits: n_cells < 2^32
         const size_t row = (size_t)s * a.pitch;
 
         if (a.mapq) {   // called-site planes: direct path
@@ -108,13 +166,12 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
             const uint32_t rvecs = (uint32_t)(a.rpr_pitch >> 3);
             for (uint32_t v = lane; v < rvecs; v += 32) rr[v] = zero;
             __syncwarp();   // orders the filler before the cell stores of other lanes
-            for (uint64_t c = beg + lane; c < end; c += 32) {
-                const uint32_t i = __ldg(a.cells + c) & (BV_CELL_MAX_SAMPLES - 1u);
-                if (i >= a.n_samples) continue;   // reported below
-                const uint32_t x = __ldg(a.cells_aux + c);
-                a.mapq[row + i] = (uint8_t)x;
-                a.rpr[(size_t)s * a.rpr_pitch + i] = (uint16_t)(x >> 8);
-            }
+            for_each_cell<FMT>(a.cells, beg, end, pre, lane, a.n_samples, 0xffffffffu,
+                               [&](uint32_t i, uint32_t, uint32_t, uint32_t, uint64_t c) {
+                                   const uint32_t x = __ldg(a.cells_aux + c);
+                                   a.mapq[row + i] = (uint8_t)x;
+                                   a.rpr[(size_t)s * a.rpr_pitch + i] = (uint16_t)(x >> 8);
+                               });
         }
 
         if (staged) {
@@ -131,20 +188,19 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
                     reinterpret_cast<uint4*>(B.strand)[v] = fill_strand;
                 }
                 __syncwarp();   // filler before the cells of other lanes
-                auto put = [&](uint32_t w) {
-                    const uint32_t i = w & (BV_CELL_MAX_SAMPLES - 1u);
-                    if (i >= a.n_samples) { bad = true; return; }
-                    const uint32_t k = i - off;
-                    if (k < bytes) {   // (unsigned: also false for i < off)
-                        B.base[k] = (uint8_t)((w >> 20) & 7u);
-                        B.strand[k] = (uint8_t)((w >> 23) & 3u);
-                        B.qual[k] = (uint8_t)(w >> 25);
-                    }
-                };
-#pragma unroll
-                for (int k = 0; k < kExPre; ++k)
-                    if ((uint32_t)(32 * k) + lane < n_here) put(pre[k]);
-                for (uint64_t c = beg + (uint32_t)(32 * kExPre) + lane; c < end; c += 32) put(__ldg(a.cells + c));
+                // ascending samples (BV_CELLS_U16): a pass stops at the end of its chunk; the last one runs to the end of
+                // the words so that every malformed cell (sample >= n_samples) is seen
+                const uint32_t upto = off + kExChunk >= pitch ? 0xffffffffu : off + bytes;
+                const bool good = for_each_cell<FMT>(a.cells, beg, end, pre, lane, a.n_samples, upto,
+                                                     [&](uint32_t i, uint32_t b, uint32_t st, uint32_t q, uint64_t) {
+                                                         const uint32_t k = i - off;
+                                                         if (k < bytes) {   // (unsigned: also false for i < off)
+                                                             B.base[k] = (uint8_t)b;
+                                                             B.strand[k] = (uint8_t)st;
+                                                             B.qual[k] = (uint8_t)q;
+                                                         }
+                                                     });
+                if (!good) bad = true;
                 // generic-proxy writes -> visible to the async proxy, then one lane hands the chunk to the TMA unit
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -166,17 +222,13 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
                 rs[v] = fill_strand;
             }
             __syncwarp();   // orders the filler before the cell stores of other lanes
-            auto put = [&](uint32_t w) {
-                const uint32_t i = w & (BV_CELL_MAX_SAMPLES - 1u);
-                if (i >= a.n_samples) { bad = true; return; }
-                a.base[row + i] = (uint8_t)((w >> 20) & 7u);
-                a.strand[row + i] = (uint8_t)((w >> 23) & 3u);
-                a.qual[row + i] = (uint8_t)(w >> 25);
-            };
-#pragma unroll
-            for (int k = 0; k < kExPre; ++k)
-                if ((uint32_t)(32 * k) + lane < n_here) put(pre[k]);
-            for (uint64_t c = beg + (uint32_t)(32 * kExPre) + lane; c < end; c += 32) put(__ldg(a.cells + c));
+            const bool good = for_each_cell<FMT>(a.cells, beg, end, pre, lane, a.n_samples, 0xffffffffu,
+                                                 [&](uint32_t i, uint32_t b, uint32_t st, uint32_t q, uint64_t) {
+                                                     a.base[row + i] = (uint8_t)b;
+                                                     a.strand[row + i] = (uint8_t)st;
+                                                     a.qual[row + i] = (uint8_t)q;
+                                                 });
+            if (!good) bad = true;
         }
         s = s_next; beg = nbeg; end = nend; nbeg = n2beg; nend = n2end;
 #pragma unroll

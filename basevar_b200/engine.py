@@ -108,7 +108,8 @@ class BaseTypeEngine:
         Tiles of max_sites sites go through the slot pipeline (upload of the cells, K0 expand, K1..K4, D2H of the
         records).  With out_pinned=True `out` is pinned host memory and the D2H DMA writes the records in place."""
         S = ref_base.shape[0]
-        assert cells.dtype == np.uint32 and site_start.dtype == np.uint32 and site_start.shape[0] == S + 1
+        assert cells.dtype in (np.uint32, np.uint16) and site_start.dtype == np.uint32 and site_start.shape[0] == S + 1
+        fmt = capi.CELLS_U16 if cells.dtype == np.uint16 else capi.CELLS_U32   # uint16: the delta-coded compact form
         if out is None:
             out = np.zeros(S, dtype=SITE_OUT_DTYPE)
         n_slots, step = self.params.n_slots, self.params.max_sites
@@ -124,7 +125,7 @@ class BaseTypeEngine:
             st = site_start[s0:s0 + ns + 1] - np.uint32(c0) if c0 else site_start[s0:s0 + ns + 1]
             keep[slot] = st
             t = BvSparseTile(cells[c0:].ctypes.data if c0 < cells.shape[0] else cells.ctypes.data, None, st.ctypes.data,
-                             ref_base[s0:].ctypes.data, out[s0:].ctypes.data if out_pinned else None, ns, n_samples)
+                             ref_base[s0:].ctypes.data, out[s0:].ctypes.data if out_pinned else None, ns, n_samples, fmt, 0)
             self._check(self.lib.bv_tile_submit_sparse(self._ctx, slot, C.byref(t)), "bv_tile_submit_sparse")
             pending.append((slot, s0))
             slot = (slot + 1) % n_slots
@@ -135,7 +136,8 @@ class BaseTypeEngine:
     def call_sparse_calls(self, cells, cells_aux, site_start, ref_base, n_samples):
         """call_sparse plus the called-site outputs; returns what call_host_calls returns."""
         S = ref_base.shape[0]
-        assert cells.dtype == np.uint32 and cells_aux.dtype == np.uint32 and site_start.dtype == np.uint32
+        assert cells.dtype in (np.uint32, np.uint16) and cells_aux.dtype == np.uint32 and site_start.dtype == np.uint32
+        fmt = capi.CELLS_U16 if cells.dtype == np.uint16 else capi.CELLS_U32
         G = getattr(self, "n_groups", 0)
         out = np.zeros(S, dtype=SITE_OUT_DTYPE)
         n_slots, step = self.params.n_slots, self.params.max_sites
@@ -161,7 +163,8 @@ class BaseTypeEngine:
             st = site_start[s0:s0 + ns + 1] - np.uint32(c0)
             keep[slot] = st
             off = min(c0, max(cells.shape[0] - 1, 0))
-            t = BvSparseTile(cells[off:].ctypes.data, cells_aux[off:].ctypes.data, st.ctypes.data, ref_base[s0:].ctypes.data, None, ns, n_samples)
+            t = BvSparseTile(cells[off:].ctypes.data, cells_aux[off:].ctypes.data, st.ctypes.data, ref_base[s0:].ctypes.data, None, ns, n_samples,
+                             fmt, 0)
             self._check(self.lib.bv_tile_submit_sparse_calls(self._ctx, slot, C.byref(t)), "bv_tile_submit_sparse_calls")
             pending.append((slot, s0))
             slot = (slot + 1) % n_slots
@@ -290,6 +293,35 @@ def dense_to_sparse(base, qual, strand, n_samples, mapq=None, rpr=None):
     site_start = np.zeros(base.shape[0] + 1, np.uint32)
     np.cumsum(cov.sum(axis=1), out=site_start[1:])
     return cells, aux, site_start
+
+
+def _alloc(k, dt, pinned):
+    if pinned:
+        import torch
+        tdt = {np.uint32: torch.int32, np.uint16: torch.int16, np.uint8: torch.uint8}[dt]
+        return torch.empty(max(k, 1), dtype=tdt, pin_memory=True).numpy().view(dt)[:k]
+    return np.empty(k, dt)
+
+
+def sparse_encode16(cells, site_start, aux=None, pinned=False):
+    """BV_CELLS_U32 -> BV_CELLS_U16 (2 bytes per cell, samples delta-coded; cells must ascend by sample within a site).
+    Returns (words uint16, aux uint32 | None, start uint32).  Raises BvError for cells the compact form cannot carry."""
+    lib = capi.load_library()
+    S = site_start.shape[0] - 1
+    cells = np.ascontiguousarray(cells, np.uint32)
+    site_start = np.ascontiguousarray(site_start, np.uint32)
+    n = C.c_uint64(0)
+    rc = lib.bv_sparse_encode16(cells.ctypes.data, None, site_start.ctypes.data, S, None, None, 0, None, C.byref(n))
+    if rc != capi.BV_OK:
+        raise BvError(f"bv_sparse_encode16 failed ({rc}): {lib.bv_last_error(None).decode()}")
+    words = _alloc(n.value, np.uint16, pinned)
+    aux16 = _alloc(n.value, np.uint32, pinned) if aux is not None else None
+    start = _alloc(S + 1, np.uint32, pinned)
+    rc = lib.bv_sparse_encode16(cells.ctypes.data, aux.ctypes.data if aux is not None else None, site_start.ctypes.data, S,
+                                words.ctypes.data, aux16.ctypes.data if aux is not None else None, n.value, start.ctypes.data, C.byref(n))
+    if rc != capi.BV_OK:
+        raise BvError(f"bv_sparse_encode16 failed ({rc}): {lib.bv_last_error(None).decode()}")
+    return words, aux16, start
 
 
 def synth_fill_sparse_host(model, site0, n_sites, n_samples, with_aux=False, pinned=False):

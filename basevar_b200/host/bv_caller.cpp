@@ -501,7 +501,7 @@ void BasevarCaller::submit_current() {
         T.sparse_ready = false;
         bv_sparse_tile st;
         st.cells = T.sp_cells; st.cells_aux = T.sp_aux; st.site_start = T.sp_start; st.ref_base = T.ref; st.out = nullptr;
-        st.n_sites = T.n_sites; st.n_samples = (uint32_t)n_sample_;
+        st.n_sites = T.n_sites; st.n_samples = (uint32_t)n_sample_; st.format = BV_CELLS_U32; st.reserved = 0;
         check(bv_tile_submit_sparse_calls(ctx_, (int)cur_, &st), ctx_, "bv_tile_submit_sparse_calls");
         T.pending = true;
         cur_ = (cur_ + 1) % (uint32_t)tiles_.size();

@@ -138,6 +138,7 @@ bv_sparse_tile SparsePacker::tile() const {
     bv_sparse_tile t;
     t.cells = cells_; t.cells_aux = aux_; t.site_start = site_start_; t.ref_base = ref_; t.out = nullptr;
     t.n_sites = n_sites_; t.n_samples = n_samples_;
+    t.format = BV_CELLS_U32; t.reserved = 0;
     return t;
 }
 

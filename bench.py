@@ -9,8 +9,9 @@ step    : one pass of the basetype core (kernels K1 count, K2 scalar, K3 bound, 
           (S sites x N samples).
 value   : whole-job sample-sites/s with the planes resident in HBM (kernels only, CUDA events, max over ranks).
 e2e     : the same metric through the C ABI with HOST buffers, copies inside the timed region, tiles pipelined over 3
-          streams: sparse tiles (pinned u32 cells of the covered reads -> bv_tile_submit_sparse: H2D, K0 expand, K1..K4,
-          D2H of the 128-byte records -> bv_tile_wait).  e2e_dense: the same through dense pinned planes (bv_tile_submit).
+          streams: sparse tiles (pinned u16 words of the covered reads -> bv_tile_submit_sparse: H2D, K0 expand, K1..K4,
+          D2H of the 128-byte records -> bv_tile_wait).  e2e_sparse_u32: one u32 per cell; e2e_dense: dense pinned planes
+          (bv_tile_submit).
 roofline: algorithmic bytes S*(3N+128) per step / average step time (all four kernels), against MEASURED_PEAKS.json
           hbm_gbs; the per-kernel durations are measured live with CUDA events between the kernels (bv_set_profiling).
 cpu_baseline: the UNMODIFIED reference (oracle/_ref/libbvref.so: BaseType ctor + lrt() + strand_bias) on the
@@ -247,21 +248,29 @@ def main():
     site0 = shard.rank_site_range(rank, world, S)[0]
     cells, _, site_start, s_ref = bv.synth_fill_sparse_host(model, site0, S, n_samples, pinned=True)
     t_prep = time.perf_counter() - t_prep
+    t1 = time.perf_counter()
+    words16, _, start16 = bv.sparse_encode16(cells, site_start, pinned=True)   # 2 bytes per cell, samples delta-coded
+    t_prep16 = time.perf_counter() - t1
     rec_sp = torch.empty(S * 128, dtype=torch.uint8, pin_memory=True).numpy().view(bv.SITE_OUT_DTYPE)
     rec_sp[:] = 0
-    eng.call_sparse(cells, site_start, s_ref, n_samples, out=rec_sp, out_pinned=True)   # warm-up (sizes the cell buffers)
-    barrier()
-    l0 = eng.launch_count
-    up0 = eng.h2d_bytes
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        eng.call_sparse(cells, site_start, s_ref, n_samples, out=rec_sp, out_pinned=True)
-    torch.cuda.synchronize()
-    sp_s = (time.perf_counter() - t0) / args.e2e_steps
-    sp_launches = eng.launch_count - l0
-    sp_uploaded = (eng.h2d_bytes - up0) // args.e2e_steps
-    sp_s_max = shard.max_over_ranks(sp_s, dev)
-    sp_value = world * S * n_samples / sp_s_max
+
+    def sparse_leg(cell_words, starts):
+        rec_sp[:] = 0
+        eng.call_sparse(cell_words, starts, s_ref, n_samples, out=rec_sp, out_pinned=True)   # warm-up (sizes the cell buffers)
+        barrier()
+        l0, up0 = eng.launch_count, eng.h2d_bytes
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.call_sparse(cell_words, starts, s_ref, n_samples, out=rec_sp, out_pinned=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        dt_max = shard.max_over_ranks(dt, dev)
+        return {"value": world * S * n_samples / dt_max, "ms": 1e3 * dt_max, "launches": eng.launch_count - l0,
+                "uploaded": (eng.h2d_bytes - up0) // args.e2e_steps, "records": rec_sp.tobytes()}
+
+    leg32 = sparse_leg(cells, site_start)
+    leg16 = sparse_leg(words16, start16)
+    sp_launches = leg32["launches"] + leg16["launches"]
 
     # (b) dense tiles: pinned planes -> bv_tile_submit (H2D of base + strand, qual rows read in place) -> bv_tile_wait
     h_planes = [torch.empty((S, pitch), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
@@ -291,7 +300,8 @@ def main():
     # the e2e records (both transports) must be the very records of the device-resident path
     dev_rec = out.cpu().numpy().view(bv.SITE_OUT_DTYPE)
     same = bool(dev_rec.tobytes() == rec.tobytes())
-    same_sp = bool(dev_rec.tobytes() == rec_sp.tobytes())
+    same_sp = bool(dev_rec.tobytes() == leg16["records"])
+    same_sp32 = bool(dev_rec.tobytes() == leg32["records"])
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -319,12 +329,17 @@ def main():
                          "k1_bytes": S * (2 * n_samples + 128),
                          "k1_achieved": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9,
                          "k1_frac": S * (2 * n_samples + 128) / (kernel_ms["bv_count_kernel"] * 1e-3) / 1e9 / peak},
-            # e2e (headline): sparse host tiles.  h2d = 4 bytes per covered cell + the site offsets + REF bases
-            "e2e": {"value": sp_value, "unit": UNIT, "h2d_bytes_per_step": int(sp_uploaded), "d2h_bytes_per_step": int(S * 128),
-                    "ms_per_step": 1e3 * sp_s_max, "transport": "sparse tiles (bv_tile_submit_sparse): pinned u32 cells of the covered "
-                    "reads, expanded into the dense planes on the device (K0); records DMA'd into a pinned buffer",
-                    "cells_per_step": int(cells.shape[0]), "tile_sites": tile_sites, "slots": 3, "records_match_device_path": same_sp,
-                    "host_prep_s_untimed": t_prep},
+            # e2e (headline): sparse host tiles in the compact form.  h2d = 2 bytes per covered cell (+ 4 % "skip" words) + the
+            # site offsets + REF bases
+            "e2e": {"value": leg16["value"], "unit": UNIT, "h2d_bytes_per_step": int(leg16["uploaded"]), "d2h_bytes_per_step": int(S * 128),
+                    "ms_per_step": leg16["ms"], "transport": "sparse tiles, BV_CELLS_U16 (bv_tile_submit_sparse): pinned u16 words of the "
+                    "covered reads, sample indices delta-coded; expanded into the dense planes on the device (K0); records DMA'd into "
+                    "a pinned buffer", "cells_per_step": int(cells.shape[0]), "words_per_step": int(words16.shape[0]),
+                    "tile_sites": tile_sites, "slots": 3, "records_match_device_path": same_sp,
+                    "host_prep_s_untimed": t_prep + t_prep16},
+            # the same with one self-contained u32 per cell (any cell order within a site)
+            "e2e_sparse_u32": {"value": leg32["value"], "unit": UNIT, "h2d_bytes_per_step": int(leg32["uploaded"]),
+                               "d2h_bytes_per_step": int(S * 128), "ms_per_step": leg32["ms"], "records_match_device_path": same_sp32},
             # the dense-plane transport of the same workload.  h2d: bytes uploaded by cudaMemcpyAsync (base + strand planes,
             # REF bases) plus the qual rows the kernels read in place from the pinned host plane
             "e2e_dense": {"value": e2e_value, "unit": UNIT,

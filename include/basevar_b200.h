@@ -231,21 +231,43 @@ int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, voi
 /* aux word of a cell (called-site kernels): mapq | rpr << 8 */
 #define BV_CELL_AUX_PACK(mapq, rpr) ((uint32_t)(mapq) | ((uint32_t)(rpr) << 8))
 
+/* Compact form, 2 bytes per covered cell (BV_CELLS_U16): the words of a site in ASCENDING sample order,
+ *   word = gap | base << 5 | strand << 8 | phred << 9      (gap 0..30, base BV_BASE_*, strand 0 '+' / 1 '-', phred 0..127)
+ * where the cell's sample index = (index of the site's previous cell, or -1) + 1 + gap; a word with gap == 31 is no
+ * cell but "skip 31 samples" (its other bits are 0).  At 0.1x the mean gap is 9 and one word in 25 is a skip.  A cell
+ * whose strand is neither '+' nor '-' cannot be written this way (bv_sparse_encode16 says so; send the tile as
+ * BV_CELLS_U32).  cells_aux, when used, is indexed like the words (the aux word of a skip is ignored). */
+#define BV_CELLS_U32 0
+#define BV_CELLS_U16 1
+#define BV_CELL16_GAP_SKIP 31u
+#define BV_CELL16_PACK(gap, base, strand, phred) \
+    ((uint16_t)((uint32_t)(gap) | ((uint32_t)(base) << 5) | ((uint32_t)(strand) << 8) | ((uint32_t)(phred) << 9)))
+
 typedef struct bv_sparse_tile {
-    const uint32_t* cells;      /* [site_start[n_sites]] BV_CELL_PACK words, the cells of site 0 first            */
+    const void*     cells;      /* [site_start[n_sites]] words of `format`, the words of site 0 first: BV_CELL_PACK u32   */
+                                /* (any order within a site) or BV_CELL16_PACK u16 (ascending samples)                     */
     const uint32_t* cells_aux;  /* same indexing, BV_CELL_AUX_PACK words; only read by bv_tile_submit_sparse_calls */
-    const uint32_t* site_start; /* [n_sites + 1] ascending offsets into `cells`; site_start[0] == 0               */
+    const uint32_t* site_start; /* [n_sites + 1] ascending offsets into `cells`, in words; site_start[0] == 0     */
     const uint8_t*  ref_base;   /* [n_sites] as in bv_tile                                                        */
     bv_site_out*    out;        /* optional: PINNED host memory for the n_sites records; the D2H DMA then writes  */
                                 /* them in place and bv_tile_wait's `out` may be NULL                             */
     uint32_t n_sites;
     uint32_t n_samples;
+    uint32_t format;            /* BV_CELLS_U32 or BV_CELLS_U16                                                     */
+    uint32_t reserved;
 } bv_sparse_tile;
 
 /* Asynchronous, like bv_tile_submit (host memory only; pinned memory makes the copies truly asynchronous). */
 int bv_tile_submit_sparse(bv_ctx* ctx, int slot, const bv_sparse_tile* tile);
 /* The same plus the called-site kernels; collect with bv_tile_wait_calls. */
 int bv_tile_submit_sparse_calls(bv_ctx* ctx, int slot, const bv_sparse_tile* tile);
+/* BV_CELLS_U32 -> BV_CELLS_U16 on the host (plain C loop): the cells of every site must ascend by sample.  words16 has
+ * room for max_words words (bv_sparse_encode16_bound() is always enough; pass words16 == NULL to count only);
+ * start16[n_sites + 1] receives the word offsets, *n_words the word count.  BV_ERR_ARG: cells not ascending, a strand
+ * that is neither '+' nor '-', or max_words too small.  aux16 (optional, with aux32) receives the aux words re-indexed. */
+uint64_t bv_sparse_encode16_bound(uint64_t n_cells, uint32_t n_sites, uint32_t n_samples);
+int bv_sparse_encode16(const uint32_t* cells, const uint32_t* aux32, const uint32_t* site_start, uint32_t n_sites,
+                       uint16_t* words16, uint32_t* aux16, uint64_t max_words, uint32_t* start16, uint64_t* n_words);
 /* Host twin of the synthetic generator in sparse form: fills cells / cells_aux (may be NULL) / site_start / ref_base
  * for sites [site0, site0 + n_sites); *n_cells receives the number of cells, BV_ERR_ARG if it exceeds max_cells
  * (call with cells == NULL to count only). */

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_struct_layouts_match_the_header(built_lib):
     assert capi.SITE_OUT_DTYPE.itemsize == 128
-    assert C.sizeof(capi.BvParams) == 36 and C.sizeof(capi.BvTile) == 56 and C.sizeof(capi.BvSparseTile) == 48
+    assert C.sizeof(capi.BvParams) == 36 and C.sizeof(capi.BvTile) == 56 and C.sizeof(capi.BvSparseTile) == 56
     assert C.sizeof(capi.BvSynthModel) == 32 + 4 * (96 + 1024 + 256)
     offs = {n: capi.SITE_OUT_DTYPE.fields[n][1] for n in capi.SITE_OUT_DTYPE.names}
     assert offs == {"depth": 0, "depth_other": 16, "reserved0": 20, "fwd": 24, "rev": 40, "n_alt": 56, "alt": 57,
@@ -102,3 +102,47 @@ def test_sparse_host_twin_equals_the_dense_twin(built_lib):
         assert np.array_equal((cells >> 20) & 7, b[site, samp]) and np.array_equal((cells >> 23) & 3, s[site, samp])
         assert np.array_equal(cells >> 25, q[site, samp]) and np.array_equal(aux & 255, mq[site, samp])
         assert np.array_equal(aux >> 8, rpr[site, samp])
+
+
+def _decode16(words, start, n_samples):
+    """Reference decoder of BV_CELLS_U16 (plain Python): list of (site, sample, base, strand, phred, word index)."""
+    out = []
+    for s in range(len(start) - 1):
+        nxt = 0
+        for k in range(int(start[s]), int(start[s + 1])):
+            w = int(words[k]); gap = w & 31
+            if gap == 31:
+                assert w == 31
+                nxt += 31
+                continue
+            smp = nxt + gap
+            assert smp < n_samples
+            out.append((s, smp, (w >> 5) & 7, (w >> 8) & 1, w >> 9, k))
+            nxt = smp + 1
+    return out
+
+
+def test_sparse_encode16_round_trip_and_errors(built_lib):
+    """The 2-byte delta-coded form decodes to the very cells it was made from; what it cannot carry is refused."""
+    rng = np.random.default_rng(3)
+    for cov, N, S in [(0.1, 1000, 60), (0.01, 3000, 40), (0.99326, 70, 50), (0.3, 31, 40), (0.05, 63, 40)]:
+        m = bv.synth.make_model(seed=11, coverage=cov, variant_frac=0.3, multi_frac=0.3)
+        cells, aux, st, _ = bv.synth_fill_sparse_host(m, 3, S, N, with_aux=True)
+        words, aux16, st16 = bv.sparse_encode16(cells, st, aux)
+        lib = capi.load_library()
+        assert len(words) <= lib.bv_sparse_encode16_bound(len(cells), S, N)
+        dec = _decode16(words, st16, N)
+        assert len(dec) == len(cells)
+        site = np.repeat(np.arange(S), np.diff(st.astype(np.int64)))
+        for (s, smp, b, sd, q, k), w, a, ws in zip(dec, cells, aux, site):
+            assert (s, smp, b, sd, q) == (ws, int(w) & 0xFFFFF, (int(w) >> 20) & 7, (int(w) >> 23) & 3, int(w) >> 25)
+            assert aux16[k] == a
+    # an empty tile, and sites without cells
+    w, _, s16 = bv.sparse_encode16(np.zeros(0, np.uint32), np.zeros(5, np.uint32))
+    assert len(w) == 0 and not s16.any()
+    # unsorted cells and a strand that is neither + nor - have no compact form
+    st = np.array([0, 2], np.uint32)
+    with pytest.raises(bv.BvError, match="ascend"):
+        bv.sparse_encode16(capi.cell_pack([5, 3], 1, 0, 30), st)
+    with pytest.raises(bv.BvError, match="strand"):
+        bv.sparse_encode16(capi.cell_pack([3, 5], 1, [0, 2], 30), st)

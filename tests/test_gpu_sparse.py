@@ -29,6 +29,16 @@ def _both(engine, b, q, s, r, N, maf, abs_mode, label, shuffle=None):
     engine.set_params(min_af=maf, abs_mode=abs_mode)
     dense = engine.call_host(b, q, s, r, N)
     cells, _, st = bv.dense_to_sparse(b, q, s, N)
+    # the compact 2-byte form (ascending samples, strands +/- only) of the same tile
+    covered_bad_strand = bool(((s[:, :N] > 1) & ((b[:, :N] != capi.BASE_N) | (q[:, :N] != 0))).any())
+    if covered_bad_strand:
+        with pytest.raises(bv.BvError, match="strand"):
+            bv.sparse_encode16(cells, st)
+    else:
+        words, _, st16 = bv.sparse_encode16(cells, st)
+        assert len(words) >= len(cells)
+        compact = engine.call_sparse(words, st16, r, N)
+        assert compact.tobytes() == dense.tobytes(), f"{label}: 16-bit sparse and dense records differ"
     if shuffle is not None:   # cell order within a site is free
         for i in range(len(st) - 1):
             shuffle.shuffle(cells[st[i]:st[i + 1]])
@@ -120,6 +130,15 @@ def test_sparse_malformed_input_is_an_error(engine):
     with pytest.raises(bv.BvError, match="sparse tile"):
         engine.call_sparse(cells, st2, ref, N)
     engine.call_sparse(cells, st, ref, N)                      # the slot is usable again
+    # compact form: a gap that runs past the last sample
+    words, _, st16 = bv.sparse_encode16(cells, st)
+    engine.call_sparse(words, st16, ref, N)
+    w2 = words.copy(); w2[7] = (w2[7] & ~np.uint16(31)) | np.uint16(30)   # site 7's only cell: sample 7 -> 30 ... fine; then skips
+    long_ = np.concatenate([w2[:8], np.full(2, 31, np.uint16), w2[7:8], w2[8:]])   # site 7: cell, skip, skip, cell at 30+1+62+30 >= 50
+    st3 = st16.copy(); st3[8:] += 3
+    with pytest.raises(bv.BvError, match="sparse tile"):
+        engine.call_sparse(long_, st3, ref, N)
+    engine.call_sparse(words, st16, ref, N)
 
 
 @pytest.mark.parametrize("G", [0, 3])
@@ -140,5 +159,8 @@ def test_sparse_calls_equal_dense_calls(built_lib, G):
             assert s_rec.tobytes() == d_rec.tobytes()
             assert len(s_calls) > 0 and s_calls.tobytes() == d_calls.tobytes()
             assert s_groups.tobytes() == d_groups.tobytes()
+            words, aux16, st16 = bv.sparse_encode16(cells, st, aux)          # the compact form with re-indexed aux words
+            c_rec, c_calls, c_groups = eng.call_sparse_calls(words, aux16, st16, ref, N)
+            assert c_rec.tobytes() == d_rec.tobytes() and c_calls.tobytes() == d_calls.tobytes() and c_groups.tobytes() == d_groups.tobytes()
     finally:
         eng.close()
