@@ -492,6 +492,10 @@ __device__ __noinline__ double em_bins(const uint32_t* bins, double* lml, int nb
 //     at least 1, i.e. when a marginal changed by a factor e: decided exactly from the ratio of the marginals -- inside
 //     (1/2.5, 2.5) no logarithm is needed, otherwise the logarithms themselves decide -- so that `log` runs once per
 //     bin and EM call (for the reported log-likelihoods) instead of once per bin and iteration.
+// out of line: the inlined libdevice log is ~90 instructions per call site and this kernel is instruction-fetch sensitive
+#ifndef BV_EM_LOG
+#define BV_EM_LOG nlog
+#endif
 template <int NS>
 __device__ __noinline__ double em_bins_reg(const uint32_t* bins, int nb, int subset, double total) {
     QualWarp& W = warp_smem();
@@ -560,7 +564,7 @@ __device__ __noinline__ double em_bins_reg(const uint32_t* bins, int nb, int sub
         } else {
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
-                const double llh = log(mk[k]);
+                const double llh = BV_EM_LOG(mk[k]);
                 if (!first && on[k]) delta += cd[k] * fabs(llh - prev[k]);
                 prev[k] = llh;
             }
@@ -580,7 +584,7 @@ __device__ __noinline__ double em_bins_reg(const uint32_t* bins, int nb, int sub
     double ll = 0;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        const double lml = int_mode ? log(prev[k]) : prev[k];
+        const double lml = int_mode ? BV_EM_LOG(prev[k]) : prev[k];
         if (on[k]) ll += cd[k] * lml;
     }
     if (lane == 0) { W.emf[0] = f0; W.emf[1] = f1; W.emf[2] = f2; W.emf[3] = f3; }

@@ -16,6 +16,7 @@ for cfg in "C2 1000000" "C3 100000" "C5 200000"; do
 done
 timeout 300 python tools/run_kernel.py --config C5 --sites 200000 --launches 5 --abs-mode 1 2>&1 | tee -a "$O/run_kernel.log"
 timeout 300 python tools/e2e_sweep.py --config C2 --sites 1000000 --tiles 32768,131072 --slots 3 2>&1 | tee "$O/e2e_sweep.log"
+timeout 300 python tools/e2e_sweep.py --config C2 --sites 1000000 --u16 --tiles 32768,131072 --slots 3 2>&1 | tee -a "$O/e2e_sweep.log"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$O/launches.csv" \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > "$O/bench_under_ncu.log" 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bv_.*_kernel -s 5 -c 4 -f -o "$O/prof_C2" \
@@ -23,5 +24,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:bv_.
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bv_em_kernel -s 2 -c 1 -f -o "$O/prof_C5_em" \
     python tools/run_kernel.py --config C5 --sites 200000 --launches 2 > "$O/ncu_full_C5.log" 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bv_expand_kernel -s 9 -c 1 -f -o "$O/prof_K0" \
-    python tools/e2e_sweep.py --config C2 --sites 1000000 --tiles 131072 --slots 3 --reps 1 > "$O/ncu_full_K0.log" 2>&1
+    python tools/e2e_sweep.py --config C2 --sites 1000000 --u16 --tiles 131072 --slots 3 --reps 1 > "$O/ncu_full_K0.log" 2>&1
 ls -la "$O"
