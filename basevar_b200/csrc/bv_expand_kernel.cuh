@@ -69,47 +69,71 @@ __device__ __forceinline__ uint32_t load_word(const void* cells, uint64_t c) {
     return __ldg(reinterpret_cast<const uint32_t*>(cells) + c);
 }
 
-// Visits the cells of one site, 32 words per step: f(sample, base, strand, phred, word index) for the lanes that hold a
-// cell.  `upto` (BV_CELLS_U16 only; samples ascend): stops once every further cell has sample >= upto.
+// Word k of a site's prefetch registers: BV_CELLS_U32 keeps the strided order of coalesced 4-byte loads (pre[k] of lane l
+// is word 32 k + l); BV_CELLS_U16 gives every lane kExPre CONSECUTIVE words (pre[k] of lane l is word 4 l + k), so that a
+// batch of 128 delta-coded words needs one warp scan instead of four.
+template <int FMT>
+__device__ __forceinline__ uint64_t pre_index(uint32_t lane, int k) {
+    return FMT == BV_CELLS_U16 ? (uint64_t)(kExPre * lane + (uint32_t)k) : (uint64_t)(32u * (uint32_t)k + lane);
+}
+
+// Visits the cells of one site, 128 words per step: f(sample, base, strand, phred, word index) for every cell.
+// `upto` (BV_CELLS_U16 only; samples ascend): stops once every further cell has sample >= upto.
 // Returns false when a cell's sample index is >= n_samples (malformed input).
 template <int FMT, class F>
 __device__ __forceinline__ bool for_each_cell(const void* cells, uint64_t beg, uint64_t end, const uint32_t (&pre)[kExPre],
                                               uint32_t lane, uint32_t n_samples, uint32_t upto, F&& f) {
     bool good = true;
     uint32_t next = 0;   // BV_CELLS_U16: the sample index a gap of 0 would mean (warp-uniform)
-    int k = 0;
+    bool first = true;
 #pragma unroll 1
-    for (uint64_t c0 = beg; c0 < end; c0 += 32, ++k) {
-        const uint64_t c = c0 + lane;
-        const bool live = c < end;
-        uint32_t w = 0;
-        if (k < kExPre) {   // (warp-uniform) the prefetched words
-            w = k == 0 ? pre[0] : k == 1 ? pre[1] : k == 2 ? pre[2] : pre[3];
-        } else if (live) {
-            w = load_word<FMT>(cells, c);
+    for (uint64_t c0 = beg; c0 < end; c0 += 32 * kExPre) {
+        uint32_t w[kExPre];
+#pragma unroll
+        for (int k = 0; k < kExPre; ++k) {
+            const uint64_t c = c0 + pre_index<FMT>(lane, k);
+            w[k] = first ? pre[k] : (c < end ? load_word<FMT>(cells, c) : 0u);   // (`first` is warp-uniform)
         }
+        first = false;
         if (FMT == BV_CELLS_U16) {
-            const uint32_t gap = w & 31u;
-            const bool is_cell = live && gap != BV_CELL16_GAP_SKIP;
-            const uint32_t inc = live ? (gap == BV_CELL16_GAP_SKIP ? BV_CELL16_GAP_SKIP : gap + 1u) : 0u;
-            uint32_t x = inc;
+            // lane l holds words 4 l .. 4 l + 3 of the batch: local prefix of the sample increments, one scan of the lane totals
+            uint32_t inc[kExPre], tot = 0;
+#pragma unroll
+            for (int k = 0; k < kExPre; ++k) {
+                const bool live = c0 + pre_index<FMT>(lane, k) < end;
+                const uint32_t gap = w[k] & 31u;
+                inc[k] = live ? (gap == BV_CELL16_GAP_SKIP ? BV_CELL16_GAP_SKIP : gap + 1u) : 0u;
+                tot += inc[k];
+            }
+            uint32_t x = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t y = __shfl_up_sync(kFull, x, o);
                 if ((int)lane >= o) x += y;
             }
-            const uint32_t sample = next + (x - inc) + gap;
+            uint32_t at = next + (x - tot);   // the sample index a gap of 0 would mean at this lane's first word
             next += __shfl_sync(kFull, x, 31);
-            if (is_cell) {
-                if (sample >= n_samples) good = false;
-                else f(sample, (w >> 5) & 7u, (w >> 8) & 1u, w >> 9, c);
+#pragma unroll
+            for (int k = 0; k < kExPre; ++k) {
+                const uint64_t c = c0 + pre_index<FMT>(lane, k);
+                const uint32_t gap = w[k] & 31u;
+                if (c < end && gap != BV_CELL16_GAP_SKIP) {
+                    const uint32_t sample = at + gap;
+                    if (sample >= n_samples) good = false;
+                    else f(sample, (w[k] >> 5) & 7u, (w[k] >> 8) & 1u, w[k] >> 9, c);
+                }
+                at += inc[k];
             }
             if (next >= upto) break;   // warp-uniform
         } else {
-            if (live) {
-                const uint32_t sample = w & (BV_CELL_MAX_SAMPLES - 1u);
-                if (sample >= n_samples) good = false;
-                else f(sample, (w >> 20) & 7u, (w >> 23) & 3u, w >> 25, c);
+#pragma unroll
+            for (int k = 0; k < kExPre; ++k) {
+                const uint64_t c = c0 + pre_index<FMT>(lane, k);
+                if (c < end) {
+                    const uint32_t sample = w[k] & (BV_CELL_MAX_SAMPLES - 1u);
+                    if (sample >= n_samples) good = false;
+                    else f(sample, (w[k] >> 20) & 7u, (w[k] >> 23) & 3u, w[k] >> 25, c);
+                }
             }
         }
     }
@@ -140,7 +164,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
         const bool ok = e >= b && e <= a.n_cells;
 #pragma unroll
         for (int k = 0; k < kExPre; ++k) {
-            const uint64_t c = b + (uint32_t)(32 * k) + lane;
+            const uint64_t c = b + pre_index<FMT>(lane, k);
             pre[k] = (ok && c < e) ? load_word<FMT>(a.cells, c) : 0u;
         }
     };
