@@ -291,7 +291,9 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     bv::bv_bound_kernel<<<grid, bv::kBoundWarps * 32, bv::kBoundSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
-    grid = ((a.n_sites + 31) / 32 + bv::kQualWarps - 1) / bv::kQualWarps;
+    // one warp per site of the EM list, whose length the host does not know: up to every site of the tile (deep pileups with a
+    // small min_af: half of the sites of a 100,000-sample tile), so the grid covers that; warps without work leave at once
+    grid = (a.n_sites + bv::kQualWarps - 1) / bv::kQualWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
     bv::bv_em_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
