@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(kBoundWarps * 32, 1) bv_bound_kernel(const __g
 #define BV_QUAL_WARPS 24
 #endif
 constexpr int kQualWarps = BV_QUAL_WARPS;
-constexpr int kP2Chunk = 512;                // cells per buffer and plane, one 16-cell vector per lane
+#ifndef BV_P2_CHUNK
+#define BV_P2_CHUNK 512
+#endif
+constexpr int kP2Chunk = BV_P2_CHUNK;        // cells per buffer and plane: kP2Chunk / 512 16-cell vectors per lane
 
 struct __align__(128) P2Buf {                // one chunk of the base and qual planes
     uint8_t base[kP2Chunk];
@@ -339,12 +342,16 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
         }
         mbar_wait(s_bar0 + 8u * buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
-        const int lane_cells = (int)N - (int)(c * kP2Chunk) - lane * 16;
-        const uint8_t* cellp = W.p2[buf].base + lane * 16;
-        uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
-        if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(cellp);
-        if (lane_cells < 16) mask_tail(vb, lane_cells);
-        f(cellp, vb, lane_cells, c * kP2Chunk + lane * 16);
+#pragma unroll 1
+        for (int v = 0; v < kP2Chunk / 512; ++v) {
+            const int lane_cells = (int)N - (int)(c * kP2Chunk) - v * 512 - lane * 16;
+            if (v > 0 && (int)N - (int)(c * kP2Chunk) - v * 512 <= 0) break;   // (warp-uniform) the row ended in this chunk
+            const uint8_t* cellp = W.p2[buf].base + v * 512 + lane * 16;
+            uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
+            if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(cellp);
+            if (lane_cells < 16) mask_tail(vb, lane_cells);
+            f(cellp, vb, lane_cells, c * kP2Chunk + v * 512 + lane * 16);
+        }
         __syncwarp();
     }
     if (lane == 0) W.p2_phase = phase;
