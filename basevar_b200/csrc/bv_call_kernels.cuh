@@ -389,8 +389,7 @@ __global__ void __launch_bounds__(kQualWarps * 32, 1) bv_group_kernel(const __gr
     if (lane == 0) {
         W.flag_word = 0;
         W.p2_phase = 0;
-        mbar_init(&W.p2bar[0], 1);
-        mbar_init(&W.p2bar[1], 1);
+        for (int b = 0; b < kP2Bufs; ++b) mbar_init(&W.p2bar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();

@@ -264,6 +264,10 @@ constexpr int kQualWarps = BV_QUAL_WARPS;
 #define BV_P2_CHUNK 512
 #endif
 constexpr int kP2Chunk = BV_P2_CHUNK;        // cells per buffer and plane: kP2Chunk / 512 16-cell vectors per lane
+#ifndef BV_P2_BUFS
+#define BV_P2_BUFS 2
+#endif
+constexpr int kP2Bufs = BV_P2_BUFS;          // ring of row chunks per warp: kP2Bufs - 1 TMA fetches in flight ahead of the scan
 
 struct __align__(128) P2Buf {                // one chunk of the base and qual planes
     uint8_t base[kP2Chunk];
@@ -271,7 +275,7 @@ struct __align__(128) P2Buf {                // one chunk of the base and qual p
 };
 
 struct __align__(128) QualWarp {
-    P2Buf p2[2];
+    P2Buf p2[kP2Bufs];
     uint32_t hist[kHistWords];   // (base, phred) histogram, all-zero between sites; the EM's per-bin state (one double
                                  // per compact bin) overlays it once the bins are compacted
     uint32_t bins[kSmemBins];    // compact non-empty bins: (base << 29) | (phred << 22) | count
@@ -281,7 +285,7 @@ struct __align__(128) QualWarp {
     double res_chi;              // LRT: last chi_sqrt_value
     uint32_t flag_word;          // BV_FLAG_* raised inside out-of-line code
     uint32_t p2_phase;           // mbarrier phase bits of p2bar[]
-    uint64_t p2bar[2];
+    uint64_t p2bar[kP2Bufs];
     alignas(16) bv_site_out rec; // the site's record: loaded from global, completed, stored back
     uint32_t vcf_n;              // sites with ALT alleles waiting for their scalar finish (vcf_flush)
     uint32_t vcf_site[32];
@@ -323,23 +327,23 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
     const uint8_t* gq = cs.a.qual + (size_t)site * cs.a.qual_pitch;
     const uint32_t s_buf0 = smem_u32(&W.p2[0]), s_bar0 = smem_u32(&W.p2bar[0]);
     uint32_t phase = W.p2_phase;
+    auto fetch = [&](uint32_t c) {   // lane 0: chunk c into buffer c % kP2Bufs
+        const uint32_t off = c * kP2Chunk;
+        const uint32_t bytes = min((uint32_t)kP2Chunk, row_bytes - off);
+        const uint32_t b = c % (uint32_t)kP2Bufs;
+        const uint32_t bar = s_bar0 + 8u * b, dst = s_buf0 + (uint32_t)sizeof(P2Buf) * b;
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_g2s(dst, gb + off, bytes, bar);
+        bulk_g2s(dst + kP2Chunk, gq + off, bytes, bar);
+    };
     if (lane == 0) {
-        const uint32_t bytes = min((uint32_t)kP2Chunk, row_bytes);
-        mbar_expect_tx(s_bar0, 2 * bytes);
-        bulk_g2s(s_buf0, gb, bytes, s_bar0);
-        bulk_g2s(s_buf0 + kP2Chunk, gq, bytes, s_bar0);
+        for (uint32_t c = 0; c < (uint32_t)(kP2Bufs - 1) && c < nchunk; ++c) fetch(c);
     }
 #pragma unroll 1
     for (uint32_t c = 0; c < nchunk; ++c) {
-        const uint32_t buf = c & 1u;
-        if (c + 1 < nchunk && lane == 0) {   // chunk c+1 goes where chunk c-1 was (all lanes are past it: __syncwarp below)
-            const uint32_t off = (c + 1) * kP2Chunk;
-            const uint32_t bytes = min((uint32_t)kP2Chunk, row_bytes - off);
-            const uint32_t bar = s_bar0 + 8u * (buf ^ 1u), dst = s_buf0 + (uint32_t)sizeof(P2Buf) * (buf ^ 1u);
-            mbar_expect_tx(bar, 2 * bytes);
-            bulk_g2s(dst, gb + off, bytes, bar);
-            bulk_g2s(dst + kP2Chunk, gq + off, bytes, bar);
-        }
+        const uint32_t buf = c % (uint32_t)kP2Bufs;
+        // chunk c + kP2Bufs - 1 goes where chunk c - 1 was (all lanes are past it: __syncwarp below)
+        if (c + (uint32_t)(kP2Bufs - 1) < nchunk && lane == 0) fetch(c + (uint32_t)(kP2Bufs - 1));
         mbar_wait(s_bar0 + 8u * buf, (phase >> buf) & 1u);
         phase ^= 1u << buf;
 #pragma unroll 1
@@ -911,8 +915,7 @@ __global__ void __launch_bounds__(kQualWarps * 32, 1) bv_em_kernel(const __grid_
         W.flag_word = 0;
         W.p2_phase = 0;
         W.vcf_n = 0;
-        mbar_init(&W.p2bar[0], 1);
-        mbar_init(&W.p2bar[1], 1);
+        for (int b = 0; b < kP2Bufs; ++b) mbar_init(&W.p2bar[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
