@@ -252,6 +252,19 @@ struct BasevarCaller::Tile {
     uint32_t *sp_cells = nullptr, *sp_aux = nullptr, *sp_start = nullptr;
     size_t sp_cap = 0;
     bool sparse_ready = false;
+    // the same cells in the compact form (BV_CELLS_U16), encoded at submit time
+    uint16_t* sp_words16 = nullptr;
+    uint32_t *sp_aux16 = nullptr, *sp_start16 = nullptr;
+    size_t sp_cap16 = 0;
+
+    void reserve_words16(size_t n) {
+        if (n <= sp_cap16) return;
+        bv_host_free(sp_words16); bv_host_free(sp_aux16);
+        sp_words16 = nullptr; sp_aux16 = nullptr; sp_cap16 = 0;
+        const size_t cap = n + n / 4 + 4096;
+        sp_words16 = (uint16_t*)pinned(cap * sizeof(uint16_t)); sp_aux16 = (uint32_t*)pinned(cap * sizeof(uint32_t));
+        sp_cap16 = cap;
+    }
 
     void reserve_cells(size_t n) {   // contents are not kept: called once per tile, before the cells are written
         if (n <= sp_cap) return;
@@ -269,6 +282,7 @@ struct BasevarCaller::Tile {
         base = (uint8_t*)pinned(plane); qual = (uint8_t*)pinned(plane); strand = (uint8_t*)pinned(plane);
         mapq = (uint8_t*)pinned(plane); rpr = (uint16_t*)pinned(plane * 2); ref = (uint8_t*)pinned(max_sites);
         sp_start = (uint32_t*)pinned(((size_t)max_sites + 1) * sizeof(uint32_t));
+        sp_start16 = (uint32_t*)pinned(((size_t)max_sites + 1) * sizeof(uint32_t));
         meta.resize(max_sites);
         recs.resize(max_sites);
         calls.resize(max_sites);
@@ -278,6 +292,7 @@ struct BasevarCaller::Tile {
     ~Tile() {
         bv_host_free(base); bv_host_free(qual); bv_host_free(strand); bv_host_free(mapq); bv_host_free(rpr); bv_host_free(ref);
         bv_host_free(sp_start); bv_host_free(sp_cells); bv_host_free(sp_aux);
+        bv_host_free(sp_start16); bv_host_free(sp_words16); bv_host_free(sp_aux16);
     }
 };
 
@@ -502,6 +517,16 @@ void BasevarCaller::submit_current() {
         bv_sparse_tile st;
         st.cells = T.sp_cells; st.cells_aux = T.sp_aux; st.site_start = T.sp_start; st.ref_base = T.ref; st.out = nullptr;
         st.n_sites = T.n_sites; st.n_samples = (uint32_t)n_sample_; st.format = BV_CELLS_U32; st.reserved = 0;
+        // the packer's cells ascend by sample within a row: two bytes per cell (plus the aux word) instead of four, unless a
+        // cell has no compact form (a strand that is neither + nor -)
+        uint64_t n_words = 0;
+        if (bv_sparse_encode16(T.sp_cells, nullptr, T.sp_start, T.n_sites, nullptr, nullptr, 0, nullptr, &n_words) == BV_OK) {
+            T.reserve_words16((size_t)n_words);
+            if (bv_sparse_encode16(T.sp_cells, T.sp_aux, T.sp_start, T.n_sites, T.sp_words16, T.sp_aux16, T.sp_cap16, T.sp_start16,
+                                   &n_words) == BV_OK) {
+                st.cells = T.sp_words16; st.cells_aux = T.sp_aux16; st.site_start = T.sp_start16; st.format = BV_CELLS_U16;
+            }
+        }
         check(bv_tile_submit_sparse_calls(ctx_, (int)cur_, &st), ctx_, "bv_tile_submit_sparse_calls");
         T.pending = true;
         cur_ = (cur_ + 1) % (uint32_t)tiles_.size();
