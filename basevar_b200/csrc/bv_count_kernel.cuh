@@ -20,7 +20,7 @@
 namespace bv {
 
 // Two shapes of the kernel (warps per CTA x ring depth per warp), chosen by the row length at launch.  Measured on
-// B200 (profiles/r01o_k1_ring_shapes.txt): rows of <= 1,000 samples want many warps (per-site work is short, 32 warps
+// B200 (profiles/history/r01o_k1_ring_shapes.txt): rows of <= 1,000 samples want many warps (per-site work is short, 32 warps
 // keep the issue slots 82 % busy), rows of 10,000 samples want deeper rings on fewer warps (0.66 ms vs 0.93 ms per
 // 10^9 cells).
 #ifndef BV_COUNT_WARPS
