@@ -107,6 +107,27 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank's host thread -- and, by first touch, its pinned staging buffers -- on the CPUs next to its GPU (one
+    host worker per GPU, as in the C++ runner).  Returns the CPU list, or None when the topology cannot be read."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus and len(cpus) < ncpu:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def reference_arm(args, cfg, n_samples, rank, world):
     """--impl reference: the unmodified reference on the host cores, bounded sample of the same workload."""
     if rank != 0:
@@ -160,6 +181,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--tile-sites", type=int, default=131072, help="sites per host tile of the e2e legs (tools/e2e_sweep.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind the rank to the CPUs next to its GPU")
     ap.add_argument("--ref-sites-per-core", type=int, default=40000)
     args = ap.parse_args()
 
@@ -181,6 +203,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the basetype core has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -318,7 +341,8 @@ def main():
                        "n_samples": n_samples, "sites_per_gpu": S, "min_af": maf, "em_abs_mode": args.abs_mode,
                        "variant_sites": int((dev_rec["n_alt"] > 0).sum()), "mean_em_calls": float(dev_rec["em_calls"].mean()),
                        "l2": "inputs (3 planes, %.2f GB) larger than L2; no flush needed" % (3 * S * pitch / 1e9),
-                       "parallelism": f"region-sharded x{world}, no collective"},
+                       "parallelism": f"region-sharded x{world}, no collective",
+                       "host_binding": (f"rank 0 on the {len(numa_cpus)} CPUs next to its GPU" if numa_cpus else "none")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(args.config, n_samples, S), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
