@@ -6,8 +6,9 @@
  *
  *   reference interface                                         replaced by
  *   ----------------------------------------------------------  ---------------------------------
- *   struct BatchInfo                    src/basetype.h:25-43     bv_tile (packed SoA planes)
- *   BaseType::BaseType(BatchInfo*,af)   src/basetype.h:105       bv_tile_submit / bv_tile_run_device
+ *   struct BatchInfo                    src/basetype.h:25-43     bv_tile (packed SoA planes), or bv_sparse_tile: the
+ *                                                                covered cells only, expanded on the device
+ *   BaseType::BaseType(BatchInfo*,af)   src/basetype.h:105       bv_tile_submit / bv_tile_submit_sparse / bv_tile_run_device
  *                                       src/basetype.cpp:22-72   (count kernel: depths, strand table)
  *   BaseType::lrt()                     src/basetype.h:117-118   same call (scalar / bound / EM kernels)
  *                                       src/basetype.cpp:130-199
