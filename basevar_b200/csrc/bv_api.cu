@@ -925,6 +925,16 @@ int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_s
     return BV_OK;
 }
 
+uint32_t bv_suggest_tile_sites(const bv_ctx* ctx, uint32_t n_samples, uint64_t max_bytes) {
+    const uint64_t pitch = ((uint64_t)(n_samples ? n_samples : 1) + 15) / 16 * 16;
+    uint64_t fit = max_bytes / (3 * pitch);
+    if (fit < 1) fit = 1;
+    if (fit > 0xffffffffull) fit = 0xffffffffull;
+    const uint64_t sms = ctx && ctx->num_sms > 0 ? (uint64_t)ctx->num_sms : 148;
+    const uint64_t unit = sms * (n_samples > (uint32_t)bv::kLongRowSamples ? BV_COUNT_WARPS_LONG : BV_COUNT_WARPS);
+    return (uint32_t)(fit >= unit ? fit / unit * unit : fit);
+}
+
 int bv_host_alloc(void** out_ptr, size_t bytes) {
     if (!out_ptr) return set_err(nullptr, BV_ERR_ARG, "null argument");
     cudaError_t e = cudaHostAlloc(out_ptr, bytes, cudaHostAllocDefault);

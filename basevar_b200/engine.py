@@ -52,6 +52,10 @@ class BaseTypeEngine:
             self.params.em_abs_mode = abs_mode
         self._check(self.lib.bv_set_params(self._ctx, C.byref(self.params)), "bv_set_params")
 
+    def suggest_tile_sites(self, n_samples, max_bytes):
+        """Largest tile (sites) that fits max_bytes of planes and that the count kernel's persistent warps split evenly."""
+        return int(self.lib.bv_suggest_tile_sites(self._ctx, n_samples, max_bytes))
+
     @property
     def launch_count(self):
         return int(self.lib.bv_launch_count(self._ctx))

@@ -310,6 +310,13 @@ int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_s
                        uint64_t pitch, uint8_t* base, uint8_t* qual, uint8_t* strand, uint8_t* mapq,
                        uint8_t* ref_base);
 
+/* ---- tile sizing --------------------------------------------------------------------------------- */
+/* The count kernel is persistent: num_SMs x W warps take one site row each (W = 32, or 16 for rows longer than 4,096
+ * samples), so a tile whose site count is not a multiple of that leaves warps idle in the last round -- 16 % of the kernel
+ * for 10,000 rows of 100,000 samples.  Returns the largest such multiple whose three planes (n_sites x round16(n_samples)
+ * bytes each) fit max_bytes; when not even one multiple fits, the number of sites that do (at least 1). */
+uint32_t bv_suggest_tile_sites(const bv_ctx* ctx, uint32_t n_samples, uint64_t max_bytes);
+
 /* ---- pinned host memory helpers (for the packer / staging buffers of the caller) ---------------- */
 int bv_host_alloc(void** out_ptr, size_t bytes);   /* cudaHostAlloc */
 int bv_host_free(void* ptr);

@@ -146,3 +146,12 @@ def test_sparse_encode16_round_trip_and_errors(built_lib):
         bv.sparse_encode16(capi.cell_pack([5, 3], 1, 0, 30), st)
     with pytest.raises(bv.BvError, match="strand"):
         bv.sparse_encode16(capi.cell_pack([3, 5], 1, [0, 2], 30), st)
+
+
+def test_suggest_tile_sites_without_a_context(built_lib):
+    """Multiples of 148 SMs x 32 warps (16 for long rows) that fit the byte budget; small budgets give what fits."""
+    lib = capi.load_library()
+    assert lib.bv_suggest_tile_sites(None, 1000, 3 * 1008 * 10000) == 2 * 148 * 32
+    assert lib.bv_suggest_tile_sites(None, 100000, 3 * 100000 * 10737) == 4 * 148 * 16
+    assert lib.bv_suggest_tile_sites(None, 100000, 3 * 100000 * 100) == 100
+    assert lib.bv_suggest_tile_sites(None, 1000, 10) == 1
