@@ -369,7 +369,6 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
 __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, uint32_t g) {
     QualWarp& W = warp_smem();
     uint32_t qmin = 0xffu, qmax = 0, flags = 0;
-    uint32_t qmin4 = 0xffffffffu, qmax4 = 0u;
     const uint32_t gw = g * 0x01010101u;
     for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int lane_cells, uint32_t cell0) {
         // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
@@ -386,14 +385,6 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, u
             x = vg.w ^ gw; n3 |= (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
         }
         uint32_t t = ((n0 >> 7) | (n1 >> 6) | (n2 >> 5) | (n3 >> 4)) ^ 0x0f0f0f0fu;
-        // phred range of the counted cells, four cells per instruction (uncounted bytes: 0xff for the min, 0 for the max)
-        uint4 vq = make_uint4(0u, 0u, 0u, 0u);
-        if (lane_cells > 0) vq = *reinterpret_cast<const uint4*>(cellp + kP2Chunk);
-        {
-            const uint32_t u0 = (n0 >> 7) * 0xffu, u1 = (n1 >> 7) * 0xffu, u2 = (n2 >> 7) * 0xffu, u3 = (n3 >> 7) * 0xffu;   // 0xff: not counted
-            qmin4 = __vminu4(__vminu4(qmin4, vq.x | u0), __vminu4(vq.y | u1, __vminu4(vq.z | u2, vq.w | u3)));
-            qmax4 = __vmaxu4(__vmaxu4(qmax4, vq.x & ~u0), __vmaxu4(vq.y & ~u1, __vmaxu4(vq.z & ~u2, vq.w & ~u3)));
-        }
         // warp-uniform trip count, lanes that run out are predicated off: the warp never splits
         const int n = (int)__reduce_max_sync(kFull, (uint32_t)__popc(t));
 #pragma unroll 1
@@ -405,19 +396,16 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, u
             const int cell = ((top & 3) << 2) | ((top >> 3) & 3);   // word k = top & 3, byte j = top >> 3
             if (on) {
                 const uint32_t b = cellp[cell];
-                const uint32_t q = min((uint32_t)cellp[cell + kP2Chunk], (uint32_t)(kQSlots - 1));
+                const uint32_t q = min((uint32_t)cellp[cell + kP2Chunk], (uint32_t)(kQSlots - 1));   // phred > 95 shares the last slot
                 atomicAdd(&W.hist[b * kQSlots + q], 1u);
+                // phred range per counted cell: at < 1x the loop runs a few times per 16 cells, cheaper than a SIMD
+                // min / max over all of them (measured: the EM kernel of C2 0.130 vs 0.137 ms)
+                qmin = min(qmin, q);
+                qmax = max(qmax, q);
             }
         }
     });
-    {
-        const uint32_t lo = __vminu4(qmin4, qmin4 >> 16), hi = __vmaxu4(qmax4, qmax4 >> 16);
-        qmin = min(lo & 0xffu, (lo >> 8) & 0xffu);
-        qmax = max(hi & 0xffu, (hi >> 8) & 0xffu);
-        if (qmax > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;   // phred > 93: clamped into the last histogram slot
-        qmin = min(qmin, (uint32_t)(kQSlots - 1));
-        qmax = min(qmax, (uint32_t)(kQSlots - 1));
-    }
+    if (qmax > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;   // phred > 93: outside the reference's table (slots 94, 95)
     qmin = __reduce_min_sync(kFull, qmin);
     qmax = __reduce_max_sync(kFull, qmax);
     flags = __reduce_or_sync(kFull, flags);
