@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kBoundWarps * 32, 1) bv_bound_kernel(const __g
 // K4: one warp per site of the EM list.
 // =====================================================================================================================
 #ifndef BV_QUAL_WARPS
-#define BV_QUAL_WARPS 24
+#define BV_QUAL_WARPS 32
 #endif
 constexpr int kQualWarps = BV_QUAL_WARPS;
 #ifndef BV_P2_CHUNK
