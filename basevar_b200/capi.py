@@ -137,6 +137,7 @@ _SIGNATURES = [
     ("bv_h2d_bytes", C.c_uint64, [C.c_void_p]),
     ("bv_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("bv_last_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    ("bv_last_em_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("bv_tile_submit", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvTile)]),
     ("bv_tile_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("bv_tile_run_device", C.c_int, [C.c_void_p, C.POINTER(BvTile), C.c_void_p, C.c_void_p]),

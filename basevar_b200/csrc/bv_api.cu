@@ -15,12 +15,19 @@
 #include "../../include/basevar_b200.h"
 #include "bv_count_kernel.cuh"
 #include "bv_finish_kernels.cuh"
+#include "bv_em_kernels.cuh"
 #include "bv_call_kernels.cuh"
 #include "bv_expand_kernel.cuh"
 #include "bv_synth.cuh"
 
 #ifndef BV_SCALAR_CTAS_PER_SM
 #define BV_SCALAR_CTAS_PER_SM 8u
+#endif
+#ifndef BV_EM_POOL_BINS_PER_SITE
+#define BV_EM_POOL_BINS_PER_SITE 64u
+#endif
+#ifndef BV_EM_TASKS_PER_SITE
+#define BV_EM_TASKS_PER_SITE 3u
 #endif
 
 namespace bv {
@@ -96,9 +103,15 @@ __global__ void __launch_bounds__(256) bv_synth_rpr_kernel(const bv_synth_model*
 // Kernels of different tiles may overlap, so every slot (and the device-resident path) owns one.
 struct bv_scratch {
     uint32_t* d_lists = nullptr;      // 4 x cap site indices
-    uint32_t* d_counters = nullptr;   // 8 x u32
+    uint32_t* d_counters = nullptr;   // kNumCounters x u32
     uint32_t* d_bin_spill = nullptr;
     double* d_lml_spill = nullptr;
+    // K4a -> K4b -> K4c: headers of the EM sites, pool of their bins, EM tasks and their results (bv_em_kernels.cuh)
+    bv::EmSiteHdr* d_em_hdr = nullptr;
+    uint32_t* d_em_pool = nullptr;
+    uint32_t* d_em_tasks = nullptr;
+    double* d_em_res = nullptr;
+    uint32_t em_pool_cap = 0, em_task_cap = 0;
     uint32_t cap = 0;
 };
 
@@ -140,7 +153,8 @@ struct bv_ctx {
     bool zero_copy_qual = true;       // BASEVAR_B200_ZERO_COPY_QUAL=0 uploads the whole qual plane instead
     uint64_t h2d_bytes_total = 0;
     bool profiling = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int task_ctas_per_sm = 2;         // resident CTAs of bv_em_task_kernel per SM (shared memory bound)
     bool ev_valid = false;
     bool has_model = false;
     uint64_t pitch_cap = 0;
@@ -175,6 +189,7 @@ static int set_err(bv_ctx* ctx, int code, const char* fmt, ...) {
 
 static void scratch_free(bv_scratch& sc) {
     cudaFree(sc.d_lists); cudaFree(sc.d_counters); cudaFree(sc.d_bin_spill); cudaFree(sc.d_lml_spill);
+    cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res);
     sc = bv_scratch();
 }
 
@@ -182,7 +197,7 @@ static void scratch_free(bv_scratch& sc) {
 static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
     if (!sc.d_counters) {
         const size_t warps = (size_t)ctx->num_sms * bv::kQualWarps;
-        BV_CUDA(ctx, cudaMalloc(&sc.d_counters, 8 * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_counters, bv::kNumCounters * sizeof(uint32_t)));
         BV_CUDA(ctx, cudaMalloc(&sc.d_bin_spill, warps * bv::kMaxBins * sizeof(uint32_t)));
         BV_CUDA(ctx, cudaMalloc(&sc.d_lml_spill, warps * bv::kMaxBins * sizeof(double)));
     }
@@ -191,6 +206,18 @@ static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
         sc.d_lists = nullptr;
         sc.cap = 0;
         BV_CUDA(ctx, cudaMalloc(&sc.d_lists, 4 * (size_t)n_sites * sizeof(uint32_t)));
+        // EM scratch: room for every site to be an EM site; 64 bins and 3 tasks per site of the tile on average (a deep,
+        // multi-allelic pileup needs 25 and 1; what does not fit is finished inside K4a, see bv_em_kernels.cuh)
+        cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res);
+        sc.d_em_hdr = nullptr; sc.d_em_pool = nullptr; sc.d_em_tasks = nullptr; sc.d_em_res = nullptr;
+        cudaGetLastError();
+        const uint64_t pool = (uint64_t)n_sites * BV_EM_POOL_BINS_PER_SITE + 4096, tasks = (uint64_t)n_sites * BV_EM_TASKS_PER_SITE + 1024;
+        sc.em_pool_cap = (uint32_t)(pool < 0xfffffff0ull ? pool : 0xfffffff0ull);
+        sc.em_task_cap = (uint32_t)(tasks < 0x0fffffffull ? tasks : 0x0fffffffull);   // header / task indices have 28 bits
+        BV_CUDA(ctx, cudaMalloc(&sc.d_em_hdr, (size_t)n_sites * sizeof(bv::EmSiteHdr)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_em_pool, (size_t)sc.em_pool_cap * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_em_tasks, (size_t)sc.em_task_cap * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_em_res, (size_t)sc.em_task_cap * bv::kEmResDoubles * sizeof(double)));
         sc.cap = n_sites;
     }
     return BV_OK;
@@ -204,6 +231,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
                        (unsigned long long)t->pitch, t->n_samples);
     if (t->n_samples > ctx->prm.max_samples)
         return set_err(ctx, BV_ERR_ARG, "bv_tile: n_samples %u > max_samples %u", t->n_samples, ctx->prm.max_samples);
+    if (t->n_sites >= (1u << 28)) return set_err(ctx, BV_ERR_ARG, "bv_tile: more than 2^28 - 1 sites in one tile");
     if ((((uintptr_t)t->base) | ((uintptr_t)t->qual) | ((uintptr_t)t->strand)) & 15)
         return set_err(ctx, BV_ERR_ARG, "bv_tile: plane pointers must be 16-byte aligned");
     a->base = t->base; a->qual = t->qual; a->strand = t->strand; a->ref_base = t->ref_base;
@@ -220,6 +248,8 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->list_bound = sc.d_lists + sc.cap;
     a->list_em = sc.d_lists + 2 * (size_t)sc.cap;
     a->counters = sc.d_counters;
+    a->em_hdr = sc.d_em_hdr; a->em_pool = sc.d_em_pool; a->em_tasks = sc.d_em_tasks; a->em_res = sc.d_em_res;
+    a->em_pool_cap = sc.em_pool_cap; a->em_task_cap = sc.em_task_cap;
     a->list_called = nullptr;   // set_call_args() turns the called-site kernels on
     a->mapq = nullptr; a->rpr = nullptr; a->aux_pitch = 0; a->rpr_pitch = 0;
     a->sample_group = nullptr; a->calls = nullptr; a->groups = nullptr; a->n_groups = 0; a->pad0 = 0;
@@ -262,7 +292,7 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
         BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
         return BV_OK;
     }
-    if (!counters_zeroed) BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), stream));
+    if (!counters_zeroed) BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, bv::kNumCounters * sizeof(uint32_t), stream));
     const bool prof = ctx->profiling;
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[0], stream));
     // K1, persistent: one CTA per SM, each warp strides over the sites; kernel shape by row length
@@ -291,14 +321,29 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     bv::bv_bound_kernel<<<grid, bv::kBoundWarps * 32, bv::kBoundSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
-    // one warp per site of the EM list, whose length the host does not know: up to every site of the tile (deep pileups with a
-    // small min_af: half of the sites of a 100,000-sample tile), so the grid covers that; warps without work leave at once
+    // K4a: one warp per site of the EM list, whose length the host does not know: up to every site of the tile (deep pileups
+    // with a small min_af: half of the sites of a 100,000-sample tile), so the grid covers that; warps without work leave at once
     grid = (a.n_sites + bv::kQualWarps - 1) / bv::kQualWarps;
     if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
-    bv::bv_em_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
+    bv::bv_hist_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
-    if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream)); ctx->ev_valid = true; }
-    ctx->launches += 4;
+    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream));
+    // K4b: one thread per EM task, CTAs stride over the task list (its length is only known on the device)
+    {
+        uint64_t g = ((uint64_t)a.n_sites * 4 + bv::kTaskThreads - 1) / bv::kTaskThreads;
+        const uint64_t cap = (uint64_t)ctx->num_sms * ctx->task_ctas_per_sm;
+        grid = (uint32_t)(g < cap ? g : cap);
+    }
+    bv::bv_em_task_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(a);
+    BV_CUDA(ctx, cudaGetLastError());
+    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[5], stream));
+    // K4c: one thread per EM site
+    grid = (a.n_sites + 127) / 128;
+    if (grid > (uint32_t)ctx->num_sms * 8u) grid = (uint32_t)ctx->num_sms * 8u;
+    bv::bv_decide_kernel<<<grid, 128, 0, stream>>>(a);
+    BV_CUDA(ctx, cudaGetLastError());
+    if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[6], stream)); ctx->ev_valid = true; }
+    ctx->launches += 6;
     if (a.list_called) {
         // K5 / K6: the called sites (a few per mille of the tile at 0.1x); grids sized for the worst case, warps
         // without work leave at once
@@ -334,7 +379,7 @@ int bv_set_profiling(bv_ctx* ctx, int on) {
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
     if (on && !ctx->ev[0]) {
-        for (int i = 0; i < 5; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+        for (int i = 0; i < 7; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
         for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev_call[i]));
     }
     ctx->profiling = on != 0;
@@ -356,8 +401,18 @@ int bv_last_kernel_times(bv_ctx* ctx, float ms[4]) {
     if (!ctx || !ms) return set_err(ctx, BV_ERR_ARG, "null argument");
     if (!ctx->ev_valid) return set_err(ctx, BV_ERR_STATE, "no profiled tile yet (bv_set_profiling)");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
-    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
-    for (int i = 0; i < 4; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+    for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    BV_CUDA(ctx, cudaEventElapsedTime(&ms[3], ctx->ev[3], ctx->ev[6]));   // K4 = K4a + K4b + K4c
+    return BV_OK;
+}
+
+int bv_last_em_kernel_times(bv_ctx* ctx, float ms[3]) {
+    if (!ctx || !ms) return set_err(ctx, BV_ERR_ARG, "null argument");
+    if (!ctx->ev_valid) return set_err(ctx, BV_ERR_STATE, "no profiled tile yet (bv_set_profiling)");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+    for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[3 + i], ctx->ev[4 + i]));
     return BV_OK;
 }
 
@@ -415,7 +470,8 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_count_kernel<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)bv::count_smem_bytes<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>()) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_em_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_em_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_expand_kernel<BV_CELLS_U32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kExpandSmemBytes) != cudaSuccess ||
@@ -443,7 +499,7 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_out, (size_t)params->max_sites * sizeof(bv_site_out));
                 if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_out, (size_t)params->max_sites * sizeof(bv_site_out), cudaHostAllocDefault);
                 if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_calls, (size_t)params->max_sites * sizeof(bv_call_out), cudaHostAllocMapped);
-                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault);
+                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_counters, bv::kNumCounters * sizeof(uint32_t), cudaHostAllocDefault);
                 if (ce != cudaSuccess) rc = set_err(nullptr, BV_ERR_CUDA, "slot allocation failed: %s", cudaGetErrorString(ce));
                 else rc = scratch_reserve(ctx, s.scratch, params->max_sites);
             }
@@ -474,7 +530,7 @@ void bv_destroy(bv_ctx* ctx) {
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model); cudaFree(ctx->d_group);
     scratch_free(ctx->dev_scratch);
-    for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 7; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 3; ++i) if (ctx->ev_call[i]) cudaEventDestroy(ctx->ev_call[i]);
     delete ctx;
 }
@@ -645,7 +701,7 @@ static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv
     if (with_calls) {
         s.h_counters[bv::kCntCalled] = 0;
         if (tile->n_sites && tile->n_samples)
-            BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+            BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, bv::kNumCounters * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     }
     s.with_calls = with_calls;
     s.n_sites = tile->n_sites;
@@ -702,7 +758,7 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
         rc = set_call_args(ctx, &dev, &dev_aux, s.scratch, s.h_calls, s.h_groups, &a);
         if (rc != BV_OK) return rc;
     }
-    memset(s.h_counters, 0, 8 * sizeof(uint32_t));
+    memset(s.h_counters, 0, bv::kNumCounters * sizeof(uint32_t));
     if (t->n_sites && t->n_samples) {
         if (n_cells) {
             BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells, t->cells, n_cells * word_bytes, cudaMemcpyHostToDevice, s.stream));
@@ -712,7 +768,7 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
         BV_CUDA(ctx, cudaMemcpyAsync(s.d_site_start, t->site_start, ((size_t)t->n_sites + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
         BV_CUDA(ctx, cudaMemcpyAsync(s.d_ref, t->ref_base, t->n_sites, cudaMemcpyHostToDevice, s.stream));
         s.h2d_bytes = n_cells * (word_bytes + (with_calls ? sizeof(uint32_t) : 0)) + ((size_t)t->n_sites + 1) * sizeof(uint32_t) + t->n_sites;
-        BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, 8 * sizeof(uint32_t), s.stream));
+        BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, bv::kNumCounters * sizeof(uint32_t), s.stream));
         bv::ExpandArgs x;
         x.cells = s.d_cells; x.cells_aux = with_calls ? s.d_cells + s.cells_cap : nullptr; x.site_start = s.d_site_start;
         x.base = s.d_planes; x.qual = s.d_planes + plane; x.strand = s.d_planes + 2 * plane;
@@ -735,7 +791,7 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
         if (t->out && host_device_pointer(t->out)) { dst = t->out; s.out_direct = true; }
         BV_CUDA(ctx, cudaMemcpyAsync(dst, s.d_out, (size_t)t->n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
         if (t->n_samples)
-            BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+            BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, bv::kNumCounters * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     }
     s.with_calls = with_calls;
     s.n_sites = t->n_sites;

@@ -47,9 +47,29 @@ constexpr uint32_t kStateEM = 3;             // result depends on base qualities
 constexpr int kCntSlow = 0, kCntBound = 1, kCntEm = 2, kCntEmNext = 3;   // SiteKernelArgs::counters
 constexpr int kCntCalled = 4, kCntGroupNext = 5;                          // called sites (K4 -> K5, K6)
 constexpr int kCntBadCell = 6;                                            // malformed sparse input (K0, bv_expand_kernel.cuh)
+constexpr int kCntEmHdr = 7, kCntEmPool = 8, kCntEmTask = 9;              // K4a -> K4b, K4c: EM sites, their bins, their EM tasks
+constexpr int kCntEmFallback = 10;                                        // EM sites finished inside K4a (scratch pools full)
+constexpr int kNumCounters = 16;
 
 // word indices of bv_site_out seen as 32 x u32
 constexpr int kWDepth = 0, kWOther = 4, kWState = 5, kWFwd = 6, kWRev = 10, kWAlt = 14, kWInfo = 15;
+
+// One site of the EM list after K4a (bv_em_kernels.cuh): its compact (base, phred) bins in the pool, its EM tasks.
+struct __align__(16) EmSiteHdr {
+    uint32_t site;
+    uint32_t bins_off;       // first word of the site's bins in SiteKernelArgs::em_pool
+    uint32_t nb;             // number of bins
+    uint32_t task0;          // first of the site's tasks in em_tasks / em_res
+    uint32_t act;            // active alleles before the LRT (bit j = allele j)
+    uint32_t flags;          // BV_FLAG_* raised so far (K1 / K2 / histogram)
+    uint32_t depth[4];
+    uint32_t total;          // depth[0..3] + depth_other
+    uint32_t pad0;
+    double single_ll[4];     // log-likelihood of the single-allele model {j} (closed form), for the active alleles
+};
+static_assert(sizeof(EmSiteHdr) == 80, "EmSiteHdr layout");
+constexpr int kEmResDoubles = 6;             // per EM task: log-likelihood, f[4], flags (as bits of a u64)
+constexpr uint32_t kEmTaskInvalid = 0xffffffffu;
 
 struct SiteKernelArgs {
     const uint8_t* base;
@@ -64,7 +84,14 @@ struct SiteKernelArgs {
     uint32_t* list_slow;     // work lists (site indices), each with room for n_sites entries: K1 -> K2,
     uint32_t* list_bound;    //   K2 -> K3,
     uint32_t* list_em;       //   K2 and K3 -> K4
-    uint32_t* counters;      // [kCntSlow .. kCntGroupNext], zeroed before K1
+    uint32_t* counters;      // [kNumCounters], zeroed before K1
+    // K4a -> K4b -> K4c (bv_em_kernels.cuh)
+    EmSiteHdr* em_hdr;       // [n_sites]
+    uint32_t* em_pool;       // [em_pool_cap] compact bins of the EM sites, allocated with kCntEmPool
+    uint32_t* em_tasks;      // [em_task_cap] hdr index | subset << 28, allocated with kCntEmTask
+    double* em_res;          // [em_task_cap][kEmResDoubles]
+    uint32_t em_pool_cap;
+    uint32_t em_task_cap;
     // called sites (n_alt > 0): rank sums (K5) and population-group frequencies (K6); all null / 0 when not asked for
     uint32_t* list_called;   // K4 -> K5, K6: site indices, room for n_sites entries
     const uint8_t* mapq;     // [n_sites][aux_pitch]

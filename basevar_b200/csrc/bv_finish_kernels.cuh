@@ -1,5 +1,6 @@
-// bv_finish_kernels.cuh -- K2 (scalar finish, one thread per site) and K3 (quality-dependent sites, one warp per site).
-// See bv_common.cuh for the three-kernel split of the basetype core.
+// bv_finish_kernels.cuh -- K2 (scalar finish, one thread per site), K3 (likelihood-ratio bound, one warp per site) and the
+// warp-per-site device code (row histogram, EM on bins, LRT) that K4a (bv_em_kernels.cuh) and K6 (bv_call_kernels.cuh) share.
+// See bv_common.cuh for the split of the basetype core into kernels.
 #pragma once
 #include "bv_common.cuh"
 #include "bv_math.cuh"
@@ -366,9 +367,27 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
 // Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
 // grp != nullptr: only the samples of population group g are counted (__get_group_batchinfo,
 // src/basetype_caller.cpp:781-797); grp[] is padded with BV_GROUP_NONE to a multiple of 16 entries.
+//
+// Two cell loops per 16-cell vector, chosen per vector by the fullest lane (warp-uniform):
+//   sparse (< 1x pileups): the lane's counted cells one by one, found with bfind in its 16-bit mask; the warp runs as many
+//     trips as its fullest lane has cells;
+//   dense (deep pileups): all 16 cells straight from the registers that hold the vector, the mask bit as the predicate of
+//     the shared-memory atomic: 5 instructions per cell instead of 10 per trip.
+// The phred range is read off the histogram afterwards (96 slots, three per lane) instead of being tracked per cell.
+#ifndef BV_HIST_DENSE_TRIPS
+#define BV_HIST_DENSE_TRIPS 7
+#endif
+__device__ __forceinline__ void hist_word_dense(uint32_t* hist, uint32_t wb, uint32_t wq, uint32_t t, int k) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t b = (wb >> (8 * j)) & 0xffu, q = (wq >> (8 * j)) & 0xffu;
+        if (t & (1u << (8 * j + k))) atomicAdd(&hist[b * kQSlots + q], 1u);
+    }
+}
+
 __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, uint32_t g) {
     QualWarp& W = warp_smem();
-    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
+    const int lane = threadIdx.x & 31;
     const uint32_t gw = g * 0x01010101u;
     for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int lane_cells, uint32_t cell0) {
         // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
@@ -387,28 +406,44 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, u
         uint32_t t = ((n0 >> 7) | (n1 >> 6) | (n2 >> 5) | (n3 >> 4)) ^ 0x0f0f0f0fu;
         // warp-uniform trip count, lanes that run out are predicated off: the warp never splits
         const int n = (int)__reduce_max_sync(kFull, (uint32_t)__popc(t));
+        if (n >= BV_HIST_DENSE_TRIPS) {
+            // phred > 95 shares the last slot (bytes >= 0x80 never occur next to a counted base in a valid tile; they clamp too)
+            const uint4 vq = *reinterpret_cast<const uint4*>(cellp + kP2Chunk);
+            hist_word_dense(W.hist, vb.x, __vminu4(vq.x, 0x5f5f5f5fu), t, 0);
+            hist_word_dense(W.hist, vb.y, __vminu4(vq.y, 0x5f5f5f5fu), t, 1);
+            hist_word_dense(W.hist, vb.z, __vminu4(vq.z, 0x5f5f5f5fu), t, 2);
+            hist_word_dense(W.hist, vb.w, __vminu4(vq.w, 0x5f5f5f5fu), t, 3);
+        } else {
 #pragma unroll 1
-        for (int i = 0; i < n; ++i) {
-            const bool on = t != 0u;
-            int top;
-            asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
-            t &= ~(1u << (top & 31));
-            const int cell = ((top & 3) << 2) | ((top >> 3) & 3);   // word k = top & 3, byte j = top >> 3
-            if (on) {
-                const uint32_t b = cellp[cell];
-                const uint32_t q = min((uint32_t)cellp[cell + kP2Chunk], (uint32_t)(kQSlots - 1));   // phred > 95 shares the last slot
-                atomicAdd(&W.hist[b * kQSlots + q], 1u);
-                // phred range per counted cell: at < 1x the loop runs a few times per 16 cells, cheaper than a SIMD
-                // min / max over all of them (measured: the EM kernel of C2 0.130 vs 0.137 ms)
-                qmin = min(qmin, q);
-                qmax = max(qmax, q);
+            for (int i = 0; i < n; ++i) {
+                const bool on = t != 0u;
+                int top;
+                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(t));
+                t &= ~(1u << (top & 31));
+                const int cell = ((top & 3) << 2) | ((top >> 3) & 3);   // word k = top & 3, byte j = top >> 3
+                if (on) {
+                    const uint32_t b = cellp[cell];
+                    const uint32_t q = min((uint32_t)cellp[cell + kP2Chunk], (uint32_t)(kQSlots - 1));   // phred > 95 shares the last slot
+                    atomicAdd(&W.hist[b * kQSlots + q], 1u);
+                }
             }
         }
     });
+    __syncwarp();
+    // phred range of the counted cells, from the histogram: lane l looks at slots l, l + 32, l + 64
+    uint32_t nz[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int q = lane + 32 * r;
+        nz[r] = W.hist[q] | W.hist[kQSlots + q] | W.hist[2 * kQSlots + q] | W.hist[3 * kQSlots + q] | W.hist[4 * kQSlots + q];
+    }
+    const uint32_t m0 = __ballot_sync(kFull, nz[0] != 0), m1 = __ballot_sync(kFull, nz[1] != 0), m2 = __ballot_sync(kFull, nz[2] != 0);
+    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
+    if (m0 | m1 | m2) {
+        qmin = m0 ? (uint32_t)__ffs(m0) - 1u : m1 ? 31u + (uint32_t)__ffs(m1) : 63u + (uint32_t)__ffs(m2);
+        qmax = m2 ? 95u - (uint32_t)__clz(m2) : m1 ? 63u - (uint32_t)__clz(m1) : 31u - (uint32_t)__clz(m0);
+    }
     if (qmax > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;   // phred > 93: outside the reference's table (slots 94, 95)
-    qmin = __reduce_min_sync(kFull, qmin);
-    qmax = __reduce_max_sync(kFull, qmax);
-    flags = __reduce_or_sync(kFull, flags);
     return qmin | (qmax << 8) | (flags << 16);
 }
 
@@ -642,12 +677,14 @@ __device__ __forceinline__ int nth_active(uint32_t order, uint32_t mask, int k) 
 // (src/basetype.cpp:144-168).  In: the row's histogram in W.hist, phred range, depths in W.rec.depth[], active set.
 // Out: W.res_f / W.res_chi and the return value act | n_act << 4 | em_calls << 8.  The warp-uniform model state lives
 // in shared memory (W.emf / W.best_f / W.res_f), not in registers that would have to survive the calls into em_bins.
-__device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_t act, uint32_t order) {
+
+// The non-empty (base, phred) bins of W.hist, in (base, phred) order, into W.bins (the first kSmemBins of them) and into
+// this warp's global spill row (all of them); the histogram goes back to zero.  Returns the number of bins.
+__device__ __noinline__ int compact_bins(uint32_t qmin, uint32_t qmax) {
     QualWarp& W = warp_smem();
     const QualCta& cs = cta_shared();
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = blockIdx.x * kQualWarps + (threadIdx.x >> 5);
-    // histogram back to zero while the non-empty (base, phred) bins are compacted, in (base, phred) order
     int nb = 0;
     uint32_t* gbins = cs.a.bin_spill + (size_t)warp_global * kMaxBins;
 #pragma unroll 1
@@ -672,6 +709,15 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
         }
     }
     __syncwarp();
+    return nb;
+}
+
+__device__ __noinline__ uint32_t lrt_on_bins(int nb, uint32_t act, uint32_t order) {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = blockIdx.x * kQualWarps + (threadIdx.x >> 5);
+    uint32_t* gbins = cs.a.bin_spill + (size_t)warp_global * kMaxBins;
     // bins live in shared memory unless there are more than kSmemBins of them (then the global copy is used);
     // the EM's per-bin state overlays the (now all-zero) histogram
     const bool in_smem = nb <= kSmemBins;
@@ -751,6 +797,11 @@ __device__ __noinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_
     return act | ((uint32_t)n_act << 4) | (em_calls << 8);
 }
 
+__device__ __forceinline__ uint32_t lrt_multi(uint32_t qmin, uint32_t qmax, uint32_t act, uint32_t order) {
+    const int nb = compact_bins(qmin, qmax);
+    return lrt_on_bins(nb, act, order);
+}
+
 // ---- scalar finish of the sites with ALT alleles, one THREAD per queued site ------------------------------------------------
 // QUAL = -10 log10 of the chi-square survival function of the last LRT statistic (src/basetype.cpp:188-194) unless the
 // mono-allelic rule already set it, and the strand bias of the VCF row, ref vs the called ALT alleles
@@ -786,137 +837,6 @@ __device__ __noinline__ void vcf_flush() {
     __syncwarp();
     if (lane == 0) W.vcf_n = 0;
     __syncwarp();
-}
-
-// ---- one site in state kStateEM --------------------------------------------------------------------------------------------
-// Everything here is warp-uniform.  The record (counts, FS of the CVG row, flags) comes from K1 / K2.
-__device__ __noinline__ void qual_site(uint32_t site) {
-    QualWarp& W = warp_smem();
-    const QualCta& cs = cta_shared();
-    const int lane = threadIdx.x & 31;
-    if (lane < 8) reinterpret_cast<uint4*>(&W.rec)[lane] = reinterpret_cast<const uint4*>(cs.a.out + site)[lane];
-    const int ref_code = ref_code_of(cs.a.ref_base[site]);
-    __syncwarp();
-    const uint32_t d0 = W.rec.depth[0], d1 = W.rec.depth[1], d2 = W.rec.depth[2], d3 = W.rec.depth[3];
-    const uint32_t total = d0 + d1 + d2 + d3 + W.rec.depth_other;
-    const double dtot = (double)total;
-    const double min_af = cs.a.min_af;
-    if (lane == 0) W.flag_word = W.rec.flags;
-
-    // ---- lrt (src/basetype.cpp:130-199): active set (total > 0 here) ----
-    uint32_t act = 0;
-    act |= is_active(d0, total, dtot, min_af) ? 1u : 0u;
-    act |= is_active(d1, total, dtot, min_af) ? 2u : 0u;
-    act |= is_active(d2, total, dtot, min_af) ? 4u : 0u;
-    act |= is_active(d3, total, dtot, min_af) ? 8u : 0u;
-    int n_act = __popc(act);
-    double chi = 0.0;
-    uint32_t em_calls = 0;
-    const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
-    __syncwarp();
-
-    {
-        // histogram the row by (base, phred)
-        const uint32_t h = build_hist(site, nullptr, 0);
-        const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
-        if (lane == 0) W.flag_word |= h >> 16;
-        __syncwarp();
-        if (n_act >= 2) {
-            const uint32_t r = lrt_multi(qmin, qmax, act, kOrderACGT);
-            act = r & 0xfu; n_act = (int)((r >> 4) & 0xfu); em_calls = r >> 8;
-            chi = W.res_chi;
-        } else {
-            // One active allele: the reference still runs one EM; its answer is closed form (see single_allele_ll):
-            // AF == 1.0 exactly, or NaN when a phred-0 read of that base exists.
-            const int b = __ffs(act) - 1;
-            const bool bad = qmin == 0 && W.hist[b * kQSlots] != 0;
-            const double v = bad ? __longlong_as_double(0x7ff8000000000000ll) : 1.0;
-            __syncwarp();
-            if (lane < 4) W.res_f[lane] = lane == b ? v : 0.0;
-            em_calls = 1;
-            if (qmin <= qmax) {   // histogram back to zero
-#pragma unroll 1
-                for (uint32_t q = qmin + lane; q <= qmax; q += 32) {
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) W.hist[r * kQSlots + q] = 0;
-                }
-            }
-        }
-    }
-    __syncwarp();
-    uint32_t flags = W.flag_word;
-
-    // ---- ALT / QUAL (src/basetype.cpp:170-196) ----
-    // Here only the rule that needs no arithmetic (mono-allelic 5000); the chi-square survival function and the Fisher
-    // test of the VCF row are scalar, warp-uniform work: the site is queued and vcf_flush() does them one thread per site.
-    const uint32_t alt_set = act & ~ref_bit;
-    const int n_alt = __popc(alt_set);
-    double qual = 0.0;
-    const double fs_vcf = 0.0;
-    if (n_alt) {
-        const int first_act = __ffs(act) - 1;
-        const double r = (double)sel4u(first_act, d0, d1, d2, d3) / dtot;
-        if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
-    }
-
-    // ---- record ----
-    __syncwarp();
-    if (lane == 0) {
-        bv_site_out& r = W.rec;
-        r.reserved0 = kStateDone;
-        // ALT alleles in ACGT order of the active set (src/basetype.cpp:172-177)
-        uint32_t alts = 0;
-        int k = 0;
-        const double af[4] = {W.res_f[0], W.res_f[1], W.res_f[2], W.res_f[3]};
-        r.af[0] = 0.0; r.af[1] = 0.0; r.af[2] = 0.0; r.af[3] = 0.0;
-        if (alt_set & 1) { r.af[k] = af[0]; alts |= 0u << (8 * k); ++k; }
-        if (alt_set & 2) { r.af[k] = af[1]; alts |= 1u << (8 * k); ++k; }
-        if (alt_set & 4) { r.af[k] = af[2]; alts |= 2u << (8 * k); ++k; }
-        if (alt_set & 8) { r.af[k] = af[3]; alts |= 3u << (8 * k); ++k; }
-        r.n_alt = (uint8_t)n_alt;
-        r.alt[0] = (uint8_t)alts; r.alt[1] = (uint8_t)(alts >> 8); r.alt[2] = (uint8_t)(alts >> 16); r.alt[3] = (uint8_t)(alts >> 24);
-        r.n_active = (uint8_t)n_act;
-        r.flags = (uint8_t)flags;
-        r.em_calls = (uint8_t)(em_calls > 255u ? 255u : em_calls);
-        r.qual = qual;
-        r.chi2 = chi;
-        r.fs_vcf = fs_vcf;
-        // called sites go on to the rank-sum / population-group kernels (bv_call_kernels.cuh)
-        if (n_alt && cs.a.list_called) cs.a.list_called[atomicAdd(cs.a.counters + kCntCalled, 1u)] = site;
-        if (n_alt) W.vcf_site[W.vcf_n++] = site;
-    }
-    __syncwarp();
-    if (lane < 8) reinterpret_cast<uint4*>(cs.a.out + site)[lane] = reinterpret_cast<const uint4*>(&W.rec)[lane];
-    __syncwarp();   // also orders the record's stores before vcf_flush() reads them from other lanes
-    if (W.vcf_n == 32) vcf_flush();
-}
-
-// Persistent warps with dynamic work distribution over the EM list.
-__global__ void __launch_bounds__(kQualWarps * 32, 1) bv_em_kernel(const __grid_constant__ SiteKernelArgs a) {
-    QualCta& cs = cta_shared();
-    QualWarp& W = warp_smem();
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 4 * kQStride; i += blockDim.x) cs.lut[i] = a.lut[i];
-    if (threadIdx.x == 0) cs.a = a;
-    for (int i = lane; i < kHistWords; i += 32) W.hist[i] = 0;
-    if (lane == 0) {
-        W.flag_word = 0;
-        W.p2_phase = 0;
-        W.vcf_n = 0;
-        for (int b = 0; b < kP2Bufs; ++b) mbar_init(&W.p2bar[b], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    // the EM list is final (K3 is done); warps take one site at a time: the cost per site varies by an order of magnitude
-    const uint32_t n_em = a.counters[kCntEm];
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(a.counters + kCntEmNext, 1u);
-        i = __shfl_sync(kFull, i, 0);
-        if (i >= n_em) break;
-        qual_site(a.list_em[i]);
-    }
-    if (W.vcf_n) vcf_flush();
 }
 
 }  // namespace bv

@@ -76,6 +76,14 @@ class BaseTypeEngine:
         self._check(self.lib.bv_last_kernel_times(self._ctx, ms), "bv_last_kernel_times")
         return dict(zip(self.KERNEL_NAMES, (float(x) for x in ms)))
 
+    EM_KERNEL_NAMES = ("bv_hist_kernel", "bv_em_task_kernel", "bv_decide_kernel")
+
+    def last_em_kernel_times(self):
+        """Durations (ms) of the three kernels K4 consists of (histogram, EM tasks, decision) for the same tile."""
+        ms = (C.c_float * 3)()
+        self._check(self.lib.bv_last_em_kernel_times(self._ctx, ms), "bv_last_em_kernel_times")
+        return dict(zip(self.EM_KERNEL_NAMES, (float(x) for x in ms)))
+
     # -- tiles from host memory --------------------------------------------------------------------
     def call_host(self, base, qual, strand, ref_base, n_samples, out=None):
         """Run planes [S][pitch] (numpy uint8, ideally pinned) through the slot pipeline.
