@@ -12,6 +12,8 @@
 
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects itself
+
 #include "../../include/basevar_b200.h"
 #include "bv_count_kernel.cuh"
 #include "bv_finish_kernels.cuh"
@@ -26,9 +28,15 @@
 #ifndef BV_EM_POOL_BINS_PER_SITE
 #define BV_EM_POOL_BINS_PER_SITE 64u
 #endif
-#ifndef BV_EM_TASKS_PER_SITE
-#define BV_EM_TASKS_PER_SITE 3u
-#endif
+
+// NVTX range over a scope ("Tracing"): nsys / ncu timelines show the host side of every tile
+// (submit, wait) and the launch sequence K0, K1, K2, K3, K4a, K4b, K5, K6 under these names.
+struct BvRange {
+    explicit BvRange(const char* name) { nvtxRangePushA(name); }
+    ~BvRange() { nvtxRangePop(); }
+    BvRange(const BvRange&) = delete;
+    BvRange& operator=(const BvRange&) = delete;
+};
 
 namespace bv {
 
@@ -111,7 +119,7 @@ struct bv_scratch {
     uint32_t* d_em_pool = nullptr;
     uint32_t* d_em_tasks = nullptr;
     double* d_em_res = nullptr;
-    uint32_t em_pool_cap = 0, em_task_cap = 0;
+    uint32_t em_pool_cap = 0, em_task_cap[3] = {0, 0, 0};
     uint32_t cap = 0;
 };
 
@@ -153,8 +161,8 @@ struct bv_ctx {
     bool zero_copy_qual = true;       // BASEVAR_B200_ZERO_COPY_QUAL=0 uploads the whole qual plane instead
     uint64_t h2d_bytes_total = 0;
     bool profiling = false;
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int task_ctas_per_sm = 2;         // resident CTAs of bv_em_task_kernel per SM (shared memory bound)
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int task_ctas_per_sm = 4;         // resident CTAs of bv_em_task_kernel per SM (shared memory bound)
     bool ev_valid = false;
     bool has_model = false;
     uint64_t pitch_cap = 0;
@@ -211,13 +219,15 @@ static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
         cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res);
         sc.d_em_hdr = nullptr; sc.d_em_pool = nullptr; sc.d_em_tasks = nullptr; sc.d_em_res = nullptr;
         cudaGetLastError();
-        const uint64_t pool = (uint64_t)n_sites * BV_EM_POOL_BINS_PER_SITE + 4096, tasks = (uint64_t)n_sites * BV_EM_TASKS_PER_SITE + 1024;
-        sc.em_pool_cap = (uint32_t)(pool < 0xfffffff0ull ? pool : 0xfffffff0ull);
-        sc.em_task_cap = (uint32_t)(tasks < 0x0fffffffull ? tasks : 0x0fffffffull);   // header / task indices have 28 bits
+        const uint64_t pool = (uint64_t)n_sites * BV_EM_POOL_BINS_PER_SITE + 4096;
+        sc.em_pool_cap = (uint32_t)(pool < 0x7ffffff0ull ? pool : 0x7ffffff0ull);
+        // task slots for subsets of 2, 3 and 4 alleles: 2, 1 and 1/2 per site of the tile (header indices have 28 bits)
+        sc.em_task_cap[0] = 2u * n_sites + 1024u; sc.em_task_cap[1] = n_sites + 512u; sc.em_task_cap[2] = n_sites / 2u + 256u;
+        const size_t n_task = (size_t)sc.em_task_cap[0] + sc.em_task_cap[1] + sc.em_task_cap[2];
         BV_CUDA(ctx, cudaMalloc(&sc.d_em_hdr, (size_t)n_sites * sizeof(bv::EmSiteHdr)));
         BV_CUDA(ctx, cudaMalloc(&sc.d_em_pool, (size_t)sc.em_pool_cap * sizeof(uint32_t)));
-        BV_CUDA(ctx, cudaMalloc(&sc.d_em_tasks, (size_t)sc.em_task_cap * sizeof(uint32_t)));
-        BV_CUDA(ctx, cudaMalloc(&sc.d_em_res, (size_t)sc.em_task_cap * bv::kEmResDoubles * sizeof(double)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_em_tasks, n_task * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_em_res, n_task * bv::kEmResDoubles * sizeof(double)));
         sc.cap = n_sites;
     }
     return BV_OK;
@@ -231,7 +241,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
                        (unsigned long long)t->pitch, t->n_samples);
     if (t->n_samples > ctx->prm.max_samples)
         return set_err(ctx, BV_ERR_ARG, "bv_tile: n_samples %u > max_samples %u", t->n_samples, ctx->prm.max_samples);
-    if (t->n_sites >= (1u << 28)) return set_err(ctx, BV_ERR_ARG, "bv_tile: more than 2^28 - 1 sites in one tile");
+    if (t->n_sites > (1u << 22)) return set_err(ctx, BV_ERR_ARG, "bv_tile: more than 2^22 sites in one tile");
     if ((((uintptr_t)t->base) | ((uintptr_t)t->qual) | ((uintptr_t)t->strand)) & 15)
         return set_err(ctx, BV_ERR_ARG, "bv_tile: plane pointers must be 16-byte aligned");
     a->base = t->base; a->qual = t->qual; a->strand = t->strand; a->ref_base = t->ref_base;
@@ -249,7 +259,8 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->list_em = sc.d_lists + 2 * (size_t)sc.cap;
     a->counters = sc.d_counters;
     a->em_hdr = sc.d_em_hdr; a->em_pool = sc.d_em_pool; a->em_tasks = sc.d_em_tasks; a->em_res = sc.d_em_res;
-    a->em_pool_cap = sc.em_pool_cap; a->em_task_cap = sc.em_task_cap;
+    a->em_pool_cap = sc.em_pool_cap;
+    for (int k = 0; k < 3; ++k) a->em_task_cap[k] = sc.em_task_cap[k];
     a->list_called = nullptr;   // set_call_args() turns the called-site kernels on
     a->mapq = nullptr; a->rpr = nullptr; a->aux_pitch = 0; a->rpr_pitch = 0;
     a->sample_group = nullptr; a->calls = nullptr; a->groups = nullptr; a->n_groups = 0; a->pad0 = 0;
@@ -287,6 +298,7 @@ static int set_call_args(bv_ctx* ctx, const bv_tile* t, const bv_tile_aux* aux, 
 // The basetype core of one tile: K1 (counts, every cell), K2 (scalar finish, one thread per site), K3 / K4 (sites whose
 // result depends on base qualities: likelihood-ratio bound, then EM + LRT).  Stream ordered; see csrc/bv_common.cuh.
 static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStream_t stream, bool counters_zeroed = false) {
+    BvRange range("bv: launch K1 count, K2 scalar, K3 bound, K4a hist, K4b em_task (+ K5 ranksum, K6 group)");
     if (a.n_sites == 0) return BV_OK;
     if (a.n_samples == 0) {   // no cells: every record is all-zero
         BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
@@ -323,27 +335,24 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[3], stream));
     // K4a: one warp per site of the EM list, whose length the host does not know: up to every site of the tile (deep pileups
     // with a small min_af: half of the sites of a 100,000-sample tile), so the grid covers that; warps without work leave at once
-    grid = (a.n_sites + bv::kQualWarps - 1) / bv::kQualWarps;
-    if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
-    bv::bv_hist_kernel<<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
+    if (a.n_samples > (uint32_t)bv::kLongRowSamples) {
+        grid = (a.n_sites + bv::kLongWarps - 1) / bv::kLongWarps;
+        if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+        bv::bv_hist_kernel<true><<<grid, bv::kLongWarps * 32, bv::kHistLongSmemBytes, stream>>>(a);
+    } else {
+        grid = (a.n_sites + bv::kQualWarps - 1) / bv::kQualWarps;
+        if (grid > (uint32_t)ctx->num_sms) grid = (uint32_t)ctx->num_sms;
+        bv::bv_hist_kernel<false><<<grid, bv::kQualWarps * 32, bv::kQualSmemBytes, stream>>>(a);
+    }
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[4], stream));
-    // K4b: one thread per EM task, CTAs stride over the task list (its length is only known on the device)
-    {
-        uint64_t g = ((uint64_t)a.n_sites * 4 + bv::kTaskThreads - 1) / bv::kTaskThreads;
-        const uint64_t cap = (uint64_t)ctx->num_sms * ctx->task_ctas_per_sm;
-        grid = (uint32_t)(g < cap ? g : cap);
-    }
+    // K4b: groups of lanes per EM task, CTAs stride over the task lists (their lengths are only known on the device, where the
+    // kernel picks the group size from them): always the grid that fills the GPU, CTAs without work leave at once
+    grid = (uint32_t)ctx->num_sms * (uint32_t)ctx->task_ctas_per_sm;
     bv::bv_em_task_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
-    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[5], stream));
-    // K4c: one thread per EM site
-    grid = (a.n_sites + 127) / 128;
-    if (grid > (uint32_t)ctx->num_sms * 8u) grid = (uint32_t)ctx->num_sms * 8u;
-    bv::bv_decide_kernel<<<grid, 128, 0, stream>>>(a);
-    BV_CUDA(ctx, cudaGetLastError());
-    if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[6], stream)); ctx->ev_valid = true; }
-    ctx->launches += 6;
+    if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[5], stream)); ctx->ev_valid = true; }
+    ctx->launches += 5;
     if (a.list_called) {
         // K5 / K6: the called sites (a few per mille of the tile at 0.1x); grids sized for the worst case, warps
         // without work leave at once
@@ -366,6 +375,33 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     return BV_OK;
 }
 
+// The cells of one site, words16 known to have room for the worst case.  The common cell -- ascending, gap < 31, strand + or - --
+// is one load, a few shifts and one store; everything else leaves through the slow path of the caller.
+template <bool AUX>
+static inline const uint32_t* encode16_run(const uint32_t* __restrict__ p, const uint32_t* __restrict__ end, const uint32_t* __restrict__ aux32,
+                                           uint16_t* __restrict__& o, uint32_t* __restrict__& oa, uint32_t& next) {
+    uint32_t nx = next;
+    uint16_t* out = o;
+    uint32_t* outa = oa;
+    for (; p < end; ++p) {
+        const uint32_t w = *p, i = w & (BV_CELL_MAX_SAMPLES - 1u), f12 = w >> 20;   // f12: base | strand << 3 | phred << 5
+        uint32_t gap = i - nx;   // i < next wraps to a huge value
+        if (__builtin_expect(gap >= BV_CELL16_GAP_SKIP || (f12 & 0x10u), 0)) {
+            if ((f12 & 0x10u) || gap >= BV_CELL_MAX_SAMPLES) break;   // a strand without a 16-bit form, or descending samples: the caller reports it
+            do {   // one cell in 26 at 0.1x: "skip 31 samples" words in front of it
+                *out++ = (uint16_t)BV_CELL16_GAP_SKIP;
+                if (AUX) *outa++ = 0;
+                gap -= BV_CELL16_GAP_SKIP;
+            } while (gap >= BV_CELL16_GAP_SKIP);
+        }
+        *out++ = (uint16_t)(gap | (((f12 & 0xfu) | ((f12 >> 5) << 4)) << 5));
+        if (AUX) *outa++ = aux32 ? aux32[p - end] : 0;   // (aux32 is passed pre-offset so that aux32[p - end] is this cell's word)
+        nx = i + 1;
+    }
+    next = nx; o = out; oa = outa;
+    return p;
+}
+
 extern "C" {
 
 int bv_version(void) { return BV_VERSION_MAJOR * 1000 + BV_VERSION_MINOR; }
@@ -379,7 +415,7 @@ int bv_set_profiling(bv_ctx* ctx, int on) {
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
     if (on && !ctx->ev[0]) {
-        for (int i = 0; i < 7; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+        for (int i = 0; i < 6; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
         for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev_call[i]));
     }
     ctx->profiling = on != 0;
@@ -401,18 +437,18 @@ int bv_last_kernel_times(bv_ctx* ctx, float ms[4]) {
     if (!ctx || !ms) return set_err(ctx, BV_ERR_ARG, "null argument");
     if (!ctx->ev_valid) return set_err(ctx, BV_ERR_STATE, "no profiled tile yet (bv_set_profiling)");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
-    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[5]));
     for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
-    BV_CUDA(ctx, cudaEventElapsedTime(&ms[3], ctx->ev[3], ctx->ev[6]));   // K4 = K4a + K4b + K4c
+    BV_CUDA(ctx, cudaEventElapsedTime(&ms[3], ctx->ev[3], ctx->ev[5]));   // K4 = K4a + K4b
     return BV_OK;
 }
 
-int bv_last_em_kernel_times(bv_ctx* ctx, float ms[3]) {
+int bv_last_em_kernel_times(bv_ctx* ctx, float ms[2]) {
     if (!ctx || !ms) return set_err(ctx, BV_ERR_ARG, "null argument");
     if (!ctx->ev_valid) return set_err(ctx, BV_ERR_STATE, "no profiled tile yet (bv_set_profiling)");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
-    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
-    for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[3 + i], ctx->ev[4 + i]));
+    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[5]));
+    for (int i = 0; i < 2; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[3 + i], ctx->ev[4 + i]));
     return BV_OK;
 }
 
@@ -470,7 +506,8 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_count_kernel<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)bv::count_smem_bytes<BV_COUNT_WARPS_LONG, BV_COUNT_STAGES_LONG>()) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kHistLongSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_em_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess ||
@@ -530,7 +567,7 @@ void bv_destroy(bv_ctx* ctx) {
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model); cudaFree(ctx->d_group);
     scratch_free(ctx->dev_scratch);
-    for (int i = 0; i < 7; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 3; ++i) if (ctx->ev_call[i]) cudaEventDestroy(ctx->ev_call[i]);
     delete ctx;
 }
@@ -546,6 +583,7 @@ int bv_set_params(bv_ctx* ctx, const bv_params* p) {
 }
 
 int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, void* stream) {
+    BvRange range("bv_tile_run_device");
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     if (tile && tile->location != BV_LOC_DEVICE) return set_err(ctx, BV_ERR_ARG, "bv_tile_run_device: tile must be device resident");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -623,6 +661,7 @@ static const void* host_device_pointer(const void* p) {
 }
 
 static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv_tile_aux* aux, bool with_calls) {
+    BvRange range("bv_tile_submit (dense tile: H2D, kernels, D2H)");
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
     if (!tile) return set_err(ctx, BV_ERR_ARG, "null tile");
@@ -714,6 +753,7 @@ static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv
 // same kernels as for a dense tile.  The qual plane -- and for the called-site kernels the mapq / rpr planes -- are
 // device resident here (there is no host plane to read in place).
 static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* t, bool with_calls) {
+    BvRange range("bv_tile_submit_sparse (H2D of the cells, K0 expand, kernels, D2H)");
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
     if (!t) return set_err(ctx, BV_ERR_ARG, "null tile");
@@ -813,25 +853,37 @@ int bv_sparse_encode16(const uint32_t* cells, const uint32_t* aux32, const uint3
     uint64_t n = 0;
     for (uint32_t s = 0; s < n_sites; ++s) {
         if (start16) start16[s] = (uint32_t)n;
-        if (site_start[s + 1] < site_start[s]) return set_err(nullptr, BV_ERR_ARG, "site_start does not ascend at site %u", s);
+        const uint32_t c0 = site_start[s], c1 = site_start[s + 1];
+        if (c1 < c0) return set_err(nullptr, BV_ERR_ARG, "site_start does not ascend at site %u", s);
         uint32_t next = 0;   // the sample index a gap of 0 would mean
-        for (uint32_t c = site_start[s]; c < site_start[s + 1]; ++c) {
+        // room for the worst case of this site: every cell plus a skip word per 31 samples of the 2^20 a cell can name
+        const bool roomy = words16 && n + (uint64_t)(c1 - c0) + BV_CELL_MAX_SAMPLES / BV_CELL16_GAP_SKIP + 1 <= max_words;
+        for (uint32_t c = c0; c < c1; ++c) {
+            if (roomy) {
+                uint16_t* o = words16 + n;
+                uint32_t* oa = aux16 ? aux16 + n : nullptr;
+                const uint32_t* stop = aux16 ? encode16_run<true>(cells + c, cells + c1, aux32 ? aux32 + c1 : nullptr, o, oa, next)
+                                             : encode16_run<false>(cells + c, cells + c1, nullptr, o, oa, next);
+                n = (uint64_t)(o - words16);
+                c = (uint32_t)(stop - cells);
+                if (c >= c1) break;
+            }
             const uint32_t w = cells[c], i = w & (BV_CELL_MAX_SAMPLES - 1u), strand = (w >> 23) & 3u;
             if (i < next) return set_err(nullptr, BV_ERR_ARG, "site %u: cells do not ascend by sample (BV_CELLS_U16 needs them to)", s);
             if (strand > BV_STRAND_REV) return set_err(nullptr, BV_ERR_ARG, "site %u, sample %u: strand code %u has no 16-bit form", s, i, strand);
-            uint32_t gap = i - next;
-            while (gap >= BV_CELL16_GAP_SKIP) {
+            uint32_t g = i - next;
+            while (g >= BV_CELL16_GAP_SKIP) {
                 if (words16) {
                     if (n >= max_words) return set_err(nullptr, BV_ERR_ARG, "more than max_words words");
                     words16[n] = (uint16_t)BV_CELL16_GAP_SKIP;
                     if (aux16) aux16[n] = 0;
                 }
                 ++n;
-                gap -= BV_CELL16_GAP_SKIP;
+                g -= BV_CELL16_GAP_SKIP;
             }
             if (words16) {
                 if (n >= max_words) return set_err(nullptr, BV_ERR_ARG, "more than max_words words");
-                words16[n] = BV_CELL16_PACK(gap, (w >> 20) & 7u, strand, w >> 25);
+                words16[n] = BV_CELL16_PACK(g, (w >> 20) & 7u, strand, w >> 25);
                 if (aux16) aux16[n] = aux32 ? aux32[c] : 0;
             }
             ++n;
@@ -872,6 +924,7 @@ int bv_synth_fill_sparse_host(const bv_synth_model* model, uint64_t site0, uint3
 }
 
 int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out) {
+    BvRange range("bv_tile_wait");
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
     bv_slot& s = ctx->slots[slot];

@@ -47,7 +47,8 @@ constexpr uint32_t kStateEM = 3;             // result depends on base qualities
 constexpr int kCntSlow = 0, kCntBound = 1, kCntEm = 2, kCntEmNext = 3;   // SiteKernelArgs::counters
 constexpr int kCntCalled = 4, kCntGroupNext = 5;                          // called sites (K4 -> K5, K6)
 constexpr int kCntBadCell = 6;                                            // malformed sparse input (K0, bv_expand_kernel.cuh)
-constexpr int kCntEmHdr = 7, kCntEmPool = 8, kCntEmTask = 9;              // K4a -> K4b, K4c: EM sites, their bins, their EM tasks
+constexpr int kCntEmHdr = 7, kCntEmPool = 8;                              // K4a -> K4b: EM sites and the pool of their bins
+constexpr int kCntEmTask2 = 9, kCntEmTask3 = 11, kCntEmTask4 = 12;        // EM tasks by number of alleles in the candidate subset
 constexpr int kCntEmFallback = 10;                                        // EM sites finished inside K4a (scratch pools full)
 constexpr int kNumCounters = 16;
 
@@ -59,15 +60,15 @@ struct __align__(16) EmSiteHdr {
     uint32_t site;
     uint32_t bins_off;       // first word of the site's bins in SiteKernelArgs::em_pool
     uint32_t nb;             // number of bins
-    uint32_t task0;          // first of the site's tasks in em_tasks / em_res
-    uint32_t act;            // active alleles before the LRT (bit j = allele j)
-    uint32_t flags;          // BV_FLAG_* raised so far (K1 / K2 / histogram)
+    uint32_t act_flags;      // active alleles before the LRT (bits 0-3) | BV_FLAG_* raised so far << 8
+    uint32_t task[3];        // slot of the site's first task among the 2-, 3- and 4-allele tasks (em_tasks / em_res)
+    uint32_t remaining;      // tasks not finished yet: the thread that takes it to 0 decides the site
     uint32_t depth[4];
     uint32_t total;          // depth[0..3] + depth_other
-    uint32_t pad0;
-    double single_ll[4];     // log-likelihood of the single-allele model {j} (closed form), for the active alleles
+    uint32_t base_start[3];  // bins are sorted by base: A = [0, s0), C = [s0, s1), G = [s1, s2), T = [s2, s3), other = [s3, nb);
+                             // base_start[0] = s0 | s1 << 16, base_start[1] = s2 | s3 << 16, base_start[2] unused
 };
-static_assert(sizeof(EmSiteHdr) == 80, "EmSiteHdr layout");
+static_assert(sizeof(EmSiteHdr) == 64, "EmSiteHdr layout");
 constexpr int kEmResDoubles = 6;             // per EM task: log-likelihood, f[4], flags (as bits of a u64)
 constexpr uint32_t kEmTaskInvalid = 0xffffffffu;
 
@@ -88,10 +89,11 @@ struct SiteKernelArgs {
     // K4a -> K4b -> K4c (bv_em_kernels.cuh)
     EmSiteHdr* em_hdr;       // [n_sites]
     uint32_t* em_pool;       // [em_pool_cap] compact bins of the EM sites, allocated with kCntEmPool
-    uint32_t* em_tasks;      // [em_task_cap] hdr index | subset << 28, allocated with kCntEmTask
-    double* em_res;          // [em_task_cap][kEmResDoubles]
+    uint32_t* em_tasks;      // hdr index | subset << 28; three lists one after the other: 2-, 3- and 4-allele subsets,
+                             // em_task_cap[k] slots each, allocated with kCntEmTask2 / 3 / 4
+    double* em_res;          // [sum of em_task_cap][kEmResDoubles], indexed like em_tasks
     uint32_t em_pool_cap;
-    uint32_t em_task_cap;
+    uint32_t em_task_cap[3];
     // called sites (n_alt > 0): rank sums (K5) and population-group frequencies (K6); all null / 0 when not asked for
     uint32_t* list_called;   // K4 -> K5, K6: site indices, room for n_sites entries
     const uint8_t* mapq;     // [n_sites][aux_pitch]

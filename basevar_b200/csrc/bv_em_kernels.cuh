@@ -10,113 +10,99 @@
 //                          shared memory, compaction to bins.  A site with one active allele is finished here (closed
 //                          form).  A site with >= 2 gets a header, its bins in a pool, and one EM TASK per subset of
 //                          >= 2 active alleles (1, 4 or 11 tasks for 2, 3 or 4 active alleles; single-allele models are
-//                          closed form and travel in the header).
-//   K4b bv_em_task_kernel  one THREAD per task: the whole EM of one candidate subset over the site's bins, staged in
-//                          shared memory.  No shuffles, no warp-wide repetition of scalar work; every lane of the FP64
-//                          pipe carries a different EM.  Tasks of all sites are one flat list, so a warp's 32 EMs have
-//                          similar lengths whatever the sites' allele counts.
-//   K4c bv_decide_kernel   one THREAD per site: replays the elimination loop on the table of task results (first-minimum
-//                          argmin in the reference's subset order, threshold, flags), ALT / AF / QUAL
-//                          (chi-square survival function) and the strand-bias Fisher test of the VCF row.
+//                          closed form), listed by subset size.
+//   K4b bv_em_task_kernel  one THREAD per task: the whole EM of one candidate subset over the site's bins, staged in shared
+//                          memory.  No warp-wide repetition of scalar work, every lane of the FP64 pipe carries a different
+//                          EM.  (A tile with few tasks would leave the GPU idle behind their serial chains: it gets four
+//                          lanes per task; the sums are formed in the same order either way.)
+//                          The thread that stores the LAST result of a site then decides it: replays the elimination
+//                          loop on the table of task results (first-minimum argmin in the reference's subset order,
+//                          threshold, flags), ALT / AF / QUAL (chi-square survival function) and the strand-bias
+//                          Fisher test of the VCF row -- scalar work that overlaps with the EMs of other warps.
 //
 // At most 3 of the 11 tasks of a 4-allele site are never consulted (the elimination needs <= 8 EMs); evaluating them
 // anyway removes every dependency between EMs.  A flag an unconsulted task raises (BV_FLAG_EM_MAXITER) is not reported.
-// Scratch (headers, bin pool, task list) is sized per tile; a site that does not fit any more is finished inside K4a by
+// Scratch (headers, bin pool, task lists) is sized per tile; a site that does not fit any more is finished inside K4a by
 // the warp-per-site code K6 also uses (lrt_on_bins), so that the records never depend on the pool size.
 #pragma once
 #include "bv_finish_kernels.cuh"
 
 namespace bv {
 
-// bit m of the result: subset m (bit j = allele j) of `act` has >= 2 members, i.e. is an EM task of the site
-__device__ __forceinline__ uint32_t em_task_mask(uint32_t act) {
-    uint32_t v = 0;
-#pragma unroll
-    for (uint32_t m = 3; m < 16; ++m)
-        if ((m & ~act) == 0 && (m & (m - 1)) != 0) v |= 1u << m;
-    return v;
-}
-
 // ---- K4a: one site in state kStateEM -----------------------------------------------------------------------------------------
-// Everything here is warp-uniform.  The record (counts, FS of the CVG row, flags) comes from K1 / K2.
+// Everything here is warp-uniform.  The record (counts, FS of the CVG row, flags, active set) comes from K1 / K2.
+template <bool LONG>
 __device__ __noinline__ void hist_site(uint32_t site) {
     QualWarp& W = warp_smem();
     const QualCta& cs = cta_shared();
     const int lane = threadIdx.x & 31;
     if (lane < 8) reinterpret_cast<uint4*>(&W.rec)[lane] = reinterpret_cast<const uint4*>(cs.a.out + site)[lane];
-    const int ref_code = ref_code_of(cs.a.ref_base[site]);
     __syncwarp();
     const uint32_t d0 = W.rec.depth[0], d1 = W.rec.depth[1], d2 = W.rec.depth[2], d3 = W.rec.depth[3];
     const uint32_t total = d0 + d1 + d2 + d3 + W.rec.depth_other;
-    const double dtot = (double)total;
-    const double min_af = cs.a.min_af;
-    if (lane == 0) W.flag_word = W.rec.flags;
-
-    // ---- lrt (src/basetype.cpp:130-199): active set (total > 0 here) ----
-    uint32_t act = 0;
-    act |= is_active(d0, total, dtot, min_af) ? 1u : 0u;
-    act |= is_active(d1, total, dtot, min_af) ? 2u : 0u;
-    act |= is_active(d2, total, dtot, min_af) ? 4u : 0u;
-    act |= is_active(d3, total, dtot, min_af) ? 8u : 0u;
+    // ---- lrt (src/basetype.cpp:130-199): the active set (total > 0 here) was worked out by K2 ----
+    uint32_t act = (reinterpret_cast<const uint32_t*>(&W.rec)[kWAlt] >> 8) & 0xfu;
     int n_act = __popc(act);
-    double chi = 0.0;
-    uint32_t em_calls = 0;
-    const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
+    if (lane == 0) W.flag_word = W.rec.flags;
     __syncwarp();
 
     // histogram the row by (base, phred)
-    const uint32_t h = build_hist(site, nullptr, 0);
+    const uint32_t h = LONG ? build_hist_long(site) : build_hist(site, nullptr, 0);
     const uint32_t qmin = h & 0xffu, qmax = (h >> 8) & 0xffu;
     if (lane == 0) W.flag_word |= h >> 16;
     __syncwarp();
+    double chi = 0.0;
+    uint32_t em_calls = 0;
     if (n_act >= 2) {
         const int nb = compact_bins(qmin, qmax);
-        // ---- hand the site to K4b / K4c: bins into the pool, one task per subset of >= 2 active alleles ----
-        const uint32_t tmask = em_task_mask(act);
-        const uint32_t n_tasks = (uint32_t)__popc(tmask);
-        uint32_t off = 0, t0 = 0, hdr = 0, ok = 0;
-        if (lane == 0) {
-            off = atomicAdd(cs.a.counters + kCntEmPool, (uint32_t)nb);
-            if (off <= cs.a.em_pool_cap && (uint32_t)nb <= cs.a.em_pool_cap - off) {
-                t0 = atomicAdd(cs.a.counters + kCntEmTask, n_tasks);
-                if (t0 <= cs.a.em_task_cap && n_tasks <= cs.a.em_task_cap - t0) {
-                    hdr = atomicAdd(cs.a.counters + kCntEmHdr, 1u);
-                    ok = 1;
-                } else {
-                    ok = 2;   // task slots [t0, cap) stay unused: marked invalid below
-                }
-            }
-        }
-        ok = __shfl_sync(kFull, ok, 0); off = __shfl_sync(kFull, off, 0);
-        t0 = __shfl_sync(kFull, t0, 0); hdr = __shfl_sync(kFull, hdr, 0);
-        if (ok == 2) {
-            for (uint32_t t = t0 + lane; t < cs.a.em_task_cap && t < t0 + n_tasks; t += 32) cs.a.em_tasks[t] = kEmTaskInvalid;
-        }
-        if (ok == 1) {
+        // ---- hand the site to K4b: bins into the pool, one task per subset of >= 2 active alleles ----
+        // lane m < 16 looks after subset m; tasks are listed by subset size (2, 3, 4 alleles), in ascending subset order
+        const uint32_t m = (uint32_t)lane;
+        const int k = __popc(m);
+        const bool is_task = lane < 16 && (m & ~act) == 0u && k >= 2;
+        const uint32_t bal2 = __ballot_sync(kFull, is_task && k == 2), bal3 = __ballot_sync(kFull, is_task && k == 3),
+                       bal4 = __ballot_sync(kFull, is_task && k == 4);
+        const uint32_t n_k[3] = {(uint32_t)__popc(bal2), (uint32_t)__popc(bal3), (uint32_t)__popc(bal4)};
+        // five allocations at once: pool (lane 0), header (lane 1), task slots of each size (lanes 2-4)
+        uint32_t got = 0, want = 0, cap = 0;
+        if (lane == 0) { want = (uint32_t)nb; cap = cs.a.em_pool_cap; }
+        if (lane == 1) { want = 1u; cap = cs.a.n_sites; }
+        if (lane >= 2 && lane < 5) { want = n_k[lane - 2]; cap = cs.a.em_task_cap[lane - 2]; }
+        constexpr int kCnt[5] = {kCntEmPool, kCntEmHdr, kCntEmTask2, kCntEmTask3, kCntEmTask4};
+        if (lane < 5 && want) got = atomicAdd(cs.a.counters + kCnt[lane], want);
+        const bool fits = got <= cap && want <= cap - got;
+        const bool ok = __all_sync(kFull, fits);
+        const uint32_t off = __shfl_sync(kFull, got, 0), hdr = __shfl_sync(kFull, got, 1);
+        const uint32_t t2 = __shfl_sync(kFull, got, 2), t3 = __shfl_sync(kFull, got, 3), t4 = __shfl_sync(kFull, got, 4);
+        const uint32_t base3 = cs.a.em_task_cap[0], base4 = base3 + cs.a.em_task_cap[1];
+        // slot of this lane's task (task slots that were allocated but stay unused are marked invalid)
+        const uint32_t my_t = k == 2 ? t2 + (uint32_t)__popc(bal2 & ((1u << lane) - 1u))
+                            : k == 3 ? base3 + t3 + (uint32_t)__popc(bal3 & ((1u << lane) - 1u)) : base4 + t4;
+        const uint32_t my_cap = k == 2 ? base3 : k == 3 ? base4 : base4 + cs.a.em_task_cap[2];
+        if (is_task && my_t < my_cap) cs.a.em_tasks[my_t] = ok ? (hdr | (m << 28)) : kEmTaskInvalid;
+        if (ok) {
             const uint32_t* bins = nb <= kSmemBins ? W.bins : cs.a.bin_spill + (size_t)(blockIdx.x * kQualWarps + (threadIdx.x >> 5)) * kMaxBins;
             for (int i = lane; i < nb; i += 32) cs.a.em_pool[off + i] = bins[i];
-            // single-allele models of the active alleles: closed form (see single_allele_ll)
-            double sll = 0.0;
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                if (!(act >> b & 1u)) continue;
-                const double v = single_allele_ll(bins, nb, b);
-                if (lane == b) sll = v;
+            // first bin of each base (bins are sorted by base): lane b counts the bins of bases < b + 1
+            uint32_t below = 0;
+            for (int i = lane; i < nb; i += 32) {
+                const uint32_t b = bin_base(bins[i]);
+                below += (b < 1u) | ((uint32_t)(b < 2u) << 8) | ((uint32_t)(b < 3u) << 16) | ((uint32_t)(b < 4u) << 24);
             }
-            // task m-th subset (ascending mask value) -> slot t0 + rank
-            if (lane < 16 && (tmask >> lane & 1u))
-                cs.a.em_tasks[t0 + __popc(tmask & ((1u << lane) - 1u))] = hdr | ((uint32_t)lane << 28);
-            EmSiteHdr* H = cs.a.em_hdr + hdr;
-            if (lane < 4) H->single_ll[lane] = sll;
+            // (a lane sees at most kMaxBins / 32 = 15 bins, so the four byte counters cannot overflow before the reduction)
+            const uint32_t s0 = __reduce_add_sync(kFull, below & 0xffu), s1 = __reduce_add_sync(kFull, (below >> 8) & 0xffu),
+                           s2 = __reduce_add_sync(kFull, (below >> 16) & 0xffu), s3 = __reduce_add_sync(kFull, below >> 24);
             if (lane == 0) {
-                uint4 w0, w1, w2;
-                w0.x = site; w0.y = off; w0.z = (uint32_t)nb; w0.w = t0;
-                w1.x = act; w1.y = W.flag_word; w1.z = d0; w1.w = d1;
-                w2.x = d2; w2.y = d3; w2.z = total; w2.w = 0;
-                reinterpret_cast<uint4*>(H)[0] = w0; reinterpret_cast<uint4*>(H)[1] = w1; reinterpret_cast<uint4*>(H)[2] = w2;
+                uint4 w0, w1, w2, w3;
+                w0.x = site; w0.y = off; w0.z = (uint32_t)nb; w0.w = act | (W.flag_word << 8);
+                w1.x = t2; w1.y = base3 + t3; w1.z = base4 + t4; w1.w = n_k[0] + n_k[1] + n_k[2];
+                w2.x = d0; w2.y = d1; w2.z = d2; w2.w = d3;
+                w3.x = total; w3.y = s0 | (s1 << 16); w3.z = s2 | (s3 << 16); w3.w = 0;
+                uint4* H = reinterpret_cast<uint4*>(cs.a.em_hdr + hdr);
+                H[0] = w0; H[1] = w1; H[2] = w2; H[3] = w3;
             }
             __syncwarp();
-            return;   // the record is completed by K4c
+            return;   // the record is completed by K4b
         }
         // scratch pools full: finish the site here
         if (lane == 0) atomicAdd(cs.a.counters + kCntEmFallback, 1u);
@@ -146,12 +132,14 @@ __device__ __noinline__ void hist_site(uint32_t site) {
     // ---- ALT / QUAL (src/basetype.cpp:170-196) ----
     // Here only the rule that needs no arithmetic (mono-allelic 5000); the chi-square survival function and the Fisher
     // test of the VCF row are scalar work: the site is queued and vcf_flush() does them one thread per site.
+    const int ref_code = ref_code_of(cs.a.ref_base[site]);
+    const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
     const uint32_t alt_set = act & ~ref_bit;
     const int n_alt = __popc(alt_set);
     double qual = 0.0;
     if (n_alt) {
         const int first_act = __ffs(act) - 1;
-        const double r = (double)sel4u(first_act, d0, d1, d2, d3) / dtot;
+        const double r = (double)sel4u(first_act, d0, d1, d2, d3) / (double)total;
         if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
     }
 
@@ -187,8 +175,10 @@ __device__ __noinline__ void hist_site(uint32_t site) {
     if (W.vcf_n == 32) vcf_flush();
 }
 
-// Persistent warps with dynamic work distribution over the EM list.
-__global__ void __launch_bounds__(kQualWarps * 32, 1) bv_hist_kernel(const __grid_constant__ SiteKernelArgs a) {
+// Persistent warps with dynamic work distribution over the EM list.  LONG: the shape for rows of more than kLongRowSamples
+// samples (kLongWarps warps per CTA, build_hist_long).
+template <bool LONG>
+__global__ void __launch_bounds__((LONG ? kLongWarps : kQualWarps) * 32, 1) bv_hist_kernel(const __grid_constant__ SiteKernelArgs a) {
     QualCta& cs = cta_shared();
     QualWarp& W = warp_smem();
     const int lane = threadIdx.x & 31;
@@ -210,207 +200,372 @@ __global__ void __launch_bounds__(kQualWarps * 32, 1) bv_hist_kernel(const __gri
         if (lane == 0) i = atomicAdd(a.counters + kCntEmNext, 1u);
         i = __shfl_sync(kFull, i, 0);
         if (i >= n_em) break;
-        hist_site(a.list_em[i]);
+        hist_site<LONG>(a.list_em[i]);
     }
     if (W.vcf_n) vcf_flush();
 }
 
 // =====================================================================================================================
-// K4b: one thread per EM task.
+// K4b: one thread per EM task; the thread that finishes a site's last task decides the site.
 // =====================================================================================================================
 #ifndef BV_TASK_THREADS
 #define BV_TASK_THREADS 128
 #endif
 #ifndef BV_TASK_STAGE_BINS
-#define BV_TASK_STAGE_BINS 192
+#define BV_TASK_STAGE_BINS 96
+#endif
+#ifndef BV_TASK_G4_MAX_TASKS
+#define BV_TASK_G4_MAX_TASKS 12288
 #endif
 constexpr int kTaskThreads = BV_TASK_THREADS;
 constexpr int kStageBins = BV_TASK_STAGE_BINS;     // bins per site staged in shared memory; longer lists are read from the pool
 constexpr int kStageStride = kStageBins + 1;       // odd: the rows of 32 different sites start in 32 different banks
 
 struct __align__(16) TaskCta {
-    double ome[kQSlots];         // 1 - eps(q)
-    double e3[kQSlots];          // eps(q) / 3
-    uint32_t hdr_of[kTaskThreads];    // header index of thread t's task
-    uint32_t slot_hdr[kTaskThreads];  // header index of staging row s
-    uint32_t warp_leaders[kTaskThreads / 32];
-    uint32_t bins[kTaskThreads * kStageStride];
+    double lut[4][kQSlots];           // 1 - eps(q), eps(q) / 3, log(1 - eps(q)), log(eps(q) / 3)
+    uint32_t n_decide;                // sites whose last task finished in this round of the CTA ...
+    uint32_t decide_hdr[kTaskThreads];   // ... their headers and staging rows: decided one thread per site after the round
+    uint32_t decide_row[kTaskThreads];
+    uint32_t bins[kTaskThreads * kStageStride];   // one row per task of the round
 };
 constexpr size_t kTaskSmemBytes = sizeof(TaskCta);
 static_assert(kTaskSmemBytes <= 232448, "shared memory of the EM task kernel exceeds 227 KB");
 
-// One E-step + M-step over the bins (src/algorithm.h:148-198) under frequencies f; WITH_PREV: also the marginals under
-// the previous frequencies fp, for the convergence test of EM() (src/algorithm.h:238-250) -- recomputed rather than
-// kept per bin, so that a task needs no per-bin state.  Same operation order as the reference: lik * freq summed in
-// A, C, G, T order (alleles outside the subset have freq 0 and add an exact +0.0), column sums of the posteriors with
-// c equal reads adding c * post; posteriors are l_j * (1 / m) (one division per bin, inside the stated tolerance).
-template <bool WITH_PREV>
-__device__ __forceinline__ void em_pass(const uint32_t* bins, int nb, const double* s_ome, const double* s_e3,
-                                        const double (&f)[4], const double (&fp)[4], bool int_mode,
-                                        double (&s)[4], bool& big, double& delta, double* prev_log) {
-    s[0] = 0; s[1] = 0; s[2] = 0; s[3] = 0;
-#pragma unroll 2
-    for (int i = 0; i < nb; ++i) {
-        const uint32_t p = bins[i];
-        const uint32_t b = bin_base(p), q = bin_qual(p);
-        const double cd = (double)bin_count(p);
-        const double ome = s_ome[q], e3 = s_e3[q];
-        const double L0 = b == 0 ? ome : e3, L1 = b == 1 ? ome : e3, L2 = b == 2 ? ome : e3, L3 = b == 3 ? ome : e3;
-        const double l0 = L0 * f[0], l1 = L1 * f[1], l2 = L2 * f[2], l3 = L3 * f[3];
-        double m = 0.0;
-        m += l0; m += l1; m += l2; m += l3;
-        const double inv = 1.0 / m;
-        s[0] += cd * (l0 * inv); s[1] += cd * (l1 * inv); s[2] += cd * (l2 * inv); s[3] += cd * (l3 * inv);
-        if (WITH_PREV) {
-            if (int_mode) {
-                double mp = 0.0;
-                mp += L0 * fp[0]; mp += L1 * fp[1]; mp += L2 * fp[2]; mp += L3 * fp[3];
-                // (double)abs((int)diff) is non-zero iff |log m - log mp| >= 1, i.e. the marginal moved by a factor e:
-                // inside (1/2.5, 2.5) the ratio decides without a logarithm, otherwise the logarithms themselves do.
-                // NaN / inf convert to INT_MIN whose "abs" stays negative and ends the loop (results are NaN by then).
-                if (!(m < 2.5 * mp && mp < 2.5 * m)) {
-                    const double diff = nlog(m) - nlog(mp);
-                    if (fabs(diff) >= 1.0 && fabs(diff) < 2147483648.0) big = true;
-                }
-            } else {
-                const double llh = nlog(m);
-                double lp;
-                if (prev_log) { lp = prev_log[i]; prev_log[i] = llh; }
-                else {
-                    double mp = 0.0;
-                    mp += L0 * fp[0]; mp += L1 * fp[1]; mp += L2 * fp[2]; mp += L3 * fp[3];
-                    lp = nlog(mp);
-                }
-                delta += cd * fabs(llh - lp);
-            }
-        } else if (prev_log) {
-            prev_log[i] = nlog(m);
-        }
+// The G lanes (1 or 4, aligned) that share one task.  Sums over the bins of a task are ALWAYS formed the same way, whatever G
+// is: four partial sums over the visits u = 0, 1, 2, 3 (mod 4), combined as (p0 + p2) + (p1 + p3).  One lane keeps the four
+// partial sums itself (four independent FP64 chains); four lanes keep one each and combine them with two butterfly steps,
+// which form exactly that expression.  The records therefore do not depend on how many lanes a launch gave its tasks
+// (i.e. on how many tasks the tile had).
+struct LaneGroup {
+    int G, gl;
+    uint32_t mask;
+    __device__ __forceinline__ double sum4(double v) const {   // G == 4: every lane of the group gets (p0 + p2) + (p1 + p3)
+        v += __shfl_xor_sync(mask, v, 2);
+        v += __shfl_xor_sync(mask, v, 1);
+        return v;
+    }
+    __device__ __forceinline__ bool any(bool p) const { return (__ballot_sync(mask, p) & mask) != 0u; }
+};
+__device__ __forceinline__ double sum4(const double (&p)[4]) { return (p[0] + p[2]) + (p[1] + p[3]); }
+
+// 1 / m to ~1 ulp: the hardware's 20-bit estimate and two Newton steps (the correctly rounded division costs twice as
+// many FP64 instructions; the posteriors it feeds are inside the stated tolerance either way).  m == 0 gives NaN, where
+// 1.0 / 0 gives inf: the posteriors 0 * inf the reference then forms are NaN as well.
+__device__ __forceinline__ double rcp_fast(double m) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(m));
+    double e = fma(-m, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-m, r, 1.0);
+    return fma(r, e, r);
+}
+
+// The bins of a site are sorted by base, and a bin whose base is OUTSIDE the candidate subset (another allele, or the
+// "other" class) has the likelihood row {e3, e3, ...}: its marginal is e3 * F (F = sum of the subset's frequencies) and
+// its posteriors are f_k / F whatever its phred.  All such bins together therefore add c_out * f_k / F to the column sums
+// -- one term instead of a pass over them -- and only the bins of the subset's own bases are visited.
+template <int NA>
+struct SubsetBins {
+    int off[NA];      // visit u of [0, n) is bin u + off[k], k = the run u falls in
+    int cum[NA];      // visits before the end of run k
+    int n;            // bins of the subset's bases
+    double c_out;     // reads outside them
+    __device__ __forceinline__ int bin_of(int u) const {
+        int o = off[0];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) o = u >= cum[k - 1] ? off[k] : o;
+        return u + o;
+    }
+};
+
+// One E-step + M-step (src/algorithm.h:148-198) for a subset of NA alleles j[0] < ... < j[NA-1] under frequencies f.
+// Same operation order as the reference inside a bin: lik * freq summed in A, C, G, T order (alleles outside the subset
+// have freq 0 there and add an exact +0.0: left out), column sums of the posteriors with c equal reads adding c * post;
+// posteriors are l_j * (1 / m).
+// DELTA: also sum c * |log m - log mp| with mp the marginal under the previous frequencies fp -- EM()'s convergence sum with
+// fabs (src/algorithm.h:238-250, BV_EM_ABS_DOUBLE), as one logarithm of the ratio mp / m.
+template <int NA, bool DELTA>
+__device__ __forceinline__ void em_bin(uint32_t p, const double* lut, const int (&j)[NA], const double (&f)[NA], const double (&fp)[NA],
+                                       double (&s)[NA], double& delta) {
+    const int b = (int)bin_base(p);
+    const uint32_t q = bin_qual(p);
+    const double cd = (double)bin_count(p);
+    const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
+    double L[NA], l[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) { L[k] = b == j[k] ? ome : e3; l[k] = L[k] * f[k]; }
+    double m = l[0];
+#pragma unroll
+    for (int k = 1; k < NA; ++k) m += l[k];
+    const double inv = rcp_fast(m);
+#pragma unroll
+    for (int k = 0; k < NA; ++k) s[k] += cd * (l[k] * inv);
+    if (DELTA) {
+        double mp = L[0] * fp[0];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) mp += L[k] * fp[k];
+        delta += cd * fabs(log(mp * inv));
     }
 }
 
-__device__ __noinline__ void em_task(const SiteKernelArgs& a, const TaskCta& cs, const EmSiteHdr& H, const uint32_t* bins,
-                                     uint32_t subset, double* res) {
+template <int NA, bool DELTA>
+__device__ __forceinline__ double em_pass(const uint32_t* bins, const SubsetBins<NA>& sb, const double* lut, const int (&j)[NA],
+                                          const double (&f)[NA], const double (&fp)[NA], double (&s)[NA], const LaneGroup& lg) {
+    double delta;
+    if (lg.G == 1) {
+        double sp[4][NA], dp[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int k = 0; k < NA; ++k) sp[v][k] = 0.0;
+        int u = 0;
+#pragma unroll 1
+        for (; u + 4 <= sb.n; u += 4) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) em_bin<NA, DELTA>(bins[sb.bin_of(u + v)], lut, j, f, fp, sp[v], dp[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+            if (u + v < sb.n) em_bin<NA, DELTA>(bins[sb.bin_of(u + v)], lut, j, f, fp, sp[v], dp[v]);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) { const double p4[4] = {sp[0][k], sp[1][k], sp[2][k], sp[3][k]}; s[k] = sum4(p4); }
+        delta = sum4(dp);
+    } else {
+        double d1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) s[k] = 0.0;
+#pragma unroll 2
+        for (int u = lg.gl; u < sb.n; u += 4) em_bin<NA, DELTA>(bins[sb.bin_of(u)], lut, j, f, fp, s, d1);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) s[k] = lg.sum4(s[k]);
+        delta = DELTA ? lg.sum4(d1) : 0.0;
+    }
+    if (sb.c_out != 0.0) {
+        double F = f[0], Fp = fp[0];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) { F += f[k]; Fp += fp[k]; }
+        const double inv = rcp_fast(F);
+#pragma unroll
+        for (int k = 0; k < NA; ++k) s[k] += sb.c_out * (f[k] * inv);
+        if (DELTA) delta += sb.c_out * fabs(log(Fp * inv));
+    }
+    return delta;
+}
+
+// BV_EM_ABS_INT_TRUNC, the rare case the frequencies cannot decide: is there a bin whose log marginal moved by >= 1?
+// ((double)abs((int)diff) is non-zero iff |diff| >= 1; NaN / inf convert to INT_MIN whose "abs" stays negative.)
+__device__ __forceinline__ bool moved_by_one(double m, double mp) {
+    if (m < 2.5 * mp && mp < 2.5 * m) return false;
+    const double diff = nlog(m) - nlog(mp);
+    return fabs(diff) >= 1.0 && fabs(diff) < 2147483648.0;
+}
+template <int NA>
+__device__ __noinline__ bool em_moved_bin(const uint32_t* bins, const SubsetBins<NA>& sb, const double* lut, const int (&j)[NA],
+                                          const double (&f)[NA], const double (&fp)[NA], const LaneGroup& lg) {
+    if (sb.c_out != 0.0) {   // the bins outside the subset: marginals e3 * F
+        double F = f[0], Fp = fp[0];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) { F += f[k]; Fp += fp[k]; }
+        if (moved_by_one(F, Fp)) return true;
+    }
+    bool found = false;
+    for (int u = lg.gl; u < sb.n && !found; u += lg.G) {   // (a yes / no answer: the order of the visits does not matter)
+        const uint32_t p = bins[sb.bin_of(u)];
+        const int b = (int)bin_base(p);
+        const uint32_t q = bin_qual(p);
+        const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
+        double m = 0.0, mp = 0.0;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) { const double L = b == j[k] ? ome : e3; m += L * f[k]; mp += L * fp[k]; }
+        found = moved_by_one(m, mp);
+    }
+    return lg.any(found);
+}
+
+// The whole EM of one candidate subset (src/algorithm.h:210-255; _f, src/basetype.cpp:105-128).  res: log-likelihood under
+// the second-to-last frequencies (what _f() sums), the estimated frequencies, flags.
+template <int NA>
+__device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* lut, const EmSiteHdr& H, const uint32_t* bins,
+                                        uint32_t subset, double* res, const LaneGroup& lg) {
     const int nb = (int)H.nb;
     const double total = (double)H.total;
     const bool int_mode = a.abs_mode == BV_EM_ABS_INT_TRUNC;
-    const bool in[4] = {(subset & 1u) != 0, (subset & 2u) != 0, (subset & 4u) != 0, (subset & 8u) != 0};
-    // initial frequencies: depth/total for the subset's members, 0 elsewhere, NOT renormalised (src/basetype.cpp:93-103)
-    double f[4], fp[4], s[4];
+    const int st[6] = {0, (int)(H.base_start[0] & 0xffffu), (int)(H.base_start[0] >> 16), (int)(H.base_start[1] & 0xffffu),
+                       (int)(H.base_start[1] >> 16), nb};
+    int j[NA];
+    SubsetBins<NA> sb;
+    {
+        uint32_t left = subset;
+        int seen = 0;
+        uint32_t c_in = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { f[j] = in[j] ? (double)H.depth[j] / total : 0.0; fp[j] = 0.0; }
-    double prev_buf[kStageBins];   // double mode: log marginals of the previous E-step (local memory, lanes interleaved)
-    double* prev_log = (!int_mode && nb <= kStageBins) ? prev_buf : nullptr;
-    bool big = false;
-    double delta = 0.0;
+        for (int k = 0; k < NA; ++k) {
+            j[k] = __ffs(left) - 1;
+            left &= left - 1u;
+            int b0 = 0, b1 = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) if (j[k] == b) { b0 = st[b]; b1 = st[b + 1]; c_in += H.depth[b]; }
+            sb.off[k] = b0 - seen;
+            seen += b1 - b0;
+            sb.cum[k] = seen;
+        }
+        sb.n = seen;
+        sb.c_out = (double)(H.total - c_in);
+    }
+    // initial frequencies: depth/total for the subset's members, NOT renormalised (src/basetype.cpp:93-103)
+    double f[NA], fp[NA], s[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (j[k] == b) d = H.depth[b];
+        f[k] = (double)d / total;
+        fp[k] = f[k];
+    }
     uint64_t flags = 0;
-    em_pass<false>(bins, nb, cs.ome, cs.e3, f, fp, int_mode, s, big, delta, prev_log);
+    em_pass<NA, false>(bins, sb, lut, j, f, fp, s, lg);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { fp[j] = f[j]; f[j] = in[j] ? s[j] / total : 0.0; }
+    for (int k = 0; k < NA; ++k) { fp[k] = f[k]; f[k] = s[k] / total; }
     int it = a.em_max_iter;
     for (;;) {
-        big = false; delta = 0.0;
-        em_pass<true>(bins, nb, cs.ome, cs.e3, f, fp, int_mode, s, big, delta, prev_log);
+        bool more;
+        if (int_mode) {
+            em_pass<NA, false>(bins, sb, lut, j, f, fp, s, lg);
+            // Every marginal is a non-negative combination of the frequencies, so its ratio between two E-steps lies between
+            // the smallest and the largest ratio of the frequencies (e = 2.71828...): all of those inside (1/2.718, 2.718) =>
+            // no log marginal moved by 1; all >= 2.7183 or all <= 1/2.7183 => every one did; otherwise the bins decide.
+            bool calm = true, up = true, down = true;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { fp[j] = f[j]; f[j] = in[j] ? s[j] / total : 0.0; }
-        const bool more = int_mode ? big : !(delta < a.em_eps);
+            for (int k = 0; k < NA; ++k) {
+                calm = calm && f[k] < 2.718 * fp[k] && fp[k] < 2.718 * f[k];
+                up = up && f[k] >= 2.7183 * fp[k] && fp[k] > 0.0 && f[k] < 1e300;
+                down = down && fp[k] >= 2.7183 * f[k] && f[k] > 0.0 && fp[k] < 1e300;
+            }
+            more = calm ? false : (up || down) ? true : em_moved_bin<NA>(bins, sb, lut, j, f, fp, lg);
+        } else {
+            const double delta = em_pass<NA, true>(bins, sb, lut, j, f, fp, s, lg);
+            more = !(delta < a.em_eps);
+        }
+#pragma unroll
+        for (int k = 0; k < NA; ++k) { fp[k] = f[k]; f[k] = s[k] / total; }
         --it;
         if (it == 0) flags |= BV_FLAG_EM_MAXITER;
         if (!more || it == 0) break;
     }
-    // log marginal likelihoods under the second-to-last frequencies (those of the last E-step), summed: what _f() adds up
-    // (src/basetype.cpp:119-120)
-    double ll = 0.0;
-#pragma unroll 2
-    for (int i = 0; i < nb; ++i) {
-        const uint32_t p = bins[i];
-        const uint32_t b = bin_base(p), q = bin_qual(p);
-        const double ome = cs.ome[q], e3 = cs.e3[q];
-        double lml;
-        if (prev_log) lml = prev_log[i];
-        else {
-            double mp = 0.0;
-            mp += (b == 0 ? ome : e3) * fp[0]; mp += (b == 1 ? ome : e3) * fp[1];
-            mp += (b == 2 ? ome : e3) * fp[2]; mp += (b == 3 ? ome : e3) * fp[3];
-            lml = nlog(mp);
+    // Sum of c * log marginal under fp, the frequencies of the last E-step: one logarithm per bin of the subset's bases;
+    // a bin outside them has the marginal e3(q) * F: log e3 comes from the table, log F is one logarithm for all of them.
+    auto lml_term = [&](int u) {
+        const uint32_t p = bins[sb.bin_of(u)];
+        const int b = (int)bin_base(p);
+        const uint32_t q = bin_qual(p);
+        const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
+        double m = (b == j[0] ? ome : e3) * fp[0];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) m += (b == j[k] ? ome : e3) * fp[k];
+        return (double)bin_count(p) * log(m);
+    };
+    double ll;
+    if (lg.G == 1) {
+        double lp[4] = {0.0, 0.0, 0.0, 0.0};
+        int u = 0;
+#pragma unroll 1
+        for (; u + 4 <= sb.n; u += 4) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) lp[v] += lml_term(u + v);
         }
-        ll += (double)bin_count(p) * lml;
+#pragma unroll
+        for (int v = 0; v < 3; ++v)
+            if (u + v < sb.n) lp[v] += lml_term(u + v);
+        ll = sum4(lp);
+    } else {
+        double l1 = 0.0;
+#pragma unroll 2
+        for (int u = lg.gl; u < sb.n; u += 4) l1 += lml_term(u);
+        ll = lg.sum4(l1);
     }
-    res[0] = ll; res[1] = f[0]; res[2] = f[1]; res[3] = f[2]; res[4] = f[3];
+    if (sb.c_out != 0.0) {
+        // the bins outside the subset: table look-ups only, summed in bin order by every lane of the group alike
+        uint32_t in_set = 0;
+#pragma unroll
+        for (int k = 0; k < NA; ++k) in_set |= 1u << j[k];
+        double lo = 0.0;
+#pragma unroll 1
+        for (int b = 0; b < 5; ++b) {
+            if (in_set >> b & 1u) continue;
+            for (int i = st[b]; i < st[b + 1]; ++i) {
+                const uint32_t p = bins[i];
+                lo += (double)bin_count(p) * lut[kLutLogMis * kQSlots + bin_qual(p)];
+            }
+        }
+        double F = fp[0];
+#pragma unroll
+        for (int k = 1; k < NA; ++k) F += fp[k];
+        ll += lo + sb.c_out * log(F);
+    }
+    if (lg.gl != 0) return;
+    double fo[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (j[k] == b) fo[b] = f[k];
+    }
+    res[0] = ll; res[1] = fo[0]; res[2] = fo[1]; res[3] = fo[2]; res[4] = fo[3];
     res[5] = __longlong_as_double((long long)flags);
 }
 
-__global__ void __launch_bounds__(kTaskThreads) bv_em_task_kernel(const __grid_constant__ SiteKernelArgs a) {
-    TaskCta& cs = *reinterpret_cast<TaskCta*>(bv_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int q = tid; q < kQSlots; q += kTaskThreads) {
-        cs.ome[q] = a.lut[kLutOneMinusEps * kQStride + q];
-        cs.e3[q] = a.lut[kLutEpsThird * kQStride + q];
-    }
-    const uint32_t n_tasks = min(a.counters[kCntEmTask], a.em_task_cap);
-#pragma unroll 1
-    for (uint32_t t0 = blockIdx.x * kTaskThreads; t0 < n_tasks; t0 += gridDim.x * kTaskThreads) {
-        const uint32_t t = t0 + tid;
-        const uint32_t word = t < n_tasks ? a.em_tasks[t] : kEmTaskInvalid;
-        const bool valid = word != kEmTaskInvalid;
-        const uint32_t hdr = word & 0x0fffffffu, subset = word >> 28;
-        __syncthreads();   // the previous round's readers of cs.bins / cs.hdr_of are done
-        cs.hdr_of[tid] = valid ? hdr : kEmTaskInvalid;
-        __syncthreads();
-        // staging rows: one per run of equal headers (the tasks of a site are consecutive)
-        const bool leader = valid && (tid == 0 || cs.hdr_of[tid - 1] != hdr);
-        const uint32_t bal = __ballot_sync(kFull, leader);
-        if (lane == 0) cs.warp_leaders[warp] = (uint32_t)__popc(bal);
-        __syncthreads();
-        uint32_t row = (uint32_t)__popc(bal & ((2u << lane) - 1u)) - 1u;   // leaders up to and including this thread, minus one
-        for (int w = 0; w < warp; ++w) row += cs.warp_leaders[w];
-        // (a non-leader's row is the row of the last leader before it; a CTA's first valid thread is always a leader)
-        if (leader) cs.slot_hdr[row] = hdr;
-        uint32_t n_rows = 0;
-        for (int w = 0; w < kTaskThreads / 32; ++w) n_rows += cs.warp_leaders[w];
-        __syncthreads();
-        for (uint32_t r = warp; r < n_rows; r += kTaskThreads / 32) {
-            const EmSiteHdr& H = a.em_hdr[cs.slot_hdr[r]];
-            const uint32_t nb = H.nb, off = H.bins_off;
-            if (nb <= (uint32_t)kStageBins)
-                for (uint32_t i = lane; i < nb; i += 32) cs.bins[r * kStageStride + i] = a.em_pool[off + i];
-        }
-        __syncthreads();
-        if (valid) {
-            const EmSiteHdr& H = a.em_hdr[hdr];
-            const uint32_t* bins = H.nb <= (uint32_t)kStageBins ? cs.bins + row * kStageStride : a.em_pool + H.bins_off;
-            em_task(a, cs, H, bins, subset, a.em_res + (size_t)t * kEmResDoubles);
-        }
-    }
-}
-
-// =====================================================================================================================
-// K4c: one thread per EM site: backward elimination on the task results, ALT / AF / QUAL, FS of the VCF row.
-// =====================================================================================================================
-__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHdr& H) {
+// ---- the site's decision, after its last task has finished ----------------------------------------------------------------------
+// Backward elimination (src/basetype.cpp:144-168) on the task results, ALT / AF / QUAL (:170-196), FS of the VCF row.
+// bins: the site's bins (this thread's staging row or the pool).
+__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const double* lut, const EmSiteHdr& H, const uint32_t* bins) {
     const uint32_t site = H.site;
     bv_site_out* rec = a.out + site;
     const int ref_code = ref_code_of(a.ref_base[site]);
     const uint32_t dep[4] = {H.depth[0], H.depth[1], H.depth[2], H.depth[3]};
     const uint32_t total = H.total;
     const double dtot = (double)total;
-    uint32_t act = H.act & 0xfu;
+    const uint32_t act0 = H.act_flags & 0xfu;
+    uint32_t act = act0;
     int n_act = __popc(act);
-    uint32_t flags = H.flags;
-    const uint32_t tmask = em_task_mask(act);
-    auto result = [&](uint32_t sub) { return a.em_res + (size_t)(H.task0 + (uint32_t)__popc(tmask & ((1u << sub) - 1u))) * kEmResDoubles; };
-
-    // (src/basetype.cpp:144-168) full model, then backward elimination
+    uint32_t flags = H.act_flags >> 8;
+    // result of the task of subset `sub`: tasks of one size are listed in ascending subset order
+    auto result = [&](uint32_t sub) {
+        const int k = __popc(sub);
+        uint32_t below = 0;
+        for (uint32_t m = 3; m < sub; ++m) below += ((m & ~act0) == 0u && __popc(m) == k) ? 1u : 0u;
+        return a.em_res + (size_t)(H.task[k - 2] + below) * kEmResDoubles;
+    };
     const double* r0 = result(act);
-    double lr_alt = r0[0];
-    double res_f[4] = {r0[1], r0[2], r0[3], r0[4]};
-    flags |= (uint32_t)__double_as_longlong(r0[5]);
+    double lr_alt = __ldcg(r0);
+    double res_f[4] = {__ldcg(r0 + 1), __ldcg(r0 + 2), __ldcg(r0 + 3), __ldcg(r0 + 4)};
+    flags |= (uint32_t)__double_as_longlong(__ldcg(r0 + 5));
     double chi = 0.0;
     uint32_t em_calls = 1;
 #pragma unroll 1
     for (int n = n_act - 1; n > 0; --n) {
         // the n-subsets of the n+1 active bases in the lexicographic order of
         // src/external/combinations.h:19-84: the i-th subset drops the (n-i)-th active base
+        double single_ll[2] = {0.0, 0.0};
+        if (n == 1) {
+            // Log-likelihoods of the two single-allele models (EMs whose answer is closed form): after the first M-step
+            // f_b == 1.0 exactly (every posterior is x/x), so every later marginal is L_b itself and the reported log marginal
+            // is log(1-eps) or log(eps/3), both tabulated on the host with glibc.  A bin of base b with phred 0 has
+            // L_b == 0: the reference then divides 0/0 and everything becomes NaN.
+            const int b0 = __ffs(act) - 1, b1 = 31 - __clz(act);
+            bool bad0 = false, bad1 = false;
+            for (int i = 0; i < (int)H.nb; ++i) {
+                const uint32_t p = bins[i];
+                const int b = (int)bin_base(p);
+                const uint32_t q = bin_qual(p);
+                const double cd = (double)bin_count(p);
+                const double lm = lut[kLutLogMatch * kQSlots + q], lx = lut[kLutLogMis * kQSlots + q];
+                single_ll[0] += cd * (b == b0 ? lm : lx);
+                single_ll[1] += cd * (b == b1 ? lm : lx);
+                bad0 = bad0 || (b == b0 && q == 0);
+                bad1 = bad1 || (b == b1 && q == 0);
+            }
+            if (bad0) single_ll[0] = __longlong_as_double(0x7ff8000000000000ll);
+            if (bad1) single_ll[1] = __longlong_as_double(0x7ff8000000000000ll);
+        }
         double best_chi = 0, best_lr = 0, best_f[4] = {0, 0, 0, 0};
         uint32_t best_set = 0;
 #pragma unroll 1
@@ -418,17 +573,19 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
             const uint32_t sub = act & ~(1u << nth_active(kOrderACGT, act, n - i));
             double f0sum = 0.0;   // the subset's initial frequencies, summed in A,C,G,T order
 #pragma unroll
-            for (int j = 0; j < 4; ++j) f0sum += (sub >> j & 1u) ? (double)dep[j] / dtot : 0.0;
+            for (int b = 0; b < 4; ++b) f0sum += (sub >> b & 1u) ? (double)dep[b] / dtot : 0.0;
             if (f0sum == 0) flags |= BV_FLAG_ZERO_SUBSET;   // the reference throws (basetype.cpp:113)
             double lr, f[4] = {0, 0, 0, 0};
             if (n == 1) {
                 const int single = __ffs(sub) - 1;
-                lr = H.single_ll[single];
-                f[single] = (lr != lr) ? lr : 1.0;
+                lr = single == __ffs(act) - 1 ? single_ll[0] : single_ll[1];
+                const double v = (lr != lr) ? lr : 1.0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) if (b == single) f[b] = v;
             } else {
                 const double* r = result(sub);
-                lr = r[0]; f[0] = r[1]; f[1] = r[2]; f[2] = r[3]; f[3] = r[4];
-                flags |= (uint32_t)__double_as_longlong(r[5]);
+                lr = __ldcg(r); f[0] = __ldcg(r + 1); f[1] = __ldcg(r + 2); f[2] = __ldcg(r + 3); f[3] = __ldcg(r + 4);
+                flags |= (uint32_t)__double_as_longlong(__ldcg(r + 5));
             }
             if (em_calls < 255) ++em_calls;
             const double c = 2 * (lr_alt - lr);
@@ -459,16 +616,13 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
     const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
     const uint32_t alt_set = act & ~ref_bit;
     const int n_alt = __popc(alt_set);
-    double qual = 0.0;
+    double qual = 0.0, fs_vcf = 0.0;
     if (n_alt) {
         const int first_act = __ffs(act) - 1;
         const double r = (double)dep[first_act] / dtot;
         if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
         else qual = qual_from_chi(chi);
-    }
-    // ---- strand bias of the VCF row, ref vs the called ALT alleles (src/basetype.cpp:244-295, basetype_caller.cpp:1164) ----
-    double fs_vcf = 0.0;
-    if (n_alt) {
+        // strand bias of the VCF row, ref vs the called ALT alleles (src/basetype.cpp:244-295, basetype_caller.cpp:1164)
         const uint32_t f[4] = {rec->fwd[0], rec->fwd[1], rec->fwd[2], rec->fwd[3]};
         const uint32_t rv[4] = {rec->rev[0], rec->rev[1], rec->rev[2], rec->rev[3]};
         int rf = 0, rr = 0, vf = 0, vr = 0, af_ = 0, ar = 0;
@@ -486,8 +640,14 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
     int k = 0;
     double af[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-        if (alt_set >> b & 1u) { af[k] = res_f[b]; alts |= (uint32_t)b << (8 * k); ++k; }
+    for (int b = 0; b < 4; ++b) {
+        if (alt_set >> b & 1u) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) if (kk == k) af[kk] = res_f[b];
+            alts |= (uint32_t)b << (8 * k);
+            ++k;
+        }
+    }
     uint32_t* w = reinterpret_cast<uint32_t*>(rec);
     w[kWState] = kStateDone;
     w[kWAlt] = (uint32_t)n_alt | (alts << 8);                       // n_alt, alt[0..2]
@@ -500,9 +660,81 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
     if (n_alt && a.list_called) a.list_called[atomicAdd(a.counters + kCntCalled, 1u)] = site;
 }
 
-__global__ void __launch_bounds__(128) bv_decide_kernel(const __grid_constant__ SiteKernelArgs a) {
-    const uint32_t n_hdr = a.counters[kCntEmHdr];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hdr; i += gridDim.x * blockDim.x) decide_site(a, a.em_hdr[i]);
+__global__ void __launch_bounds__(kTaskThreads) bv_em_task_kernel(const __grid_constant__ SiteKernelArgs a) {
+    TaskCta& cs = *reinterpret_cast<TaskCta*>(bv_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 4 * kQSlots; i += kTaskThreads) cs.lut[i / kQSlots][i % kQSlots] = a.lut[(i / kQSlots) * kQStride + i % kQSlots];
+    const double* lut = &cs.lut[0][0];
+    // the three task lists, one after the other
+    uint32_t n_list[3], blk_end[3], base[3];
+    n_list[0] = min(a.counters[kCntEmTask2], a.em_task_cap[0]);
+    n_list[1] = min(a.counters[kCntEmTask3], a.em_task_cap[1]);
+    n_list[2] = min(a.counters[kCntEmTask4], a.em_task_cap[2]);
+    base[0] = 0; base[1] = a.em_task_cap[0]; base[2] = a.em_task_cap[0] + a.em_task_cap[1];
+    // Lanes per task: one -- a thread per task -- unless the tile has so few tasks that most of the GPU would stand idle
+    // behind their serial chains: then four (the sums are formed the same way either way, see LaneGroup).
+    LaneGroup lg;
+    {
+        const uint64_t n_tasks = (uint64_t)n_list[0] + n_list[1] + n_list[2];
+        int G = n_tasks <= (uint64_t)BV_TASK_G4_MAX_TASKS ? 4 : 1;
+#ifdef BV_TASK_FORCE_G
+        G = BV_TASK_FORCE_G;   // tuning builds (1 or 4)
+#endif
+        lg.G = G;
+        lg.gl = lane & (G - 1);
+        lg.mask = (G == 1 ? 1u : 0xfu) << (lane & ~(G - 1));
+    }
+    const uint32_t tpc = (uint32_t)(kTaskThreads / lg.G);   // tasks per CTA and round
+    const uint32_t slot = (uint32_t)tid / (uint32_t)lg.G;    // this thread's task of the round = its staging row
+    blk_end[0] = (n_list[0] + tpc - 1) / tpc;
+    blk_end[1] = blk_end[0] + (n_list[1] + tpc - 1) / tpc;
+    blk_end[2] = blk_end[1] + (n_list[2] + tpc - 1) / tpc;
+#pragma unroll 1
+    for (uint32_t v = blockIdx.x; v < blk_end[2]; v += gridDim.x) {
+        const int li = v < blk_end[0] ? 0 : v < blk_end[1] ? 1 : 2;   // (CTA-uniform) tasks of one subset size per round
+        const uint32_t idx = (v - (li ? blk_end[li - 1] : 0u)) * tpc + slot;
+        const uint32_t t = base[li] + idx;
+        const uint32_t word = idx < n_list[li] ? a.em_tasks[t] : kEmTaskInvalid;
+        const bool valid = word != kEmTaskInvalid;
+        const uint32_t hdr = word & 0x0fffffffu, subset = word >> 28;
+        __syncthreads();   // the previous round's readers of cs.bins are done (first round: the tables are written)
+        if (tid == 0) cs.n_decide = 0;
+        EmSiteHdr* const Hg = a.em_hdr + hdr;
+        EmSiteHdr H;
+        const uint32_t* bins = nullptr;
+        if (valid) {
+            H = *Hg;
+            // the site's bins into this task's row (the group's lanes share the copy); longer lists are read from the pool
+            if (H.nb <= (uint32_t)kStageBins) {
+                for (uint32_t i = lg.gl; i < H.nb; i += lg.G) cs.bins[slot * kStageStride + i] = a.em_pool[H.bins_off + i];
+                bins = cs.bins + slot * kStageStride;
+            } else {
+                bins = a.em_pool + H.bins_off;
+            }
+        }
+        __syncthreads();
+        if (valid) {
+            double* res = a.em_res + (size_t)t * kEmResDoubles;
+            if (li == 0) em_task<2>(a, lut, H, bins, subset, res, lg);
+            else if (li == 1) em_task<3>(a, lut, H, bins, subset, res, lg);
+            else em_task<4>(a, lut, H, bins, subset, res, lg);
+            if (lg.gl == 0) {
+                __threadfence();
+                if (atomicSub(&Hg->remaining, 1u) == 1u) {   // every task of the site has stored its result: queue the decision
+                    const uint32_t k = atomicAdd(&cs.n_decide, 1u);
+                    cs.decide_hdr[k] = hdr; cs.decide_row[k] = slot;
+                }
+            }
+        }
+        __syncthreads();
+        // the decisions of this round, one thread per site (scalar work: a lane per site keeps the warps full)
+        if ((uint32_t)tid < cs.n_decide) {
+            __threadfence();
+            const EmSiteHdr Hd = a.em_hdr[cs.decide_hdr[tid]];
+            const uint32_t* dbins = Hd.nb <= (uint32_t)kStageBins ? cs.bins + cs.decide_row[tid] * kStageStride : a.em_pool + Hd.bins_off;
+            decide_site(a, lut, Hd, dbins);
+        }
+    }
 }
 
 }  // namespace bv

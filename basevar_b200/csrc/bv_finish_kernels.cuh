@@ -77,11 +77,13 @@ __device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_
         if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(a.logfact, rf, rr, af_, ar);
     }
     uint32_t state = need_qual ? kStateEM : kStateDone;
+    // the active set travels in bits 8-11 of the alt word (K4a), the minor allele of a bound site in bits 0-1 (K3)
+    if (need_qual) rec[kWAlt] = act << 8;
     if (n_act == 2 && (act & ref_bit)) {
         const int o_code = __ffs(act & ~ref_bit) - 1;
         if (sel4u(ref_code, d0, d1, d2, d3) >= 22 && sel4u(o_code, d0, d1, d2, d3) <= 4) {
             state = kStateBound;
-            rec[kWAlt] = (uint32_t)o_code;
+            rec[kWAlt] = (uint32_t)o_code | (act << 8);
         }
     }
     // n_active | flags | em_calls (a single active allele costs the reference one EM call)
@@ -163,9 +165,11 @@ __global__ void __launch_bounds__(kBoundWarps * 32, 1) bv_bound_kernel(const __g
         const bool valid = g * 32u + lane < n_bound;
         const uint32_t my_site = valid ? a.list_bound[g * 32u + lane] : 0u;
         const uint32_t todo = __ballot_sync(kFull, valid);
-        uint32_t my_o = 0, my_info = 0;
+        uint32_t my_o = 0, my_info = 0, my_act = 0;
         if (valid) {
-            my_o = g_out[(size_t)my_site * 32 + kWAlt] & 3u;
+            my_o = g_out[(size_t)my_site * 32 + kWAlt];
+            my_act = my_o & 0xf00u;
+            my_o &= 3u;
             my_info = g_out[(size_t)my_site * 32 + kWInfo];
         }
         // producer cursor over the units (site, chunk) of this group: one unit ahead of the scan
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kBoundWarps * 32, 1) bv_bound_kernel(const __g
             const bool pass = bad == 0 && G < kBoundLimit;
             if (lane == l) {
                 uint32_t* rec = g_out + (size_t)my_site * 32;
-                rec[kWAlt] = 0;
+                rec[kWAlt] = pass ? 0u : my_act;
                 // pass: single active allele REF, no EM ran: n_active 1, em_calls 0
                 if (pass) rec[kWInfo] = (1u << 8) | (((my_info >> 16) & 0xffu) | BV_FLAG_LRT_BOUND) << 16;
                 rec[kWState] = pass ? kStateDone : kStateEM;
@@ -362,6 +366,27 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
     if (lane == 0) W.p2_phase = phase;
 }
 
+// phred range of the counted cells of W.hist as qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell):
+// lane l looks at slots l, l + 32, l + 64
+__device__ __forceinline__ uint32_t hist_phred_range() {
+    QualWarp& W = warp_smem();
+    const int lane = threadIdx.x & 31;
+    uint32_t nz[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int q = lane + 32 * r;
+        nz[r] = W.hist[q] | W.hist[kQSlots + q] | W.hist[2 * kQSlots + q] | W.hist[3 * kQSlots + q] | W.hist[4 * kQSlots + q];
+    }
+    const uint32_t m0 = __ballot_sync(kFull, nz[0] != 0), m1 = __ballot_sync(kFull, nz[1] != 0), m2 = __ballot_sync(kFull, nz[2] != 0);
+    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
+    if (m0 | m1 | m2) {
+        qmin = m0 ? (uint32_t)__ffs(m0) - 1u : m1 ? 31u + (uint32_t)__ffs(m1) : 63u + (uint32_t)__ffs(m2);
+        qmax = m2 ? 95u - (uint32_t)__clz(m2) : m1 ? 63u - (uint32_t)__clz(m1) : 31u - (uint32_t)__clz(m0);
+    }
+    if (qmax > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;   // phred > 93: outside the reference's table (slots 94, 95)
+    return qmin | (qmax << 8) | (flags << 16);
+}
+
 // (base, phred) histogram of the covered cells of one row into W.hist
 // (BaseType::BaseType, src/basetype.cpp:45-71: one likelihood row per counted read, a function of base and phred only).
 // Returns qmin | qmax << 8 | flags << 16 (qmin > qmax: no counted cell).
@@ -377,17 +402,25 @@ __device__ __forceinline__ void for_each_p2_chunk(uint32_t site, F&& f) {
 #ifndef BV_HIST_DENSE_TRIPS
 #define BV_HIST_DENSE_TRIPS 7
 #endif
-__device__ __forceinline__ void hist_word_dense(uint32_t* hist, uint32_t wb, uint32_t wq, uint32_t t, int k) {
+// hist[idx] += 1 for the lanes with `on`, as ONE predicated instruction (no branch around it)
+__device__ __forceinline__ void hist_add_if(uint32_t hist_s, uint32_t idx, uint32_t on) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.u32 p, %0, 0;\n\t"
+        "@p red.shared.add.u32 [%1], 1;\n\t"
+        "}" ::"r"(on), "r"(hist_s + 4u * idx) : "memory");
+}
+__device__ __forceinline__ void hist_word_dense(uint32_t hist_s, uint32_t wb, uint32_t wq, uint32_t t, int k) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const uint32_t b = (wb >> (8 * j)) & 0xffu, q = (wq >> (8 * j)) & 0xffu;
-        if (t & (1u << (8 * j + k))) atomicAdd(&hist[b * kQSlots + q], 1u);
+        hist_add_if(hist_s, b * kQSlots + q, t & (1u << (8 * j + k)));
     }
 }
 
 __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, uint32_t g) {
     QualWarp& W = warp_smem();
-    const int lane = threadIdx.x & 31;
     const uint32_t gw = g * 0x01010101u;
     for_each_p2_chunk(site, [&](const uint8_t* cellp, const uint4& vb, int lane_cells, uint32_t cell0) {
         // t: bit (8*j + k) set <=> byte j of word k holds a counted base code (< 5)
@@ -409,10 +442,11 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, u
         if (n >= BV_HIST_DENSE_TRIPS) {
             // phred > 95 shares the last slot (bytes >= 0x80 never occur next to a counted base in a valid tile; they clamp too)
             const uint4 vq = *reinterpret_cast<const uint4*>(cellp + kP2Chunk);
-            hist_word_dense(W.hist, vb.x, __vminu4(vq.x, 0x5f5f5f5fu), t, 0);
-            hist_word_dense(W.hist, vb.y, __vminu4(vq.y, 0x5f5f5f5fu), t, 1);
-            hist_word_dense(W.hist, vb.z, __vminu4(vq.z, 0x5f5f5f5fu), t, 2);
-            hist_word_dense(W.hist, vb.w, __vminu4(vq.w, 0x5f5f5f5fu), t, 3);
+            const uint32_t hist_s = smem_u32(W.hist);
+            hist_word_dense(hist_s, vb.x, __vminu4(vq.x, 0x5f5f5f5fu), t, 0);
+            hist_word_dense(hist_s, vb.y, __vminu4(vq.y, 0x5f5f5f5fu), t, 1);
+            hist_word_dense(hist_s, vb.z, __vminu4(vq.z, 0x5f5f5f5fu), t, 2);
+            hist_word_dense(hist_s, vb.w, __vminu4(vq.w, 0x5f5f5f5fu), t, 3);
         } else {
 #pragma unroll 1
             for (int i = 0; i < n; ++i) {
@@ -430,21 +464,128 @@ __device__ __noinline__ uint32_t build_hist(uint32_t site, const uint8_t* grp, u
         }
     });
     __syncwarp();
-    // phred range of the counted cells, from the histogram: lane l looks at slots l, l + 32, l + 64
-    uint32_t nz[3];
+    return hist_phred_range();
+}
+
+// ---- the same histogram for LONG rows (n_samples > kLongRowSamples): K4a only ------------------------------------------------
+// A 100,000-sample row at 0.1x has 1.6 counted cells per 16-cell vector, but the warp runs as many trips of the cell loop as
+// its FULLEST lane has cells (5 to 6): two thirds of the issue slots go to lanes that have run out.  Here a lane owns four
+// vectors of a 2,048-cell chunk and walks one 64-bit mask of their 64 cells: the fullest of 32 lanes then has ~12 cells
+// where the mean is 6.4, the fetch / wait / loop overhead of a chunk is paid once per four vectors, and the warp count
+// per SM is halved to make room for the larger buffers (16 warps x 2 buffers x 4 KB).
+#ifndef BV_LONG_WARPS
+#define BV_LONG_WARPS 16
+#endif
+#ifndef BV_LONG_VPL
+#define BV_LONG_VPL 4
+#endif
+constexpr int kLongWarps = BV_LONG_WARPS;
+constexpr int kLongVpl = BV_LONG_VPL;         // 16-cell vectors per lane and chunk: 2 or 4
+constexpr int kLongChunk = 512 * kLongVpl;    // cells per buffer and plane
+static_assert(kLongVpl == 2 || kLongVpl == 4, "BV_LONG_VPL must be 2 or 4");
+struct __align__(128) LongBuf {
+    uint8_t base[kLongChunk];
+    uint8_t qual[kLongChunk];
+};
+constexpr size_t kHistLongSmemBytes = sizeof(QualCta) + (size_t)kLongWarps * (sizeof(QualWarp) + 2 * sizeof(LongBuf));
+static_assert(kHistLongSmemBytes <= 232448, "shared memory of the long-row histogram kernel exceeds 227 KB");
+__device__ __forceinline__ LongBuf* long_bufs() {
+    return reinterpret_cast<LongBuf*>(bv_smem_raw + sizeof(QualCta) + (size_t)kLongWarps * sizeof(QualWarp)) + 2 * (threadIdx.x >> 5);
+}
+
+// bit (4k + j) of the result: byte j of word k of the vector holds a counted base code (< 5)
+__device__ __forceinline__ uint32_t counted_mask16(const uint4& vb) {
+    const uint32_t w[4] = {vb.x, vb.y, vb.z, vb.w};
+    uint32_t t = 0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int q = lane + 32 * r;
-        nz[r] = W.hist[q] | W.hist[kQSlots + q] | W.hist[2 * kQSlots + q] | W.hist[3 * kQSlots + q] | W.hist[4 * kQSlots + q];
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t c = ~(((w[k] | 0x80808080u) - 0x05050505u) | w[k]) & 0x80808080u;   // bit 7 of every counted byte
+        // the four bits 7, 15, 23, 31 land in bits 32..35 of the 64-bit product (all other partial products miss them)
+        t |= (__umulhi(c, 0x02040810u) & 0xfu) << (4 * k);
     }
-    const uint32_t m0 = __ballot_sync(kFull, nz[0] != 0), m1 = __ballot_sync(kFull, nz[1] != 0), m2 = __ballot_sync(kFull, nz[2] != 0);
-    uint32_t qmin = 0xffu, qmax = 0, flags = 0;
-    if (m0 | m1 | m2) {
-        qmin = m0 ? (uint32_t)__ffs(m0) - 1u : m1 ? 31u + (uint32_t)__ffs(m1) : 63u + (uint32_t)__ffs(m2);
-        qmax = m2 ? 95u - (uint32_t)__clz(m2) : m1 ? 63u - (uint32_t)__clz(m1) : 31u - (uint32_t)__clz(m0);
+    return t;
+}
+
+__device__ __noinline__ uint32_t build_hist_long(uint32_t site) {
+    QualWarp& W = warp_smem();
+    const QualCta& cs = cta_shared();
+    LongBuf* const LB = long_bufs();
+    const int lane = threadIdx.x & 31;
+    const uint32_t N = cs.a.n_samples;
+    const uint32_t row_bytes = (N + 15u) & ~15u;
+    const uint32_t nchunk = (row_bytes + kLongChunk - 1) / kLongChunk;
+    const uint8_t* gb = cs.a.base + (size_t)site * cs.a.pitch;
+    const uint8_t* gq = cs.a.qual + (size_t)site * cs.a.qual_pitch;
+    const uint32_t s_buf0 = smem_u32(LB), s_bar0 = smem_u32(&W.p2bar[0]), hist_s = smem_u32(W.hist);
+    uint32_t phase = W.p2_phase;
+    auto fetch = [&](uint32_t c) {   // lane 0: chunk c into buffer c & 1
+        const uint32_t off = c * kLongChunk;
+        const uint32_t bytes = min((uint32_t)kLongChunk, row_bytes - off);
+        const uint32_t b = c & 1u;
+        const uint32_t bar = s_bar0 + 8u * b, dst = s_buf0 + (uint32_t)sizeof(LongBuf) * b;
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_g2s(dst, gb + off, bytes, bar);
+        bulk_g2s(dst + kLongChunk, gq + off, bytes, bar);
+    };
+    if (lane == 0) fetch(0);
+#pragma unroll 1
+    for (uint32_t c = 0; c < nchunk; ++c) {
+        const uint32_t buf = c & 1u;
+        if (c + 1 < nchunk && lane == 0) fetch(c + 1);   // into the buffer chunk c - 1 used (all lanes are past it: __syncwarp below)
+        mbar_wait(s_bar0 + 8u * buf, (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        const uint8_t* const cb = LB[buf].base + lane * 16;   // this lane's vector v is at cb + 512 v, its quals kLongChunk further
+        // counted cells of this lane's vectors: vectors 0, 1 in lo (bit 16 v + cell), vectors 2, 3 in hi
+        uint32_t lo = 0, hi = 0;
+        uint4 vbs[kLongVpl];
+#pragma unroll
+        for (int v = 0; v < kLongVpl; ++v) {
+            const int lane_cells = (int)N - (int)(c * kLongChunk) - v * 512 - lane * 16;
+            uint4 vb = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);
+            if (lane_cells > 0) vb = *reinterpret_cast<const uint4*>(cb + 512 * v);
+            if (lane_cells < 16) mask_tail(vb, lane_cells);
+            vbs[v] = vb;
+            const uint32_t tv = counted_mask16(vb) << (16 * (v & 1));
+            if (v < 2) lo |= tv; else hi |= tv;
+        }
+        const int n = (int)__reduce_max_sync(kFull, (uint32_t)(__popc(lo) + __popc(hi)));
+        if (n >= kLongVpl * BV_HIST_DENSE_TRIPS) {
+#pragma unroll
+            for (int v = 0; v < kLongVpl; ++v) {
+                const uint4 vq = *reinterpret_cast<const uint4*>(cb + 512 * v + kLongChunk);
+                const uint32_t wb[4] = {vbs[v].x, vbs[v].y, vbs[v].z, vbs[v].w};
+                const uint32_t wq[4] = {__vminu4(vq.x, 0x5f5f5f5fu), __vminu4(vq.y, 0x5f5f5f5fu), __vminu4(vq.z, 0x5f5f5f5fu), __vminu4(vq.w, 0x5f5f5f5fu)};
+                const uint32_t tv = ((v < 2 ? lo : hi) >> (16 * (v & 1))) & 0xffffu;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t b = (wb[k] >> (8 * j)) & 0xffu, q = (wq[k] >> (8 * j)) & 0xffu;
+                        hist_add_if(hist_s, b * kQSlots + q, tv & (1u << (4 * k + j)));
+                    }
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) {
+                // this lane's next counted cell: from lo while it has any, then from hi (32-bit operations only)
+                const bool in_lo = lo != 0u;
+                const uint32_t w = in_lo ? lo : hi;
+                int top;
+                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(w));
+                const uint32_t rest = w & ~(1u << (top & 31));
+                lo = in_lo ? rest : lo;
+                hi = in_lo ? hi : rest;
+                const int at = (in_lo ? 0 : 1024) + ((top & 16) << 5) + (top & 15);   // vector 2 * (hi) + (top >> 4), cell top & 15
+                hist_add_if(hist_s, (uint32_t)cb[at & (kLongChunk - 1)] * kQSlots + min((uint32_t)cb[(at & (kLongChunk - 1)) + kLongChunk], (uint32_t)(kQSlots - 1)),
+                            w != 0u);   // phred > 95 shares the last slot
+            }
+        }
+        __syncwarp();
     }
-    if (qmax > BV_QUAL_MAX) flags |= BV_FLAG_BAD_QUAL;   // phred > 93: outside the reference's table (slots 94, 95)
-    return qmin | (qmax << 8) | (flags << 16);
+    if (lane == 0) W.p2_phase = phase;
+    __syncwarp();
+    return hist_phred_range();
 }
 
 // ---- EM on compact bins (src/algorithm.h:210-255) ----------------------------------------------------------------

@@ -76,11 +76,11 @@ class BaseTypeEngine:
         self._check(self.lib.bv_last_kernel_times(self._ctx, ms), "bv_last_kernel_times")
         return dict(zip(self.KERNEL_NAMES, (float(x) for x in ms)))
 
-    EM_KERNEL_NAMES = ("bv_hist_kernel", "bv_em_task_kernel", "bv_decide_kernel")
+    EM_KERNEL_NAMES = ("bv_hist_kernel", "bv_em_task_kernel")
 
     def last_em_kernel_times(self):
-        """Durations (ms) of the three kernels K4 consists of (histogram, EM tasks, decision) for the same tile."""
-        ms = (C.c_float * 3)()
+        """Durations (ms) of the two kernels K4 consists of (row histograms, EM tasks + decisions) for the same tile."""
+        ms = (C.c_float * 2)()
         self._check(self.lib.bv_last_em_kernel_times(self._ctx, ms), "bv_last_em_kernel_times")
         return dict(zip(self.EM_KERNEL_NAMES, (float(x) for x in ms)))
 
@@ -144,6 +144,39 @@ class BaseTypeEngine:
         for ps, p0 in pending:
             self._check(self.lib.bv_tile_wait(self._ctx, ps, None if out_pinned else out[p0:].ctypes.data), "bv_tile_wait")
         return out
+
+    def sparse_tiles(self, cells, site_start, ref_base, n_samples, out_pinned=None):
+        """The tile descriptors call_sparse would submit, built once (list of ctypes structs + the arrays they point into).
+        out_pinned: pinned SITE_OUT_DTYPE array [S] the records are DMA'd into."""
+        S = ref_base.shape[0]
+        assert cells.dtype in (np.uint32, np.uint16) and site_start.dtype == np.uint32 and site_start.shape[0] == S + 1
+        fmt = capi.CELLS_U16 if cells.dtype == np.uint16 else capi.CELLS_U32
+        step = self.params.max_sites
+        tiles = []
+        for s0 in range(0, max(S, 1), step):
+            ns = min(step, S - s0)
+            c0 = int(site_start[s0])
+            st = np.ascontiguousarray(site_start[s0:s0 + ns + 1] - np.uint32(c0))
+            t = BvSparseTile(cells[c0:].ctypes.data if c0 < cells.shape[0] else cells.ctypes.data, None, st.ctypes.data,
+                             ref_base[s0:].ctypes.data, out_pinned[s0:].ctypes.data if out_pinned is not None else None, ns, n_samples, fmt, 0)
+            tiles.append((t, s0, st))
+        return tiles
+
+    def run_sparse_tiles(self, tiles, repeats=1, out=None):
+        """Submit the tiles `repeats` times over the slots without draining the pipeline in between (the steps of a
+        benchmark run, or the tiles of a long region); every slot is waited for before its next submit and at the end."""
+        n_slots = self.params.n_slots
+        pending, slot = [], 0
+        for _ in range(repeats):
+            for t, s0, _keep in tiles:
+                if len(pending) == n_slots:
+                    ps, p0 = pending.pop(0)
+                    self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data if out is not None else None), "bv_tile_wait")
+                self._check(self.lib.bv_tile_submit_sparse(self._ctx, slot, C.byref(t)), "bv_tile_submit_sparse")
+                pending.append((slot, s0))
+                slot = (slot + 1) % n_slots
+        for ps, p0 in pending:
+            self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data if out is not None else None), "bv_tile_wait")
 
     def call_sparse_calls(self, cells, cells_aux, site_start, ref_base, n_samples):
         """call_sparse plus the called-site outputs; returns what call_host_calls returns."""

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <memory>
 #include <stdexcept>
 
 namespace bvhost {
@@ -109,6 +110,35 @@ uint64_t BgzfReader::tell() const {
     return block_addr_ << 16 | (uint64_t)upos_;
 }
 
+std::vector<std::pair<uint64_t, uint64_t>> BgzfReader::block_table() const {
+    std::vector<std::pair<uint64_t, uint64_t>> t;
+    uint64_t addr = 0, uoff = 0;
+    for (;;) {
+        uint8_t h[12];
+        const size_t got = pread_full(fd_, h, 12, addr);
+        if (got == 0) break;
+        if (got < 12 || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4))
+            throw std::runtime_error("[ERROR] " + path_ + " is not a BGZF file (compress FASTA with bgzip, not gzip)");
+        const unsigned xlen = le16(h + 10);
+        std::vector<uint8_t> extra(xlen);
+        if (pread_full(fd_, extra.data(), xlen, addr + 12) != xlen) throw std::runtime_error("[ERROR] " + path_ + ": truncated BGZF block");
+        int bsize = -1;
+        for (unsigned o = 0; o + 4 <= xlen;) {
+            const unsigned slen = le16(extra.data() + o + 2);
+            if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2 && o + 6 <= xlen) bsize = le16(extra.data() + o + 4);
+            o += 4 + slen;
+        }
+        if (bsize < 0) throw std::runtime_error("[ERROR] " + path_ + " is not a BGZF file (compress FASTA with bgzip, not gzip)");
+        uint8_t tail[4];
+        if (pread_full(fd_, tail, 4, addr + (uint64_t)bsize + 1 - 4) != 4) throw std::runtime_error("[ERROR] " + path_ + ": truncated BGZF block");
+        const uint32_t isize = le32(tail);
+        if (isize) t.emplace_back(addr, uoff);
+        uoff += isize;
+        addr += (uint64_t)bsize + 1;
+    }
+    return t;
+}
+
 size_t BgzfReader::read(void* dst, size_t n) {
     size_t got = 0;
     while (got < n) {
@@ -174,15 +204,24 @@ bool BamReader::sample_name(std::string& out) const {
 void BamReader::load_index() {
     if (index_loaded_) return;
     const std::string& fn = bgzf_.path();
-    std::string idx = fn + ".bai";
+    // fn.bai, fn with its extension replaced by .bai, then the same two with .csi (hts_idx_load's order for BAM)
+    const size_t dot = fn.rfind('.');
+    const std::string stem = dot == std::string::npos ? fn : fn.substr(0, dot);
+    const std::string cand[4] = {fn + ".bai", stem + ".bai", fn + ".csi", stem + ".csi"};
+    std::string idx;
     struct stat st;
-    if (::stat(idx.c_str(), &st) != 0) {
-        const size_t dot = fn.rfind('.');
-        idx = (dot == std::string::npos ? fn : fn.substr(0, dot)) + ".bai";
-        if (::stat(idx.c_str(), &st) != 0) throw std::runtime_error("[ERROR] could not load the index of " + fn + " (.bai; CSI is not supported)");
-    }
-    std::vector<uint8_t> d((size_t)st.st_size);
-    {
+    for (const std::string& c : cand)
+        if (::stat(c.c_str(), &st) == 0) { idx = c; break; }
+    if (idx.empty()) throw std::runtime_error("[ERROR] could not load the index of " + fn + " (.bai or .csi)");
+    std::vector<uint8_t> d;
+    if (idx.size() > 4 && idx.compare(idx.size() - 4, 4, ".csi") == 0) {
+        // a CSI file is BGZF compressed (SAM specification, CSIv1)
+        BgzfReader z(idx);
+        std::vector<uint8_t> buf(1 << 16);
+        size_t n;
+        while ((n = z.read(buf.data(), buf.size())) > 0) d.insert(d.end(), buf.begin(), buf.begin() + n);
+    } else {
+        d.resize((size_t)st.st_size);
         const int fd = ::open(idx.c_str(), O_RDONLY);
         if (fd < 0) throw std::runtime_error("[ERROR] " + idx + " open failure.");
         const size_t got = pread_full(fd, d.data(), d.size(), 0);
@@ -191,9 +230,24 @@ void BamReader::load_index() {
     }
     auto need = [&](size_t o, size_t n) { if (o + n > d.size()) throw std::runtime_error("[ERROR] " + idx + ": truncated index"); };
     need(0, 8);
-    if (memcmp(d.data(), "BAI\1", 4) != 0) throw std::runtime_error("[ERROR] " + idx + " is not a BAI index");
-    const uint32_t n_ref = le32(d.data() + 4);
-    size_t o = 8;
+    size_t o;
+    bool csi = false;
+    if (memcmp(d.data(), "BAI\1", 4) == 0) {
+        idx_min_shift_ = 14; idx_depth_ = 5;
+        o = 4;
+    } else if (memcmp(d.data(), "CSI\1", 4) == 0) {
+        need(4, 12);
+        idx_min_shift_ = (int)le32(d.data() + 4); idx_depth_ = (int)le32(d.data() + 8);
+        const uint32_t l_aux = le32(d.data() + 12);
+        if (idx_min_shift_ < 0 || idx_min_shift_ > 30 || idx_depth_ < 0 || idx_depth_ > 9) throw std::runtime_error("[ERROR] " + idx + ": unsupported CSI geometry");
+        o = 16 + (size_t)l_aux;
+        csi = true;
+    } else {
+        throw std::runtime_error("[ERROR] " + idx + " is neither a BAI nor a CSI index");
+    }
+    need(o, 4);
+    const uint32_t n_ref = le32(d.data() + o); o += 4;
+    const uint32_t meta_bin = (uint32_t)((((uint64_t)1 << (3 * (idx_depth_ + 1))) - 1) / 7 + 1);   // 37450 for BAI: metadata, not chunks
     index_.assign(n_ref, RefIndex());
     for (uint32_t r = 0; r < n_ref; ++r) {
         need(o, 4);
@@ -201,19 +255,23 @@ void BamReader::load_index() {
         RefIndex& R = index_[r];
         R.bins.reserve(n_bin);
         for (uint32_t k = 0; k < n_bin; ++k) {
-            need(o, 8);
-            const uint32_t bin = le32(d.data() + o), n_chunk = le32(d.data() + o + 4); o += 8;
+            need(o, csi ? 16 : 8);
+            const uint32_t bin = le32(d.data() + o);
+            if (csi) o += 8;   // loffset: the per-bin form of the linear index; not needed for correctness (records are filtered)
+            const uint32_t n_chunk = le32(d.data() + o + 4); o += 8;
             need(o, (size_t)n_chunk * 16);
             std::vector<Chunk> cs(n_chunk);
             for (uint32_t c = 0; c < n_chunk; ++c) { cs[c].beg = le64(d.data() + o); cs[c].end = le64(d.data() + o + 8); o += 16; }
-            if (bin != 37450) R.bins.emplace_back(bin, std::move(cs));   // 37450 holds metadata, not chunks
+            if (bin != meta_bin) R.bins.emplace_back(bin, std::move(cs));
         }
         std::sort(R.bins.begin(), R.bins.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
-        need(o, 4);
-        const uint32_t n_intv = le32(d.data() + o); o += 4;
-        need(o, (size_t)n_intv * 8);
-        R.linear.resize(n_intv);
-        for (uint32_t i = 0; i < n_intv; ++i) { R.linear[i] = le64(d.data() + o); o += 8; }
+        if (!csi) {
+            need(o, 4);
+            const uint32_t n_intv = le32(d.data() + o); o += 4;
+            need(o, (size_t)n_intv * 8);
+            R.linear.resize(n_intv);
+            for (uint32_t i = 0; i < n_intv; ++i) { R.linear[i] = le64(d.data() + o); o += 8; }
+        }
     }
     index_loaded_ = true;
 }
@@ -228,19 +286,18 @@ void BamReader::query(int tid, int64_t beg0, int64_t end0) {
     q_tid_ = tid;
     q_beg_ = beg0 < 0 ? 0 : beg0;
     q_end_ = end0;
-    const int64_t max_end = (int64_t)1 << 29;
+    const int64_t max_end = (int64_t)1 << (idx_min_shift_ + 3 * idx_depth_);   // 2^29 for BAI
     if (q_end_ > max_end) q_end_ = max_end;
     if (tid < 0 || (size_t)tid >= index_.size() || q_beg_ >= q_end_) { finished_ = true; return; }
     const RefIndex& R = index_[(size_t)tid];
-    // bins that may hold records overlapping [beg, end): SAM specification section 5.3 (reg2bins)
+    // bins that may hold records overlapping [beg, end): SAM specification section 5.3 (reg2bins), for any (min_shift, depth)
     std::vector<uint32_t> bins;
     const int64_t b = q_beg_, e = q_end_ - 1;
-    bins.push_back(0);
-    for (int64_t k = 1 + (b >> 26); k <= 1 + (e >> 26); ++k) bins.push_back((uint32_t)k);
-    for (int64_t k = 9 + (b >> 23); k <= 9 + (e >> 23); ++k) bins.push_back((uint32_t)k);
-    for (int64_t k = 73 + (b >> 20); k <= 73 + (e >> 20); ++k) bins.push_back((uint32_t)k);
-    for (int64_t k = 585 + (b >> 17); k <= 585 + (e >> 17); ++k) bins.push_back((uint32_t)k);
-    for (int64_t k = 4681 + (b >> 14); k <= 4681 + (e >> 14); ++k) bins.push_back((uint32_t)k);
+    for (int l = 0; l <= idx_depth_; ++l) {
+        const int sh = idx_min_shift_ + 3 * (idx_depth_ - l);
+        const int64_t t = (((int64_t)1 << (3 * l)) - 1) / 7;
+        for (int64_t k = t + (b >> sh); k <= t + (e >> sh); ++k) bins.push_back((uint32_t)k);
+    }
     // records starting before this offset end before the 16-kb window of beg: they cannot overlap
     uint64_t min_off = 0;
     if (!R.linear.empty()) {
@@ -317,9 +374,18 @@ bool BamReader::next(BamRec& rec) {
 }
 
 // ---- FASTA --------------------------------------------------------------------------------------------------------------
+// A ".gz" reference must be BGZF (bgzip), as for htslib's faidx (src/fasta.cpp:9-48 -> fai_load): offsets in the .fai index
+// are offsets into the UNCOMPRESSED text; the block table maps them to BGZF virtual offsets.
 Fasta::Fasta(const std::string& path) : path_(path) {
-    if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0)
-        throw std::invalid_argument("[ERROR] compressed FASTA is not supported: " + path);
+    {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw std::invalid_argument("[ERROR] " + path + " open failure.");
+        uint8_t h[2] = {0, 0};
+        const size_t got = pread_full(fd, h, 2, 0);
+        ::close(fd);
+        bgzf_ = got == 2 && h[0] == 31 && h[1] == 139;
+    }
+    if (bgzf_) blocks_ = BgzfReader(path).block_table();
     std::ifstream fai(path + ".fai");
     if (!fai) { build_index(); return; }
     std::string line;
@@ -340,8 +406,13 @@ Fasta::Fasta(const std::string& path) : path_(path) {
 }
 
 void Fasta::build_index() {
-    FILE* f = fopen(path_.c_str(), "rb");
-    if (!f) throw std::invalid_argument("[ERROR] " + path_ + " open failure.");
+    FILE* f = nullptr;
+    std::unique_ptr<BgzfReader> z;
+    if (bgzf_) z.reset(new BgzfReader(path_));
+    else {
+        f = fopen(path_.c_str(), "rb");
+        if (!f) throw std::invalid_argument("[ERROR] " + path_ + " open failure.");
+    }
     std::vector<char> buf(1 << 20);
     uint64_t off = 0;
     bool in_name = false, at_line_start = true;
@@ -361,7 +432,7 @@ void Fasta::build_index() {
         entries_.push_back(cur);
     };
     size_t n;
-    while ((n = fread(buf.data(), 1, buf.size(), f)) > 0) {
+    while ((n = z ? z->read(buf.data(), buf.size()) : fread(buf.data(), 1, buf.size(), f)) > 0) {
         for (size_t i = 0; i < n; ++i, ++off) {
             const char c = buf[i];
             if (in_name) {
@@ -383,7 +454,7 @@ void Fasta::build_index() {
     }
     end_line();
     flush();
-    fclose(f);
+    if (f) fclose(f);
 }
 
 const Fasta::Entry& Fasta::entry(const std::string& name) const {
@@ -401,15 +472,25 @@ std::string Fasta::fetch(const std::string& name) const {
     std::string out;
     out.reserve(e.length);
     if (e.length == 0) throw std::invalid_argument("Fasta::fetch - Fetch empty sequence on " + name);   // src/fasta.cpp:65
-    const int fd = ::open(path_.c_str(), O_RDONLY);
-    if (fd < 0) throw std::invalid_argument("[ERROR] " + path_ + " open failure.");
     const uint64_t lines = e.line_bases ? (e.length + e.line_bases - 1) / e.line_bases : 1;
     const uint64_t span = e.length + lines * (e.line_width - e.line_bases);
     std::vector<char> buf(1 << 22);
     uint64_t done = 0;
+    std::unique_ptr<BgzfReader> z;
+    int fd = -1;
+    if (bgzf_) {
+        z.reset(new BgzfReader(path_));
+        auto it = std::upper_bound(blocks_.begin(), blocks_.end(), e.offset, [](uint64_t v, const std::pair<uint64_t, uint64_t>& b) { return v < b.second; });
+        if (it == blocks_.begin()) throw std::invalid_argument("Fasta::fetch - Fail to fetch sequence.");
+        --it;
+        z->seek(it->first << 16 | (e.offset - it->second));
+    } else {
+        fd = ::open(path_.c_str(), O_RDONLY);
+        if (fd < 0) throw std::invalid_argument("[ERROR] " + path_ + " open failure.");
+    }
     while (done < span && out.size() < e.length) {
         const size_t want = (size_t)std::min<uint64_t>(buf.size(), span - done);
-        const size_t got = pread_full(fd, buf.data(), want, e.offset + done);
+        const size_t got = z ? z->read(buf.data(), want) : pread_full(fd, buf.data(), want, e.offset + done);
         if (got == 0) break;
         for (size_t i = 0; i < got && out.size() < e.length; ++i) {
             const char c = buf[i];
@@ -417,7 +498,7 @@ std::string Fasta::fetch(const std::string& name) const {
         }
         done += got;
     }
-    ::close(fd);
+    if (fd >= 0) ::close(fd);
     return out;
 }
 

@@ -14,10 +14,13 @@
 //   BamRecord::mapq / is_duplicate / is_qc_fail /             BamRec fields + helpers below
 //     map_strand / map_ref_start_pos / map_ref_end_pos
 //     src/bam_record.h:132-247
-//   ngslib::Fasta(fn), operator[](ref_id), nseq, iseq_name,   Fasta (plain-text FASTA + .fai; the index is computed
-//     seq_length   src/fasta.cpp:17-95                         in memory when the .fai file is missing)
+//   ngslib::Fasta(fn), operator[](ref_id), nseq, iseq_name,   Fasta: plain-text or BGZF-compressed FASTA (bgzip, the only
+//     seq_length   src/fasta.cpp:17-95                         compressed form faidx accepts) + .fai; the index is computed
+//                                                              in memory when the .fai file is missing, and the block table
+//                                                              of a compressed file (what .gzi stores) is always read off the
+//                                                              BGZF block headers
 //
-// Not supported (the constructor / open() throws): CRAM and SAM input, BGZF-compressed FASTA, CSI indices.
+// Not supported (the constructor / open() throws): CRAM and SAM input, plain-gzip FASTA.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -39,6 +42,9 @@ public:
     uint64_t tell() const;                 // virtual offset of the next byte (start of the next block when one is used up)
     size_t read(void* dst, size_t n);      // bytes read; fewer than n only at end of file
     const std::string& path() const { return path_; }
+    // (compressed address, uncompressed start offset) of every non-empty block, from the block headers alone (no inflate):
+    // what a .gzi index stores.  throws when the file is not BGZF.
+    std::vector<std::pair<uint64_t, uint64_t>> block_table() const;
 
 private:
     bool load_block();                     // the block at next_addr_; false at end of file
@@ -80,7 +86,8 @@ public:
     int name2id(const std::string& name) const;    // -1 when the header does not list it
     bool sample_name(std::string& out) const;      // SM of the first @RG line; false when that line has none (or there is no @RG)
 
-    // Records overlapping [beg0, end0) on tid, through the .bai index (fn + ".bai", else fn with .bam replaced by .bai).
+    // Records overlapping [beg0, end0) on tid, through the index: fn + ".bai", fn with .bam replaced by .bai, or the same
+    // two names with .csi.
     void query(int tid, int64_t beg0, int64_t end0);
     // Without query(): every record of the file in order.  Returns false when the iteration is over.
     bool next(BamRec& rec);
@@ -100,6 +107,7 @@ private:
     std::vector<int64_t> ref_lens_;
     std::vector<RefIndex> index_;
     bool index_loaded_ = false;
+    int idx_min_shift_ = 14, idx_depth_ = 5;   // BAI geometry; a CSI index brings its own
     uint64_t first_record_voffset_ = 0;
     // iterator state
     bool querying_ = false, finished_ = false;
@@ -126,7 +134,10 @@ private:
     struct Entry { uint64_t length, offset, line_bases, line_width; };
     const Entry& entry(const std::string& name) const;
     void build_index();
+    size_t read_at(void* dst, size_t n, uint64_t off) const;   // uncompressed bytes [off, off + n) of the file
     std::string path_;
+    bool bgzf_ = false;
+    std::vector<std::pair<uint64_t, uint64_t>> blocks_;   // BGZF: (compressed address, uncompressed offset) per block
     std::vector<std::string> names_;
     std::vector<Entry> entries_;
 };

@@ -553,7 +553,7 @@ void BasevarCaller::drain(uint32_t slot) {
     T.pending = false;
     std::fill(T.call_of_site.begin(), T.call_of_site.begin() + T.n_sites, -1);
     for (uint32_t k = 0; k < n_calls; ++k) T.call_of_site[T.calls[k].site] = (int32_t)k;
-    std::string cvg_text, vcf_text;
+    std::string cvg_text, vcf_text, flip_text;
     for (uint32_t i = 0; i < T.n_sites; ++i) {
         const SiteCells c{T.base + (size_t)i * T.pitch, T.qual + (size_t)i * T.pitch, T.strand + (size_t)i * T.pitch, (uint32_t)n_sample_};
         const bv_site_out& rec = T.recs[i];
@@ -562,6 +562,13 @@ void BasevarCaller::drain(uint32_t slot) {
             throw std::runtime_error("[ERROR] The sum of frequence of active bases must always > 0. Check: " + T.meta[i].ref_id + ":" +
                                      std::to_string(T.meta[i].ref_pos));
         cvg_text += out_cvg_line(T.meta[i], c, rec);
+        if ((rec.flags & (BV_FLAG_NEAR_LRT | BV_FLAG_LRT_TIE)) && opt_.flip_log) {
+            flip_text += T.meta[i].ref_id + "\t" + std::to_string(T.meta[i].ref_pos) + "\t";
+            if (rec.flags & BV_FLAG_NEAR_LRT) flip_text += "NEAR_LRT";
+            if ((rec.flags & BV_FLAG_NEAR_LRT) && (rec.flags & BV_FLAG_LRT_TIE)) flip_text += ",";
+            if (rec.flags & BV_FLAG_LRT_TIE) flip_text += "LRT_TIE";
+            flip_text += "\n";
+        }
         if (rec.n_alt) {   // only SNPs reach the VCF (cpp:745)
             const int32_t k = T.call_of_site[i];
             if (k < 0) throw std::runtime_error("[BUG] called site without its rank-sum record");
@@ -571,6 +578,7 @@ void BasevarCaller::drain(uint32_t slot) {
     }
     if (!cvg_text.empty() && cvg_) cvg_(cvg_text.data(), cvg_text.size());
     if (!vcf_text.empty() && vcf_) vcf_(vcf_text.data(), vcf_text.size());
+    if (!flip_text.empty()) opt_.flip_log(flip_text.data(), flip_text.size());
     T.n_sites = 0;
 }
 

@@ -40,6 +40,10 @@ struct CallerOptions {
     uint32_t n_slots = 2;
     int em_abs_mode = BV_EM_ABS_INT_TRUNC;
     bool sparse_upload = true;   // tiles whose packer lists its covered cells cross PCIe as bv_sparse_tile (see TileRows)
+    // Receives one line "CHROM\tPOS\tFLAG[,FLAG]\n" per covered position whose record carries BV_FLAG_NEAR_LRT (an LRT
+    // statistic within 1e-9 of the threshold) or BV_FLAG_LRT_TIE (two candidate subsets tie to rounding): the positions
+    // where the call can legitimately differ from the reference's, whose own choice hangs on rounding noise there.
+    std::function<void(const char*, size_t)> flip_log;
 };
 
 // ---- number formatting of the reference's text outputs ---------------------------------------------------------------

@@ -178,14 +178,14 @@ struct BamPileup::Impl {
     uint32_t span_beg = 0, span_end = 0;
 };
 
-BamPileup::BamPileup(const std::vector<std::string>& bam_files, int mapq_thd, int n_threads)
+BamPileup::BamPileup(const std::vector<std::string>& bam_files, int mapq_thd, int n_threads, int n_instances)
     : files_(bam_files), mapq_thd_(mapq_thd), n_threads_(std::max(1, n_threads)), impl_(new Impl) {
     impl_->readers.resize(files_.size());
     impl_->piles.resize(files_.size());
     struct rlimit rl;
     if (getrlimit(RLIMIT_NOFILE, &rl) == 0) {
         if (rl.rlim_cur < rl.rlim_max) { rl.rlim_cur = rl.rlim_max; setrlimit(RLIMIT_NOFILE, &rl); getrlimit(RLIMIT_NOFILE, &rl); }
-        impl_->keep_open = (uint64_t)files_.size() + 256 < (uint64_t)rl.rlim_cur;
+        impl_->keep_open = (uint64_t)files_.size() * (uint64_t)std::max(1, n_instances) + 256 < (uint64_t)rl.rlim_cur;
     }
 }
 
@@ -424,6 +424,8 @@ std::string BaseTypeRunner::usage() {
            "  --gpus=LIST                  Comma delimited CUDA devices to shard the regions over. [0]\n"
            "  --tile-sites=INT             Positions per GPU tile. [8192]\n"
            "  --dense-upload               Upload the packed planes of a tile instead of its covered cells.\n"
+           "  --flip-log=FILE              List the positions whose LRT sat on its threshold or tied (CHROM POS FLAGS):\n"
+           "                               there a call may differ from the CPU caller's, whose choice is rounding noise.\n"
            "  -h, --help                   Show this help message and exit.";
 }
 
@@ -441,7 +443,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
         {"output-vcf", required_argument, NULL, '1'},  {"output-cvg", required_argument, NULL, '2'},
         {"filename-has-samplename", no_argument, NULL, '3'}, {"smart-rerun", no_argument, NULL, '4'},
         {"gpus", required_argument, NULL, '5'},        {"tile-sites", required_argument, NULL, '6'},
-        {"dense-upload", no_argument, NULL, '7'},
+        {"dense-upload", no_argument, NULL, '7'},      {"flip-log", required_argument, NULL, '8'},
         {"help", no_argument, NULL, 'h'},              {0, 0, 0, 0}};
     BaseTypeARGS a;
     optind = 1;
@@ -470,6 +472,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
             }
             case '6': ss >> a.tile_sites; break;
             case '7': a.dense_upload = true; break;
+            case '8': a.flip_log = optarg; break;
             case 'h': std::cout << usage() << std::endl; exit(1);
             default: std::cerr << "Unknown argument: " << (char)c << std::endl; exit(1);
         }
@@ -574,6 +577,52 @@ void BaseTypeRunner::finish_arguments() {
     }
 }
 
+// Text a shard produces before its turn to write: kept in memory up to a bound, then in a temporary file next to the output
+// (the reference spills per-task temporary files and merges them, src/basetype_utils.cpp:90-123).
+namespace {
+class SpillBuffer {
+public:
+    SpillBuffer(std::string path, size_t mem_cap) : path_(std::move(path)), cap_(mem_cap) {}
+    ~SpillBuffer() { discard(); }
+    SpillBuffer(const SpillBuffer&) = delete;
+    SpillBuffer& operator=(const SpillBuffer&) = delete;
+    bool empty() const { return mem_.empty() && !f_; }
+    void append(const char* d, size_t n) {
+        if (!f_ && mem_.size() + n <= cap_) { mem_.append(d, n); return; }
+        if (!f_) {
+            f_ = fopen(path_.c_str(), "wb+");
+            if (!f_) throw std::runtime_error("[ERROR] " + path_ + " open failure.");
+        }
+        if (!mem_.empty()) { put(mem_.data(), mem_.size()); mem_.clear(); mem_.shrink_to_fit(); }
+        put(d, n);
+    }
+    template <class W>
+    void move_to(W& w) {   // everything, in order, into the writer; the buffer is empty afterwards
+        if (f_) {
+            fflush(f_);
+            rewind(f_);
+            std::vector<char> buf(1 << 20);
+            size_t n;
+            while ((n = fread(buf.data(), 1, buf.size(), f_)) > 0) w.write(buf.data(), n);
+        }
+        if (!mem_.empty()) w.write(mem_.data(), mem_.size());
+        discard();
+    }
+    void discard() {
+        if (f_) { fclose(f_); f_ = nullptr; std::remove(path_.c_str()); }
+        mem_.clear();
+    }
+private:
+    void put(const char* d, size_t n) {
+        if (fwrite(d, 1, n, f_) != n) throw std::runtime_error("[ERROR] " + path_ + ": write failure (disk full?)");
+    }
+    std::string path_;
+    size_t cap_;
+    std::string mem_;
+    FILE* f_ = nullptr;
+};
+}  // namespace
+
 void BaseTypeRunner::run() {
     std::vector<std::string> add_group_info;
     for (const auto& kv : groups_idx_)
@@ -596,6 +645,7 @@ void BaseTypeRunner::run() {
     const size_t N = args_.input_bf.size();
     // positions decoded per pass: bounded by the reference's own step and by the memory of the per-sample cell lists
     const uint64_t span_len = std::max<uint64_t>(args_.tile_sites, std::min<uint64_t>(PILEUP_STEP_REGION_LEN, (uint64_t)4e8 / std::max<size_t>(N, 1)));
+    std::string flips;   // positions flagged NEAR_LRT / LRT_TIE, in coordinate order
 
     for (const auto& iv : intervals_) {
         const std::string& ref_id = std::get<0>(iv);
@@ -603,8 +653,18 @@ void BaseTypeRunner::run() {
         const std::string fa_seq = reference_->fetch(ref_id);
         // contiguous shards cut at the reference's 100-kb task boundaries (cpp:474-510), one per GPU
         const std::vector<Shard> shards = shard_region(reg_beg, (uint64_t)reg_end + 1, (int)devices.size());
-        struct ShardOut { std::string vcf, cvg; std::exception_ptr err; uint64_t launches = 0; };
+        // a shard that is not next in line keeps at most 64 MiB of each text in memory; the rest waits in a temporary file
+        struct ShardOut {
+            std::unique_ptr<SpillBuffer> vcf, cvg;
+            std::string flips;
+            std::exception_ptr err;
+            uint64_t launches = 0;
+        };
         std::vector<ShardOut> outs(shards.size());
+        for (size_t si = 0; si < shards.size(); ++si) {
+            outs[si].vcf.reset(new SpillBuffer(args_.output_vcf + ".shard" + std::to_string(si) + ".tmp", (size_t)64 << 20));
+            outs[si].cvg.reset(new SpillBuffer(args_.output_cvg + ".shard" + std::to_string(si) + ".tmp", (size_t)64 << 20));
+        }
         std::mutex out_mu;
         size_t next_to_write = 0;   // shard whose text streams straight to the files; later shards buffer until their turn
         std::vector<bool> done(shards.size(), false);
@@ -618,17 +678,18 @@ void BaseTypeRunner::run() {
                 opt.n_slots = 2;
                 opt.em_abs_mode = args_.em_abs_mode;
                 opt.sparse_upload = !args_.dense_upload;
-                auto sink = [&out_mu, &next_to_write, si](std::string* buf, TextWriter* w) {
+                opt.flip_log = [&O](const char* d, size_t n) { O.flips.append(d, n); };
+                auto sink = [&out_mu, &next_to_write, si](SpillBuffer* buf, TextWriter* w) {
                     return [=, &out_mu, &next_to_write](const char* d, size_t n) {
                         std::lock_guard<std::mutex> g(out_mu);
                         if (si == next_to_write) {   // this shard's turn: earlier text first, then straight to the file
-                            if (!buf->empty()) { w->write(buf->data(), buf->size()); buf->clear(); }
+                            if (!buf->empty()) buf->move_to(*w);
                             w->write(d, n);
                         } else buf->append(d, n);
                     };
                 };
-                BasevarCaller caller(N, groups_idx_, (double)args_.min_af, sink(&O.vcf, &vcf_out), sink(&O.cvg, &cvg_out), opt);
-                BamPileup pile(args_.input_bf, args_.mapq, std::max(1, args_.thread_num / (int)shards.size()));
+                BasevarCaller caller(N, groups_idx_, (double)args_.min_af, sink(O.vcf.get(), &vcf_out), sink(O.cvg.get(), &cvg_out), opt);
+                BamPileup pile(args_.input_bf, args_.mapq, std::max(1, args_.thread_num / (int)shards.size()), (int)shards.size());
                 for (uint64_t sb = sh.beg; sb < sh.end; sb += span_len) {
                     const uint64_t se = std::min<uint64_t>(sb + span_len, sh.end) - 1;
                     if (!pile.load_span(ref_id, fa_seq, reg_beg, reg_end, (uint32_t)sb, (uint32_t)se)) continue;
@@ -650,10 +711,10 @@ void BaseTypeRunner::run() {
             while (next_to_write < shards.size() && done[next_to_write]) {
                 ShardOut& W = outs[next_to_write];
                 if (!W.err) {
-                    if (!W.vcf.empty()) vcf_out.write(W.vcf.data(), W.vcf.size());
-                    if (!W.cvg.empty()) cvg_out.write(W.cvg.data(), W.cvg.size());
+                    W.vcf->move_to(vcf_out);
+                    W.cvg->move_to(cvg_out);
                 }
-                W.vcf.clear(); W.cvg.clear();
+                W.vcf->discard(); W.cvg->discard();
                 ++next_to_write;
             }
         };
@@ -666,10 +727,21 @@ void BaseTypeRunner::run() {
         for (auto& O : outs) {
             launches_ += O.launches;
             if (O.err) std::rethrow_exception(O.err);
+            flips += O.flips;   // shards are in coordinate order
         }
     }
     vcf_out.close();
     cvg_out.close();
+    if (!flips.empty()) {
+        const size_t n_flagged = (size_t)std::count(flips.begin(), flips.end(), '\n');
+        std::cerr << "[INFO] " << n_flagged << " position(s) with an LRT statistic on its threshold or a tie between candidate allele sets"
+                  << (args_.flip_log.empty() ? " (--flip-log=FILE lists them)" : ": listed in " + args_.flip_log) << std::endl;
+    }
+    if (!args_.flip_log.empty()) {
+        std::ofstream fl(args_.flip_log.c_str());
+        if (!fl) throw std::invalid_argument("[ERROR] Cannot open file: " + args_.flip_log);
+        fl << "#CHROM\tPOS\tFLAGS\n" << flips;
+    }
 }
 
 }  // namespace bvhost

@@ -58,7 +58,9 @@ void pileup_sample(BamReader& bam, int tid, const std::string& fa_seq, uint32_t 
 
 class BamPileup {
 public:
-    BamPileup(const std::vector<std::string>& bam_files, int mapq_thd, int n_threads);
+    // n_instances: how many BamPileup objects over the same files live at once (one per GPU shard): the descriptor budget
+    // of the process is shared between them, so readers stay open only when n_files x n_instances descriptors fit.
+    BamPileup(const std::vector<std::string>& bam_files, int mapq_thd, int n_threads, int n_instances = 1);
     ~BamPileup();
     size_t n_samples() const { return files_.size(); }
     // SM of the first @RG (bam_header.cpp:62-83) or the file name up to its first '.' (cpp:279-283)
@@ -96,6 +98,7 @@ struct BaseTypeARGS {   // src/basetype_utils.h:74-96
     uint32_t tile_sites = 8192;
     int em_abs_mode = BV_EM_ABS_INT_TRUNC;
     bool dense_upload = false;   // upload the packed planes instead of the covered cells (bv_tile instead of bv_sparse_tile)
+    std::string flip_log;        // file for the positions flagged NEAR_LRT / LRT_TIE (CHROM, POS, FLAGS); empty: count only
 };
 
 class BaseTypeRunner {

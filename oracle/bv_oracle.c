@@ -304,6 +304,11 @@ static int lrt_core(const double* lik, size_t d, const double* depth, int total,
             double s = 0.0;
             for (size_t i = 0; i < d; ++i) s += lml[i];
             double c = 2 * (lr_alt - s);
+            /* Diagnostic only (the decision below is the reference's strict first minimum): two candidates whose statistics
+             * agree to 1e-10 of the log-likelihoods they are differences of are a TIE -- alleles with identical read multisets;
+             * which of them the reference keeps hangs on the rounding noise of its read-order sums.  The parity tests accept a
+             * different pick of the CUDA path only at sites THIS flag (or NEAR_LRT below) marks. */
+            if (!first && fabs(c - best_chi) <= 1e-10 * (fabs(lr_alt) + fabs(s))) flags |= BV_FLAG_LRT_TIE;
             if (first || c < best_chi) { /* std::min_element: first minimum, '<' only */
                 first = 0;
                 best_chi = c; best_lr = s;

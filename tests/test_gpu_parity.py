@@ -204,7 +204,9 @@ def test_golden_fixtures_from_the_compiled_reference(engine, path):
         want = z[key].view(capi.SITE_OUT_DTYPE)
         engine.set_params(min_af=maf, abs_mode=mode)
         got = engine.call_host(z["base"], z["qual"], z["strand"], z["ref_base"], n)
-        ie, fe, flips = util.compare_records(got, want, check_diag=False)
+        # the reference's records carry no tie / threshold flags: the oracle's flags for the same planes say where a flip may be listed
+        soft = L.oracle_tile(z["base"], z["qual"], z["strand"], z["ref_base"], n, maf, mode)["flags"]
+        ie, fe, flips = util.compare_records(got, want, check_diag=False, soft_flags=soft)
         # the reference shim reports BAD_STRAND / ZERO_SUBSET through exceptions only; ties are decided by the
         # reference's rounding noise, so tie sites may flip (listed)
         assert len(ie) == 0, f"{os.path.basename(path)} mode {mode}: exact mismatch at {ie[:5]}: got {util.describe(got[ie[0]])} want {util.describe(want[ie[0]])}"

@@ -121,6 +121,43 @@ def test_packer_matches_reference_batchfiles_on_bam100(host_built, tmp_path_fact
         assert _dump(host_built, fa, lst, region) == want
 
 
+RANGE = os.path.join(ROOT, "tests", "golden", "range")
+
+
+def test_bgzf_fasta_and_the_references_own_tiny_fixture(host_built, tmp_path):
+    """/root/reference/tests/data/work.log.sh:1 -- `-R ce.fa.gz -I range.bam -I range.bam`: a bgzip-compressed FASTA with no
+    .fai beside it (src/fasta.cpp:9-48 -> fai_load builds the index), one sample.  Our rows == the batchfile rows the
+    unmodified reference wrote for it (tests/golden/make_golden_range.py)."""
+    lst = tmp_path / "bam.list"
+    lst.write_text(os.path.join(RANGE, "range.bam") + "\n")
+    want = gzip.open(os.path.join(RANGE, "batch.rows.txt.gz"), "rb").read()
+    got = _dump(host_built, os.path.join(RANGE, "ce.fa.gz"), lst, "CHROMOSOME_I:900-1200")
+    assert got == want and got.count(b"\n") == 3 + 301
+    # the same text from the plain FASTA and from a compressed one that has its .fai
+    with gzip.open(os.path.join(RANGE, "ce.fa.gz"), "rb") as fi, open(tmp_path / "ce.fa", "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    assert _dump(host_built, tmp_path / "ce.fa", lst, "CHROMOSOME_I:900-1200") == want
+    # plain gzip is refused, as by faidx
+    with open(tmp_path / "plain.fa.gz", "wb") as fo:
+        fo.write(gzip.compress(b">c\nACGT\n"))
+    p = subprocess.run([os.path.join(host_built, "pileup_dump"), str(tmp_path / "plain.fa.gz"), str(lst), "c:1-4", "10", "1"], capture_output=True, text=True)
+    assert p.returncode != 0 and "bgzip" in p.stderr
+
+
+def test_csi_index(host_built, tmp_path):
+    """A BAM file with a CSI index only (written by the reference's htslib, min_shift 14): same rows, and index queries
+    equal a linear scan."""
+    bam = tmp_path / "range_csi.bam"
+    shutil.copy(os.path.join(RANGE, "range.bam"), bam)
+    shutil.copy(os.path.join(RANGE, "range_csi.bam.csi"), str(bam) + ".csi")
+    lst = tmp_path / "bam.list"
+    lst.write_text(str(bam) + "\n")
+    want = gzip.open(os.path.join(RANGE, "batch.rows.txt.gz"), "rb").read()
+    assert _dump(host_built, os.path.join(RANGE, "ce.fa.gz"), lst, "CHROMOSOME_I:900-1200") == want
+    p = subprocess.run([os.path.join(host_built, "pileup_dump"), "--query-check", str(bam), "3", "300"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "query-check ok" in p.stdout, p.stdout + p.stderr
+
+
 def _rows(text):
     return [l for l in text.split("\n") if l and not l.startswith("##")]
 
@@ -153,4 +190,22 @@ def test_command_end_to_end_on_synthetic_bams_gpu(host_built, syn, tmp_path, tag
     assert _meta(got_v) == _meta(want_v)
     assert sum(l.startswith("##contig=") for l in got_v.split("\n")) == 2
     assert _rows(got_v) == _rows(want_v) and len(_rows(want_v)) == 1 + 29
+    assert got_c == want_c
+
+
+@pytest.mark.gpu
+def test_command_on_the_references_own_tiny_fixture_gpu(host_built, tmp_path):
+    """The reference's own end-to-end test command (tests/data/work.log.sh:1), options spelled as there: VCF rows at 962, 1006,
+    1028, 1035, 1045 with QUAL 0.000000 LowQual CM_DP=2, CVG text identical."""
+    vcf, cvg = tmp_path / "vz.vcf", tmp_path / "t.cvg"
+    bam = os.path.join(RANGE, "range.bam")
+    cmd = [CLI, "basetype", "--mapq=10", "--min-af=0.05", "--batch-count=1", "--thread=1", "--regions=CHROMOSOME_I:900-1200",
+           "--output-vcf", str(vcf), "--output-cvg", str(cvg), "-R", os.path.join(RANGE, "ce.fa.gz"), "-I", bam, "-I", bam]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    want_v = gzip.open(os.path.join(RANGE, "vz.vcf.gz"), "rt").read()
+    want_c = gzip.open(os.path.join(RANGE, "t.cvg.gz"), "rt").read()
+    got_v, got_c = open(vcf).read(), open(cvg).read()
+    assert _meta(got_v) == _meta(want_v)
+    assert _rows(got_v) == _rows(want_v) and [l.split("\t")[1] for l in _rows(got_v)[1:]] == ["962", "1006", "1028", "1035", "1045"]
     assert got_c == want_c

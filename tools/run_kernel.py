@@ -51,4 +51,4 @@ print(f"{args.config} N={N} S={S}: launches ms {['%.3f' % m for m in ms]}; best 
       f"{S * (3 * N + 128) / best / 1e6:.1f} GB/s algorithmic; variant sites {(rec['n_alt'] > 0).sum()}, "
       f"em_calls mean {rec['em_calls'].mean():.3f}, n_active hist {np.bincount(rec['n_active'], minlength=5).tolist()}; "
       f"kernel ms {' '.join(f'{k[3:-7]}={v:.3f}' for k, v in kt.items())}; bound sites {int(((rec['flags'] & 0x20) != 0).sum())}, "
-      f"EM sites {int((rec['em_calls'] >= 3).sum())}; K4 = {' + '.join(f'{k[3:-7]} {v:.3f}' for k, v in ekt.items())}")
+      f"EM sites {int((rec['em_calls'] >= 3).sum())}; K4 = {' + '.join(f'{k[3:-7]} {v:.3f}' for k, v in ekt.items())}; flags hist {np.bincount(rec['flags'], minlength=256).nonzero()[0].tolist()}")
