@@ -76,7 +76,7 @@ class BvTile(C.Structure):
         ("n_sites", C.c_uint32),
         ("n_samples", C.c_uint32),
         ("location", C.c_int32),
-        ("reserved", C.c_int32),
+        ("out_mode", C.c_int32),
     ]
 
 
@@ -94,11 +94,13 @@ class BvSparseTile(C.Structure):
         ("n_sites", C.c_uint32),
         ("n_samples", C.c_uint32),
         ("format", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("out_mode", C.c_uint32),
     ]
 
 
 CELLS_U32, CELLS_U16 = 0, 1
+OUT_RECORDS, OUT_COMPACT = 0, 1
+SITE_BRIEF_DTYPE = np.dtype([("w0", "<u4"), ("w1", "<u4")])   # struct bv_site_brief
 
 
 def cell_pack(sample, base, strand, phred):
@@ -140,6 +142,8 @@ _SIGNATURES = [
     ("bv_last_em_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("bv_tile_submit", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvTile)]),
     ("bv_tile_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    ("bv_tile_wait_compact", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),
+    ("bv_site_expand", None, [C.c_void_p, C.c_uint8, C.c_float, C.c_void_p]),
     ("bv_tile_run_device", C.c_int, [C.c_void_p, C.POINTER(BvTile), C.c_void_p, C.c_void_p]),
     ("bv_last_call_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("bv_set_groups", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),

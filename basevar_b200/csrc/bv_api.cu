@@ -147,6 +147,11 @@ struct bv_slot {
     bool sparse = false;
     bool out_direct = false;              // the D2H copy went straight into the caller's pinned buffer
     bv_site_out* out_user = nullptr;      // bv_sparse_tile::out
+    // compact record transport (BV_OUT_COMPACT)
+    bool compact = false;
+    const uint8_t* h_ref = nullptr;       // the tile's REF bases (host memory of the caller, valid until the wait)
+    uint2* d_brief = nullptr;             // [max_sites]
+    bv_site_brief* h_brief = nullptr;     // [max_sites] pinned
 };
 
 struct bv_ctx {
@@ -261,6 +266,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->em_hdr = sc.d_em_hdr; a->em_pool = sc.d_em_pool; a->em_tasks = sc.d_em_tasks; a->em_res = sc.d_em_res;
     a->em_pool_cap = sc.em_pool_cap;
     for (int k = 0; k < 3; ++k) a->em_task_cap[k] = sc.em_task_cap[k];
+    a->brief = nullptr; a->full_out = nullptr;   // set by the submit paths of compact tiles
     a->list_called = nullptr;   // set_call_args() turns the called-site kernels on
     a->mapq = nullptr; a->rpr = nullptr; a->aux_pitch = 0; a->rpr_pitch = 0;
     a->sample_group = nullptr; a->calls = nullptr; a->groups = nullptr; a->n_groups = 0; a->pad0 = 0;
@@ -302,6 +308,7 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     if (a.n_sites == 0) return BV_OK;
     if (a.n_samples == 0) {   // no cells: every record is all-zero
         BV_CUDA(ctx, cudaMemsetAsync(a.out, 0, (size_t)a.n_sites * sizeof(bv_site_out), stream));
+        if (a.brief) BV_CUDA(ctx, cudaMemsetAsync(a.brief, 0, (size_t)a.n_sites * sizeof(uint2), stream));
         return BV_OK;
     }
     if (!counters_zeroed) BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, bv::kNumCounters * sizeof(uint32_t), stream));
@@ -400,6 +407,25 @@ static inline const uint32_t* encode16_run(const uint32_t* __restrict__ p, const
     }
     next = nx; o = out; oa = outa;
     return p;
+}
+
+// The records of a tile on their way back: all of them (BV_OUT_RECORDS), or the briefs plus the full records of the sites that
+// need one (BV_OUT_COMPACT; the pack kernel writes those into the slot's pinned list itself).
+static int return_records(bv_ctx* ctx, bv_slot& s, const bv::SiteKernelArgs& a, uint32_t n_sites, bv_site_out* dst) {
+    if (!n_sites) return BV_OK;
+    if (!s.compact) {
+        BV_CUDA(ctx, cudaMemcpyAsync(dst, s.d_out, (size_t)n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
+        return BV_OK;
+    }
+    if (a.n_samples) {
+        uint32_t grid = (n_sites + 255) / 256;
+        if (grid > (uint32_t)ctx->num_sms * 8u) grid = (uint32_t)ctx->num_sms * 8u;
+        bv::bv_pack_kernel<<<grid, 256, 0, s.stream>>>(a);
+        BV_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    }
+    BV_CUDA(ctx, cudaMemcpyAsync(s.h_brief, s.d_brief, (size_t)n_sites * sizeof(uint2), cudaMemcpyDeviceToHost, s.stream));
+    return BV_OK;
 }
 
 extern "C" {
@@ -534,7 +560,10 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_planes, 3 * plane);
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_ref, params->max_sites);
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_out, (size_t)params->max_sites * sizeof(bv_site_out));
-                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_out, (size_t)params->max_sites * sizeof(bv_site_out), cudaHostAllocDefault);
+                // mapped: compact tiles have the device write their full records straight into it
+                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_out, (size_t)params->max_sites * sizeof(bv_site_out), cudaHostAllocMapped);
+                if (ce == cudaSuccess) ce = cudaMalloc(&s.d_brief, (size_t)params->max_sites * sizeof(uint2));
+                if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_brief, (size_t)params->max_sites * sizeof(bv_site_brief), cudaHostAllocDefault);
                 if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_calls, (size_t)params->max_sites * sizeof(bv_call_out), cudaHostAllocMapped);
                 if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_counters, bv::kNumCounters * sizeof(uint32_t), cudaHostAllocDefault);
                 if (ce != cudaSuccess) rc = set_err(nullptr, BV_ERR_CUDA, "slot allocation failed: %s", cudaGetErrorString(ce));
@@ -557,6 +586,8 @@ void bv_destroy(bv_ctx* ctx) {
             cudaFree(s.d_planes); cudaFree(s.d_ref); cudaFree(s.d_out);
             scratch_free(s.scratch);
             if (s.h_out) cudaFreeHost(s.h_out);
+            if (s.h_brief) cudaFreeHost(s.h_brief);
+            cudaFree(s.d_brief);
             if (s.h_calls) cudaFreeHost(s.h_calls);
             if (s.h_groups) cudaFreeHost(s.h_groups);
             if (s.h_counters) cudaFreeHost(s.h_counters);
@@ -672,6 +703,9 @@ static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv
     s.qual_host = nullptr;
     s.h2d_bytes = 0;
     s.sparse = false; s.out_direct = false; s.out_user = nullptr;
+    s.compact = tile->location == BV_LOC_HOST && tile->out_mode == BV_OUT_COMPACT;
+    s.h_ref = tile->location == BV_LOC_HOST ? tile->ref_base : nullptr;
+    if (s.compact && with_calls) return set_err(ctx, BV_ERR_ARG, "BV_OUT_COMPACT is not available with the called-site kernels");
     bv_tile dev = *tile;
     if (tile->location == BV_LOC_HOST) {
         if (!tile->base || !tile->qual || !tile->strand || !tile->ref_base) return set_err(ctx, BV_ERR_ARG, "bv_tile: null pointer");
@@ -706,6 +740,8 @@ static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv
     int rc = fill_kernel_args(ctx, &dev, s.d_out, s.scratch, &a);
     if (rc != BV_OK) return rc;
     if (tile->location == BV_LOC_HOST && s.qual_host) { a.qual = s.qual_host; a.qual_pitch = tile->pitch; }
+    if (s.compact) { a.brief = s.d_brief; a.full_out = static_cast<bv_site_out*>(const_cast<void*>(host_device_pointer(s.h_out))); }
+    if (s.compact && !a.full_out) return set_err(ctx, BV_ERR_CUDA, "pinned staging is not device accessible");
     if (with_calls) {
         bv_tile_aux dev_aux = *aux;
         if (tile->location == BV_LOC_HOST && tile->n_sites) {
@@ -735,10 +771,10 @@ static int tile_submit_impl(bv_ctx* ctx, int slot, const bv_tile* tile, const bv
     }
     rc = launch_site_kernel(ctx, a, s.stream);
     if (rc != BV_OK) return rc;
-    if (tile->n_sites)
-        BV_CUDA(ctx, cudaMemcpyAsync(s.h_out, s.d_out, (size_t)tile->n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
-    if (with_calls) {
-        s.h_counters[bv::kCntCalled] = 0;
+    rc = return_records(ctx, s, a, tile->n_sites, s.h_out);
+    if (rc != BV_OK) return rc;
+    if (with_calls || s.compact) {
+        s.h_counters[bv::kCntCalled] = 0; s.h_counters[bv::kCntFull] = 0;
         if (tile->n_sites && tile->n_samples)
             BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, bv::kNumCounters * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     }
@@ -775,6 +811,9 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
     s.qual_host = nullptr;
     s.h2d_bytes = 0;
     s.sparse = true; s.out_direct = false; s.out_user = t->out;
+    s.compact = t->out_mode == BV_OUT_COMPACT;
+    s.h_ref = t->ref_base;
+    if (s.compact && (with_calls || t->out)) return set_err(ctx, BV_ERR_ARG, "BV_OUT_COMPACT: `out` must be NULL and the called-site kernels are not available");
     if (n_cells > s.cells_cap) {   // grows only; sized by the first tiles of a run
         if (s.d_cells) BV_CUDA(ctx, cudaFree(s.d_cells));
         s.d_cells = nullptr; s.cells_cap = 0;
@@ -788,10 +827,14 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
     if (with_calls && !s.d_aux) BV_CUDA(ctx, cudaMalloc(&s.d_aux, 3 * plane));
     bv_tile dev;
     dev.base = s.d_planes; dev.qual = s.d_planes + plane; dev.strand = s.d_planes + 2 * plane; dev.ref_base = s.d_ref;
-    dev.pitch = dp; dev.n_sites = t->n_sites; dev.n_samples = t->n_samples; dev.location = BV_LOC_DEVICE; dev.reserved = 0;
+    dev.pitch = dp; dev.n_sites = t->n_sites; dev.n_samples = t->n_samples; dev.location = BV_LOC_DEVICE; dev.out_mode = BV_OUT_RECORDS;
     bv::SiteKernelArgs a;
     int rc = fill_kernel_args(ctx, &dev, s.d_out, s.scratch, &a);
     if (rc != BV_OK) return rc;
+    if (s.compact) {
+        a.brief = s.d_brief; a.full_out = static_cast<bv_site_out*>(const_cast<void*>(host_device_pointer(s.h_out)));
+        if (!a.full_out) return set_err(ctx, BV_ERR_CUDA, "pinned staging is not device accessible");
+    }
     if (with_calls) {
         bv_tile_aux dev_aux;
         dev_aux.mapq = s.d_aux; dev_aux.rpr = reinterpret_cast<const uint16_t*>(s.d_aux + plane); dev_aux.rpr_pitch = dp;
@@ -829,7 +872,8 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
     if (t->n_sites) {
         bv_site_out* dst = s.h_out;
         if (t->out && host_device_pointer(t->out)) { dst = t->out; s.out_direct = true; }
-        BV_CUDA(ctx, cudaMemcpyAsync(dst, s.d_out, (size_t)t->n_sites * sizeof(bv_site_out), cudaMemcpyDeviceToHost, s.stream));
+        rc = return_records(ctx, s, a, t->n_sites, dst);
+        if (rc != BV_OK) return rc;
         if (t->n_samples)
             BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, bv::kNumCounters * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     }
@@ -935,10 +979,52 @@ int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out) {
     BV_CUDA(ctx, e);
     if (s.sparse && s.n_sites && s.h_counters[bv::kCntBadCell])
         return set_err(ctx, BV_ERR_ARG, "sparse tile: cell with sample >= n_samples or site_start not ascending / beyond the cell count");
+    if (s.compact) {   // collected in compact form (bv_tile_wait_compact), or expanded here for a caller that wants records
+        if (out) {
+            const uint32_t n_full = s.h_counters[bv::kCntFull];
+            for (uint32_t i = 0; i < s.n_sites; ++i) {
+                const bv_site_brief& b = s.h_brief[i];
+                if (b.w0 & 0x80000000u) {
+                    const uint32_t k = b.w0 & 0x7fffffffu;
+                    if (k >= n_full) return set_err(ctx, BV_ERR_STATE, "compact tile: record index out of range");
+                    out[i] = s.h_out[k];
+                } else bv_site_expand(&b, s.h_ref ? s.h_ref[i] : 0, ctx->prm.min_af, &out[i]);
+            }
+        }
+        return BV_OK;
+    }
     const bv_site_out* rec = s.out_direct ? s.out_user : s.h_out;
     if (s.out_user && !s.out_direct && s.n_sites) memcpy(s.out_user, s.h_out, (size_t)s.n_sites * sizeof(bv_site_out));
     if (out && out != rec && s.n_sites) memcpy(out, rec, (size_t)s.n_sites * sizeof(bv_site_out));
     return BV_OK;
+}
+
+int bv_tile_wait_compact(bv_ctx* ctx, int slot, const bv_site_brief** brief, const bv_site_out** full, uint32_t* n_full) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (slot < 0 || (uint32_t)slot >= ctx->prm.n_slots || !ctx->slots) return set_err(ctx, BV_ERR_ARG, "bad slot %d", slot);
+    if (!brief || !full || !n_full) return set_err(ctx, BV_ERR_ARG, "bv_tile_wait_compact: null argument");
+    bv_slot& s = ctx->slots[slot];
+    if (s.busy && !s.compact) return set_err(ctx, BV_ERR_STATE, "slot %d was not submitted with BV_OUT_COMPACT", slot);
+    int rc = bv_tile_wait(ctx, slot, nullptr);
+    if (rc != BV_OK) return rc;
+    *brief = s.h_brief; *full = s.h_out; *n_full = s.n_sites ? s.h_counters[bv::kCntFull] : 0;
+    return BV_OK;
+}
+
+void bv_site_expand(const bv_site_brief* b, uint8_t ref_base, float min_af, bv_site_out* out) {
+    memset(out, 0, sizeof(*out));
+    if (!b || (b->w0 & 0x80000000u) || b->w0 == 0) return;
+    unsigned rc = ref_base;
+    if (rc >= 'a' && rc <= 'z') rc -= 32;
+    const int code = rc == 'A' ? 0 : rc == 'C' ? 1 : rc == 'G' ? 2 : rc == 'T' ? 3 : -1;
+    if (code < 0) return;
+    out->depth[code] = b->w0;
+    out->fwd[code] = b->w0 - b->w1;
+    out->rev[code] = b->w1;
+    // one active allele (the reference's single-column EM: f = 1, no ALT) when 1.0 >= min_af
+    const uint8_t n_active = (1.0 >= (double)min_af) ? 1 : 0;
+    out->n_active = n_active;
+    out->em_calls = n_active;
 }
 
 int bv_tile_wait_calls(bv_ctx* ctx, int slot, bv_site_out* out, bv_call_out* calls, uint32_t max_calls,

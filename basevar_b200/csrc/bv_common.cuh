@@ -49,6 +49,7 @@ constexpr int kCntCalled = 4, kCntGroupNext = 5;                          // cal
 constexpr int kCntBadCell = 6;                                            // malformed sparse input (K0, bv_expand_kernel.cuh)
 constexpr int kCntEmHdr = 7, kCntEmPool = 8;                              // K4a -> K4b: EM sites and the pool of their bins
 constexpr int kCntEmTask2 = 9, kCntEmTask3 = 11, kCntEmTask4 = 12;        // EM tasks by number of alleles in the candidate subset
+constexpr int kCntFull = 13;                                              // full records of a compact tile (bv_pack_kernel)
 constexpr int kCntEmFallback = 10;                                        // EM sites finished inside K4a (scratch pools full)
 constexpr int kNumCounters = 16;
 
@@ -94,6 +95,9 @@ struct SiteKernelArgs {
     double* em_res;          // [sum of em_task_cap][kEmResDoubles], indexed like em_tasks
     uint32_t em_pool_cap;
     uint32_t em_task_cap[3];
+    // compact record transport (BV_OUT_COMPACT): null unless the tile asked for it
+    uint2* brief;            // [n_sites] device copy of the briefs: K1 writes them, bv_pack_kernel completes them
+    bv_site_out* full_out;   // pinned host memory (mapped): the full records, written by bv_pack_kernel
     // called sites (n_alt > 0): rank sums (K5) and population-group frequencies (K6); all null / 0 when not asked for
     uint32_t* list_called;   // K4 -> K5, K6: site indices, room for n_sites entries
     const uint8_t* mapq;     // [n_sites][aux_pitch]

@@ -224,6 +224,8 @@ __global__ void __launch_bounds__(kCountWarps * 32, 1) bv_count_kernel(const __g
             if (slow_n == kSlowBatch) flush_slow();
         }
         g_out[(size_t)site * 32 + lane] = w;
+        // compact transport: the two counts the whole record of such a site follows from; 0xffffffff = needs its full record
+        if (a.brief != nullptr && lane == 0) a.brief[site] = fl == 0 ? make_uint2(n_ref, n_rev) : make_uint2(0xffffffffu, 0u);
         ref_raw = ref_next;
     }
     if (slow_n) flush_slow();

@@ -260,6 +260,15 @@ __device__ __forceinline__ double rcp_fast(double m) {
     return fma(r, e, r);
 }
 
+// log(r) for the ratio of two marginals of consecutive E-steps: once the EM settles r is within 2^-10 of 1 for every bin,
+// and t - t^2/2 + t^3/3 - t^4/4 (t = r - 1, exact) is then good to 2e-16 of t -- below the rounding of a full logarithm,
+// which costs ten times as many instructions.  The sum these terms go into is only compared with 0.001.
+__device__ __forceinline__ double log_ratio(double r) {
+    const double t = r - 1.0;
+    if (fabs(t) < 0.0009765625) return t * fma(t, fma(t, fma(t, -0.25, 1.0 / 3.0), -0.5), 1.0);
+    return log(r);
+}
+
 // The bins of a site are sorted by base, and a bin whose base is OUTSIDE the candidate subset (another allele, or the
 // "other" class) has the likelihood row {e3, e3, ...}: its marginal is e3 * F (F = sum of the subset's frequencies) and
 // its posteriors are f_k / F whatever its phred.  All such bins together therefore add c_out * f_k / F to the column sums
@@ -304,7 +313,7 @@ __device__ __forceinline__ void em_bin(uint32_t p, const double* lut, const int 
         double mp = L[0] * fp[0];
 #pragma unroll
         for (int k = 1; k < NA; ++k) mp += L[k] * fp[k];
-        delta += cd * fabs(log(mp * inv));
+        delta += cd * fabs(log_ratio(mp * inv));
     }
 }
 
@@ -347,7 +356,7 @@ __device__ __forceinline__ double em_pass(const uint32_t* bins, const SubsetBins
         const double inv = rcp_fast(F);
 #pragma unroll
         for (int k = 0; k < NA; ++k) s[k] += sb.c_out * (f[k] * inv);
-        if (DELTA) delta += sb.c_out * fabs(log(Fp * inv));
+        if (DELTA) delta += sb.c_out * fabs(log_ratio(Fp * inv));
     }
     return delta;
 }
@@ -701,17 +710,22 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_task_kernel(const __grid_c
         if (tid == 0) cs.n_decide = 0;
         EmSiteHdr* const Hg = a.em_hdr + hdr;
         EmSiteHdr H;
-        const uint32_t* bins = nullptr;
-        if (valid) {
-            H = *Hg;
-            // the site's bins into this task's row (the group's lanes share the copy); longer lists are read from the pool
-            if (H.nb <= (uint32_t)kStageBins) {
-                for (uint32_t i = lg.gl; i < H.nb; i += lg.G) cs.bins[slot * kStageStride + i] = a.em_pool[H.bins_off + i];
-                bins = cs.bins + slot * kStageStride;
-            } else {
-                bins = a.em_pool + H.bins_off;
-            }
+        if (valid) H = *Hg;
+        // Staging, warp by warp: the tasks of a site are neighbours in the list, so one row serves a run of lanes with the same
+        // header; all 32 lanes copy it (coalesced), one run after the other.  Lists longer than a row are read from the pool.
+        const uint32_t hdr_prev = __shfl_up_sync(kFull, valid ? hdr : kEmTaskInvalid, 1);
+        const bool leader = valid && (lane == 0 || hdr_prev != hdr);
+        const uint32_t lead = __ballot_sync(kFull, leader);
+        const uint32_t row = (uint32_t)(tid & ~31) + (uint32_t)__popc(lead & ((2u << lane) - 1u)) - 1u;   // row of the last leader up to this lane
+        for (uint32_t todo = lead; todo; todo &= todo - 1u) {
+            const int src = __ffs(todo) - 1;
+            const uint32_t nb = __shfl_sync(kFull, H.nb, src), off = __shfl_sync(kFull, H.bins_off, src);
+            const uint32_t r = (uint32_t)(tid & ~31) + (uint32_t)__popc(lead & ((2u << src) - 1u)) - 1u;
+            if (nb <= (uint32_t)kStageBins)
+                for (uint32_t i = lane; i < nb; i += 32) cs.bins[r * kStageStride + i] = a.em_pool[off + i];
         }
+        const uint32_t* bins = nullptr;
+        if (valid) bins = H.nb <= (uint32_t)kStageBins ? cs.bins + row * kStageStride : a.em_pool + H.bins_off;
         __syncthreads();
         if (valid) {
             double* res = a.em_res + (size_t)t * kEmResDoubles;
@@ -722,7 +736,7 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_task_kernel(const __grid_c
                 __threadfence();
                 if (atomicSub(&Hg->remaining, 1u) == 1u) {   // every task of the site has stored its result: queue the decision
                     const uint32_t k = atomicAdd(&cs.n_decide, 1u);
-                    cs.decide_hdr[k] = hdr; cs.decide_row[k] = slot;
+                    cs.decide_hdr[k] = hdr; cs.decide_row[k] = row;
                 }
             }
         }

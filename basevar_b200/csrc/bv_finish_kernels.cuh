@@ -95,6 +95,41 @@ __device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_
 }
 
 // =====================================================================================================================
+// K7 bv_pack_kernel (BV_OUT_COMPACT tiles, after everything else): the sites K1 could not finish from their counts get their
+// full record copied into the pinned host list -- the kernel writes across PCIe itself, 8 lanes per 128-byte record, the
+// records of a warp's sites next to each other -- and their brief becomes the record's index in that list.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) bv_pack_kernel(const __grid_constant__ SiteKernelArgs a) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_sites = a.n_sites;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint4* const src = reinterpret_cast<const uint4*>(a.out);
+    uint4* const dst = reinterpret_cast<uint4*>(a.full_out);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n_sites; i += stride) {   // warp-uniform trips
+        const bool need = i < n_sites && a.brief[i].x == 0xffffffffu;
+        const uint32_t m = __ballot_sync(kFull, need);
+        if (m == 0) continue;
+        uint32_t pos = 0;
+        if (lane == __ffs(m) - 1) pos = atomicAdd(a.counters + kCntFull, (uint32_t)__popc(m));
+        pos = __shfl_sync(kFull, pos, __ffs(m) - 1);
+        const uint32_t my_pos = pos + (uint32_t)__popc(m & ((1u << lane) - 1u));
+        if (need) a.brief[i] = make_uint2(0x80000000u | my_pos, 0u);
+        // four records per step: lanes 8r .. 8r + 7 copy the r-th of them, 16 bytes each
+        const uint32_t cnt = (uint32_t)__popc(m);
+        for (uint32_t k0 = 0; k0 < cnt; k0 += 4) {
+            const uint32_t k = k0 + (uint32_t)(lane >> 3);
+            // the k-th set bit of m
+            uint32_t mm = m;
+            for (uint32_t t = 0; t < k && mm; ++t) mm &= mm - 1u;
+            const bool on = k < cnt;
+            const int src_lane = on ? __ffs(mm) - 1 : 0;
+            const uint32_t site = (i & ~31u) + (uint32_t)src_lane;
+            if (on) dst[(size_t)(pos + k) * 8 + (lane & 7)] = src[(size_t)site * 8 + (lane & 7)];
+        }
+    }
+}
+
+// =====================================================================================================================
 // K3: one warp per site of the bound list -- a bound that decides the LRT without running the EM.
 //
 // Site with exactly two active alleles, REF (r) and one other base (o) carried by a few reads: the signature of

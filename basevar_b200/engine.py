@@ -145,9 +145,10 @@ class BaseTypeEngine:
             self._check(self.lib.bv_tile_wait(self._ctx, ps, None if out_pinned else out[p0:].ctypes.data), "bv_tile_wait")
         return out
 
-    def sparse_tiles(self, cells, site_start, ref_base, n_samples, out_pinned=None):
+    def sparse_tiles(self, cells, site_start, ref_base, n_samples, out_pinned=None, compact=False):
         """The tile descriptors call_sparse would submit, built once (list of ctypes structs + the arrays they point into).
-        out_pinned: pinned SITE_OUT_DTYPE array [S] the records are DMA'd into."""
+        out_pinned: pinned SITE_OUT_DTYPE array [S] the records are DMA'd into.  compact: BV_OUT_COMPACT tiles (8 bytes per
+        site + the full records of the sites that need one; collect with run_sparse_tiles(..., compact=...))."""
         S = ref_base.shape[0]
         assert cells.dtype in (np.uint32, np.uint16) and site_start.dtype == np.uint32 and site_start.shape[0] == S + 1
         fmt = capi.CELLS_U16 if cells.dtype == np.uint16 else capi.CELLS_U32
@@ -158,25 +159,52 @@ class BaseTypeEngine:
             c0 = int(site_start[s0])
             st = np.ascontiguousarray(site_start[s0:s0 + ns + 1] - np.uint32(c0))
             t = BvSparseTile(cells[c0:].ctypes.data if c0 < cells.shape[0] else cells.ctypes.data, None, st.ctypes.data,
-                             ref_base[s0:].ctypes.data, out_pinned[s0:].ctypes.data if out_pinned is not None else None, ns, n_samples, fmt, 0)
+                             ref_base[s0:].ctypes.data, out_pinned[s0:].ctypes.data if out_pinned is not None and not compact else None,
+                             ns, n_samples, fmt, capi.OUT_COMPACT if compact else capi.OUT_RECORDS)
             tiles.append((t, s0, st))
         return tiles
 
-    def run_sparse_tiles(self, tiles, repeats=1, out=None):
+    def run_sparse_tiles(self, tiles, repeats=1, out=None, compact=None):
         """Submit the tiles `repeats` times over the slots without draining the pipeline in between (the steps of a
-        benchmark run, or the tiles of a long region); every slot is waited for before its next submit and at the end."""
+        benchmark run, or the tiles of a long region); every slot is waited for before its next submit and at the end.
+        compact: for BV_OUT_COMPACT tiles a callable (site0, n_sites, briefs, full_records) that consumes a tile's compact
+        result (numpy views of the slot's pinned staging, valid during the call only); None drops them (timing runs)."""
         n_slots = self.params.n_slots
         pending, slot = [], 0
+
+        def wait(ps, p0, ns, is_compact):
+            if not is_compact:
+                self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data if out is not None else None), "bv_tile_wait")
+                return
+            pb, pf, nf = C.c_void_p(), C.c_void_p(), C.c_uint32(0)
+            self._check(self.lib.bv_tile_wait_compact(self._ctx, ps, C.byref(pb), C.byref(pf), C.byref(nf)), "bv_tile_wait_compact")
+            if compact is not None and ns:
+                briefs = np.ctypeslib.as_array(C.cast(pb, C.POINTER(C.c_uint32)), shape=(ns * 2,)).view(capi.SITE_BRIEF_DTYPE)
+                full = (np.ctypeslib.as_array(C.cast(pf, C.POINTER(C.c_uint8)), shape=(nf.value * 128,)).view(SITE_OUT_DTYPE)
+                        if nf.value else np.zeros(0, SITE_OUT_DTYPE))
+                compact(p0, ns, briefs, full)
+
         for _ in range(repeats):
             for t, s0, _keep in tiles:
                 if len(pending) == n_slots:
-                    ps, p0 = pending.pop(0)
-                    self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data if out is not None else None), "bv_tile_wait")
+                    wait(*pending.pop(0))
                 self._check(self.lib.bv_tile_submit_sparse(self._ctx, slot, C.byref(t)), "bv_tile_submit_sparse")
-                pending.append((slot, s0))
+                pending.append((slot, s0, int(t.n_sites), t.out_mode == capi.OUT_COMPACT))
                 slot = (slot + 1) % n_slots
-        for ps, p0 in pending:
-            self._check(self.lib.bv_tile_wait(self._ctx, ps, out[p0:].ctypes.data if out is not None else None), "bv_tile_wait")
+        for p in pending:
+            wait(*p)
+
+    def expand_compact(self, briefs, full, ref_base, out):
+        """Records of one compact tile into out[:n] (host helper bv_site_expand for the brief-only sites)."""
+        is_full = (briefs["w0"] & 0x80000000) != 0
+        idx = np.nonzero(is_full)[0]
+        out[idx] = full[briefs["w0"][idx] & 0x7fffffff]
+        tmp = np.zeros(1, SITE_OUT_DTYPE)
+        b = np.ascontiguousarray(briefs)
+        for i in np.nonzero(~is_full)[0]:
+            self.lib.bv_site_expand(b[i:].ctypes.data, int(ref_base[i]), self.params.min_af, tmp.ctypes.data)
+            out[i] = tmp[0]
+        return out
 
     def call_sparse_calls(self, cells, cells_aux, site_start, ref_base, n_samples):
         """call_sparse plus the called-site outputs; returns what call_host_calls returns."""

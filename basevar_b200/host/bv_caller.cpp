@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <stdexcept>
 
@@ -473,11 +474,21 @@ void BasevarCaller::call(const std::vector<std::string>& lines) {
     if (T.n_sites == opt_.tile_sites) submit_current();
 }
 
+namespace {
+struct StageClock {   // adds the scope's wall time to *acc (no-op when acc is null)
+    double* acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit StageClock(double* a) : acc(a) { if (acc) t0 = std::chrono::steady_clock::now(); }
+    ~StageClock() { if (acc) *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+}  // namespace
+
 TileRows BasevarCaller::begin_tile(uint32_t n_rows) {
     if (n_rows == 0 || n_rows > opt_.tile_sites) throw std::invalid_argument("[ERROR] begin_tile: row count outside the tile");
     if (!tiles_[cur_]->pending && tiles_[cur_]->n_sites) submit_current();   // rows queued through call() go first
     Tile& T = *tiles_[cur_];
     if (T.pending) drain(cur_);
+    StageClock clk(opt_.times ? &opt_.times->tile_reset : nullptr);
     const size_t cells = (size_t)n_rows * T.pitch;
     memset(T.base, BV_BASE_N, cells); memset(T.qual, 0, cells); memset(T.strand, BV_STRAND_NONE, cells); memset(T.mapq, 0, cells);
     memset(T.rpr, 0, (size_t)n_rows * T.rpr_pitch * sizeof(uint16_t));
@@ -512,20 +523,19 @@ void BasevarCaller::commit_tile() {
 void BasevarCaller::submit_current() {
     Tile& T = *tiles_[cur_];
     if (T.pending || T.n_sites == 0) return;   // a pending tile still holds the rows it was submitted with
+    StageClock clk(opt_.times ? &opt_.times->encode_submit : nullptr);
     if (T.sparse_ready) {   // the packer listed the covered cells: 8 bytes per read instead of 5 per sample-site
         T.sparse_ready = false;
         bv_sparse_tile st;
         st.cells = T.sp_cells; st.cells_aux = T.sp_aux; st.site_start = T.sp_start; st.ref_base = T.ref; st.out = nullptr;
-        st.n_sites = T.n_sites; st.n_samples = (uint32_t)n_sample_; st.format = BV_CELLS_U32; st.reserved = 0;
+        st.n_sites = T.n_sites; st.n_samples = (uint32_t)n_sample_; st.format = BV_CELLS_U32; st.out_mode = BV_OUT_RECORDS;
         // the packer's cells ascend by sample within a row: two bytes per cell (plus the aux word) instead of four, unless a
         // cell has no compact form (a strand that is neither + nor -)
+        // (one pass: the buffer is sized for the worst case, so that the encoder never has to count first)
         uint64_t n_words = 0;
-        if (bv_sparse_encode16(T.sp_cells, nullptr, T.sp_start, T.n_sites, nullptr, nullptr, 0, nullptr, &n_words) == BV_OK) {
-            T.reserve_words16((size_t)n_words);
-            if (bv_sparse_encode16(T.sp_cells, T.sp_aux, T.sp_start, T.n_sites, T.sp_words16, T.sp_aux16, T.sp_cap16, T.sp_start16,
-                                   &n_words) == BV_OK) {
-                st.cells = T.sp_words16; st.cells_aux = T.sp_aux16; st.site_start = T.sp_start16; st.format = BV_CELLS_U16;
-            }
+        T.reserve_words16((size_t)bv_sparse_encode16_bound(T.sp_start[T.n_sites], T.n_sites, (uint32_t)n_sample_) + BV_CELL_MAX_SAMPLES / BV_CELL16_GAP_SKIP + 2);
+        if (bv_sparse_encode16(T.sp_cells, T.sp_aux, T.sp_start, T.n_sites, T.sp_words16, T.sp_aux16, T.sp_cap16, T.sp_start16, &n_words) == BV_OK) {
+            st.cells = T.sp_words16; st.cells_aux = T.sp_aux16; st.site_start = T.sp_start16; st.format = BV_CELLS_U16;
         }
         check(bv_tile_submit_sparse_calls(ctx_, (int)cur_, &st), ctx_, "bv_tile_submit_sparse_calls");
         T.pending = true;
@@ -535,7 +545,7 @@ void BasevarCaller::submit_current() {
     bv_tile t;
     t.base = T.base; t.qual = T.qual; t.strand = T.strand; t.ref_base = T.ref;
     t.pitch = T.pitch; t.n_sites = T.n_sites; t.n_samples = (uint32_t)n_sample_;
-    t.location = BV_LOC_HOST; t.reserved = 0;
+    t.location = BV_LOC_HOST; t.out_mode = BV_OUT_RECORDS;
     bv_tile_aux a;
     a.mapq = T.mapq; a.rpr = T.rpr; a.rpr_pitch = T.rpr_pitch;
     check(bv_tile_submit_calls(ctx_, (int)cur_, &t, &a), ctx_, "bv_tile_submit_calls");
@@ -548,8 +558,12 @@ void BasevarCaller::drain(uint32_t slot) {
     if (!T.pending) return;
     uint32_t n_calls = 0;
     const size_t G = group_names_.size();
-    check(bv_tile_wait_calls(ctx_, (int)slot, T.recs.data(), T.calls.data(), (uint32_t)T.calls.size(), &n_calls,
-                             G ? T.groups.data() : nullptr), ctx_, "bv_tile_wait_calls");
+    {
+        StageClock clk(opt_.times ? &opt_.times->gpu_wait : nullptr);
+        check(bv_tile_wait_calls(ctx_, (int)slot, T.recs.data(), T.calls.data(), (uint32_t)T.calls.size(), &n_calls,
+                                 G ? T.groups.data() : nullptr), ctx_, "bv_tile_wait_calls");
+    }
+    StageClock clk_text(opt_.times ? &opt_.times->text : nullptr);
     T.pending = false;
     std::fill(T.call_of_site.begin(), T.call_of_site.begin() + T.n_sites, -1);
     for (uint32_t k = 0; k < n_calls; ++k) T.call_of_site[T.calls[k].site] = (int32_t)k;

@@ -34,6 +34,20 @@ namespace bvhost {
 
 using TextSink = std::function<void(const char* data, size_t len)>;
 
+// Wall seconds per stage of the host pipeline, accumulated by whoever runs it (one instance per host worker).
+struct StageTimes {
+    double decode = 0;         // BAM records -> per-sample cell lists (BamPileup::load_span)
+    double scatter = 0;        // cell lists -> site-major rows and the tile's cell list (BamPileup::scatter)
+    double tile_reset = 0;     // begin_tile: clearing the tile's rows
+    double encode_submit = 0;  // u32 cells -> u16 words, bv_tile_submit*
+    double gpu_wait = 0;       // bv_tile_wait*: time the host stood waiting for the device
+    double text = 0;           // records -> VCF / CVG rows (and handing them to the sinks)
+    void add(const StageTimes& o) {
+        decode += o.decode; scatter += o.scatter; tile_reset += o.tile_reset; encode_submit += o.encode_submit;
+        gpu_wait += o.gpu_wait; text += o.text;
+    }
+};
+
 struct CallerOptions {
     int device = 0;
     uint32_t tile_sites = 8192;
@@ -44,6 +58,7 @@ struct CallerOptions {
     // statistic within 1e-9 of the threshold) or BV_FLAG_LRT_TIE (two candidate subsets tie to rounding): the positions
     // where the call can legitimately differ from the reference's, whose own choice hangs on rounding noise there.
     std::function<void(const char*, size_t)> flip_log;
+    StageTimes* times = nullptr;   // when set, BasevarCaller adds its stages' wall time here
 };
 
 // ---- number formatting of the reference's text outputs ---------------------------------------------------------------

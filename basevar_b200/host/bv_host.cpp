@@ -87,7 +87,7 @@ bv_tile TilePacker::tile() const {
     bv_tile t;
     t.base = base_; t.qual = qual_; t.strand = strand_; t.ref_base = ref_;
     t.pitch = pitch_; t.n_sites = n_sites_; t.n_samples = n_samples_;
-    t.location = BV_LOC_HOST; t.reserved = 0;
+    t.location = BV_LOC_HOST; t.out_mode = BV_OUT_RECORDS;
     return t;
 }
 
@@ -138,7 +138,7 @@ bv_sparse_tile SparsePacker::tile() const {
     bv_sparse_tile t;
     t.cells = cells_; t.cells_aux = aux_; t.site_start = site_start_; t.ref_base = ref_; t.out = nullptr;
     t.n_sites = n_sites_; t.n_samples = n_samples_;
-    t.format = BV_CELLS_U32; t.reserved = 0;
+    t.format = BV_CELLS_U32; t.out_mode = BV_OUT_RECORDS;
     return t;
 }
 

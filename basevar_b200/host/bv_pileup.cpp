@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -424,6 +425,7 @@ std::string BaseTypeRunner::usage() {
            "  --gpus=LIST                  Comma delimited CUDA devices to shard the regions over. [0]\n"
            "  --tile-sites=INT             Positions per GPU tile. [8192]\n"
            "  --dense-upload               Upload the packed planes of a tile instead of its covered cells.\n"
+           "  --timing                     Print the wall seconds per stage of the host pipeline (JSON, stderr).\n"
            "  --flip-log=FILE              List the positions whose LRT sat on its threshold or tied (CHROM POS FLAGS):\n"
            "                               there a call may differ from the CPU caller's, whose choice is rounding noise.\n"
            "  -h, --help                   Show this help message and exit.";
@@ -444,6 +446,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
         {"filename-has-samplename", no_argument, NULL, '3'}, {"smart-rerun", no_argument, NULL, '4'},
         {"gpus", required_argument, NULL, '5'},        {"tile-sites", required_argument, NULL, '6'},
         {"dense-upload", no_argument, NULL, '7'},      {"flip-log", required_argument, NULL, '8'},
+        {"timing", no_argument, NULL, '9'},
         {"help", no_argument, NULL, 'h'},              {0, 0, 0, 0}};
     BaseTypeARGS a;
     optind = 1;
@@ -473,6 +476,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
             case '6': ss >> a.tile_sites; break;
             case '7': a.dense_upload = true; break;
             case '8': a.flip_log = optarg; break;
+            case '9': a.timing = true; break;
             case 'h': std::cout << usage() << std::endl; exit(1);
             default: std::cerr << "Unknown argument: " << (char)c << std::endl; exit(1);
         }
@@ -657,6 +661,7 @@ void BaseTypeRunner::run() {
         struct ShardOut {
             std::unique_ptr<SpillBuffer> vcf, cvg;
             std::string flips;
+            StageTimes times;
             std::exception_ptr err;
             uint64_t launches = 0;
         };
@@ -679,6 +684,10 @@ void BaseTypeRunner::run() {
                 opt.em_abs_mode = args_.em_abs_mode;
                 opt.sparse_upload = !args_.dense_upload;
                 opt.flip_log = [&O](const char* d, size_t n) { O.flips.append(d, n); };
+                opt.times = &O.times;
+                auto seconds_since = [](std::chrono::steady_clock::time_point t0) {
+                    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                };
                 auto sink = [&out_mu, &next_to_write, si](SpillBuffer* buf, TextWriter* w) {
                     return [=, &out_mu, &next_to_write](const char* d, size_t n) {
                         std::lock_guard<std::mutex> g(out_mu);
@@ -692,11 +701,16 @@ void BaseTypeRunner::run() {
                 BamPileup pile(args_.input_bf, args_.mapq, std::max(1, args_.thread_num / (int)shards.size()), (int)shards.size());
                 for (uint64_t sb = sh.beg; sb < sh.end; sb += span_len) {
                     const uint64_t se = std::min<uint64_t>(sb + span_len, sh.end) - 1;
-                    if (!pile.load_span(ref_id, fa_seq, reg_beg, reg_end, (uint32_t)sb, (uint32_t)se)) continue;
+                    auto t0 = std::chrono::steady_clock::now();
+                    const bool any = pile.load_span(ref_id, fa_seq, reg_beg, reg_end, (uint32_t)sb, (uint32_t)se);
+                    O.times.decode += seconds_since(t0);
+                    if (!any) continue;
                     for (uint64_t p = sb; p <= se; p += args_.tile_sites) {
                         const uint32_t n = (uint32_t)std::min<uint64_t>(args_.tile_sites, se - p + 1);
                         TileRows rows = caller.begin_tile(n);
+                        t0 = std::chrono::steady_clock::now();
                         pile.scatter((uint32_t)p, n, ref_id, fa_seq, rows);
+                        O.times.scatter += seconds_since(t0);
                         caller.commit_tile();
                     }
                 }
@@ -728,6 +742,7 @@ void BaseTypeRunner::run() {
             launches_ += O.launches;
             if (O.err) std::rethrow_exception(O.err);
             flips += O.flips;   // shards are in coordinate order
+            times_.add(O.times);
         }
     }
     vcf_out.close();
@@ -736,6 +751,14 @@ void BaseTypeRunner::run() {
         const size_t n_flagged = (size_t)std::count(flips.begin(), flips.end(), '\n');
         std::cerr << "[INFO] " << n_flagged << " position(s) with an LRT statistic on its threshold or a tie between candidate allele sets"
                   << (args_.flip_log.empty() ? " (--flip-log=FILE lists them)" : ": listed in " + args_.flip_log) << std::endl;
+    }
+    if (args_.timing) {   // summed over the host workers (one per GPU shard); the shards run side by side
+        char buf[512];
+        snprintf(buf, sizeof(buf), "{\"stage_seconds\": {\"bam_decode\": %.3f, \"scatter\": %.3f, \"tile_reset\": %.3f, \"encode_submit\": %.3f, "
+                 "\"gpu_wait\": %.3f, \"text\": %.3f}, \"workers\": %zu, \"kernel_launches\": %llu}",
+                 times_.decode, times_.scatter, times_.tile_reset, times_.encode_submit, times_.gpu_wait, times_.text, devices.size(),
+                 (unsigned long long)launches_);
+        std::cerr << buf << std::endl;
     }
     if (!args_.flip_log.empty()) {
         std::ofstream fl(args_.flip_log.c_str());

@@ -99,6 +99,7 @@ struct BaseTypeARGS {   // src/basetype_utils.h:74-96
     int em_abs_mode = BV_EM_ABS_INT_TRUNC;
     bool dense_upload = false;   // upload the packed planes instead of the covered cells (bv_tile instead of bv_sparse_tile)
     std::string flip_log;        // file for the positions flagged NEAR_LRT / LRT_TIE (CHROM, POS, FLAGS); empty: count only
+    bool timing = false;         // print the wall time per stage of the host pipeline (JSON, one line on stderr)
 };
 
 class BaseTypeRunner {
@@ -123,6 +124,7 @@ private:
     std::map<std::string, std::vector<size_t>> groups_idx_;
     std::vector<std::tuple<std::string, uint32_t, uint32_t>> intervals_;
     uint64_t launches_ = 0;
+    StageTimes times_;   // summed over the host workers
 };
 
 // BGZF output (".gz" outputs, basetype_utils.cpp:97) or plain text.

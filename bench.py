@@ -425,11 +425,20 @@ def main():
     rec_sp = torch.empty(Se * 128, dtype=torch.uint8, pin_memory=True).numpy().view(bv.SITE_OUT_DTYPE)
     e2e_launches = 0
 
-    def sparse_leg(cell_words, starts, steps):
+    def sparse_leg(cell_words, starts, steps, compact=False):
+        """Tiles of the given cell words through the slots, `steps` passes back to back.  compact: BV_OUT_COMPACT tiles (8 bytes
+        per site + a full record for the sites that need one, written by the device into the slot's pinned staging)."""
         nonlocal e2e_launches
         rec_sp[:] = 0
-        tiles = eng.sparse_tiles(cell_words, starts, s_ref, n_samples, out_pinned=rec_sp)
-        eng.run_sparse_tiles(tiles, 1)   # warm-up (sizes the cell buffers)
+        tiles = eng.sparse_tiles(cell_words, starts, s_ref, n_samples, out_pinned=rec_sp, compact=compact)
+        d2h = [0]
+
+        def expand(s0, ns, briefs, full):   # verification pass only (not timed): rebuild the records from the compact form
+            d2h[0] += 8 * ns + 128 * len(full)
+            eng.expand_compact(briefs, full, s_ref[s0:s0 + ns], rec_sp[s0:s0 + ns])
+
+        eng.run_sparse_tiles(tiles, 1, compact=expand if compact else None)   # warm-up (sizes the cell buffers); fills rec_sp
+        records = rec_sp.tobytes()
         barrier()
         l0, up0 = eng.launch_count, eng.h2d_bytes
         t0 = time.perf_counter()
@@ -439,10 +448,11 @@ def main():
         dt_max = shard.max_over_ranks(dt, dev)
         e2e_launches += eng.launch_count - l0
         return {"value": world * Se * n_samples / dt_max, "ms": 1e3 * dt_max, "uploaded": (eng.h2d_bytes - up0) // steps,
-                "records": rec_sp.tobytes(), "tiles": len(tiles)}
+                "records": records if compact else rec_sp.tobytes(), "tiles": len(tiles), "d2h": d2h[0] if compact else Se * 128}
 
-    leg16 = sparse_leg(words16, start16, args.e2e_steps)
+    leg16 = sparse_leg(words16, start16, args.e2e_steps, compact=True)
     same_sp = bool(dev_rec[:Se].tobytes() == leg16["records"])
+    leg16_full = sparse_leg(words16, start16, max(3, args.e2e_steps // 2))
 
     # the same with the host encoder inside the clock: u32 cells (what a packer has per covered read) -> u16 words by worker
     # threads, one tile each, into a ring of pinned buffers; the main thread submits in order
@@ -520,8 +530,8 @@ def main():
         # bare copies of the headline leg's bytes (pinned, both directions at once, all ranks at once): what the host fabric gives
         h_up = torch.empty(int(leg16["uploaded"]), dtype=torch.uint8, pin_memory=True)
         d_up = torch.empty_like(h_up, device=dev)
-        d_dn = torch.empty(Se * 128, dtype=torch.uint8, device=dev)
-        h_dn = torch.empty(Se * 128, dtype=torch.uint8, pin_memory=True)
+        d_dn = torch.empty(int(leg16["d2h"]), dtype=torch.uint8, device=dev)
+        h_dn = torch.empty(int(leg16["d2h"]), dtype=torch.uint8, pin_memory=True)
         s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
         for reps in (1, args.e2e_steps):
             barrier()
@@ -533,8 +543,8 @@ def main():
                     h_dn.copy_(d_dn, non_blocking=True)
             torch.cuda.synchronize()
             fab = shard.max_over_ranks((time.perf_counter() - t0) / reps, dev)
-        extra["fabric"] = {"ms_per_step": 1e3 * fab, "h2d_gbs_per_gpu": leg16["uploaded"] / fab / 1e9, "d2h_gbs_per_gpu": Se * 128 / fab / 1e9,
-                           "aggregate_gbs": world * (leg16["uploaded"] + Se * 128) / fab / 1e9,
+        extra["fabric"] = {"ms_per_step": 1e3 * fab, "h2d_gbs_per_gpu": leg16["uploaded"] / fab / 1e9, "d2h_gbs_per_gpu": leg16["d2h"] / fab / 1e9,
+                           "aggregate_gbs": world * (leg16["uploaded"] + leg16["d2h"]) / fab / 1e9,
                            "e2e_fraction_of_fabric": fab / (leg16["ms"] * 1e-3),
                            "what": "cudaMemcpyAsync of the e2e leg's H2D and D2H bytes per step from / to pinned memory on two streams, every rank "
                                    "at the same time, no kernels: the floor the host memory / PCIe fabric sets for the e2e step"}
@@ -581,11 +591,15 @@ def main():
             "roofline": main_res.roofline(avg_ms, kernel_ms, peak, peak_src),
             # e2e (headline): sparse host tiles in the compact form.  h2d = 2 bytes per covered cell (+ 4 % "skip" words) + the
             # site offsets + REF bases
-            "e2e": {"value": leg16["value"], "unit": UNIT, "h2d_bytes_per_step": int(leg16["uploaded"]), "d2h_bytes_per_step": int(Se * 128),
+            "e2e": {"value": leg16["value"], "unit": UNIT, "h2d_bytes_per_step": int(leg16["uploaded"]), "d2h_bytes_per_step": int(leg16["d2h"]),
                     "ms_per_step": leg16["ms"], "steps": args.e2e_steps, "sites_per_gpu": Se,
                     "transport": "sparse tiles, BV_CELLS_U16 (bv_tile_submit_sparse): pinned u16 words of the covered reads, sample indices "
-                                 "delta-coded; expanded into the dense planes on the device (K0); records DMA'd into a pinned buffer; tiles "
-                                 "and steps pipelined over the slots (no drain between steps)",
+                                 "delta-coded; expanded into the dense planes on the device (K0); results in compact form (BV_OUT_COMPACT: 8 "
+                                 "bytes per site + the 128-byte record of every site that is not all-REF, written by the device into pinned "
+                                 "staging; bv_site_expand rebuilds the rest); tiles and steps pipelined over the slots (no drain between steps)",
+                    "full_records": {"value": leg16_full["value"], "ms_per_step": leg16_full["ms"], "d2h_bytes_per_step": int(Se * 128),
+                                     "records_match_device_path": bool(dev_rec[:Se].tobytes() == leg16_full["records"]),
+                                     "what": "the same with BV_OUT_RECORDS: a 128-byte record for every site"},
                     "cells_per_step": int(cells32.shape[0]), "words_per_step": int(words16.shape[0]),
                     "tile_sites": tile_sites, "slots": args.slots, "records_match_device_path": same_sp,
                     "host_prep_s_untimed": t_prep + t_prep16},

@@ -112,7 +112,7 @@ typedef struct bv_tile {
     uint32_t n_sites;
     uint32_t n_samples;
     int32_t  location;       /* BV_LOC_HOST (pinned or pageable) or BV_LOC_DEVICE                         */
-    int32_t  reserved;
+    int32_t  out_mode;       /* BV_OUT_RECORDS, or BV_OUT_COMPACT (host tiles; collect with bv_tile_wait_compact) */
 } bv_tile;
 
 /* ---- per-site result record: fixed 128 bytes --------------------------------------------------- */
@@ -133,6 +133,20 @@ typedef struct bv_site_out {
     double   fs_cvg;         /* FS of strand_bias(ref, all non-ref ACGT): the CVG row (caller.cpp:1245)   */
     double   fs_vcf;         /* FS of strand_bias(ref, ALT set): the VCF row (caller.cpp:1164); 0 if !n_alt */
 } bv_site_out;
+
+/* ---- compact record transport ---------------------------------------------------------------------
+ * At < 1x nine sites in ten show nothing but the reference base (or nothing at all): their whole 128-byte record follows
+ * from two counts.  With BV_OUT_COMPACT a tile returns 8 bytes for every site and a full record only for the others (~12 %
+ * at 0.1x): 24 bytes per site instead of 128 across PCIe and through the host's memory.
+ *   w0 bit 31 clear: every counted read shows REF: w0 = depth[REF], w1 = how many of them are on the '-' strand (both 0
+ *                    when no read is counted, or REF is not A/C/G/T); bv_site_expand() rebuilds the record;
+ *   w0 bit 31 set:   w0 & 0x7fffffff = index of the site's record in the tile's list of full records. */
+#define BV_OUT_RECORDS 0
+#define BV_OUT_COMPACT 1
+typedef struct bv_site_brief {
+    uint32_t w0;
+    uint32_t w1;
+} bv_site_brief;
 
 /* ---- synthetic pileup model (bench / tests); integer thresholds only, so that the device       */
 /* generator and its host twin are bit-identical                                                   */
@@ -211,6 +225,14 @@ int bv_tile_submit(bv_ctx* ctx, int slot, const bv_tile* tile);
 /* Blocks until the slot is done and copies n_sites records to `out` (host memory). */
 int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out);
 
+/* For a tile submitted with out_mode == BV_OUT_COMPACT: blocks until the slot is done; *brief receives n_sites entries,
+ * *full the *n_full full records they point into.  Both arrays are pinned staging of the slot (the records were written
+ * there by the device): valid until the slot's next submit, no copy is made. */
+int bv_tile_wait_compact(bv_ctx* ctx, int slot, const bv_site_brief** brief, const bv_site_out** full, uint32_t* n_full);
+/* The record of a site whose brief has bit 31 of w0 clear (plain C, no CUDA).  ref_base: the site's REF character as
+ * given in the tile; min_af: bv_params::min_af. */
+void bv_site_expand(const bv_site_brief* brief, uint8_t ref_base, float min_af, bv_site_out* out);
+
 /* Device-resident path: planes AND the output buffer are device pointers; nothing is copied.
  * `stream` is a cudaStream_t (NULL = the legacy default stream).  Stream ordered, returns at once. */
 int bv_tile_run_device(bv_ctx* ctx, const bv_tile* tile, bv_site_out* d_out, void* stream);
@@ -257,7 +279,7 @@ typedef struct bv_sparse_tile {
     uint32_t n_sites;
     uint32_t n_samples;
     uint32_t format;            /* BV_CELLS_U32 or BV_CELLS_U16                                                     */
-    uint32_t reserved;
+    uint32_t out_mode;          /* BV_OUT_RECORDS, or BV_OUT_COMPACT (`out` must be NULL; collect with bv_tile_wait_compact) */
 } bv_sparse_tile;
 
 /* Asynchronous, like bv_tile_submit (host memory only; pinned memory makes the copies truly asynchronous). */

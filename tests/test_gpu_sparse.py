@@ -164,3 +164,38 @@ def test_sparse_calls_equal_dense_calls(built_lib, G):
             assert c_rec.tobytes() == d_rec.tobytes() and c_calls.tobytes() == d_calls.tobytes() and c_groups.tobytes() == d_groups.tobytes()
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("fmt16", [False, True])
+def test_compact_record_transport(fmt16):
+    """BV_OUT_COMPACT: 8 bytes per site plus a full record for the sites that need one; expanded, the records are byte for byte
+    those of the ordinary transport, and bv_tile_wait() of a compact tile expands them itself."""
+    N, S = 1000, 20000
+    model = bv.synth.make_model(seed=777, coverage=0.1, variant_frac=0.05, multi_frac=0.3)
+    maf = bv.cli_min_af(0.01, N)
+    cells, _, st, ref = bv.synth_fill_sparse_host(model, 5000, S, N)
+    if fmt16:
+        cells, _, st = bv.sparse_encode16(cells, st)
+    eng = bv.BaseTypeEngine(device=0, max_samples=N, max_sites=4096, n_slots=3, min_af=maf)
+    try:
+        want = eng.call_sparse(cells, st, ref, N)
+        got = np.zeros(S, capi.SITE_OUT_DTYPE)
+        stats = {"full": 0, "tiles": 0}
+
+        def take(s0, ns, briefs, full):
+            stats["full"] += len(full); stats["tiles"] += 1
+            assert len(briefs) == ns
+            eng.expand_compact(briefs, full, ref[s0:s0 + ns], got[s0:s0 + ns])
+
+        tiles = eng.sparse_tiles(cells, st, ref, N, compact=True)
+        eng.run_sparse_tiles(tiles, 2, compact=take)
+        assert got.tobytes() == want.tobytes()
+        assert stats["tiles"] == 2 * len(tiles) and 0 < stats["full"] < 2 * 0.25 * S      # ~12 % of the sites need a full record
+        # a compact tile collected with bv_tile_wait(): the library expands it
+        t = tiles[1][0]
+        eng._check(eng.lib.bv_tile_submit_sparse(eng._ctx, 0, C.byref(t)), "submit")
+        out = np.zeros(int(t.n_sites), capi.SITE_OUT_DTYPE)
+        eng._check(eng.lib.bv_tile_wait(eng._ctx, 0, out.ctypes.data), "wait")
+        assert out.tobytes() == want[4096:4096 + int(t.n_sites)].tobytes()
+    finally:
+        eng.close()
