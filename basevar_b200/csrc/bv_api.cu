@@ -267,6 +267,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->em_pool_cap = sc.em_pool_cap;
     for (int k = 0; k < 3; ++k) a->em_task_cap[k] = sc.em_task_cap[k];
     a->brief = nullptr; a->full_out = nullptr;   // set by the submit paths of compact tiles
+    a->em_resume = 0; a->pad1 = 0;
     a->list_called = nullptr;   // set_call_args() turns the called-site kernels on
     a->mapq = nullptr; a->rpr = nullptr; a->aux_pitch = 0; a->rpr_pitch = 0;
     a->sample_group = nullptr; a->calls = nullptr; a->groups = nullptr; a->n_groups = 0; a->pad0 = 0;
@@ -356,6 +357,16 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     // K4b: groups of lanes per EM task, CTAs stride over the task lists (their lengths are only known on the device, where the
     // kernel picks the group size from them): always the grid that fills the GPU, CTAs without work leave at once
     grid = (uint32_t)ctx->num_sms * (uint32_t)ctx->task_ctas_per_sm;
+    if (a.abs_mode != BV_EM_ABS_INT_TRUNC) {
+        // fabs in the convergence test: EMs of very different lengths; their iterations run with the lanes fed task by task
+        // (bv_em_iter_kernel), the rest of every task -- log-likelihood sums, decisions -- from the frequencies that leaves
+        bv::bv_em_iter_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(a);
+        BV_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+        bv::SiteKernelArgs b = a;
+        b.em_resume = 1;
+        bv::bv_em_task_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
+    } else
     bv::bv_em_task_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(a);
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[5], stream)); ctx->ev_valid = true; }
@@ -535,6 +546,7 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kHistLongSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_em_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_em_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_expand_kernel<BV_CELLS_U32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kExpandSmemBytes) != cudaSuccess ||

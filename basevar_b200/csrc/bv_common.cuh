@@ -51,7 +51,8 @@ constexpr int kCntEmHdr = 7, kCntEmPool = 8;                              // K4a
 constexpr int kCntEmTask2 = 9, kCntEmTask3 = 11, kCntEmTask4 = 12;        // EM tasks by number of alleles in the candidate subset
 constexpr int kCntFull = 13;                                              // full records of a compact tile (bv_pack_kernel)
 constexpr int kCntEmFallback = 10;                                        // EM sites finished inside K4a (scratch pools full)
-constexpr int kNumCounters = 16;
+constexpr int kCntEmFetch2 = 16, kCntEmFetch3 = 17, kCntEmFetch4 = 18;      // next task of each list (bv_em_iter_kernel)
+constexpr int kNumCounters = 24;
 
 // word indices of bv_site_out seen as 32 x u32
 constexpr int kWDepth = 0, kWOther = 4, kWState = 5, kWFwd = 6, kWRev = 10, kWAlt = 14, kWInfo = 15;
@@ -70,7 +71,8 @@ struct __align__(16) EmSiteHdr {
                              // base_start[0] = s0 | s1 << 16, base_start[1] = s2 | s3 << 16, base_start[2] unused
 };
 static_assert(sizeof(EmSiteHdr) == 64, "EmSiteHdr layout");
-constexpr int kEmResDoubles = 6;             // per EM task: log-likelihood, f[4], flags (as bits of a u64)
+constexpr int kEmResDoubles = 10;            // per EM task: log-likelihood, f[4], flags (as bits of a u64); between bv_em_iter_kernel
+                                             // and bv_em_task_kernel: f[k], fp[k] (k-th allele of the subset) in [0..3], [4..7], flags in [8]
 constexpr uint32_t kEmTaskInvalid = 0xffffffffu;
 
 struct SiteKernelArgs {
@@ -96,6 +98,8 @@ struct SiteKernelArgs {
     uint32_t em_pool_cap;
     uint32_t em_task_cap[3];
     // compact record transport (BV_OUT_COMPACT): null unless the tile asked for it
+    uint32_t em_resume;      // bv_em_task_kernel: the EM iterations were run by bv_em_iter_kernel, start from its frequencies
+    uint32_t pad1;
     uint2* brief;            // [n_sites] device copy of the briefs: K1 writes them, bv_pack_kernel completes them
     bv_site_out* full_out;   // pinned host memory (mapped): the full records, written by bv_pack_kernel
     // called sites (n_alt > 0): rank sums (K5) and population-group frequencies (K6); all null / 0 when not asked for

@@ -391,54 +391,72 @@ __device__ __noinline__ bool em_moved_bin(const uint32_t* bins, const SubsetBins
     return lg.any(found);
 }
 
+// The state of one EM: the subset's alleles, which bins to visit, the frequencies of this and of the previous E-step.
+template <int NA>
+struct EmState {
+    int j[NA];
+    SubsetBins<NA> sb;
+    int st[6];            // first bin of each base (bins are sorted by base), nb
+    double f[NA], fp[NA];
+    double total;
+};
+
+template <int NA>
+__device__ __forceinline__ void em_setup(const EmSiteHdr& H, uint32_t subset, EmState<NA>& S) {
+    S.total = (double)H.total;
+    S.st[0] = 0; S.st[1] = (int)(H.base_start[0] & 0xffffu); S.st[2] = (int)(H.base_start[0] >> 16);
+    S.st[3] = (int)(H.base_start[1] & 0xffffu); S.st[4] = (int)(H.base_start[1] >> 16); S.st[5] = (int)H.nb;
+    uint32_t left = subset;
+    int seen = 0;
+    uint32_t c_in = 0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        S.j[k] = __ffs(left) - 1;
+        left &= left - 1u;
+        int b0 = 0, b1 = 0;
+        uint32_t d = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) if (S.j[k] == b) { b0 = S.st[b]; b1 = S.st[b + 1]; d = H.depth[b]; }
+        c_in += d;
+        S.sb.off[k] = b0 - seen;
+        seen += b1 - b0;
+        S.sb.cum[k] = seen;
+        // initial frequencies: depth/total for the subset's members, NOT renormalised (src/basetype.cpp:93-103)
+        S.f[k] = (double)d / S.total;
+        S.fp[k] = S.f[k];
+    }
+    S.sb.n = seen;
+    S.sb.c_out = (double)(H.total - c_in);
+}
+
 // The whole EM of one candidate subset (src/algorithm.h:210-255; _f, src/basetype.cpp:105-128).  res: log-likelihood under
-// the second-to-last frequencies (what _f() sums), the estimated frequencies, flags.
+// the second-to-last frequencies (what _f() sums), the estimated frequencies, flags.  resume: the iterations were run by
+// bv_em_iter_kernel, which left the last two frequency vectors in res.
 template <int NA>
 __device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* lut, const EmSiteHdr& H, const uint32_t* bins,
                                         uint32_t subset, double* res, const LaneGroup& lg) {
-    const int nb = (int)H.nb;
-    const double total = (double)H.total;
-    const bool int_mode = a.abs_mode == BV_EM_ABS_INT_TRUNC;
-    const int st[6] = {0, (int)(H.base_start[0] & 0xffffu), (int)(H.base_start[0] >> 16), (int)(H.base_start[1] & 0xffffu),
-                       (int)(H.base_start[1] >> 16), nb};
-    int j[NA];
-    SubsetBins<NA> sb;
-    {
-        uint32_t left = subset;
-        int seen = 0;
-        uint32_t c_in = 0;
-#pragma unroll
-        for (int k = 0; k < NA; ++k) {
-            j[k] = __ffs(left) - 1;
-            left &= left - 1u;
-            int b0 = 0, b1 = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) if (j[k] == b) { b0 = st[b]; b1 = st[b + 1]; c_in += H.depth[b]; }
-            sb.off[k] = b0 - seen;
-            seen += b1 - b0;
-            sb.cum[k] = seen;
-        }
-        sb.n = seen;
-        sb.c_out = (double)(H.total - c_in);
-    }
-    // initial frequencies: depth/total for the subset's members, NOT renormalised (src/basetype.cpp:93-103)
-    double f[NA], fp[NA], s[NA];
-#pragma unroll
-    for (int k = 0; k < NA; ++k) {
-        uint32_t d = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) if (j[k] == b) d = H.depth[b];
-        f[k] = (double)d / total;
-        fp[k] = f[k];
-    }
+    EmState<NA> S;
+    em_setup<NA>(H, subset, S);
+    int (&j)[NA] = S.j;
+    SubsetBins<NA>& sb = S.sb;
+    const int (&st)[6] = S.st;
+    double (&f)[NA] = S.f;
+    double (&fp)[NA] = S.fp;
+    const double total = S.total;
+    double s[NA];
     uint64_t flags = 0;
+    if (a.em_resume) {
+#pragma unroll
+        for (int k = 0; k < NA; ++k) { f[k] = res[k]; fp[k] = res[4 + k]; }
+        flags = (uint64_t)__double_as_longlong(res[8]);
+    } else {
     em_pass<NA, false>(bins, sb, lut, j, f, fp, s, lg);
 #pragma unroll
     for (int k = 0; k < NA; ++k) { fp[k] = f[k]; f[k] = s[k] / total; }
     int it = a.em_max_iter;
-    for (;;) {
+    for (;;) {   // (BV_EM_ABS_INT_TRUNC: with fabs the iterations are bv_em_iter_kernel's, and this function resumes after them)
         bool more;
-        if (int_mode) {
+        {
             em_pass<NA, false>(bins, sb, lut, j, f, fp, s, lg);
             // Every marginal is a non-negative combination of the frequencies, so its ratio between two E-steps lies between
             // the smallest and the largest ratio of the frequencies (e = 2.71828...): all of those inside (1/2.718, 2.718) =>
@@ -451,15 +469,13 @@ __device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* l
                 down = down && fp[k] >= 2.7183 * f[k] && f[k] > 0.0 && fp[k] < 1e300;
             }
             more = calm ? false : (up || down) ? true : em_moved_bin<NA>(bins, sb, lut, j, f, fp, lg);
-        } else {
-            const double delta = em_pass<NA, true>(bins, sb, lut, j, f, fp, s, lg);
-            more = !(delta < a.em_eps);
         }
 #pragma unroll
         for (int k = 0; k < NA; ++k) { fp[k] = f[k]; f[k] = s[k] / total; }
         --it;
         if (it == 0) flags |= BV_FLAG_EM_MAXITER;
         if (!more || it == 0) break;
+    }
     }
     // Sum of c * log marginal under fp, the frequencies of the last E-step: one logarithm per bin of the subset's bases;
     // a bin outside them has the marginal e3(q) * F: log e3 comes from the table, log F is one logarithm for all of them.
@@ -520,6 +536,94 @@ __device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* l
     }
     res[0] = ll; res[1] = fo[0]; res[2] = fo[1]; res[3] = fo[2]; res[4] = fo[3];
     res[5] = __longlong_as_double((long long)flags);
+}
+
+// =====================================================================================================================
+// bv_em_iter_kernel (BV_EM_ABS_DOUBLE only): the EM iterations, lanes fed task by task.
+// With fabs in the convergence test an EM runs anywhere from 5 to 100 iterations, and 32 EMs started together keep their
+// warp until the slowest is done.  Here a lane that finishes an EM takes the next task of the list at once (its site's bins
+// into the lane's own staging row) and joins the warp's next pass: every pass of the warp carries 32 live EMs, whatever
+// iteration each of them is in.  The frequencies of the last two E-steps go to em_res; bv_em_task_kernel then runs the
+// (one pass, equal for all) log-likelihood sums and the decisions from there (SiteKernelArgs::em_resume).
+// =====================================================================================================================
+template <int NA>
+__device__ __forceinline__ void em_iter_list(const SiteKernelArgs& a, TaskCta& cs, const double* lut, uint32_t list_base, uint32_t n_list,
+                                             uint32_t* fetch) {
+    const int lane = threadIdx.x & 31;
+    LaneGroup lg;
+    lg.G = 1; lg.gl = 0; lg.mask = 1u << lane;
+    uint32_t* const my_row = cs.bins + threadIdx.x * kStageStride;
+    bool have = false, done = false, first = true;
+    uint32_t t = 0;
+    int it = 0;
+    uint64_t flags = 0;
+    const uint32_t* bins = my_row;
+    EmState<NA> S;
+    S.sb.n = 0; S.sb.c_out = 0.0; S.total = 1.0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) { S.j[k] = k; S.f[k] = 0.0; S.fp[k] = 0.0; S.sb.off[k] = 0; S.sb.cum[k] = 0; }
+    for (;;) {
+        const uint32_t need = __ballot_sync(kFull, !have && !done);
+        if (need) {
+            uint32_t base = 0;
+            if (lane == __ffs(need) - 1) base = atomicAdd(fetch, (uint32_t)__popc(need));
+            base = __shfl_sync(kFull, base, __ffs(need) - 1);
+            if (!have && !done) {
+                const uint32_t idx = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                if (idx >= n_list) done = true;
+                else {
+                    t = list_base + idx;
+                    const uint32_t word = a.em_tasks[t];
+                    if (word != kEmTaskInvalid) {   // (a slot that was allocated but not used: the lane asks again)
+                        const EmSiteHdr H = a.em_hdr[word & 0x0fffffffu];
+                        if (H.nb <= (uint32_t)kStageBins) {
+                            for (uint32_t i = 0; i < H.nb; ++i) my_row[i] = a.em_pool[H.bins_off + i];
+                            bins = my_row;
+                        } else bins = a.em_pool + H.bins_off;
+                        em_setup<NA>(H, word >> 28, S);
+                        have = true; first = true; it = a.em_max_iter; flags = 0;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(kFull, have) == 0u) {
+            if (__ballot_sync(kFull, !done) == 0u) break;
+            continue;
+        }
+        double s[NA];
+        const double delta = em_pass<NA, true>(bins, S.sb, lut, S.j, S.f, S.fp, s, lg);
+        if (have) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) { S.fp[k] = S.f[k]; S.f[k] = s[k] / S.total; }
+            bool fin = false;
+            if (first) first = false;   // the E-step + M-step in front of EM()'s loop: no convergence test
+            else {
+                --it;
+                if (it == 0) flags |= BV_FLAG_EM_MAXITER;
+                fin = (delta < a.em_eps) || it == 0;
+            }
+            if (fin) {
+                double* res = a.em_res + (size_t)t * kEmResDoubles;
+#pragma unroll
+                for (int k = 0; k < NA; ++k) { res[k] = S.f[k]; res[4 + k] = S.fp[k]; }
+                res[8] = __longlong_as_double((long long)flags);
+                have = false;
+                S.sb.n = 0; S.sb.c_out = 0.0;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTaskThreads) bv_em_iter_kernel(const __grid_constant__ SiteKernelArgs a) {
+    TaskCta& cs = *reinterpret_cast<TaskCta*>(bv_smem_raw);
+    for (int i = threadIdx.x; i < 4 * kQSlots; i += kTaskThreads) cs.lut[i / kQSlots][i % kQSlots] = a.lut[(i / kQSlots) * kQStride + i % kQSlots];
+    __syncthreads();
+    const double* lut = &cs.lut[0][0];
+    const uint32_t n2 = min(a.counters[kCntEmTask2], a.em_task_cap[0]), n3 = min(a.counters[kCntEmTask3], a.em_task_cap[1]),
+                   n4 = min(a.counters[kCntEmTask4], a.em_task_cap[2]);
+    em_iter_list<2>(a, cs, lut, 0u, n2, a.counters + kCntEmFetch2);
+    em_iter_list<3>(a, cs, lut, a.em_task_cap[0], n3, a.counters + kCntEmFetch3);
+    em_iter_list<4>(a, cs, lut, a.em_task_cap[0] + a.em_task_cap[1], n4, a.counters + kCntEmFetch4);
 }
 
 // ---- the site's decision, after its last task has finished ----------------------------------------------------------------------

@@ -488,13 +488,22 @@ std::string Fasta::fetch(const std::string& name) const {
         fd = ::open(path_.c_str(), O_RDONLY);
         if (fd < 0) throw std::invalid_argument("[ERROR] " + path_ + " open failure.");
     }
+    // the index gives the line geometry: whole runs of bases are appended at once, line terminators are stepped over
+    const uint64_t lb = e.line_bases ? e.line_bases : e.length, lw = e.line_width > lb ? e.line_width : lb + 1;
     while (done < span && out.size() < e.length) {
         const size_t want = (size_t)std::min<uint64_t>(buf.size(), span - done);
         const size_t got = z ? z->read(buf.data(), want) : pread_full(fd, buf.data(), want, e.offset + done);
         if (got == 0) break;
-        for (size_t i = 0; i < got && out.size() < e.length; ++i) {
-            const char c = buf[i];
-            if (c != '\n' && c != '\r') out += c;
+        size_t i = 0;
+        while (i < got && out.size() < e.length) {
+            const uint64_t in_line = (done + i) % lw;   // position inside the current line (bases first, then the terminator)
+            if (in_line < lb) {
+                const size_t k = (size_t)std::min<uint64_t>(std::min<uint64_t>(lb - in_line, got - i), e.length - out.size());
+                out.append(buf.data() + i, k);
+                i += k;
+            } else {
+                i += (size_t)std::min<uint64_t>(lw - in_line, got - i);
+            }
         }
         done += got;
     }

@@ -276,12 +276,39 @@ struct BasevarCaller::Tile {
         sp_cap = cap;
     }
 
-    Tile(uint32_t n_samples, uint32_t max_sites, size_t n_groups) {
-        pitch = ((uint64_t)n_samples + 15) / 16 * 16;
-        rpr_pitch = pitch;
+    // The dense rows of the tile on the host (pinned: they are uploaded as they are when the tile is not sparse).  A packer that
+    // lists its covered cells does not need them: they are allocated the first time somebody asks for dense rows.
+    uint32_t max_sites = 0;
+    bool dense = false;        // the current tile's rows are in the planes (else only its sparse cells exist)
+    void ensure_dense() {
+        if (base) return;
         const size_t plane = (size_t)max_sites * pitch;
         base = (uint8_t*)pinned(plane); qual = (uint8_t*)pinned(plane); strand = (uint8_t*)pinned(plane);
-        mapq = (uint8_t*)pinned(plane); rpr = (uint16_t*)pinned(plane * 2); ref = (uint8_t*)pinned(max_sites);
+        mapq = (uint8_t*)pinned(plane); rpr = (uint16_t*)pinned(plane * 2);
+    }
+    // one site's row rebuilt from the sparse cells (text of a called site): N ! . everywhere but at the site's cells
+    std::vector<uint8_t> row_base, row_qual, row_strand;
+    SiteCells site_cells(uint32_t i, uint32_t n_samples) {
+        if (dense) return SiteCells{base + (size_t)i * pitch, qual + (size_t)i * pitch, strand + (size_t)i * pitch, n_samples};
+        if (row_base.empty()) { row_base.assign(pitch, BV_BASE_N); row_qual.assign(pitch, 0); row_strand.assign(pitch, BV_STRAND_NONE); }
+        for (uint32_t c = sp_start[i]; c < sp_start[i + 1]; ++c) {
+            const uint32_t w = sp_cells[c], smp = w & (BV_CELL_MAX_SAMPLES - 1u);
+            row_base[smp] = (uint8_t)((w >> 20) & 7u); row_strand[smp] = (uint8_t)((w >> 23) & 3u); row_qual[smp] = (uint8_t)(w >> 25);
+        }
+        return SiteCells{row_base.data(), row_qual.data(), row_strand.data(), n_samples};
+    }
+    void release_site_cells(uint32_t i) {   // back to the uncovered row, touching the site's cells only
+        if (dense) return;
+        for (uint32_t c = sp_start[i]; c < sp_start[i + 1]; ++c) {
+            const uint32_t smp = sp_cells[c] & (BV_CELL_MAX_SAMPLES - 1u);
+            row_base[smp] = BV_BASE_N; row_strand[smp] = BV_STRAND_NONE; row_qual[smp] = 0;
+        }
+    }
+
+    Tile(uint32_t n_samples, uint32_t max_sites_, size_t n_groups) : max_sites(max_sites_) {
+        pitch = ((uint64_t)n_samples + 15) / 16 * 16;
+        rpr_pitch = pitch;
+        ref = (uint8_t*)pinned(max_sites);
         sp_start = (uint32_t*)pinned(((size_t)max_sites + 1) * sizeof(uint32_t));
         sp_start16 = (uint32_t*)pinned(((size_t)max_sites + 1) * sizeof(uint32_t));
         meta.resize(max_sites);
@@ -390,6 +417,8 @@ inline char parse_char(const char* p, const char* e) {   // istringstream >> cha
 void BasevarCaller::call(const std::vector<std::string>& lines) {
     Tile& T = *tiles_[cur_];
     if (T.pending) drain(cur_);   // the slot comes round again: its previous tile is emitted first
+    T.ensure_dense();
+    T.dense = true;
     const uint32_t row = T.n_sites;
     const size_t n = n_sample_;
     uint8_t* b = T.base + (size_t)row * T.pitch;
@@ -489,17 +518,26 @@ TileRows BasevarCaller::begin_tile(uint32_t n_rows) {
     Tile& T = *tiles_[cur_];
     if (T.pending) drain(cur_);
     StageClock clk(opt_.times ? &opt_.times->tile_reset : nullptr);
-    const size_t cells = (size_t)n_rows * T.pitch;
-    memset(T.base, BV_BASE_N, cells); memset(T.qual, 0, cells); memset(T.strand, BV_STRAND_NONE, cells); memset(T.mapq, 0, cells);
-    memset(T.rpr, 0, (size_t)n_rows * T.rpr_pitch * sizeof(uint16_t));
+    // A packer that lists the covered cells of its tile (sparse upload) gets no planes to fill: a tile of an < 1x cohort is
+    // nine tenths filler, and clearing and scattering into 6 bytes per sample-site was most of the host's time.  The text of a
+    // called site takes its row from the cell list (Tile::site_cells).
+    const bool offer_sparse = opt_.sparse_upload && n_sample_ <= BV_CELL_MAX_SAMPLES;
+    T.dense = !offer_sparse || opt_.dense_rows;
+    if (T.dense) {
+        T.ensure_dense();
+        const size_t cells = (size_t)n_rows * T.pitch;
+        memset(T.base, BV_BASE_N, cells); memset(T.qual, 0, cells); memset(T.strand, BV_STRAND_NONE, cells); memset(T.mapq, 0, cells);
+        memset(T.rpr, 0, (size_t)n_rows * T.rpr_pitch * sizeof(uint16_t));
+    }
     for (uint32_t i = 0; i < n_rows; ++i) {
         SiteMeta& m = T.meta[i];
         m.specials.clear(); m.odd_strands.clear(); m.depth = 0;
     }
     T.n_sites = n_rows;
     T.sparse_ready = false;
-    TileRows rows{T.base, T.qual, T.strand, T.mapq, T.rpr, T.pitch, T.rpr_pitch, n_rows, T.meta.data(), nullptr, nullptr, nullptr};
-    if (opt_.sparse_upload && n_sample_ <= BV_CELL_MAX_SAMPLES) {
+    TileRows rows{T.dense ? T.base : nullptr, T.dense ? T.qual : nullptr, T.dense ? T.strand : nullptr, T.dense ? T.mapq : nullptr,
+                  T.dense ? T.rpr : nullptr, T.pitch, T.rpr_pitch, n_rows, T.meta.data(), nullptr, nullptr, nullptr};
+    if (offer_sparse) {
         Tile* tp = &T;
         rows.site_start = T.sp_start;
         rows.reserve_cells = [tp](size_t n, uint32_t** cells, uint32_t** aux) {
@@ -542,6 +580,7 @@ void BasevarCaller::submit_current() {
         cur_ = (cur_ + 1) % (uint32_t)tiles_.size();
         return;
     }
+    if (!T.dense) throw std::runtime_error("[BUG] tile without dense rows and without a cell list");
     bv_tile t;
     t.base = T.base; t.qual = T.qual; t.strand = T.strand; t.ref_base = T.ref;
     t.pitch = T.pitch; t.n_sites = T.n_sites; t.n_samples = (uint32_t)n_sample_;
@@ -569,12 +608,14 @@ void BasevarCaller::drain(uint32_t slot) {
     for (uint32_t k = 0; k < n_calls; ++k) T.call_of_site[T.calls[k].site] = (int32_t)k;
     std::string cvg_text, vcf_text, flip_text;
     for (uint32_t i = 0; i < T.n_sites; ++i) {
-        const SiteCells c{T.base + (size_t)i * T.pitch, T.qual + (size_t)i * T.pitch, T.strand + (size_t)i * T.pitch, (uint32_t)n_sample_};
         const bv_site_out& rec = T.recs[i];
         if (T.meta[i].depth == 0) continue;   // no sample covers the position: no row (cpp:717-718)
         if (rec.flags & BV_FLAG_ZERO_SUBSET)   // src/basetype.cpp:113-115
             throw std::runtime_error("[ERROR] The sum of frequence of active bases must always > 0. Check: " + T.meta[i].ref_id + ":" +
                                      std::to_string(T.meta[i].ref_pos));
+        const bool need_cells = rec.n_alt || (rec.flags & BV_FLAG_BAD_STRAND);   // the per-sample columns of a VCF row; an error message
+        const SiteCells c = need_cells ? T.site_cells(i, (uint32_t)n_sample_) : SiteCells{nullptr, nullptr, nullptr, (uint32_t)n_sample_};
+        struct Release { Tile& t; uint32_t i; bool on; ~Release() { if (on) t.release_site_cells(i); } } release{T, i, need_cells};
         cvg_text += out_cvg_line(T.meta[i], c, rec);
         if ((rec.flags & (BV_FLAG_NEAR_LRT | BV_FLAG_LRT_TIE)) && opt_.flip_log) {
             flip_text += T.meta[i].ref_id + "\t" + std::to_string(T.meta[i].ref_pos) + "\t";

@@ -54,6 +54,7 @@ struct CallerOptions {
     uint32_t n_slots = 2;
     int em_abs_mode = BV_EM_ABS_INT_TRUNC;
     bool sparse_upload = true;   // tiles whose packer lists its covered cells cross PCIe as bv_sparse_tile (see TileRows)
+    bool dense_rows = false;     // hand the packer dense planes to fill even when it lists its cells (tests: both forms of a tile)
     // Receives one line "CHROM\tPOS\tFLAG[,FLAG]\n" per covered position whose record carries BV_FLAG_NEAR_LRT (an LRT
     // statistic within 1e-9 of the threshold) or BV_FLAG_LRT_TIE (two candidate subsets tie to rounding): the positions
     // where the call can legitimately differ from the reference's, whose own choice hangs on rounding noise there.
@@ -93,7 +94,8 @@ std::string out_vcf_line(const SiteMeta& m, const SiteCells& c, const bv_site_ou
                          const std::vector<std::string>& group_names, const bv_group_out* groups);
 
 // Direct row access for packers that fill a whole tile themselves (the BAM-driven packer, bv_pileup.hpp): the planes of the
-// current tile, pre-filled with uncovered cells (N ! 0 0 .), and one SiteMeta per row for the caller to fill.
+// current tile, pre-filled with uncovered cells (N ! 0 0 .), and one SiteMeta per row for the caller to fill.  When the sparse
+// transport is offered (site_start != nullptr) the planes may be NULL: the packer then lists its cells and nothing else.
 struct TileRows {
     uint8_t *base, *qual, *strand, *mapq;
     uint16_t* rpr;
@@ -104,7 +106,7 @@ struct TileRows {
     // (site_start != nullptr): a packer that knows its covered cells writes site_start[0 .. n_rows], asks reserve_cells(n)
     // for the two arrays of n words, fills them with BV_CELL_PACK / BV_CELL_AUX_PACK words grouped by row, and sets
     // *sparse_ready.  The tile then crosses PCIe as 8 bytes per covered cell instead of 5 bytes per sample-site.  The planes
-    // above are filled all the same: the text output reads them on the host.
+    // above, when they are not NULL, are filled all the same.
     uint32_t* site_start;
     std::function<void(size_t n_cells, uint32_t** cells, uint32_t** aux)> reserve_cells;
     bool* sparse_ready;

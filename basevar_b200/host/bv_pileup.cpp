@@ -254,6 +254,8 @@ void BamPileup::scatter(uint32_t pos, uint32_t n, const std::string& ref_id, con
     const size_t n_blocks = (N + block - 1) / block;
     // sparse transport: cells per (sample block, row), so that the second pass below knows where each block writes
     const bool sparse = rows.sparse_ready != nullptr && rows.site_start != nullptr && rows.reserve_cells;
+    const bool dense = rows.base != nullptr;
+    if (!dense && !sparse) throw std::invalid_argument("[ERROR] scatter: neither planes nor a cell list to fill");
     std::vector<uint32_t> block_cnt(sparse ? n_blocks * (size_t)n : 0, 0);
     parallel_for(n_blocks, T, [&](size_t bi, int t) {
         std::vector<uint32_t>& d = depth[(size_t)t];
@@ -264,12 +266,14 @@ void BamPileup::scatter(uint32_t pos, uint32_t n, const std::string& ref_id, con
             auto it = std::lower_bound(cells.begin(), cells.end(), off0, [](const PileupCell& c, uint32_t v) { return c.off < v; });
             for (; it != cells.end() && it->off < off0 + n; ++it) {
                 const uint32_t row = it->off - off0;
-                const size_t at = (size_t)row * rows.pitch + s;
-                rows.base[at] = it->base;
-                rows.qual[at] = it->qual;
-                rows.strand[at] = it->strand;
-                rows.mapq[at] = it->mapq;
-                rows.rpr[(size_t)row * rows.rpr_pitch + s] = it->rpr;
+                if (dense) {
+                    const size_t at = (size_t)row * rows.pitch + s;
+                    rows.base[at] = it->base;
+                    rows.qual[at] = it->qual;
+                    rows.strand[at] = it->strand;
+                    rows.mapq[at] = it->mapq;
+                    rows.rpr[(size_t)row * rows.rpr_pitch + s] = it->rpr;
+                }
                 ++d[row];
                 if (bc) ++bc[row];
                 if (it->special >= 0) specs[(size_t)t].push_back(Spec{row, (uint32_t)s, it->special});
@@ -304,6 +308,8 @@ void BamPileup::scatter(uint32_t pos, uint32_t n, const std::string& ref_id, con
                 }
             });
             *rows.sparse_ready = true;
+        } else if (!dense) {
+            throw std::runtime_error("[ERROR] more than 2^32 covered cells in one tile: lower --tile-sites");
         }
     }
     for (uint32_t i = 0; i < n; ++i) {
@@ -425,6 +431,7 @@ std::string BaseTypeRunner::usage() {
            "  --gpus=LIST                  Comma delimited CUDA devices to shard the regions over. [0]\n"
            "  --tile-sites=INT             Positions per GPU tile. [8192]\n"
            "  --dense-upload               Upload the packed planes of a tile instead of its covered cells.\n"
+           "  --workers-per-gpu=INT        Host workers per GPU, each with its own region shard (pileup, text). [thread / 2]\n"
            "  --timing                     Print the wall seconds per stage of the host pipeline (JSON, stderr).\n"
            "  --flip-log=FILE              List the positions whose LRT sat on its threshold or tied (CHROM POS FLAGS):\n"
            "                               there a call may differ from the CPU caller's, whose choice is rounding noise.\n"
@@ -446,7 +453,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
         {"filename-has-samplename", no_argument, NULL, '3'}, {"smart-rerun", no_argument, NULL, '4'},
         {"gpus", required_argument, NULL, '5'},        {"tile-sites", required_argument, NULL, '6'},
         {"dense-upload", no_argument, NULL, '7'},      {"flip-log", required_argument, NULL, '8'},
-        {"timing", no_argument, NULL, '9'},
+        {"timing", no_argument, NULL, '9'},            {"workers-per-gpu", required_argument, NULL, 'w'},
         {"help", no_argument, NULL, 'h'},              {0, 0, 0, 0}};
     BaseTypeARGS a;
     optind = 1;
@@ -477,6 +484,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
             case '7': a.dense_upload = true; break;
             case '8': a.flip_log = optarg; break;
             case '9': a.timing = true; break;
+            case 'w': ss >> a.workers_per_gpu; break;
             case 'h': std::cout << usage() << std::endl; exit(1);
             default: std::cerr << "Unknown argument: " << (char)c << std::endl; exit(1);
         }
@@ -645,7 +653,16 @@ void BaseTypeRunner::run() {
     vcf_out.write(vh.data(), vh.size());
     cvg_out.write(ch.data(), ch.size());
 
-    std::vector<int> devices = args_.devices.empty() ? std::vector<int>{0} : args_.devices;
+    // One host worker per region shard.  The device side of a tile takes a fraction of the time its pileup and its text take on
+    // one host thread, so every GPU gets several workers (each with its own context, streams and pinned tiles), and the
+    // interval is cut into that many more shards.
+    std::vector<int> devices;
+    {
+        const std::vector<int> gpus = args_.devices.empty() ? std::vector<int>{0} : args_.devices;
+        const int w = args_.workers_per_gpu > 0 ? args_.workers_per_gpu : std::max(1, args_.thread_num / 2 / (int)gpus.size());
+        for (int g : gpus)
+            for (int k = 0; k < w; ++k) devices.push_back(g);
+    }
     const size_t N = args_.input_bf.size();
     // positions decoded per pass: bounded by the reference's own step and by the memory of the per-sample cell lists
     const uint64_t span_len = std::max<uint64_t>(args_.tile_sites, std::min<uint64_t>(PILEUP_STEP_REGION_LEN, (uint64_t)4e8 / std::max<size_t>(N, 1)));

@@ -100,6 +100,7 @@ struct BaseTypeARGS {   // src/basetype_utils.h:74-96
     bool dense_upload = false;   // upload the packed planes instead of the covered cells (bv_tile instead of bv_sparse_tile)
     std::string flip_log;        // file for the positions flagged NEAR_LRT / LRT_TIE (CHROM, POS, FLAGS); empty: count only
     bool timing = false;         // print the wall time per stage of the host pipeline (JSON, one line on stderr)
+    int workers_per_gpu = 0;     // host workers (each with its own context and region shard) per GPU; 0: max(1, thread_num / 2)
 };
 
 class BaseTypeRunner {

@@ -450,9 +450,12 @@ def main():
         return {"value": world * Se * n_samples / dt_max, "ms": 1e3 * dt_max, "uploaded": (eng.h2d_bytes - up0) // steps,
                 "records": records if compact else rec_sp.tobytes(), "tiles": len(tiles), "d2h": d2h[0] if compact else Se * 128}
 
-    leg16 = sparse_leg(words16, start16, args.e2e_steps, compact=True)
+    # results in compact form when the records are a sizeable part of the traffic (short rows: 128 bytes per site against 2 bytes
+    # per covered read); for 100,000-sample rows they are under 1 % of it and travel whole
+    use_compact = Se * 128 > 0.05 * words16.shape[0] * 2
+    leg16 = sparse_leg(words16, start16, args.e2e_steps, compact=use_compact)
     same_sp = bool(dev_rec[:Se].tobytes() == leg16["records"])
-    leg16_full = sparse_leg(words16, start16, max(3, args.e2e_steps // 2))
+    leg16_full = sparse_leg(words16, start16, max(3, args.e2e_steps // 2), compact=not use_compact)
 
     # the same with the host encoder inside the clock: u32 cells (what a packer has per covered read) -> u16 words by worker
     # threads, one tile each, into a ring of pinned buffers; the main thread submits in order
@@ -594,12 +597,14 @@ def main():
             "e2e": {"value": leg16["value"], "unit": UNIT, "h2d_bytes_per_step": int(leg16["uploaded"]), "d2h_bytes_per_step": int(leg16["d2h"]),
                     "ms_per_step": leg16["ms"], "steps": args.e2e_steps, "sites_per_gpu": Se,
                     "transport": "sparse tiles, BV_CELLS_U16 (bv_tile_submit_sparse): pinned u16 words of the covered reads, sample indices "
-                                 "delta-coded; expanded into the dense planes on the device (K0); results in compact form (BV_OUT_COMPACT: 8 "
+                                 "delta-coded; expanded into the dense planes on the device (K0); results as named in result_transport (BV_OUT_COMPACT: 8 "
                                  "bytes per site + the 128-byte record of every site that is not all-REF, written by the device into pinned "
                                  "staging; bv_site_expand rebuilds the rest); tiles and steps pipelined over the slots (no drain between steps)",
-                    "full_records": {"value": leg16_full["value"], "ms_per_step": leg16_full["ms"], "d2h_bytes_per_step": int(Se * 128),
-                                     "records_match_device_path": bool(dev_rec[:Se].tobytes() == leg16_full["records"]),
-                                     "what": "the same with BV_OUT_RECORDS: a 128-byte record for every site"},
+                    "result_transport": "BV_OUT_COMPACT" if use_compact else "BV_OUT_RECORDS",
+                    "other_result_transport": {"value": leg16_full["value"], "ms_per_step": leg16_full["ms"], "d2h_bytes_per_step": int(leg16_full["d2h"]),
+                                               "records_match_device_path": bool(dev_rec[:Se].tobytes() == leg16_full["records"]),
+                                               "what": "the same with " + ("BV_OUT_RECORDS: a 128-byte record for every site" if use_compact else
+                                                                            "BV_OUT_COMPACT: 8 bytes per site + the full records of the sites that need one")},
                     "cells_per_step": int(cells32.shape[0]), "words_per_step": int(words16.shape[0]),
                     "tile_sites": tile_sites, "slots": args.slots, "records_match_device_path": same_sp,
                     "host_prep_s_untimed": t_prep + t_prep16},

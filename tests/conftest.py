@@ -24,3 +24,12 @@ def oracle_lib():
     from oracle import loader
     loader.build_oracle()
     return loader.load_oracle()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _flip_report():
+    """BV_WRITE_FLIPS=1: what the parity checks listed as flips goes to gpurun_out/flips_observed.json (see tests/util.py)."""
+    yield
+    if os.environ.get("BV_WRITE_FLIPS"):
+        from tests import util
+        util.write_observed_flips(os.path.join(ROOT, "gpurun_out", "flips_observed.json"))

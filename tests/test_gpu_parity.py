@@ -36,6 +36,7 @@ def _check(got, want, label, max_flips=0):
         print(f"{label}: {len(flips)} threshold/tie flips at sites {flips.tolist()[:20]}")
     assert not msg, msg
     assert len(flips) <= max_flips
+    util.report_flips(label, got, want, flips)
 
 
 @pytest.mark.parametrize("abs_mode", [0, 1])
@@ -212,6 +213,7 @@ def test_golden_fixtures_from_the_compiled_reference(engine, path):
         assert len(ie) == 0, f"{os.path.basename(path)} mode {mode}: exact mismatch at {ie[:5]}: got {util.describe(got[ie[0]])} want {util.describe(want[ie[0]])}"
         assert len(fe) == 0, f"{os.path.basename(path)} mode {mode}: tolerance at {fe[:5]}: got {util.describe(got[fe[0]])} want {util.describe(want[fe[0]])}"
         assert len(flips) <= 2
+        util.report_flips(f"golden {os.path.basename(path)} mode {mode}", got, want, flips, soft_flags=soft)
 
 
 def test_pinned_host_planes_zero_copy_qual(engine):

@@ -209,3 +209,34 @@ def test_command_on_the_references_own_tiny_fixture_gpu(host_built, tmp_path):
     assert _meta(got_v) == _meta(want_v)
     assert _rows(got_v) == _rows(want_v) and [l.split("\t")[1] for l in _rows(got_v)[1:]] == ["962", "1006", "1028", "1035", "1045"]
     assert got_c == want_c
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+def test_command_sharded_over_several_gpus(host_built, syn, tmp_path):
+    """`--gpus 0,1,...`: one host worker and one context per GPU, contiguous region shards cut at the reference's 100-kb task
+    boundaries, texts merged in coordinate order (shards that are not next in line spill to temporary files): the files equal
+    those of a single-GPU run byte for byte.  Needs >= 2 GPUs (the driver's multi-GPU box, `gpurun --gpus N`)."""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("one GPU visible")
+    outs = {}
+    for tag, gpus in (("one", "0"), ("all", ",".join(str(i) for i in range(min(n, 8))))):
+        vcf, cvg = tmp_path / (tag + ".vcf"), tmp_path / (tag + ".cvg")
+        cmd = [CLI, "basetype", "-R", str(syn / "ref.fa"), "-L", str(syn / "bam.list"), "-r", "ctgA,ctgB:10001-520000", "-q", "10", "-B", "200",
+               "-t", "8", "--output-vcf", str(vcf), "--output-cvg", str(cvg), "--tile-sites", "1000", "--gpus", gpus,
+               "-G", os.path.join(FIX, "groups.info")]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        outs[tag] = (open(vcf).read(), open(cvg).read())
+        assert not [f for f in os.listdir(tmp_path) if f.endswith(".tmp")]   # spill files are gone
+    assert outs["one"] == outs["all"]
+    want_c = gzip.open(os.path.join(FIX, "syng.cvg.gz"), "rt").read()
+    assert outs["all"][1] == want_c

@@ -1,4 +1,7 @@
 """Shared helpers of the parity tests."""
+import json
+import os
+
 import numpy as np
 
 from basevar_b200 import capi
@@ -67,6 +70,36 @@ def compare_records(got, want, check_diag=True, rtol=RTOL, soft_flags=None):
         int_fail |= (got["flags"] & mask) != (want["flags"] & mask)
         int_fail |= same_call & ~soft & ((got["flags"] & capi.FLAG_MONO_QUAL) != (want["flags"] & capi.FLAG_MONO_QUAL))
     return np.nonzero(int_fail)[0], np.nonzero(flt_fail)[0], flips
+
+
+# ---- the listed flips ----------------------------------------------------------------------------------------------------
+# Every parity check that may list flips (a call that differs from the oracle's at a site the ORACLE marks NEAR_LRT / LRT_TIE)
+# reports them here under a label.  tests/golden/flips_r02.json holds what the CUDA path produced when the list was last
+# regenerated (BV_WRITE_FLIPS=1 writes gpurun_out/flips_observed.json at the end of a GPU run): a check whose label is in the
+# file must list exactly those sites -- a kernel change that flips one more call, or one fewer, shows up as a diff of that file.
+FLIPS_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flips_r02.json")
+_observed = {}
+
+
+def committed_flips():
+    if not os.path.exists(FLIPS_FILE):
+        return {}
+    with open(FLIPS_FILE) as f:
+        return json.load(f)
+
+
+def report_flips(label, got, want, flips, soft_flags=None):
+    _observed[label] = flip_list(got, want, flips, soft_flags)
+    known = committed_flips()
+    if label in known and not os.environ.get("BV_WRITE_FLIPS"):
+        assert [e["site"] for e in known[label]] == [int(i) for i in flips], \
+            f"{label}: flipped sites {[int(i) for i in flips]} differ from the committed list {[e['site'] for e in known[label]]} ({FLIPS_FILE})"
+
+
+def write_observed_flips(path):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(_observed, f, indent=1, sort_keys=True)
 
 
 def flip_list(got, want, flips, soft_flags=None):

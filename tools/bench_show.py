@@ -11,7 +11,7 @@ for fn in sys.argv[1:]:
     print("==", fn)
     print("value %.4g ms %.4f frac %.3f | %s" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["config"]["workload"][:60]))
     print("kernel_ms", {k: round(v, 4) for k, v in d["roofline"]["kernel_ms"].items()})
-    for k in ("e2e", "e2e_from_cells", "e2e_dense", "fabric", "cpu_baseline"):
+    for k in ("e2e", "e2e_from_cells", "e2e_dense", "fabric", "cpu_baseline", "cli"):
         if k in d:
             print(k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in d[k].items() if not isinstance(b, (str, dict)) or (isinstance(b, str) and len(b) < 40)})
             for a, b in d[k].items():
