@@ -119,6 +119,7 @@ struct bv_scratch {
     uint32_t* d_em_pool = nullptr;
     uint32_t* d_em_tasks = nullptr;
     double* d_em_res = nullptr;
+    double* d_em_single = nullptr;    // [cap][4] log-likelihoods of the single-allele models of the EM sites (K4a -> K4b)
     uint32_t em_pool_cap = 0, em_task_cap[3] = {0, 0, 0};
     uint32_t cap = 0;
 };
@@ -167,7 +168,7 @@ struct bv_ctx {
     uint64_t h2d_bytes_total = 0;
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int task_ctas_per_sm = 4;         // resident CTAs of bv_em_task_kernel per SM (shared memory bound)
+    int task_ctas_per_sm = 4;         // resident CTAs of bv_em_task_kernel per SM (asked of the runtime in bv_create)
     bool ev_valid = false;
     bool has_model = false;
     uint64_t pitch_cap = 0;
@@ -202,7 +203,7 @@ static int set_err(bv_ctx* ctx, int code, const char* fmt, ...) {
 
 static void scratch_free(bv_scratch& sc) {
     cudaFree(sc.d_lists); cudaFree(sc.d_counters); cudaFree(sc.d_bin_spill); cudaFree(sc.d_lml_spill);
-    cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res);
+    cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res); cudaFree(sc.d_em_single);
     sc = bv_scratch();
 }
 
@@ -221,8 +222,8 @@ static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
         BV_CUDA(ctx, cudaMalloc(&sc.d_lists, 4 * (size_t)n_sites * sizeof(uint32_t)));
         // EM scratch: room for every site to be an EM site; 64 bins and 3 tasks per site of the tile on average (a deep,
         // multi-allelic pileup needs 25 and 1; what does not fit is finished inside K4a, see bv_em_kernels.cuh)
-        cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res);
-        sc.d_em_hdr = nullptr; sc.d_em_pool = nullptr; sc.d_em_tasks = nullptr; sc.d_em_res = nullptr;
+        cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res); cudaFree(sc.d_em_single);
+        sc.d_em_hdr = nullptr; sc.d_em_pool = nullptr; sc.d_em_tasks = nullptr; sc.d_em_res = nullptr; sc.d_em_single = nullptr;
         cudaGetLastError();
         const uint64_t pool = (uint64_t)n_sites * BV_EM_POOL_BINS_PER_SITE + 4096;
         sc.em_pool_cap = (uint32_t)(pool < 0x7ffffff0ull ? pool : 0x7ffffff0ull);
@@ -233,6 +234,7 @@ static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
         BV_CUDA(ctx, cudaMalloc(&sc.d_em_pool, (size_t)sc.em_pool_cap * sizeof(uint32_t)));
         BV_CUDA(ctx, cudaMalloc(&sc.d_em_tasks, n_task * sizeof(uint32_t)));
         BV_CUDA(ctx, cudaMalloc(&sc.d_em_res, n_task * bv::kEmResDoubles * sizeof(double)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_em_single, (size_t)n_sites * 4 * sizeof(double)));
         sc.cap = n_sites;
     }
     return BV_OK;
@@ -263,7 +265,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->list_bound = sc.d_lists + sc.cap;
     a->list_em = sc.d_lists + 2 * (size_t)sc.cap;
     a->counters = sc.d_counters;
-    a->em_hdr = sc.d_em_hdr; a->em_pool = sc.d_em_pool; a->em_tasks = sc.d_em_tasks; a->em_res = sc.d_em_res;
+    a->em_hdr = sc.d_em_hdr; a->em_pool = sc.d_em_pool; a->em_tasks = sc.d_em_tasks; a->em_res = sc.d_em_res; a->em_single = sc.d_em_single;
     a->em_pool_cap = sc.em_pool_cap;
     for (int k = 0; k < 3; ++k) a->em_task_cap[k] = sc.em_task_cap[k];
     a->brief = nullptr; a->full_out = nullptr;   // set by the submit paths of compact tiles
@@ -554,6 +556,12 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             rc = set_err(nullptr, BV_ERR_CUDA, "cudaFuncSetAttribute failed: %s (device is not sm_100?)",
                          cudaGetErrorString(cudaGetLastError()));
             break;
+        }
+        {   // the EM task kernel's grid: what is resident at once (registers / shared memory decide)
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bv::bv_em_task_kernel, bv::kTaskThreads, bv::kTaskSmemBytes) == cudaSuccess && nb > 0)
+                ctx->task_ctas_per_sm = nb;
+            cudaGetLastError();
         }
         {
             const char* z = getenv("BASEVAR_B200_ZERO_COPY_QUAL");

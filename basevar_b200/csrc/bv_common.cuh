@@ -95,6 +95,7 @@ struct SiteKernelArgs {
     uint32_t* em_tasks;      // hdr index | subset << 28; three lists one after the other: 2-, 3- and 4-allele subsets,
                              // em_task_cap[k] slots each, allocated with kCntEmTask2 / 3 / 4
     double* em_res;          // [sum of em_task_cap][kEmResDoubles], indexed like em_tasks
+    double* em_single;       // [n_sites][4], indexed like em_hdr: log-likelihood of the single-allele model of each ACTIVE base
     uint32_t em_pool_cap;
     uint32_t em_task_cap[3];
     // compact record transport (BV_OUT_COMPACT): null unless the tile asked for it

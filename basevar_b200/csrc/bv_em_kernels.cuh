@@ -27,6 +27,14 @@
 #pragma once
 #include "bv_finish_kernels.cuh"
 
+#ifndef BV_HIST_STATIC
+#define BV_HIST_STATIC 1        // 0: the EM list is dealt out through a shared fetch counter (tuning builds)
+#endif
+#ifndef BV_TASK_WARP_ROUNDS
+#define BV_TASK_WARP_ROUNDS 0   // 1: bv_em_task_kernel works in rounds of one warp, no barriers, decisions queued per warp (tuning builds:
+                                // 2-4 % faster on C3 / C4 / C5 with fabs, 1.5 % slower on C2)
+#endif
+
 namespace bv {
 
 // ---- K4a: one site in state kStateEM -----------------------------------------------------------------------------------------
@@ -92,6 +100,13 @@ __device__ __noinline__ void hist_site(uint32_t site) {
             // (a lane sees at most kMaxBins / 32 = 15 bins, so the four byte counters cannot overflow before the reduction)
             const uint32_t s0 = __reduce_add_sync(kFull, below & 0xffu), s1 = __reduce_add_sync(kFull, (below >> 8) & 0xffu),
                            s2 = __reduce_add_sync(kFull, (below >> 16) & 0xffu), s3 = __reduce_add_sync(kFull, below >> 24);
+            // log-likelihoods of the four single-allele models (closed form, see single_allele_ll): the last elimination round of
+            // the site's decision consults two of them
+            {
+                double sl[4];
+                single_allele_ll4(bins, nb, sl);
+                if (lane < 4) cs.a.em_single[(size_t)hdr * 4 + lane] = lane == 0 ? sl[0] : lane == 1 ? sl[1] : lane == 2 ? sl[2] : sl[3];
+            }
             if (lane == 0) {
                 uint4 w0, w1, w2, w3;
                 w0.x = site; w0.y = off; w0.z = (uint32_t)nb; w0.w = act | (W.flag_word << 8);
@@ -193,8 +208,21 @@ __global__ void __launch_bounds__((LONG ? kLongWarps : kQualWarps) * 32, 1) bv_h
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // the EM list is final (K3 is done); warps take one site at a time: the cost per site varies by an order of magnitude
+    // The EM list is final (K3 is done).  A site costs one pass over its row, the same for every site of a tile, so the sites
+    // are dealt out statically -- entry i to warp i mod (all warps), neighbours in the list to different SMs -- and the next
+    // entry is read while this one is worked on.  (A shared fetch counter cost every site a round trip to one L2 address that
+    // 4,736 warps queue on: 17 % of the kernel's stall samples on deep pileups.)
     const uint32_t n_em = a.counters[kCntEm];
+#if BV_HIST_STATIC
+    const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t i = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    uint32_t site_next = i < n_em ? a.list_em[i] : 0u;
+    for (; i < n_em; i += total_warps) {
+        const uint32_t site = site_next;
+        if (i + total_warps < n_em) site_next = a.list_em[i + total_warps];
+        hist_site<LONG>(site);
+    }
+#else
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(a.counters + kCntEmNext, 1u);
@@ -202,6 +230,7 @@ __global__ void __launch_bounds__((LONG ? kLongWarps : kQualWarps) * 32, 1) bv_h
         if (i >= n_em) break;
         hist_site<LONG>(a.list_em[i]);
     }
+#endif
     if (W.vcf_n) vcf_flush();
 }
 
@@ -213,6 +242,9 @@ __global__ void __launch_bounds__((LONG ? kLongWarps : kQualWarps) * 32, 1) bv_h
 #endif
 #ifndef BV_TASK_STAGE_BINS
 #define BV_TASK_STAGE_BINS 96
+#endif
+#ifndef BV_TASK_MIN_CTAS
+#define BV_TASK_MIN_CTAS 1      // resident CTAs per SM the compiler has to leave registers for
 #endif
 #ifndef BV_TASK_G4_MAX_TASKS
 #define BV_TASK_G4_MAX_TASKS 12288
@@ -226,6 +258,7 @@ struct __align__(16) TaskCta {
     uint32_t n_decide;                // sites whose last task finished in this round of the CTA ...
     uint32_t decide_hdr[kTaskThreads];   // ... their headers and staging rows: decided one thread per site after the round
     uint32_t decide_row[kTaskThreads];
+    uint32_t dq[kTaskThreads / 32][64];  // per warp: headers of completed sites waiting for their decision (BV_TASK_WARP_ROUNDS)
     uint32_t bins[kTaskThreads * kStageStride];   // one row per task of the round
 };
 constexpr size_t kTaskSmemBytes = sizeof(TaskCta);
@@ -628,8 +661,7 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_iter_kernel(const __grid_c
 
 // ---- the site's decision, after its last task has finished ----------------------------------------------------------------------
 // Backward elimination (src/basetype.cpp:144-168) on the task results, ALT / AF / QUAL (:170-196), FS of the VCF row.
-// bins: the site's bins (this thread's staging row or the pool).
-__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const double* lut, const EmSiteHdr& H, const uint32_t* bins) {
+__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHdr& H, uint32_t hdr_index) {
     const uint32_t site = H.site;
     bv_site_out* rec = a.out + site;
     const int ref_code = ref_code_of(a.ref_base[site]);
@@ -659,25 +691,11 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const double* 
         // src/external/combinations.h:19-84: the i-th subset drops the (n-i)-th active base
         double single_ll[2] = {0.0, 0.0};
         if (n == 1) {
-            // Log-likelihoods of the two single-allele models (EMs whose answer is closed form): after the first M-step
-            // f_b == 1.0 exactly (every posterior is x/x), so every later marginal is L_b itself and the reported log marginal
-            // is log(1-eps) or log(eps/3), both tabulated on the host with glibc.  A bin of base b with phred 0 has
-            // L_b == 0: the reference then divides 0/0 and everything becomes NaN.
+            // Log-likelihoods of the two single-allele models (EMs whose answer is closed form; NaN when a phred-0 read of that
+            // base exists): K4a left them with the header (single_allele_ll4).
             const int b0 = __ffs(act) - 1, b1 = 31 - __clz(act);
-            bool bad0 = false, bad1 = false;
-            for (int i = 0; i < (int)H.nb; ++i) {
-                const uint32_t p = bins[i];
-                const int b = (int)bin_base(p);
-                const uint32_t q = bin_qual(p);
-                const double cd = (double)bin_count(p);
-                const double lm = lut[kLutLogMatch * kQSlots + q], lx = lut[kLutLogMis * kQSlots + q];
-                single_ll[0] += cd * (b == b0 ? lm : lx);
-                single_ll[1] += cd * (b == b1 ? lm : lx);
-                bad0 = bad0 || (b == b0 && q == 0);
-                bad1 = bad1 || (b == b1 && q == 0);
-            }
-            if (bad0) single_ll[0] = __longlong_as_double(0x7ff8000000000000ll);
-            if (bad1) single_ll[1] = __longlong_as_double(0x7ff8000000000000ll);
+            single_ll[0] = __ldcg(a.em_single + (size_t)hdr_index * 4 + b0);
+            single_ll[1] = __ldcg(a.em_single + (size_t)hdr_index * 4 + b1);
         }
         double best_chi = 0, best_lr = 0, best_f[4] = {0, 0, 0, 0};
         uint32_t best_set = 0;
@@ -773,7 +791,7 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const double* 
     if (n_alt && a.list_called) a.list_called[atomicAdd(a.counters + kCntCalled, 1u)] = site;
 }
 
-__global__ void __launch_bounds__(kTaskThreads) bv_em_task_kernel(const __grid_constant__ SiteKernelArgs a) {
+__global__ void __launch_bounds__(kTaskThreads, BV_TASK_MIN_CTAS) bv_em_task_kernel(const __grid_constant__ SiteKernelArgs a) {
     TaskCta& cs = *reinterpret_cast<TaskCta*>(bv_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 4 * kQSlots; i += kTaskThreads) cs.lut[i / kQSlots][i % kQSlots] = a.lut[(i / kQSlots) * kQStride + i % kQSlots];
@@ -797,6 +815,84 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_task_kernel(const __grid_c
         lg.gl = lane & (G - 1);
         lg.mask = (G == 1 ? 1u : 0xfu) << (lane & ~(G - 1));
     }
+#if BV_TASK_WARP_ROUNDS
+    // Rounds of ONE WARP: 32 / G tasks of one list, staged into the warp's own 32 rows, run, and the sites they complete decided
+    // by the same warp -- nothing in a round waits for another warp.  (Rounds of a whole CTA cost a barrier per phase: a fifth of
+    // the kernel's stall samples, and on multi-allelic pileups three warps stood idle while the first one ran the few decisions
+    // of the round.)  Round v of the three lists taken together goes to warp v mod (all warps).
+    __syncthreads();   // the tables are written
+    const uint32_t tpw = 32u / (uint32_t)lg.G;                 // tasks per round
+    const uint32_t slot = (uint32_t)lane / (uint32_t)lg.G;      // this lane's task of the round
+    blk_end[0] = (n_list[0] + tpw - 1) / tpw;
+    blk_end[1] = blk_end[0] + (n_list[1] + tpw - 1) / tpw;
+    blk_end[2] = blk_end[1] + (n_list[2] + tpw - 1) / tpw;
+    const uint32_t warps_per_cta = kTaskThreads / 32, total_warps = gridDim.x * warps_per_cta;
+    const uint32_t row0 = (uint32_t)(tid & ~31);
+    uint32_t dq_n = 0;   // (warp-uniform) completed sites waiting in cs.dq[warp]
+#pragma unroll 1
+    for (uint32_t v = (uint32_t)(tid >> 5) * gridDim.x + blockIdx.x; v < blk_end[2]; v += total_warps) {
+        const int li = v < blk_end[0] ? 0 : v < blk_end[1] ? 1 : 2;   // (warp-uniform) tasks of one subset size per round
+        const uint32_t idx = (v - (li ? blk_end[li - 1] : 0u)) * tpw + slot;
+        const uint32_t t = base[li] + idx;
+        const uint32_t word = idx < n_list[li] ? a.em_tasks[t] : kEmTaskInvalid;
+        const bool valid = word != kEmTaskInvalid;
+        const uint32_t hdr = word & 0x0fffffffu, subset = word >> 28;
+        EmSiteHdr* const Hg = a.em_hdr + hdr;
+        EmSiteHdr H;
+        if (valid) H = *Hg;
+        // Staging: the tasks of a site are neighbours in the list, so one row serves a run of lanes with the same header; all 32
+        // lanes copy it (coalesced), one run after the other.  Lists longer than a row are read from the pool.
+        const uint32_t hdr_prev = __shfl_up_sync(kFull, valid ? hdr : kEmTaskInvalid, 1);
+        const bool leader = valid && (lane == 0 || hdr_prev != hdr);
+        const uint32_t lead = __ballot_sync(kFull, leader);
+        const uint32_t row = row0 + (uint32_t)__popc(lead & ((2u << lane) - 1u)) - 1u;   // row of the last leader up to this lane
+        __syncwarp();   // the previous round's readers of the warp's rows are done
+        for (uint32_t todo = lead; todo; todo &= todo - 1u) {
+            const int src = __ffs(todo) - 1;
+            const uint32_t nb = __shfl_sync(kFull, H.nb, src), off = __shfl_sync(kFull, H.bins_off, src);
+            const uint32_t r = row0 + (uint32_t)__popc(lead & ((2u << src) - 1u)) - 1u;
+            if (nb <= (uint32_t)kStageBins)
+                for (uint32_t i = lane; i < nb; i += 32) cs.bins[r * kStageStride + i] = a.em_pool[off + i];
+        }
+        const uint32_t* bins = nullptr;
+        if (valid) bins = H.nb <= (uint32_t)kStageBins ? cs.bins + row * kStageStride : a.em_pool + H.bins_off;
+        __syncwarp();
+        bool last = false;
+        if (valid) {
+            double* res = a.em_res + (size_t)t * kEmResDoubles;
+            if (li == 0) em_task<2>(a, lut, H, bins, subset, res, lg);
+            else if (li == 1) em_task<3>(a, lut, H, bins, subset, res, lg);
+            else em_task<4>(a, lut, H, bins, subset, res, lg);
+            if (lg.gl == 0) {
+                __threadfence();
+                last = atomicSub(&Hg->remaining, 1u) == 1u;   // every task of the site has stored its result
+            }
+        }
+        // The sites this round completed wait in the warp's queue until 32 of them are there: the decision is scalar work (one lane
+        // per site), and a 4-allele site completes once per 11 tasks -- decided round by round, 3 lanes in 32 would run it.
+        // (A decision needs the task results and the single-allele log-likelihoods K4a left with the header, not the bins.)
+        const uint32_t dm = __ballot_sync(kFull, last);
+        if (dm) {
+            if (last) cs.dq[tid >> 5][dq_n + (uint32_t)__popc(dm & ((1u << lane) - 1u))] = hdr;
+            dq_n += (uint32_t)__popc(dm);
+            __syncwarp();
+            if (dq_n >= 32u) {
+                dq_n -= 32u;
+                const uint32_t d_hdr = cs.dq[tid >> 5][dq_n + (uint32_t)lane];
+                __threadfence();
+                const EmSiteHdr Hd = a.em_hdr[d_hdr];
+                decide_site(a, Hd, d_hdr);
+                __syncwarp();
+            }
+        }
+    }
+    if ((uint32_t)lane < dq_n) {
+        const uint32_t d_hdr = cs.dq[tid >> 5][lane];
+        __threadfence();
+        const EmSiteHdr Hd = a.em_hdr[d_hdr];
+        decide_site(a, Hd, d_hdr);
+    }
+#else
     const uint32_t tpc = (uint32_t)(kTaskThreads / lg.G);   // tasks per CTA and round
     const uint32_t slot = (uint32_t)tid / (uint32_t)lg.G;    // this thread's task of the round = its staging row
     blk_end[0] = (n_list[0] + tpc - 1) / tpc;
@@ -849,10 +945,10 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_task_kernel(const __grid_c
         if ((uint32_t)tid < cs.n_decide) {
             __threadfence();
             const EmSiteHdr Hd = a.em_hdr[cs.decide_hdr[tid]];
-            const uint32_t* dbins = Hd.nb <= (uint32_t)kStageBins ? cs.bins + cs.decide_row[tid] * kStageStride : a.em_pool + Hd.bins_off;
-            decide_site(a, lut, Hd, dbins);
+            decide_site(a, Hd, cs.decide_hdr[tid]);
         }
     }
+#endif
 }
 
 }  // namespace bv

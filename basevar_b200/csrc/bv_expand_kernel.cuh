@@ -5,15 +5,18 @@
 // bytes of the dense planes.  K0 turns it back into the planes every other kernel reads (the layout BatchInfo is
 // replaced by, src/basetype.h:25-43).  One warp per site:
 //
-//   staged path (rows up to kExStagedMaxPitch bytes): the row is built chunk by chunk in shared memory -- the
-//   "uncovered" filler (`N`, phred 0, strand none: the reference's `N ! 0 0 .`, src/basetype_caller.cpp:1063-1075)
-//   with 16-byte stores, then the site's cells scattered into it with byte stores -- and leaves as three TMA bulk stores
-//   (cp.async.bulk.global.shared::cta; SASS UBLKCP) from one of two buffers per warp, so that the next chunk is built
-//   while the previous one drains.  Every plane byte goes to HBM exactly once, in full lines, and no thread waits for a
-//   store; offsets (two sites ahead) and cells (one site ahead) are prefetched into registers.  Cells may come in any
-//   order within a site, so a row of k chunks scans the site's cells k times (they stay in L1): fine up to a few chunks;
-//   direct path (longer rows): filler and cells are written to global memory directly; the scatter hits lines the same
-//   warp has just written and merges in L2.
+//   staged path: the row is built chunk by chunk (1 KB per plane) in shared memory -- the "uncovered" filler (`N`, phred 0,
+//   strand none: the reference's `N ! 0 0 .`, src/basetype_caller.cpp:1063-1075) with 16-byte stores, then the site's cells
+//   scattered into it with byte stores -- and leaves as three TMA bulk stores (cp.async.bulk.global.shared::cta; SASS UBLKCP)
+//   from one of two buffers per warp, so that the next chunk is built while the previous one drains.  Every plane byte goes to
+//   HBM exactly once, in full lines, and no thread waits for a store; offsets (two sites ahead) and cells (one site ahead) are
+//   prefetched into registers.  BV_CELLS_U16 words ascend by sample, so they are consumed front to back across the chunks
+//   (stream_cells16: about one extra batch of 128 words per chunk) and rows of ANY length are staged: a 9,472-site tile of
+//   100,000-sample rows (2.84 GB of planes) takes 0.73 ms = 3.9 TB/s where the direct path below took 2.9 ms
+//   (gpurun r2t, profiles/r02_k0_long_rows.txt).  BV_CELLS_U32 cells may come in any order within a site, so a row of k
+//   chunks scans the site's cells k times (they stay in L1): staged up to 16 chunks;
+//   direct path (longer BV_CELLS_U32 rows): filler and cells are written to global memory directly; the scatter hits lines the
+//   same warp has just written and merges in L2.
 //
 // Two cell formats (include/basevar_b200.h): BV_CELLS_U32, one self-contained word per cell, any order within a site;
 // BV_CELLS_U16, two bytes per cell with the sample index delta-coded against the previous cell of the site (ascending
@@ -140,6 +143,58 @@ __device__ __forceinline__ bool for_each_cell(const void* cells, uint64_t beg, u
     return good;
 }
 
+// BV_CELLS_U16 (samples ascend within a site): the words of a site consumed front to back, chunk by chunk of the row.
+// `cur` (warp-uniform) is the first word not consumed yet and the sample index a gap of 0 would mean there.  Visits batches of
+// 128 words from the cursor on -- f(sample, base, strand, phred, word index) for every cell -- and moves the cursor past every
+// batch whose cells all lie below `limit`; a batch that reaches beyond it is visited again by the next call (for the next chunk
+// of the row, whose f ignores the cells below its own range): about one batch per 1,024-sample chunk at 0.1x, whatever the
+// length of the row.  Returns false when a cell's sample index is >= n_samples.
+struct CellCursor {
+    uint64_t c;
+    uint32_t next;
+};
+template <class F>
+__device__ __forceinline__ bool stream_cells16(const void* cells, uint64_t beg, uint64_t end, const uint32_t (&pre)[kExPre], uint32_t lane,
+                                               uint32_t n_samples, uint32_t limit, CellCursor& cur, F&& f) {
+    bool good = true;
+#pragma unroll 1
+    while (cur.c < end) {
+        const bool first = cur.c == beg;   // (warp-uniform) the batch the caller prefetched
+        uint32_t w[kExPre], inc[kExPre], tot = 0;
+#pragma unroll
+        for (int k = 0; k < kExPre; ++k) {
+            const uint64_t c = cur.c + pre_index<BV_CELLS_U16>(lane, k);
+            w[k] = first ? pre[k] : (c < end ? load_word<BV_CELLS_U16>(cells, c) : 0u);
+            const uint32_t gap = w[k] & 31u;
+            inc[k] = c < end ? (gap == BV_CELL16_GAP_SKIP ? BV_CELL16_GAP_SKIP : gap + 1u) : 0u;
+            tot += inc[k];
+        }
+        uint32_t x = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFull, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        uint32_t at = cur.next + (x - tot);
+        const uint32_t after = cur.next + __shfl_sync(kFull, x, 31);
+#pragma unroll
+        for (int k = 0; k < kExPre; ++k) {
+            const uint64_t c = cur.c + pre_index<BV_CELLS_U16>(lane, k);
+            const uint32_t gap = w[k] & 31u;
+            if (c < end && gap != BV_CELL16_GAP_SKIP) {
+                const uint32_t sample = at + gap;
+                if (sample >= n_samples) good = false;
+                else f(sample, (w[k] >> 5) & 7u, (w[k] >> 8) & 1u, w[k] >> 9, c);
+            }
+            at += inc[k];
+        }
+        if (after > limit) break;   // (warp-uniform) the batch reaches into the next chunk
+        cur.c += 32 * kExPre;
+        cur.next = after;
+    }
+    return good;
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const ExpandArgs a) {
     const uint32_t lane = threadIdx.x & 31;
@@ -147,7 +202,9 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
     const uint32_t n_warps = gridDim.x * kExpandWarps;
     ExpandWarp& W = reinterpret_cast<ExpandWarp*>(bv_smem_raw)[threadIdx.x >> 5];
     const uint32_t pitch = (uint32_t)a.pitch;
-    const bool staged = a.pitch <= kExStagedMaxPitch;
+    // BV_CELLS_U16 rows of any length are staged (their cells are consumed front to back, stream_cells16); BV_CELLS_U32 cells
+    // come in any order, so every chunk of the row scans all of them: staged up to kExStagedMaxPitch, written directly beyond
+    const bool staged = FMT == BV_CELLS_U16 || a.pitch <= kExStagedMaxPitch;
     const uint4 fill_base = make_uint4(0x05050505u, 0x05050505u, 0x05050505u, 0x05050505u);     // BV_BASE_N
     const uint4 fill_strand = make_uint4(0x02020202u, 0x02020202u, 0x02020202u, 0x02020202u);   // BV_STRAND_NONE
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -199,6 +256,8 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
         }
 
         if (staged) {
+            CellCursor cursor;
+            cursor.c = beg; cursor.next = 0;
 #pragma unroll 1
             for (uint32_t off = 0; off < pitch; off += kExChunk) {
                 const uint32_t bytes = min((uint32_t)kExChunk, pitch - off);
@@ -215,15 +274,16 @@ __global__ void __launch_bounds__(kExpandWarps * 32, 2) bv_expand_kernel(const E
                 // ascending samples (BV_CELLS_U16): a pass stops at the end of its chunk; the last one runs to the end of
                 // the words so that every malformed cell (sample >= n_samples) is seen
                 const uint32_t upto = off + kExChunk >= pitch ? 0xffffffffu : off + bytes;
-                const bool good = for_each_cell<FMT>(a.cells, beg, end, pre, lane, a.n_samples, upto,
-                                                     [&](uint32_t i, uint32_t b, uint32_t st, uint32_t q, uint64_t) {
-                                                         const uint32_t k = i - off;
-                                                         if (k < bytes) {   // (unsigned: also false for i < off)
-                                                             B.base[k] = (uint8_t)b;
-                                                             B.strand[k] = (uint8_t)st;
-                                                             B.qual[k] = (uint8_t)q;
-                                                         }
-                                                     });
+                auto put = [&](uint32_t i, uint32_t b, uint32_t st, uint32_t q, uint64_t) {
+                    const uint32_t k = i - off;
+                    if (k < bytes) {   // (unsigned: also false for i < off)
+                        B.base[k] = (uint8_t)b;
+                        B.strand[k] = (uint8_t)st;
+                        B.qual[k] = (uint8_t)q;
+                    }
+                };
+                const bool good = FMT == BV_CELLS_U16 ? stream_cells16(a.cells, beg, end, pre, lane, a.n_samples, upto, cursor, put)
+                                                      : for_each_cell<FMT>(a.cells, beg, end, pre, lane, a.n_samples, upto, put);
                 if (!good) bad = true;
                 // generic-proxy writes -> visible to the async proxy, then one lane hands the chunk to the TMA unit
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

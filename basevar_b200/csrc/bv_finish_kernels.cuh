@@ -831,6 +831,35 @@ __device__ __noinline__ double single_allele_ll(const uint32_t* bins, int nb, in
     return ll;
 }
 
+// The same for all four bases in one pass over the bins: out[b] is, bit for bit, single_allele_ll(bins, nb, b) (every lane sums
+// the same bins in the same order, the lanes' sums meet in the same butterfly).  K4a leaves them with the site's header, so the
+// thread that later decides the site needs no pass over the bins.
+__device__ __noinline__ void single_allele_ll4(const uint32_t* bins, int nb, double (&out)[4]) {
+    const double* s_lut = cta_shared().lut;
+    const int lane = threadIdx.x & 31;
+    double ll[4] = {0, 0, 0, 0};
+    uint32_t bad = 0;
+#pragma unroll 1
+    for (int i = lane; i < nb; i += 32) {
+        const uint32_t p = bins[i];
+        const uint32_t b = bin_base(p), q = bin_qual(p);
+        const double c = (double)bin_count(p);
+        const double lm = s_lut[kLutLogMatch * kQStride + q], lx = s_lut[kLutLogMis * kQStride + q];
+        if (q == 0 && b < 4u) bad |= 1u << b;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ll[k] += c * ((int)b == k ? lm : lx);
+    }
+    bad = __reduce_or_sync(kFull, bad);
+    // warp_sum's butterfly, the four sums side by side (four independent chains instead of four calls one after the other)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ll[k] += __shfl_xor_sync(kFull, ll[k], o);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = (bad >> k & 1u) ? __longlong_as_double(0x7ff8000000000000ll) : ll[k];
+}
+
 // The k-th (k >= 0) active base of an ORDERED base list: `order` packs the list two bits per position (position 0 in
 // bits 0-1), `mask` says which alleles are active.  BaseType::lrt() passes A,C,G,T (kOrderACGT); the population-group
 // calls pass [REF, ALT...] (src/basetype_caller.cpp:750-753), and the order decides which subset wins a tie and which

@@ -32,6 +32,26 @@ BV_FN double ff_lbinom(const LF& lf, int n, int k) {   // kfunc.c:197-201
     return lf(n) - lf(k) - lf(n - k);
 }
 
+// num / den in the tail recurrences.  On the device: num * (1 / den) with the reciprocal from the hardware's estimate and two
+// Newton steps (~1 ulp; the correctly rounded FP64 division costs six times as many instructions and the tails are hundreds
+// of steps long on deep pileups).  The difference, a few ulp per step, is far inside the 1e-8 slack of every decision here.
+#ifndef BV_FF_RCP
+#define BV_FF_RCP 1
+#endif
+BV_FN double ff_div(double num, double den) {
+#if defined(__CUDA_ARCH__) && BV_FF_RCP
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    return num * r;
+#else
+    return num / den;
+#endif
+}
+
 template <class LF, class EXP>
 BV_FN double ff_pmf(const LF& lf, const EXP& ex, int i, int n1_, int n_1, int n) {   // kfunc.c:209-212
     return ex(ff_lbinom(lf, n1_, i) + ff_lbinom(lf, n - n1_, n_1 - i) - ff_lbinom(lf, n, n_1));
@@ -65,7 +85,7 @@ BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_
                 left += p;
                 if (i == lo || p < 1e-18 * left) break;
                 // pmf(i-1) = pmf(i) * i * n22(i) / ((n1_-i+1) (n_1-i+1)),  n22(i) = i + n - n1_ - n_1   (kfunc.c:234-236)
-                p *= ((double)i * (double)(i + n - n1_ - n_1)) / ((double)(n1_ - i + 1) * (double)(n_1 - i + 1));   // products < 2^53: exact
+                p *= ff_div((double)i * (double)(i + n - n1_ - n_1), (double)(n1_ - i + 1) * (double)(n_1 - i + 1));   // products < 2^53: exact
                 --i;
             }
         }
@@ -88,7 +108,7 @@ BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_
                 right += p;
                 if (i == hi || p < 1e-18 * right) break;
                 // pmf(i+1) = pmf(i) * (n1_-i) (n_1-i) / ((i+1) n22(i+1))                                  (kfunc.c:228-230)
-                p *= ((double)(n1_ - i) * (double)(n_1 - i)) / ((double)(i + 1) * (double)(i + 1 + n - n1_ - n_1));
+                p *= ff_div((double)(n1_ - i) * (double)(n_1 - i), (double)(i + 1) * (double)(i + 1 + n - n1_ - n_1));
                 ++i;
             }
         }

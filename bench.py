@@ -518,13 +518,14 @@ def main():
     # What a packer holds per covered read is one u32 cell.  Two ways from there, both with everything inside the clock:
     # ship the u32 cells as they are (BV_CELLS_U32: twice the bytes, no host work), or re-code them to u16 words on the host
     # first (bv_sparse_encode16 on worker threads).  e2e_from_cells reports the faster of the two, both are listed.
-    leg32 = sparse_leg(cells32, start32, args.e2e_steps)
+    leg32 = sparse_leg(cells32, start32, args.e2e_steps, compact=use_compact)
     leg_enc = from_cells_leg(max(3, args.e2e_steps // 2))
     leg_cells = {"value": max(leg32["value"], leg_enc["value"]), "unit": UNIT,
                  "ms_per_step": min(leg32["ms"], leg_enc["ms_per_step"]),
                  "via": "BV_CELLS_U32 as is" if leg32["value"] >= leg_enc["value"] else "host encoder -> BV_CELLS_U16",
                  "u32_as_is": {"value": leg32["value"], "ms_per_step": leg32["ms"], "h2d_bytes_per_step": int(leg32["uploaded"]),
-                               "d2h_bytes_per_step": int(Se * 128), "steps": args.e2e_steps,
+                               "d2h_bytes_per_step": int(leg32["d2h"]), "steps": args.e2e_steps,
+                               "result_transport": "BV_OUT_COMPACT" if use_compact else "BV_OUT_RECORDS",
                                "records_match_device_path": bool(dev_rec[:Se].tobytes() == leg32["records"])},
                  "host_encode16": leg_enc}
 

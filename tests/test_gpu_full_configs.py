@@ -14,33 +14,34 @@ def _assert_ok(r):
     assert r["depth_conservation_violations"] == 0
     assert r["strand_sum_violations"] == 0
     assert r["tiling_invariant"], (r["checksum"], r["checksum_b"])
-    assert r["spot_exact_mismatches"] == 0 and r["spot_float_mismatches"] == 0 and r["spot_flips"] <= 2
+    # flips: calls that differ at sites the ORACLE marks as sitting on the LRT threshold or as a tie of two subsets (tests/util.py)
+    assert r["spot_exact_mismatches"] == 0 and r["spot_float_mismatches"] == 0 and r["spot_flips"] <= max(2, r["spot_sites"] // 1000)
     assert r["variant_sites"] > 0 and r["covered_sites"] > 0.9 * r["sites"]
 
 
 def test_c2_full_size(built_lib, oracle_lib):
-    r = full_configs.run_config("C2", spot=2000)
+    r = full_configs.run_config("C2", spot=20000)
     assert r["sites"] == 1_000_000 and r["n_samples"] == 1_000
     _assert_ok(r)
 
 
 def test_c3_full_size(built_lib, oracle_lib):
     """10,000 samples x 10,000,000 sites = 1e11 sample-sites, about 300 GB of planes streamed through one GPU."""
-    r = full_configs.run_config("C3", spot=400)
+    r = full_configs.run_config("C3", spot=10000)
     assert r["sites"] == 10_000_000 and r["n_samples"] == 10_000
     _assert_ok(r)
 
 
 def test_c4_one_shard_of_eight(built_lib, oracle_lib):
     """100,000 samples x 64,000,000 sites over 8 GPUs: GPU 3's contiguous shard (8,000,000 sites = 8e11 sample-sites)."""
-    r = full_configs.run_config("C4", shard=(3, 8), spot=48)
+    r = full_configs.run_config("C4", shard=(3, 8), spot=2000)
     assert r["sites"] == 8_000_000 and r["site_range"] == [24_000_000, 32_000_000] and r["n_samples"] == 100_000
     _assert_ok(r)
 
 
 @pytest.mark.parametrize("abs_mode", [0, 1])
 def test_c5_full_size_both_abs_modes(built_lib, oracle_lib, abs_mode):
-    r = full_configs.run_config("C5", abs_mode=abs_mode, spot=600)
+    r = full_configs.run_config("C5", abs_mode=abs_mode, spot=10000)
     assert r["sites"] == 1_000_000 and r["n_samples"] == 2_000
     _assert_ok(r)
     assert r["variant_sites"] > 200_000

@@ -73,6 +73,24 @@ def test_sparse_equals_dense_and_oracle(engine, name, S, N, kw, abs_mode):
     assert (got["n_alt"] > 0).sum() > 0
 
 
+def test_sparse_rows_of_100000_samples(built_lib):
+    """BASELINE configs[3] rows (100,000 samples, 98 staged chunks per row) through both cell formats: the 16-bit words are consumed
+    front to back across the chunks (stream_cells16), the 32-bit cells take K0's direct path."""
+    N, S = 100_000, 48
+    model = bv.synth.make_model(seed=77, coverage=0.1, variant_frac=0.3)
+    b, q, s, _, r = bv.synth_fill_host(model, 5_000_000, S, N)
+    eng = bv.BaseTypeEngine(device=0, max_samples=N, max_sites=32, n_slots=2, min_af=bv.cli_min_af(0.01, N))
+    try:
+        _both(eng, b, q, s, r, N, bv.cli_min_af(0.01, N), 0, "N=100000")
+        # a site whose only cells sit at the very end of the row, and one with a single cell at sample 0
+        b2 = np.full_like(b[:3], 5); q2 = np.zeros_like(q[:3]); s2 = np.full_like(s[:3], 2)
+        b2[0, N - 3:N] = [0, 1, 2]; q2[0, N - 3:N] = 30; s2[0, N - 3:N] = [0, 1, 0]
+        b2[1, 0] = 3; q2[1, 0] = 40; s2[1, 0] = 1
+        _both(eng, b2, q2, s2, np.array([65, 67, 71], np.uint8), N, bv.cli_min_af(0.01, N), 0, "N=100000 sparse ends")
+    finally:
+        eng.close()
+
+
 def test_sparse_generator_twin(engine):
     """bv_synth_fill_sparse_host == the dense host twin in sparse form, and runs to the same records."""
     model = bv.synth.config_model("C2")

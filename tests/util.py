@@ -65,7 +65,12 @@ def compare_records(got, want, check_diag=True, rtol=RTOL, soft_flags=None):
     if check_diag:
         # sites whose LRT outcome was proven by the bound carry no chi2 (BV_FLAG_LRT_BOUND)
         bound = (got["flags"] & capi.FLAG_LRT_BOUND) != 0
-        flt_fail |= same_call & ~soft & ~bound & ~close(got["chi2"], want["chi2"], rtol, atol=1e-9)
+        # chi2 = 2 (LL_full - LL_sub) is a difference of two sums over the site's d reads, which the reference forms read by
+        # read: their rounding noise grows with d and does not cancel.  On the 10,000-read rows of BASELINE configs[3] the
+        # reference is ~1e-9 away from an 80-bit evaluation of its own formulas, which the histogram sums match to 2e-13
+        # (tools/hp_chi2.py), so the absolute slack grows with the depth.
+        depth = got["depth"].sum(axis=1).astype(np.float64) + got["depth_other"]
+        flt_fail |= same_call & ~soft & ~bound & ~close(got["chi2"], want["chi2"], rtol, atol=1e-9 + 1e-12 * depth)
         mask = capi.FLAG_BAD_STRAND
         int_fail |= (got["flags"] & mask) != (want["flags"] & mask)
         int_fail |= same_call & ~soft & ((got["flags"] & capi.FLAG_MONO_QUAL) != (want["flags"] & capi.FLAG_MONO_QUAL))

@@ -27,5 +27,5 @@ for r in rows:
 ti = sum(v[0] for v in agg.values()) or 1
 ts = sum(v[1] for v in agg.values()) or 1
 print(f"{want}: warp instructions {ti}, samples {ts}")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top_n]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1 if "--by-samples" in sys.argv else 0])[:top_n]:
     print(f"{k[0]}:{k[1]:4d} inst {100 * v[0] / ti:5.1f}% samp {100 * v[1] / ts:5.1f}% {dict(v[2].most_common(2))} | {v[3]}")
