@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbasevar_b200.so")
-SOURCES = [os.path.join(CSRC, "bv_api.cu")]
+SOURCES = [os.path.join(CSRC, "bv_api.cu"), os.path.join(CSRC, "bv_encode16.cpp")]   # the .cpp goes to the host compiler as is
 DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("bv_common.cuh", "bv_count_kernel.cuh", "bv_finish_kernels.cuh", "bv_em_kernels.cuh", "bv_call_kernels.cuh", "bv_expand_kernel.cuh", "bv_math.cuh",
                                                   "bv_fisher_fast.h", "bv_synth.cuh")] + [
     os.path.join(HERE, "..", "include", "basevar_b200.h")]

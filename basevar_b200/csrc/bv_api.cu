@@ -25,6 +25,9 @@
 #ifndef BV_SCALAR_CTAS_PER_SM
 #define BV_SCALAR_CTAS_PER_SM 8u
 #endif
+#ifndef BV_TASK_HI_CTAS
+#define BV_TASK_HI_CTAS 4
+#endif
 #ifndef BV_EM_POOL_BINS_PER_SITE
 #define BV_EM_POOL_BINS_PER_SITE 64u
 #endif
@@ -168,7 +171,8 @@ struct bv_ctx {
     uint64_t h2d_bytes_total = 0;
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int task_ctas_per_sm = 4;         // resident CTAs of bv_em_task_kernel per SM (asked of the runtime in bv_create)
+    int task_ctas_per_sm = 3;         // resident CTAs per SM of bv_em_task_kernel<1> (asked of the runtime in bv_create) ...
+    int task_ctas_per_sm_hi = 4;      // ... and of bv_em_task_kernel<BV_TASK_HI_CTAS>, the build for tiles with many EM tasks
     bool ev_valid = false;
     bool has_model = false;
     uint64_t pitch_cap = 0;
@@ -269,7 +273,8 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->em_pool_cap = sc.em_pool_cap;
     for (int k = 0; k < 3; ++k) a->em_task_cap[k] = sc.em_task_cap[k];
     a->brief = nullptr; a->full_out = nullptr;   // set by the submit paths of compact tiles
-    a->em_resume = 0; a->pad1 = 0;
+    a->em_resume = 0;
+    a->em_task_split = (uint32_t)ctx->num_sms * (uint32_t)ctx->task_ctas_per_sm_hi * (uint32_t)bv::kTaskThreads;   // one round of resident threads
     a->list_called = nullptr;   // set_call_args() turns the called-site kernels on
     a->mapq = nullptr; a->rpr = nullptr; a->aux_pitch = 0; a->rpr_pitch = 0;
     a->sample_group = nullptr; a->calls = nullptr; a->groups = nullptr; a->n_groups = 0; a->pad0 = 0;
@@ -359,17 +364,21 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     // K4b: groups of lanes per EM task, CTAs stride over the task lists (their lengths are only known on the device, where the
     // kernel picks the group size from them): always the grid that fills the GPU, CTAs without work leave at once
     grid = (uint32_t)ctx->num_sms * (uint32_t)ctx->task_ctas_per_sm;
+    const uint32_t grid_hi = (uint32_t)ctx->num_sms * (uint32_t)ctx->task_ctas_per_sm_hi;
+    bv::SiteKernelArgs b = a;
     if (a.abs_mode != BV_EM_ABS_INT_TRUNC) {
         // fabs in the convergence test: EMs of very different lengths; their iterations run with the lanes fed task by task
         // (bv_em_iter_kernel), the rest of every task -- log-likelihood sums, decisions -- from the frequencies that leaves
         bv::bv_em_iter_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(a);
         BV_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
-        bv::SiteKernelArgs b = a;
         b.em_resume = 1;
-        bv::bv_em_task_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
-    } else
-    bv::bv_em_task_kernel<<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(a);
+    }
+    // two builds of the kernel (registers / occupancy); the tile's task count decides on the device which of them works
+    bv::bv_em_task_kernel<1><<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
+    BV_CUDA(ctx, cudaGetLastError());
+    bv::bv_em_task_kernel<BV_TASK_HI_CTAS><<<grid_hi, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
+    ctx->launches += 1;
     BV_CUDA(ctx, cudaGetLastError());
     if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[5], stream)); ctx->ev_valid = true; }
     ctx->launches += 5;
@@ -421,6 +430,13 @@ static inline const uint32_t* encode16_run(const uint32_t* __restrict__ p, const
     next = nx; o = out; oa = outa;
     return p;
 }
+
+namespace bv {   // bv_encode16.cpp: the same loop, eight cells per step (AVX2, chosen at run time)
+bool encode16_have_avx2();
+template <bool AUX>
+const uint32_t* encode16_run_avx2(const uint32_t* __restrict__ p, const uint32_t* __restrict__ end, const uint32_t* __restrict__ aux32,
+                                  uint16_t* __restrict__& o, uint32_t* __restrict__& oa, uint32_t& next);
+}  // namespace bv
 
 // The records of a tile on their way back: all of them (BV_OUT_RECORDS), or the briefs plus the full records of the sites that
 // need one (BV_OUT_COMPACT; the pack kernel writes those into the slot's pinned list itself).
@@ -547,7 +563,8 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kHistLongSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_em_task_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_em_task_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_em_task_kernel<BV_TASK_HI_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_em_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_ranksum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kCallSmemBytes) != cudaSuccess ||
@@ -559,8 +576,10 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         }
         {   // the EM task kernel's grid: what is resident at once (registers / shared memory decide)
             int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bv::bv_em_task_kernel, bv::kTaskThreads, bv::kTaskSmemBytes) == cudaSuccess && nb > 0)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bv::bv_em_task_kernel<1>, bv::kTaskThreads, bv::kTaskSmemBytes) == cudaSuccess && nb > 0)
                 ctx->task_ctas_per_sm = nb;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bv::bv_em_task_kernel<BV_TASK_HI_CTAS>, bv::kTaskThreads, bv::kTaskSmemBytes) == cudaSuccess && nb > 0)
+                ctx->task_ctas_per_sm_hi = nb;
             cudaGetLastError();
         }
         {
@@ -915,6 +934,7 @@ int bv_sparse_encode16(const uint32_t* cells, const uint32_t* aux32, const uint3
                        uint16_t* words16, uint32_t* aux16, uint64_t max_words, uint32_t* start16, uint64_t* n_words) {
     if (!site_start || !n_words || (n_sites && site_start[n_sites] && !cells)) return set_err(nullptr, BV_ERR_ARG, "null argument");
     uint64_t n = 0;
+    static const bool have_avx2 = bv::encode16_have_avx2() && !getenv("BASEVAR_B200_NO_AVX2");
     for (uint32_t s = 0; s < n_sites; ++s) {
         if (start16) start16[s] = (uint32_t)n;
         const uint32_t c0 = site_start[s], c1 = site_start[s + 1];
@@ -922,12 +942,17 @@ int bv_sparse_encode16(const uint32_t* cells, const uint32_t* aux32, const uint3
         uint32_t next = 0;   // the sample index a gap of 0 would mean
         // room for the worst case of this site: every cell plus a skip word per 31 samples of the 2^20 a cell can name
         const bool roomy = words16 && n + (uint64_t)(c1 - c0) + BV_CELL_MAX_SAMPLES / BV_CELL16_GAP_SKIP + 1 <= max_words;
+        // the vector loop stores eight words at a time, so it wants eight words of slack behind the worst case
+        const bool wide = roomy && c1 - c0 >= 16 && n + (uint64_t)(c1 - c0) + BV_CELL_MAX_SAMPLES / BV_CELL16_GAP_SKIP + 9 <= max_words && have_avx2;
         for (uint32_t c = c0; c < c1; ++c) {
             if (roomy) {
                 uint16_t* o = words16 + n;
                 uint32_t* oa = aux16 ? aux16 + n : nullptr;
-                const uint32_t* stop = aux16 ? encode16_run<true>(cells + c, cells + c1, aux32 ? aux32 + c1 : nullptr, o, oa, next)
-                                             : encode16_run<false>(cells + c, cells + c1, nullptr, o, oa, next);
+                const uint32_t* stop =
+                    wide ? (aux16 ? bv::encode16_run_avx2<true>(cells + c, cells + c1, aux32 ? aux32 + c1 : nullptr, o, oa, next)
+                                  : bv::encode16_run_avx2<false>(cells + c, cells + c1, nullptr, o, oa, next))
+                         : (aux16 ? encode16_run<true>(cells + c, cells + c1, aux32 ? aux32 + c1 : nullptr, o, oa, next)
+                                  : encode16_run<false>(cells + c, cells + c1, nullptr, o, oa, next));
                 n = (uint64_t)(o - words16);
                 c = (uint32_t)(stop - cells);
                 if (c >= c1) break;

@@ -100,7 +100,7 @@ struct SiteKernelArgs {
     uint32_t em_task_cap[3];
     // compact record transport (BV_OUT_COMPACT): null unless the tile asked for it
     uint32_t em_resume;      // bv_em_task_kernel: the EM iterations were run by bv_em_iter_kernel, start from its frequencies
-    uint32_t pad1;
+    uint32_t em_task_split;  // tiles with more EM tasks than this run bv_em_task_kernel<4>, the others bv_em_task_kernel<1>
     uint2* brief;            // [n_sites] device copy of the briefs: K1 writes them, bv_pack_kernel completes them
     bv_site_out* full_out;   // pinned host memory (mapped): the full records, written by bv_pack_kernel
     // called sites (n_alt > 0): rank sums (K5) and population-group frequencies (K6); all null / 0 when not asked for

@@ -243,9 +243,6 @@ __global__ void __launch_bounds__((LONG ? kLongWarps : kQualWarps) * 32, 1) bv_h
 #ifndef BV_TASK_STAGE_BINS
 #define BV_TASK_STAGE_BINS 96
 #endif
-#ifndef BV_TASK_MIN_CTAS
-#define BV_TASK_MIN_CTAS 1      // resident CTAs per SM the compiler has to leave registers for
-#endif
 #ifndef BV_TASK_G4_MAX_TASKS
 #define BV_TASK_G4_MAX_TASKS 12288
 #endif
@@ -791,7 +788,18 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
     if (n_alt && a.list_called) a.list_called[atomicAdd(a.counters + kCntCalled, 1u)] = site;
 }
 
-__global__ void __launch_bounds__(kTaskThreads, BV_TASK_MIN_CTAS) bv_em_task_kernel(const __grid_constant__ SiteKernelArgs a) {
+// Two builds of the kernel, launched one after the other; the task count (known on the device only) picks the one that works,
+// the other leaves at once.  kMinCtas = 1: the compiler takes the registers it wants (154: three CTAs per SM), fastest while
+// the tasks of a tile fit one round of resident threads.  kMinCtas = 4: 126 registers, four CTAs per SM, 12 % faster once
+// they do not (deep multi-allelic pileups: 185,000 tasks per 200,000 sites of C5) and 7-14 % slower below
+// (gpurun r2u, profiles/r02_em_task_occupancy.txt).
+template <int kMinCtas>
+__global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(const __grid_constant__ SiteKernelArgs a) {
+    {
+        const uint64_t n_all = (uint64_t)min(a.counters[kCntEmTask2], a.em_task_cap[0]) + min(a.counters[kCntEmTask3], a.em_task_cap[1]) +
+                               min(a.counters[kCntEmTask4], a.em_task_cap[2]);
+        if ((n_all > (uint64_t)a.em_task_split) != (kMinCtas > 1)) return;
+    }
     TaskCta& cs = *reinterpret_cast<TaskCta*>(bv_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 4 * kQSlots; i += kTaskThreads) cs.lut[i / kQSlots][i % kQSlots] = a.lut[(i / kQSlots) * kQStride + i % kQSlots];

@@ -415,6 +415,18 @@ inline char parse_char(const char* p, const char* e) {   // istringstream >> cha
 }  // namespace
 
 void BasevarCaller::call(const std::vector<std::string>& lines) {
+    try {
+        call_row(lines);
+    } catch (...) {
+        // The reference writes position by position, so everything before a malformed row is on disk when it throws
+        // (src/basetype_caller.cpp:586-611).  Here up to n_slots tiles of earlier positions are still queued or in flight: they
+        // are emitted first (the row that failed was not counted), then the error goes on.
+        try { finish(); } catch (...) {}
+        throw;
+    }
+}
+
+void BasevarCaller::call_row(const std::vector<std::string>& lines) {
     Tile& T = *tiles_[cur_];
     if (T.pending) drain(cur_);   // the slot comes round again: its previous tile is emitted first
     T.ensure_dense();

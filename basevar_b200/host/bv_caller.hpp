@@ -143,6 +143,7 @@ public:
 
 private:
     struct Tile;
+    void call_row(const std::vector<std::string>& smp_bf_line_vector);
     void submit_current();
     void drain(uint32_t slot);
 

@@ -8,6 +8,6 @@ mkdir -p variants
 for v in $1; do
   name=${v%%:*}; defs=$(echo "${v#*:}" | sed 's/,/ -D/g; s/^/-D/')
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -shared \
-       $defs -o "variants/libbv_$name.so" csrc/bv_api.cu
+       $defs -o "variants/libbv_$name.so" csrc/bv_api.cu csrc/bv_encode16.cpp
 done
 ls variants
