@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# round 2, session a: parity of the three-kernel K4 + timings on every shape
+# parity suite + kernel timings of every BASELINE shape, for this build and for tuning variants: bash tools/gpu_parity_timings.sh <tag> "<variants>"
 set -u
 TAG="${1:-r2a}"; VARS="${2:-}"
 O=gpurun_out/$TAG; mkdir -p "$O"

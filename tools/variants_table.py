@@ -1,4 +1,4 @@
-"""Table of a tools/gpu_r2a.sh / gpu_variants.sh log: python tools/variants_table.py gpurun_out/<tag>/run_kernel.log"""
+"""Table of a tools/gpu_parity_timings.sh / gpu_variants.sh log: python tools/variants_table.py gpurun_out/<tag>/run_kernel.log"""
 import re
 import sys
 
