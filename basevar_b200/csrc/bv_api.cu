@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
@@ -156,6 +157,11 @@ struct bv_slot {
     const uint8_t* h_ref = nullptr;       // the tile's REF bases (host memory of the caller, valid until the wait)
     uint2* d_brief = nullptr;             // [max_sites]
     bv_site_brief* h_brief = nullptr;     // [max_sites] pinned
+    // BASEVAR_B200_TRACE=1: the tile's timeline on its stream (upload begins / ends, kernels end, results are back)
+    cudaEvent_t ev_up = nullptr;          // this tile's upload is complete (recorded on the context's copy stream)
+    cudaEvent_t ev_trace[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint64_t tile_no = 0;
+    double t_submit = 0;                  // host clock at submit, seconds since the context's first traced submit
 };
 
 struct bv_ctx {
@@ -182,9 +188,20 @@ struct bv_ctx {
     uint32_t n_groups = 0;
     cudaEvent_t ev_call[3] = {nullptr, nullptr, nullptr};
     bool ev_call_valid = false;
+    cudaStream_t copy_stream = nullptr;   // uploads of sparse host tiles, in submit order (see tile_submit_sparse_impl)
+    bool trace = false;               // BASEVAR_B200_TRACE=1: one line per sparse host tile on stderr at its wait
+    cudaEvent_t ev_trace0 = nullptr;  // recorded at the first traced submit: the origin of the timeline
+    uint64_t tiles_traced = 0;
+    double t_trace0 = 0;
 };
 
 static char g_err[512] = "";
+
+static double host_seconds() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 static int set_err(bv_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
@@ -583,6 +600,10 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaGetLastError();
         }
         {
+            const char* z = getenv("BASEVAR_B200_TRACE");
+            ctx->trace = z && z[0] == '1';
+        }
+        {
             const char* z = getenv("BASEVAR_B200_ZERO_COPY_QUAL");
             if (z && z[0] == '0') ctx->zero_copy_qual = false;
         }
@@ -593,9 +614,11 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             ctx->slots = new (std::nothrow) bv_slot[params->n_slots];
             if (!ctx->slots) { rc = set_err(nullptr, BV_ERR_NOMEM, "out of host memory"); break; }
             const size_t plane = (size_t)params->max_sites * ctx->pitch_cap;
+            if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = set_err(nullptr, BV_ERR_CUDA, "cudaStreamCreate failed"); break; }
             for (uint32_t i = 0; i < params->n_slots && rc == BV_OK; ++i) {
                 bv_slot& s = ctx->slots[i];
                 cudaError_t ce = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+                if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s.ev_up, cudaEventDisableTiming);
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_planes, 3 * plane);
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_ref, params->max_sites);
                 if (ce == cudaSuccess) ce = cudaMalloc(&s.d_out, (size_t)params->max_sites * sizeof(bv_site_out));
@@ -632,6 +655,8 @@ void bv_destroy(bv_ctx* ctx) {
             if (s.h_counters) cudaFreeHost(s.h_counters);
             cudaFree(s.d_aux);
             cudaFree(s.d_cells); cudaFree(s.d_site_start);
+            for (int k = 0; k < 4; ++k) if (s.ev_trace[k]) cudaEventDestroy(s.ev_trace[k]);
+            if (s.ev_up) cudaEventDestroy(s.ev_up);
         }
         delete[] ctx->slots;
     }
@@ -639,6 +664,8 @@ void bv_destroy(bv_ctx* ctx) {
     scratch_free(ctx->dev_scratch);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 3; ++i) if (ctx->ev_call[i]) cudaEventDestroy(ctx->ev_call[i]);
+    if (ctx->ev_trace0) cudaEventDestroy(ctx->ev_trace0);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     delete ctx;
 }
 
@@ -881,15 +908,36 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
         if (rc != BV_OK) return rc;
     }
     memset(s.h_counters, 0, bv::kNumCounters * sizeof(uint32_t));
-    if (t->n_sites && t->n_samples) {
-        if (n_cells) {
-            BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells, t->cells, n_cells * word_bytes, cudaMemcpyHostToDevice, s.stream));
-            if (with_calls)
-                BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells + s.cells_cap, t->cells_aux, n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+    const bool trace = ctx->trace && t->n_sites && t->n_samples;
+    // Uploads go through ONE stream, in submit order.  On the slots' own streams the uploads of the tiles in flight run side by
+    // side and share the link: they all finish together, then their kernels run with the link idle, and the pipeline moves in
+    // waves (100,000-sample tiles, 4 slots: 75 % of the bare-copy rate; profiles/r02_tile_timeline.txt).  First in, first out,
+    // tile k's kernels run under tile k + 1's upload.
+    cudaStream_t up = ctx->copy_stream;
+    if (trace) {
+        if (!ctx->ev_trace0) {
+            BV_CUDA(ctx, cudaEventCreate(&ctx->ev_trace0));
+            BV_CUDA(ctx, cudaEventRecord(ctx->ev_trace0, up));
+            ctx->t_trace0 = host_seconds();
         }
-        BV_CUDA(ctx, cudaMemcpyAsync(s.d_site_start, t->site_start, ((size_t)t->n_sites + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
-        BV_CUDA(ctx, cudaMemcpyAsync(s.d_ref, t->ref_base, t->n_sites, cudaMemcpyHostToDevice, s.stream));
+        for (int k = 0; k < 4; ++k) if (!s.ev_trace[k]) BV_CUDA(ctx, cudaEventCreate(&s.ev_trace[k]));
+        s.tile_no = ctx->tiles_traced++;
+        s.t_submit = host_seconds() - ctx->t_trace0;
+        BV_CUDA(ctx, cudaEventRecord(s.ev_trace[0], up));
+    }
+    if (t->n_sites && t->n_samples) {
+        // (the small arrays first: when they come from pageable memory the call waits for what is queued in front of them)
+        BV_CUDA(ctx, cudaMemcpyAsync(s.d_site_start, t->site_start, ((size_t)t->n_sites + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, up));
+        BV_CUDA(ctx, cudaMemcpyAsync(s.d_ref, t->ref_base, t->n_sites, cudaMemcpyHostToDevice, up));
+        if (n_cells) {
+            BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells, t->cells, n_cells * word_bytes, cudaMemcpyHostToDevice, up));
+            if (with_calls)
+                BV_CUDA(ctx, cudaMemcpyAsync(s.d_cells + s.cells_cap, t->cells_aux, n_cells * sizeof(uint32_t), cudaMemcpyHostToDevice, up));
+        }
         s.h2d_bytes = n_cells * (word_bytes + (with_calls ? sizeof(uint32_t) : 0)) + ((size_t)t->n_sites + 1) * sizeof(uint32_t) + t->n_sites;
+        if (trace) BV_CUDA(ctx, cudaEventRecord(s.ev_trace[1], up));
+        BV_CUDA(ctx, cudaEventRecord(s.ev_up, up));
+        BV_CUDA(ctx, cudaStreamWaitEvent(s.stream, s.ev_up, 0));
         BV_CUDA(ctx, cudaMemsetAsync(a.counters, 0, bv::kNumCounters * sizeof(uint32_t), s.stream));
         bv::ExpandArgs x;
         x.cells = s.d_cells; x.cells_aux = with_calls ? s.d_cells + s.cells_cap : nullptr; x.site_start = s.d_site_start;
@@ -908,6 +956,7 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
     }
     rc = launch_site_kernel(ctx, a, s.stream, /*counters_zeroed=*/true);
     if (rc != BV_OK) return rc;
+    if (trace) BV_CUDA(ctx, cudaEventRecord(s.ev_trace[2], s.stream));
     if (t->n_sites) {
         bv_site_out* dst = s.h_out;
         if (t->out && host_device_pointer(t->out)) { dst = t->out; s.out_direct = true; }
@@ -916,6 +965,7 @@ static int tile_submit_sparse_impl(bv_ctx* ctx, int slot, const bv_sparse_tile* 
         if (t->n_samples)
             BV_CUDA(ctx, cudaMemcpyAsync(s.h_counters, a.counters, bv::kNumCounters * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     }
+    if (trace) BV_CUDA(ctx, cudaEventRecord(s.ev_trace[3], s.stream));
     s.with_calls = with_calls;
     s.n_sites = t->n_sites;
     s.busy = true;
@@ -1019,9 +1069,18 @@ int bv_tile_wait(bv_ctx* ctx, int slot, bv_site_out* out) {
     bv_slot& s = ctx->slots[slot];
     if (!s.busy) return set_err(ctx, BV_ERR_STATE, "slot %d has nothing submitted", slot);
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double t_wait0 = ctx->trace ? host_seconds() - ctx->t_trace0 : 0.0;
     cudaError_t e = cudaStreamSynchronize(s.stream);
     s.busy = false;
     BV_CUDA(ctx, e);
+    if (ctx->trace && s.sparse && s.ev_trace[3] && s.n_sites) {
+        float ms[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&ms[k], ctx->ev_trace0, s.ev_trace[k]);
+        fprintf(stderr, "bv trace: tile %llu slot %d: submit at %.3f ms (host); upload %.3f .. %.3f, kernels until %.3f, results back %.3f (device); "
+                        "wait %.3f .. %.3f (host); %.1f MB up\n",
+                (unsigned long long)s.tile_no, slot, 1e3 * s.t_submit, ms[0], ms[1], ms[2], ms[3], 1e3 * t_wait0,
+                1e3 * (host_seconds() - ctx->t_trace0), s.h2d_bytes / 1e6);
+    }
     if (s.sparse && s.n_sites && s.h_counters[bv::kCntBadCell])
         return set_err(ctx, BV_ERR_ARG, "sparse tile: cell with sample >= n_samples or site_start not ascending / beyond the cell count");
     if (s.compact) {   // collected in compact form (bv_tile_wait_compact), or expanded here for a caller that wants records

@@ -157,7 +157,9 @@ class BaseTypeEngine:
         for s0 in range(0, max(S, 1), step):
             ns = min(step, S - s0)
             c0 = int(site_start[s0])
-            st = np.ascontiguousarray(site_start[s0:s0 + ns + 1] - np.uint32(c0))
+            # (pinned when the records are: a pageable source makes cudaMemcpyAsync wait for the uploads queued in front of it)
+            st = _alloc(ns + 1, np.uint32, out_pinned is not None)
+            st[:] = site_start[s0:s0 + ns + 1] - np.uint32(c0)
             t = BvSparseTile(cells[c0:].ctypes.data if c0 < cells.shape[0] else cells.ctypes.data, None, st.ctypes.data,
                              ref_base[s0:].ctypes.data, out_pinned[s0:].ctypes.data if out_pinned is not None and not compact else None,
                              ns, n_samples, fmt, capi.OUT_COMPACT if compact else capi.OUT_RECORDS)

@@ -437,8 +437,10 @@ def main():
             d2h[0] += 8 * ns + 128 * len(full)
             eng.expand_compact(briefs, full, s_ref[s0:s0 + ns], rec_sp[s0:s0 + ns])
 
-        eng.run_sparse_tiles(tiles, 1, compact=expand if compact else None)   # warm-up (sizes the cell buffers); fills rec_sp
+        eng.run_sparse_tiles(tiles, 1, compact=expand if compact else None)   # warm-up; fills rec_sp
         records = rec_sp.tobytes()
+        # every slot sizes its cell buffer at its first tile (cudaMalloc synchronises the device): a pass that reaches all slots
+        eng.run_sparse_tiles(tiles, -(-args.slots // len(tiles)))
         barrier()
         l0, up0 = eng.launch_count, eng.h2d_bytes
         t0 = time.perf_counter()
@@ -502,7 +504,7 @@ def main():
                     eng._check(lib.bv_tile_wait(eng._ctx, ps, None), "bv_tile_wait")
 
         rec_sp[:] = 0
-        run(1)
+        run(-(-n_slots // len(tiles)))   # warm-up that reaches every slot
         barrier()
         l0 = eng.launch_count
         t0 = time.perf_counter()
