@@ -353,7 +353,7 @@ def main():
     ap.add_argument("--abs-mode", type=int, default=0, help="0 = as-built int abs() in EM, 1 = fabs")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--slots", type=int, default=4, help="in-flight tiles of the e2e legs (each slot: a stream, device planes, pinned staging)")
-    ap.add_argument("--tile-sites", type=int, default=0, help="sites per host tile of the e2e legs (default 131072; one K1 round for long rows)")
+    ap.add_argument("--tile-sites", type=int, default=0, help="sites per host tile of the e2e legs (default 262144: ~40 us of copy set-up per tile; one K1 round, 9472, for long rows)")
     ap.add_argument("--e2e-sites", type=int, default=0, help="sites per GPU of the e2e legs (default: the workload's, 2 tiles for C4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the `configs` block (C3, C4 shape, C5 x 2 abs modes)")
@@ -396,7 +396,7 @@ def main():
     n_samples = cfg["n_samples"]
     pitch = (n_samples + 15) // 16 * 16
     long_rows = n_samples > 4096
-    tile_sites = int(args.tile_sites or (9472 if long_rows else 131072))
+    tile_sites = int(args.tile_sites or (9472 if long_rows else 262144))
     tile_sites = min(tile_sites, S)
     main_res = Resident(bv, torch, dev, local_rank, name, cfg, S, site0, args.abs_mode, n_slots=args.slots, tile_sites=tile_sites)
     eng, model, maf = main_res.eng, main_res.model, main_res.maf
