@@ -1,21 +1,25 @@
 // bv_common.cuh -- definitions shared by the kernels of the basetype core (sm_100a).
 //
-// The per-site statistical core of `basevar basetype` runs as three kernels, split by the KIND of work so that every
-// kernel is small and all of its warps execute the same code (one fused kernel was measured instruction-cache bound:
+// The per-site statistical core of `basevar basetype` runs as a sequence of small kernels, split by the KIND of work so that
+// every kernel is small and all of its warps execute the same code (one fused kernel was measured instruction-cache bound:
 // 59 % of its stall samples were "no instruction" with 24 warps per SM spread over 76 KB of code):
 //
+//   K0  bv_expand_kernel  (bv_expand_kernel.cuh)   sparse host tiles only: the covered cells -> the dense planes in HBM.
 //   K1  bv_count_kernel   (bv_count_kernel.cuh)    every site, every cell: streams the base + strand planes through
 //        per-warp TMA rings and counts -- per-base depths and the 2x4 strand table.  Sites whose reads all equal REF get
 //        their final record here; the others get their counts and the state BV_STATE_SCALAR.
 //   K2  bv_scalar_kernel  (bv_finish_kernels.cuh)  one THREAD per site in state SCALAR: active alleles, strand-bias
-//        Fisher test; final record unless the result depends on base qualities (then state BV_STATE_QUAL).
+//        Fisher test; final record unless the result depends on base qualities (then state BOUND or EM).
 //   K3  bv_bound_kernel   (bv_finish_kernels.cuh)  one warp per site in state BOUND (REF plus one minor allele carried by
 //        a few reads -- sequencing errors): fetches the row's base + qual planes and settles the LRT by a rigorous bound
 //        on the likelihood ratio, without running the EM; what the bound cannot decide goes to state EM.
-//   K4  bv_em_kernel      (bv_finish_kernels.cuh)  one warp per site in state EM: (base, phred) histogram of the row,
-//        EM + LRT backward elimination on the bins.  QUAL (chi-square survival function) and the strand-bias Fisher test
-//        of the VCF row are scalar work that a warp would do 32 times over: the warp queues its sites with ALT alleles
-//        and finishes them 32 at a time, one THREAD per site.
+//   K4a bv_hist_kernel    (bv_em_kernels.cuh)      one warp per site in state EM: (base, phred) histogram of the row, compact
+//        bins, one EM task per candidate subset of the active alleles.
+//   K4b bv_em_task_kernel (bv_em_kernels.cuh)      one THREAD per EM task (the whole EM of one subset on the site's bins); the
+//        thread that finishes a site's last task replays the LRT elimination on the results and completes the record (QUAL,
+//        Fisher test of the VCF row).  bv_em_iter_kernel runs the iterations first when the convergence test uses fabs.
+//   K5 / K6 (bv_call_kernels.cuh) rank sums and population-group frequencies of the called sites; K7 bv_pack_kernel
+//        (bv_finish_kernels.cuh) the compact result transport.
 //
 // Work moves between the kernels through compact lists of site indices (appended with warp-aggregated atomics, so their
 // order varies from run to run; every site is independent, so the records do not).  The record's `reserved0` word

@@ -1,4 +1,4 @@
-// bv_count_kernel.cuh -- K1: the streaming pass over every cell (see bv_common.cuh for the three-kernel split).
+// bv_count_kernel.cuh -- K1: the streaming pass over every cell (see bv_common.cuh for the split of the core into kernels).
 //
 // One warp owns one genomic site at a time (sites are the embarrassingly parallel axis, samples the reduction axis).
 // Persistent CTAs, one per SM; every warp streams its own sequence of site rows (warp w: sites w, w + W, ...) through

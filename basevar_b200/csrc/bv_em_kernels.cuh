@@ -1,4 +1,5 @@
-// bv_em_kernels.cuh -- K4: the sites whose result depends on base qualities (state kStateEM), as three kernels.
+// bv_em_kernels.cuh -- K4: the sites whose result depends on base qualities (state kStateEM): K4a bv_hist_kernel, K4b bv_em_task_kernel
+// (+ bv_em_iter_kernel when the EM's convergence test uses fabs).
 //
 // The reference runs, per such site, one EM over the full active set and then backward elimination: for every
 // (n-1)-subset of the n active alleles another EM, keep the best, stop when 2 dLL >= 24 (BaseType::lrt,
@@ -824,10 +825,11 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         lg.mask = (G == 1 ? 1u : 0xfu) << (lane & ~(G - 1));
     }
 #if BV_TASK_WARP_ROUNDS
-    // Rounds of ONE WARP: 32 / G tasks of one list, staged into the warp's own 32 rows, run, and the sites they complete decided
-    // by the same warp -- nothing in a round waits for another warp.  (Rounds of a whole CTA cost a barrier per phase: a fifth of
-    // the kernel's stall samples, and on multi-allelic pileups three warps stood idle while the first one ran the few decisions
-    // of the round.)  Round v of the three lists taken together goes to warp v mod (all warps).
+    // Tuning build (off by default).  Rounds of ONE WARP: 32 / G tasks of one list, staged into the warp's own 32 rows, run, and
+    // the sites they complete queued for decision by the same warp -- nothing in a round waits for another warp, where rounds of
+    // a whole CTA cost a barrier per phase (a fifth of the kernel's stall samples).  Measured (profiles/r02_variants.txt): 2-4 %
+    // faster on C3 / C4 / C5 with fabs, even on C5, 1.5 % slower on C2 -- the CTA's warps in lockstep share the instruction
+    // cache better than warps in different phases.  Round v of the three lists taken together goes to warp v mod (all warps).
     __syncthreads();   // the tables are written
     const uint32_t tpw = 32u / (uint32_t)lg.G;                 // tasks per round
     const uint32_t slot = (uint32_t)lane / (uint32_t)lg.G;      // this lane's task of the round
