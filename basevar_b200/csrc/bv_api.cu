@@ -1225,6 +1225,36 @@ int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_s
     return BV_OK;
 }
 
+int bv_fisher_fs(bv_ctx* ctx, const int32_t* tables, uint32_t n, double* fs_out) {
+    if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
+    if (n == 0) return BV_OK;
+    if (!tables || !fs_out) return set_err(ctx, BV_ERR_ARG, "bv_fisher_fs: null argument");
+    for (uint32_t i = 0; i < n; ++i) {
+        int64_t tot = 0;
+        for (int k = 0; k < 4; ++k) {
+            if (tables[4 * (size_t)i + k] < 0) return set_err(ctx, BV_ERR_ARG, "bv_fisher_fs: negative count in table %u", i);
+            tot += tables[4 * (size_t)i + k];
+        }
+        // the log-factorial table holds lgamma(k + 1) for k <= max_samples + 1
+        if (tot > (int64_t)ctx->prm.max_samples + 1) return set_err(ctx, BV_ERR_ARG, "bv_fisher_fs: table %u has %lld reads > max_samples + 1", i, (long long)tot);
+    }
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    int4* d_t = nullptr;
+    double* d_fs = nullptr;
+    cudaError_t e = cudaMalloc(&d_t, (size_t)n * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMalloc(&d_fs, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_t, tables, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        bv::bv_fs_kernel<<<(n + 127) / 128, 128>>>(d_t, d_fs, n, ctx->d_logfact);
+        e = cudaGetLastError();
+        ctx->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(fs_out, d_fs, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_t); cudaFree(d_fs);
+    BV_CUDA(ctx, e);
+    return BV_OK;
+}
+
 uint32_t bv_suggest_tile_sites(const bv_ctx* ctx, uint32_t n_samples, uint64_t max_bytes) {
     const uint64_t pitch = ((uint64_t)(n_samples ? n_samples : 1) + 15) / 16 * 16;
     uint64_t fit = max_bytes / (3 * pitch);

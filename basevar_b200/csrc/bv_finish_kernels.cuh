@@ -94,6 +94,17 @@ __device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_
     return state;
 }
 
+// FS of free-standing 2x2 strand tables (bv_fisher_fs): one thread per table, the rule of scalar_site above.
+__global__ void __launch_bounds__(128) bv_fs_kernel(const int4* __restrict__ tables, double* __restrict__ fs, uint32_t n,
+                                                    const double* __restrict__ logfact) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 t = tables[i];   // ref_fwd, ref_rev, alt_fwd, alt_rev
+    double v = 0.0;
+    if ((t.z | t.w) != 0 && (t.x | t.y) != 0) v = fs_from_table(logfact, t.x, t.y, t.z, t.w);
+    fs[i] = v;
+}
+
 // =====================================================================================================================
 // K7 bv_pack_kernel (BV_OUT_COMPACT tiles, after everything else): the sites K1 could not finish from their counts get their
 // full record copied into the pinned host list -- the kernel writes across PCIe itself, 8 lanes per 128-byte record, the

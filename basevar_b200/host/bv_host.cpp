@@ -156,6 +156,7 @@ Context::Context(int device, float min_af, uint32_t max_samples, uint32_t max_si
     p.max_sites = max_sites;
     p.n_slots = n_slots;
     check(bv_create(device, &p, &ctx_), nullptr, "bv_create");
+    max_samples_ = max_samples;
 }
 Context::~Context() { bv_destroy(ctx_); }
 void Context::submit(int slot, const bv_tile& tile) { check(bv_tile_submit(ctx_, slot, &tile), ctx_, "bv_tile_submit"); }
@@ -174,6 +175,12 @@ std::vector<bv_site_out> Context::run(const bv_sparse_tile& tile) {
     return out;
 }
 uint64_t Context::launch_count() const { return bv_launch_count(ctx_); }
+double Context::fisher_fs(int ref_fwd, int ref_rev, int alt_fwd, int alt_rev) {
+    const int32_t t[4] = {ref_fwd, ref_rev, alt_fwd, alt_rev};
+    double fs = 0.0;
+    check(bv_fisher_fs(ctx_, t, 1, &fs), ctx_, "bv_fisher_fs");
+    return fs;
+}
 
 // ---- BaseType ---------------------------------------------------------------------------------------------------------
 BaseType::BaseType(const BatchInfo* bi, const bv_site_out& rec)
@@ -250,7 +257,7 @@ double BaseType::get_lrt_af(char b) const {
 // ---- strand_bias -------------------------------------------------------------------------------------------------------
 static int code_of(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
 
-StrandBiasInfo strand_bias(const char ref_base, const std::string alt_bases_string, const bv_site_out& rec) {
+StrandBiasInfo strand_bias(const char ref_base, const std::string alt_bases_string, const bv_site_out& rec, Context* ctx) {
     if (rec.flags & BV_FLAG_BAD_STRAND)   // src/basetype.cpp:271-273
         throw std::runtime_error("[ERROR] Get strange strand symbol: ");
     StrandBiasInfo s;
@@ -274,7 +281,22 @@ StrandBiasInfo strand_bias(const char ref_base, const std::string alt_bases_stri
     if (((alt_set ^ cvg_set) & covered) == 0) s.fs = rec.fs_cvg;
     else if (rec.n_alt && ((alt_set ^ vcf_set) & covered) == 0) s.fs = rec.fs_vcf;
     else if ((s.alt_fwd | s.alt_rev) == 0 || (s.ref_fwd | s.ref_rev) == 0) s.fs = 0.0;   // one possible table: p == 1
-    else throw std::invalid_argument("[ERROR] strand_bias: FS of this ALT set was not computed on the device");
+    else {
+        // neither of the two sets the record carries FS for: the 2x2 table goes to the device (bv_fisher_fs, the code of kernel K2)
+        const uint32_t reads = (uint32_t)(s.ref_fwd + s.ref_rev + s.alt_fwd + s.alt_rev);
+        if (!ctx) {
+            if (!t_one.ctx || t_one.ctx->max_samples() + 1 < reads) {
+                const char* d = getenv("BASEVAR_B200_DEVICE");
+                t_one.ctx.reset();
+                t_one.packer.reset();
+                t_one.n = std::max<uint32_t>(reads, 1);
+                t_one.min_af = 0.01f;
+                t_one.ctx.reset(new Context(d ? atoi(d) : 0, t_one.min_af, t_one.n, 1, 1));
+            }
+            ctx = t_one.ctx.get();
+        }
+        s.fs = ctx->fisher_fs(s.ref_fwd, s.ref_rev, s.alt_fwd, s.alt_rev);
+    }
     // src/basetype.cpp:286, int32 products as in the reference
     s.sor = (s.ref_rev * s.alt_fwd > 0) ? (double)(s.ref_fwd * s.alt_rev) / (double)(s.ref_rev * s.alt_fwd) : 10000;
     return s;

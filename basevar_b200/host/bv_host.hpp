@@ -159,10 +159,14 @@ public:
     uint32_t n_slots() const { return n_slots_; }
     uint64_t launch_count() const;
     bv_ctx* raw() { return ctx_; }
+    uint32_t max_samples() const { return max_samples_; }
+    // FS of free-standing 2x2 strand tables {ref_fwd, ref_rev, alt_fwd, alt_rev} on the device (bv_fisher_fs)
+    double fisher_fs(int ref_fwd, int ref_rev, int alt_fwd, int alt_rev);
 
 private:
     bv_ctx* ctx_ = nullptr;
     uint32_t n_slots_;
+    uint32_t max_samples_ = 0;
 };
 
 // ---- per-site mirror of the reference's class --------------------------------------------------------------------------
@@ -202,10 +206,11 @@ private:
 };
 
 // strand_bias(ref, ALT string) from a device record (src/basetype.cpp:244-295).  The counts come from the record's 2x4
-// strand table for any ALT set; FS is available for the two sets the reference asks for -- all non-REF bases (CVG row,
-// basetype_caller.cpp:1236-1245) and the called ALT alleles (VCF row, :1164); any other set throws std::invalid_argument.
+// strand table for any ALT set; FS is read from the record for the two sets the reference asks for -- all non-REF bases (CVG
+// row, basetype_caller.cpp:1236-1245) and the called ALT alleles (VCF row, :1164) -- and computed on the device for any other
+// set (bv_fisher_fs; `ctx`, or the calling thread's default context, created on first use on device BASEVAR_B200_DEVICE or 0).
 // A record flagged BV_FLAG_BAD_STRAND throws the reference's "[ERROR] Get strange strand symbol" error.
-StrandBiasInfo strand_bias(const char ref_base, const std::string alt_bases_string, const bv_site_out& rec);
+StrandBiasInfo strand_bias(const char ref_base, const std::string alt_bases_string, const bv_site_out& rec, Context* ctx = nullptr);
 
 // ---- region sharding over the GPUs of one box ---------------------------------------------------------------------------
 struct Shard {

@@ -16,7 +16,7 @@
  *   chi2_test -> kf_gammaq              src/algorithm.h:44-46    same call
  *   strand_bias(...)                    src/basetype.h:178-181   same call (fwd/rev counts + FS)
  *                                       src/basetype.cpp:244-295
- *   fisher_exact_test -> kt_fisher_exact src/algorithm.h:62-74   same call
+ *   fisher_exact_test -> kt_fisher_exact src/algorithm.h:62-74   same call; bv_fisher_fs for a free-standing 2x2 table
  *   getters get_alt_bases/get_lrt_af/   src/basetype.h:120-151   fields of bv_site_out
  *     get_var_qual/get_total_depth/get_base_depth
  *   per-site driver _basevar_caller     src/basetype_caller.cpp:667-765   caller loops over bv_site_out
@@ -333,6 +333,15 @@ int bv_synth_fill_rpr_host(const bv_synth_model* model, uint64_t site0, uint32_t
 int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_sites, uint32_t n_samples,
                        uint64_t pitch, uint8_t* base, uint8_t* qual, uint8_t* strand, uint8_t* mapq,
                        uint8_t* ref_base);
+
+/* ---- strand-bias statistic of arbitrary 2x2 tables ------------------------------------------------ */
+/* strand_bias() (src/basetype.cpp:244-295) takes ANY set of ALT bases; the records carry FS for the two sets the caller
+ * asks for (all non-REF bases: CVG row; the called ALT alleles: VCF row).  For any other set the 2x2 table follows from the
+ * record's per-base strand counts and this call computes its FS on the device with the code of kernel K2 (two-sided Fisher
+ * exact test restated from htslib/kfunc.c:245-313, FS rule src/basetype.cpp:277-283).  tables: n x {ref_fwd, ref_rev,
+ * alt_fwd, alt_rev} in host memory, every table's total <= bv_params::max_samples + 1; fs_out: n doubles (host).
+ * Blocking; a table with an empty row gives 0 (one possible outcome, p == 1). */
+int bv_fisher_fs(bv_ctx* ctx, const int32_t* tables, uint32_t n, double* fs_out);
 
 /* ---- tile sizing --------------------------------------------------------------------------------- */
 /* The count kernel is persistent: num_SMs x W warps take one site row each (W = 32, or 16 for rows longer than 4,096

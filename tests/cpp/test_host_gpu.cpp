@@ -128,6 +128,23 @@ int main(int argc, char** argv) {
         }
     }
     CHECK(n_var > 50);
+    // strand_bias over an ALT set the record carries no FS for: the 2x2 table goes to the device (bv_fisher_fs).  Known answers of
+    // kt_fisher_exact: (4,3,3,0) -> p 0.4749999999999977, (500,480,20,3) -> p 0.00050937499055459272.
+    {
+        bv_site_out r;
+        memset(&r, 0, sizeof(r));
+        r.depth[0] = 7; r.depth[1] = 3; r.depth[2] = 4; r.fwd[0] = 4; r.rev[0] = 3; r.fwd[1] = 3; r.rev[1] = 0; r.fwd[2] = 2; r.rev[2] = 2;
+        r.fs_cvg = -1.0; r.fs_vcf = -1.0;   // (not the answer for {C}: must not be picked)
+        StrandBiasInfo sc = strand_bias('A', "C", r, &ctx);
+        CHECK(sc.ref_fwd == 4 && sc.ref_rev == 3 && sc.alt_fwd == 3 && sc.alt_rev == 0);
+        CHECK(close_rel(sc.fs, 3.233063903751355));
+        StrandBiasInfo sd = strand_bias('A', "C", r);   // the calling thread's default context
+        CHECK(sd.fs == sc.fs);
+        r.fwd[0] = 500; r.rev[0] = 480; r.fwd[3] = 20; r.rev[3] = 3;
+        StrandBiasInfo st = strand_bias('A', "T", r);   // 1,003 reads: the default context grows
+        CHECK(close_rel(st.fs, 32.92962381969127));
+        printf("strand_bias over a free ALT set: FS %.6f, %.6f (device)\n", sc.fs, st.fs);
+    }
     {   // the same sites through the sparse transport: byte-identical records
         SparsePacker sp((uint32_t)N, S);
         for (int s = 0; s < S; ++s) sp.add_site(bis[s]);
