@@ -177,7 +177,8 @@ struct bv_ctx {
     uint64_t h2d_bytes_total = 0;
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int task_ctas_per_sm = 3;         // resident CTAs per SM of bv_em_task_kernel<1> (asked of the runtime in bv_create) ...
+    long long task_split_override = -1;   // BASEVAR_B200_TASK_SPLIT (tuning): tiles with more EM tasks than this run the high-occupancy build
+    int task_ctas_per_sm = 3;         // resident CTAs per SM of bv_em_task_kernel<BV_TASK_LO_CTAS> (asked of the runtime in bv_create) ...
     int task_ctas_per_sm_hi = 4;      // ... and of bv_em_task_kernel<BV_TASK_HI_CTAS>, the build for tiles with many EM tasks
     bool ev_valid = false;
     bool has_model = false;
@@ -275,6 +276,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->base = t->base; a->qual = t->qual; a->strand = t->strand; a->ref_base = t->ref_base;
     a->out = d_out;
     a->lut = ctx->d_lut;
+    a->logtab = reinterpret_cast<const double2*>(ctx->d_lut + 4 * bv::kQStride);
     a->logfact = ctx->d_logfact;
     {
         int rc = scratch_reserve(ctx, sc, t->n_sites);
@@ -291,7 +293,8 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     for (int k = 0; k < 3; ++k) a->em_task_cap[k] = sc.em_task_cap[k];
     a->brief = nullptr; a->full_out = nullptr;   // set by the submit paths of compact tiles
     a->em_resume = 0;
-    a->em_task_split = (uint32_t)ctx->num_sms * (uint32_t)ctx->task_ctas_per_sm_hi * (uint32_t)bv::kTaskThreads;   // one round of resident threads
+    a->em_task_split = ctx->task_split_override >= 0 ? (uint32_t)ctx->task_split_override
+                     : (uint32_t)ctx->num_sms * (uint32_t)ctx->task_ctas_per_sm_hi * (uint32_t)bv::kTaskThreads;   // one round of resident threads
     a->list_called = nullptr;   // set_call_args() turns the called-site kernels on
     a->mapq = nullptr; a->rpr = nullptr; a->aux_pitch = 0; a->rpr_pitch = 0;
     a->sample_group = nullptr; a->calls = nullptr; a->groups = nullptr; a->n_groups = 0; a->pad0 = 0;
@@ -392,7 +395,7 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
         b.em_resume = 1;
     }
     // two builds of the kernel (registers / occupancy); the tile's task count decides on the device which of them works
-    bv::bv_em_task_kernel<1><<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
+    bv::bv_em_task_kernel<BV_TASK_LO_CTAS><<<grid, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
     BV_CUDA(ctx, cudaGetLastError());
     bv::bv_em_task_kernel<BV_TASK_HI_CTAS><<<grid_hi, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
     ctx->launches += 1;
@@ -528,7 +531,7 @@ static int upload_tables(bv_ctx* ctx) {
     // per-phred likelihood table: eps = exp((q) * MLN10TO10) with glibc exp, exactly the reference's expression
     // (src/basetype.cpp:47, MLN10TO10 at src/basetype.h:20); 1-eps and eps/3 are single IEEE operations.
     const double MLN10TO10 = -0.23025850929940458;
-    double lut[4 * bv::kQStride];
+    double lut[4 * bv::kQStride + 2 * bv::kLogTabEntries];
     for (int q = 0; q < bv::kQStride; ++q) {
         double eps = exp((double)q * MLN10TO10);
         double ome = 1.0 - eps, e3 = eps / 3;
@@ -536,6 +539,12 @@ static int upload_tables(bv_ctx* ctx) {
         lut[bv::kLutEpsThird * bv::kQStride + q] = e3;
         lut[bv::kLutLogMatch * bv::kQStride + q] = log(ome);
         lut[bv::kLutLogMis * bv::kQStride + q] = log(e3);
+    }
+    // log_tab() of bv_em_kernels.cuh: {1 / c rounded, -log of that rounded value}, c = the midpoint of the i-th of 128 mantissa intervals
+    for (int i = 0; i < bv::kLogTabEntries; ++i) {
+        const double inv = 1.0 / (1.0 + ((double)i + 0.5) / (double)bv::kLogTabEntries);
+        lut[4 * bv::kQStride + 2 * i] = inv;
+        lut[4 * bv::kQStride + 2 * i + 1] = -(double)logl((long double)inv);
     }
     BV_CUDA(ctx, cudaMalloc(&ctx->d_lut, sizeof(lut)));
     BV_CUDA(ctx, cudaMemcpy(ctx->d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
@@ -580,7 +589,7 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
             cudaFuncSetAttribute(bv::bv_bound_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kBoundSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kHistLongSmemBytes) != cudaSuccess ||
-            cudaFuncSetAttribute(bv::bv_em_task_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
+            cudaFuncSetAttribute(bv::bv_em_task_kernel<BV_TASK_LO_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_em_task_kernel<BV_TASK_HI_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_em_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kTaskSmemBytes) != cudaSuccess ||
             cudaFuncSetAttribute(bv::bv_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bv::kQualSmemBytes) != cudaSuccess ||
@@ -593,11 +602,15 @@ int bv_create(int device, const bv_params* params, bv_ctx** out_ctx) {
         }
         {   // the EM task kernel's grid: what is resident at once (registers / shared memory decide)
             int nb = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bv::bv_em_task_kernel<1>, bv::kTaskThreads, bv::kTaskSmemBytes) == cudaSuccess && nb > 0)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bv::bv_em_task_kernel<BV_TASK_LO_CTAS>, bv::kTaskThreads, bv::kTaskSmemBytes) == cudaSuccess && nb > 0)
                 ctx->task_ctas_per_sm = nb;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bv::bv_em_task_kernel<BV_TASK_HI_CTAS>, bv::kTaskThreads, bv::kTaskSmemBytes) == cudaSuccess && nb > 0)
                 ctx->task_ctas_per_sm_hi = nb;
             cudaGetLastError();
+        }
+        {
+            const char* z = getenv("BASEVAR_B200_TASK_SPLIT");
+            if (z && z[0]) ctx->task_split_override = atoll(z);
         }
         {
             const char* z = getenv("BASEVAR_B200_TRACE");

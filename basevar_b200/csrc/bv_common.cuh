@@ -37,6 +37,7 @@ constexpr int kQSlots = 96;                  // phred slots per histogram row (0
 constexpr int kHistWords = 5 * kQSlots;      // (A,C,G,T,other) x phred
 constexpr int kSmemBins = 160;               // compact bins kept in shared memory; more spill to global scratch
 constexpr int kMaxBins = kHistWords;         // upper bound on distinct (base, phred) bins
+constexpr int kLogTabEntries = 128;
 constexpr int kLutOneMinusEps = 0;           // lut[0][q] = 1 - eps(q)
 constexpr int kLutEpsThird = 1;              // lut[1][q] = eps(q) / 3
 constexpr int kLutLogMatch = 2;              // lut[2][q] = log(1 - eps(q))   (glibc)
@@ -86,6 +87,7 @@ struct SiteKernelArgs {
     const uint8_t* ref_base;
     bv_site_out* out;
     const double* lut;       // [4][kQStride]
+    const double2* logtab;   // [kLogTabEntries] {1 / c, -log(1 / c)}, c = 1 + (i + 1/2) / 128: log_tab() of bv_em_kernels.cuh
     const double* logfact;   // [max_samples + 2], lgamma(k+1) from glibc
     uint32_t* bin_spill;     // [K4 warps][kMaxBins] global copy of the compact bins (used when > kSmemBins)
     double* lml_spill;       // [K4 warps][kMaxBins] per-bin EM state for the same case

@@ -241,6 +241,13 @@ __global__ void __launch_bounds__((LONG ? kLongWarps : kQualWarps) * 32, 1) bv_h
 #ifndef BV_TASK_THREADS
 #define BV_TASK_THREADS 128
 #endif
+#ifndef BV_TASK_LO_CTAS
+#define BV_TASK_LO_CTAS 3       // resident CTAs per SM the two builds of bv_em_task_kernel are compiled for: tiles with few EM tasks ...
+#endif
+#ifndef BV_TASK_HI_CTAS
+#define BV_TASK_HI_CTAS 4       // ... and tiles with many
+#endif
+static_assert(BV_TASK_LO_CTAS != BV_TASK_HI_CTAS, "the two builds of bv_em_task_kernel are told apart by their CTA count");
 #ifndef BV_TASK_STAGE_BINS
 #define BV_TASK_STAGE_BINS 96
 #endif
@@ -253,10 +260,14 @@ constexpr int kStageStride = kStageBins + 1;       // odd: the rows of 32 differ
 
 struct __align__(16) TaskCta {
     double lut[4][kQSlots];           // 1 - eps(q), eps(q) / 3, log(1 - eps(q)), log(eps(q) / 3)
+    double2 ltab[kLogTabEntries];     // log_tab()'s table
     uint32_t n_decide;                // sites whose last task finished in this round of the CTA ...
-    uint32_t decide_hdr[kTaskThreads];   // ... their headers and staging rows: decided one thread per site after the round
-    uint32_t decide_row[kTaskThreads];
-    uint32_t dq[kTaskThreads / 32][64];  // per warp: headers of completed sites waiting for their decision (BV_TASK_WARP_ROUNDS)
+    uint32_t decide_hdr[kTaskThreads];   // ... their headers: decided one thread per site after the round
+    uint32_t n_fs;                    // decided sites whose VCF row needs a Fisher test of its own (FsQueue) ...
+    uint32_t fs_site[2 * kTaskThreads];  // ... waiting until a whole CTA of them is there
+#if BV_TASK_WARP_ROUNDS
+    uint32_t dq[kTaskThreads / 32][64];  // per warp: headers of completed sites waiting for their decision
+#endif
     uint32_t bins[kTaskThreads * kStageStride];   // one row per task of the round
 };
 constexpr size_t kTaskSmemBytes = sizeof(TaskCta);
@@ -300,96 +311,182 @@ __device__ __forceinline__ double log_ratio(double r) {
     return log(r);
 }
 
-// The bins of a site are sorted by base, and a bin whose base is OUTSIDE the candidate subset (another allele, or the
-// "other" class) has the likelihood row {e3, e3, ...}: its marginal is e3 * F (F = sum of the subset's frequencies) and
-// its posteriors are f_k / F whatever its phred.  All such bins together therefore add c_out * f_k / F to the column sums
+// log(x) through a 128-entry table: x = 2^e * z, z in [1, 2); the top seven mantissa bits pick c = 1 + (i + 1/2) / 128 with
+// tab[i] = {1 / c rounded, -log(1 / c rounded)} (glibc, bv_api.cu), r = z / c - 1 is exact in one fma and |r| < 2^-8, so
+// log(1 + r) is six terms of its series (the next one is below 3e-18).  Absolute error <= 1 ulp of the result, 2e-17 near
+// x = 1 (checked against 80-bit logl on 2e7 arguments, tools/log_tab_check.c) -- the accuracy of the libdevice logarithm it
+// replaces in the EM's sums, at a third of its instructions and WITHOUT A BRANCH: the four bins a thread works on side by side
+// stay one straight-line block whose dependency chains the compiler interleaves.  Zero, denormal, negative, inf and NaN
+// arguments raise `bad` (the value returned for them means nothing); the caller then forms its sum again with the library
+// function (em_sum_slow).
+__device__ __forceinline__ double log_tab(double x, const double2* tab, uint32_t& bad) {
+    const uint32_t hi = (uint32_t)__double2hiint(x);
+    bad |= (hi - 0x00100000u >= 0x7fe00000u) ? 1u : 0u;
+    const double2 t = tab[(hi >> 13) & 0x7fu];
+    const double z = __hiloint2double((int)((hi & 0x000fffffu) | 0x3ff00000u), __double2loint(x));
+    const double r = fma(z, t.x, -1.0);
+    double p = fma(r, -1.0 / 6.0, 0.2);
+    p = fma(r, p, -0.25);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    p = fma(r * r, p, r);
+    return fma((double)((int)(hi >> 20) - 1023), 0.693147180559945309417, t.y) + p;
+}
+
+// The bins of a site are sorted by base, so the bins of allele j[k] of a candidate subset are one RUN [r0[k], r1[k]) of the list.
+// Inside run k every bin has the likelihood row {e3, ..., 1 - eps at k, ..., e3}: its marginal is
+//     m = (1 - eps) * f_k + e3 * fo_k,        fo_k = the sum of the subset's OTHER frequencies (A, C, G, T order),
+// (for two alleles exactly the reference's lik * freq sum, src/algorithm.h:160-172), and with w = c / m its posteriors add
+// w * (1 - eps) * f_k to column k and w * e3 * f_j to every other column j.  Two sums per run are therefore enough,
+//     o_k = sum of w * (1 - eps),    a_k = sum of w * e3        (all terms positive: nothing cancels),
+// and the M-step's column sums are s_j = f_j * (o_j + sum of a_k over the other runs k): ten FP64 instructions and two
+// accumulators per bin, whatever the number of alleles (one multiply-add per allele, twice, and NA accumulators before).
+// A bin whose base is OUTSIDE the subset (another allele, or the "other" class) has the row {e3, e3, ...}: marginal e3 * F
+// (F = sum of the subset's frequencies), posteriors f_j / F whatever its phred.  All such bins together add c_out * f_j / F
 // -- one term instead of a pass over them -- and only the bins of the subset's own bases are visited.
 template <int NA>
-struct SubsetBins {
-    int off[NA];      // visit u of [0, n) is bin u + off[k], k = the run u falls in
-    int cum[NA];      // visits before the end of run k
-    int n;            // bins of the subset's bases
-    double c_out;     // reads outside them
-    __device__ __forceinline__ int bin_of(int u) const {
-        int o = off[0];
+__device__ __forceinline__ double pick(const double (&v)[NA], int k) {
+    double x = v[0];
 #pragma unroll
-        for (int k = 1; k < NA; ++k) o = u >= cum[k - 1] ? off[k] : o;
-        return u + o;
-    }
+    for (int i = 1; i < NA; ++i) x = k == i ? v[i] : x;
+    return x;
+}
+template <int NA>
+__device__ __forceinline__ int pick(const int (&v)[NA], int k) {
+    int x = v[0];
+#pragma unroll
+    for (int i = 1; i < NA; ++i) x = k == i ? v[i] : x;
+    return x;
+}
+template <int NA>
+__device__ __forceinline__ void put(double (&v)[NA], int k, double x) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) v[i] = k == i ? x : v[i];
+}
+// sum of v[i], i != k, in ascending i (the skipped entry adds an exact +0.0)
+template <int NA>
+__device__ __forceinline__ double sum_others(const double (&v)[NA], int k) {
+    double x = k == 0 ? 0.0 : v[0];
+#pragma unroll
+    for (int i = 1; i < NA; ++i) x += k == i ? 0.0 : v[i];
+    return x;
+}
+
+// The state of one EM: the subset's alleles, the runs of their bins, the frequencies of this and of the previous E-step.
+template <int NA>
+struct EmState {
+    int r0[NA], r1[NA];   // run of the bins of the subset's k-th allele
+    double f[NA], fp[NA];
+    double total;
+    double c_out;         // reads outside the subset's bases
 };
 
-// One E-step + M-step (src/algorithm.h:148-198) for a subset of NA alleles j[0] < ... < j[NA-1] under frequencies f.
-// Same operation order as the reference inside a bin: lik * freq summed in A, C, G, T order (alleles outside the subset
-// have freq 0 there and add an exact +0.0: left out), column sums of the posteriors with c equal reads adding c * post;
-// posteriors are l_j * (1 / m).
-// DELTA: also sum c * |log m - log mp| with mp the marginal under the previous frequencies fp -- EM()'s convergence sum with
-// fabs (src/algorithm.h:238-250, BV_EM_ABS_DOUBLE), as one logarithm of the ratio mp / m.
-template <int NA, bool DELTA>
-__device__ __forceinline__ void em_bin(uint32_t p, const double* lut, const int (&j)[NA], const double (&f)[NA], const double (&fp)[NA],
-                                       double (&s)[NA], double& delta) {
-    const int b = (int)bin_base(p);
+// One bin of a run under (fk, fo) = (frequency of the run's allele, sum of the others); (fpk, fpo) the same under the previous
+// frequencies.  What x collects besides the posterior sums depends on MODE:
+//   kPassDelta  c * |log m - log mp|, mp the marginal under the previous frequencies -- EM()'s convergence sum with fabs
+//               (src/algorithm.h:238-250, BV_EM_ABS_DOUBLE), as one logarithm of the ratio mp / m;
+//   kPassLL     c * log m: the log-likelihood _f() reports (src/basetype.cpp:119-120) is the one under the frequencies of the
+//               EM's LAST E-step, and whether an E-step is the last is known before it starts (see em_task), so the sum rides
+//               along with that pass instead of costing one more.
+// Posterior weights are c * (1 / m) with a Newton reciprocal.  No branches: see log_tab.
+constexpr int kPassPlain = 0, kPassDelta = 1, kPassLL = 2;
+template <int MODE>
+__device__ __forceinline__ void em_bin(uint32_t p, const double* lut, const double2* ltab, double fk, double fo, double fpk, double fpo,
+                                       double& o, double& a, double& x, uint32_t& bad) {
     const uint32_t q = bin_qual(p);
     const double cd = (double)bin_count(p);
     const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
-    double L[NA], l[NA];
-#pragma unroll
-    for (int k = 0; k < NA; ++k) { L[k] = b == j[k] ? ome : e3; l[k] = L[k] * f[k]; }
-    double m = l[0];
-#pragma unroll
-    for (int k = 1; k < NA; ++k) m += l[k];
+    const double m = ome * fk + e3 * fo;
     const double inv = rcp_fast(m);
-#pragma unroll
-    for (int k = 0; k < NA; ++k) s[k] += cd * (l[k] * inv);
-    if (DELTA) {
-        double mp = L[0] * fp[0];
-#pragma unroll
-        for (int k = 1; k < NA; ++k) mp += L[k] * fp[k];
-        delta += cd * fabs(log_ratio(mp * inv));
+    const double w = cd * inv;
+    o = fma(w, ome, o);
+    a = fma(w, e3, a);
+    if (MODE == kPassDelta) {
+        const double mp = ome * fpk + e3 * fpo;
+        x += cd * fabs(log_tab(mp * inv, ltab, bad));
     }
+    if (MODE == kPassLL) x += cd * log_tab(m, ltab, bad);
 }
 
-template <int NA, bool DELTA>
-__device__ __forceinline__ double em_pass(const uint32_t* bins, const SubsetBins<NA>& sb, const double* lut, const int (&j)[NA],
-                                          const double (&f)[NA], const double (&fp)[NA], double (&s)[NA], const LaneGroup& lg) {
-    double delta;
-    if (lg.G == 1) {
-        double sp[4][NA], dp[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-#pragma unroll
-            for (int k = 0; k < NA; ++k) sp[v][k] = 0.0;
-        int u = 0;
+// The sum x of a pass once more, with the library logarithm, for the EMs whose marginals left the normal range (a phred-0
+// read of an allele that has all the frequency: marginal 0, everything NaN from there on as in the reference).
+template <int NA, int MODE>
+__device__ __noinline__ double em_sum_slow(const uint32_t* bins, const EmState<NA>& S, const double* lut, const LaneGroup& lg) {
+    double xl[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-        for (; u + 4 <= sb.n; u += 4) {
+    for (int k = 0; k < NA; ++k) {
+        const double fk = pick<NA>(S.f, k), fo = sum_others<NA>(S.f, k), fpk = pick<NA>(S.fp, k), fpo = sum_others<NA>(S.fp, k);
+        const int r0 = pick<NA>(S.r0, k), r1 = pick<NA>(S.r1, k);
+#pragma unroll 1
+        for (int u = r0 + lg.gl; u < r1; u += lg.G) {
+            const uint32_t p = bins[u];
+            const uint32_t q = bin_qual(p);
+            const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
+            const double m = ome * fk + e3 * fo;
+            const double t = MODE == kPassLL ? nlog(m) : fabs(nlog(m) - nlog(ome * fpk + e3 * fpo));
+            const double v = (double)bin_count(p) * t;
+            const int slot = lg.G == 1 ? ((u - r0) & 3) : 0;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) em_bin<NA, DELTA>(bins[sb.bin_of(u + v)], lut, j, f, fp, sp[v], dp[v]);
+            for (int i = 0; i < 4; ++i) xl[i] += i == slot ? v : 0.0;
         }
+    }
+    return lg.G == 1 ? sum4(xl) : lg.sum4(xl[0]);
+}
+
+// One E-step + M-step (src/algorithm.h:148-198) for a subset of NA alleles under frequencies S.f: s[] = the column sums of the
+// posteriors.  Returns the sum x of em_bin (over the subset's own bins; kPassDelta: also the term of the bins outside).  Sums over
+// the bins of a run are ALWAYS formed the same way, whatever G is (see LaneGroup): visit i of the run goes to partial sum i mod 4.
+template <int NA, int MODE>
+__device__ __forceinline__ double em_pass(const uint32_t* bins, const EmState<NA>& S, const double* lut, const double2* ltab,
+                                          double (&s)[NA], const LaneGroup& lg) {
+    constexpr bool DELTA = MODE == kPassDelta;
+    double o_run[NA], a_run[NA];
+    double xl[4] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t bad = 0;
+#pragma unroll 1
+    for (int k = 0; k < NA; ++k) {
+        const double fk = pick<NA>(S.f, k), fo = sum_others<NA>(S.f, k);
+        const double fpk = DELTA ? pick<NA>(S.fp, k) : 0.0, fpo = DELTA ? sum_others<NA>(S.fp, k) : 0.0;
+        const int r0 = pick<NA>(S.r0, k), r1 = pick<NA>(S.r1, k);
+        double o, a;
+        if (lg.G == 1) {
+            double o4[4] = {0.0, 0.0, 0.0, 0.0}, a4[4] = {0.0, 0.0, 0.0, 0.0};
+            int u = r0;
+#pragma unroll 1
+            for (; u + 4 <= r1; u += 4) {
 #pragma unroll
-        for (int v = 0; v < 3; ++v)
-            if (u + v < sb.n) em_bin<NA, DELTA>(bins[sb.bin_of(u + v)], lut, j, f, fp, sp[v], dp[v]);
+                for (int v = 0; v < 4; ++v) em_bin<MODE>(bins[u + v], lut, ltab, fk, fo, fpk, fpo, o4[v], a4[v], xl[v], bad);
+            }
 #pragma unroll
-        for (int k = 0; k < NA; ++k) { const double p4[4] = {sp[0][k], sp[1][k], sp[2][k], sp[3][k]}; s[k] = sum4(p4); }
-        delta = sum4(dp);
-    } else {
-        double d1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < NA; ++k) s[k] = 0.0;
+            for (int v = 0; v < 3; ++v)
+                if (u + v < r1) em_bin<MODE>(bins[u + v], lut, ltab, fk, fo, fpk, fpo, o4[v], a4[v], xl[v], bad);
+            o = sum4(o4); a = sum4(a4);
+        } else {
+            double o1 = 0.0, a1 = 0.0;
 #pragma unroll 2
-        for (int u = lg.gl; u < sb.n; u += 4) em_bin<NA, DELTA>(bins[sb.bin_of(u)], lut, j, f, fp, s, d1);
-#pragma unroll
-        for (int k = 0; k < NA; ++k) s[k] = lg.sum4(s[k]);
-        delta = DELTA ? lg.sum4(d1) : 0.0;
+            for (int u = r0 + lg.gl; u < r1; u += 4) em_bin<MODE>(bins[u], lut, ltab, fk, fo, fpk, fpo, o1, a1, xl[0], bad);
+            o = lg.sum4(o1); a = lg.sum4(a1);
+        }
+        put<NA>(o_run, k, o);
+        put<NA>(a_run, k, a);
     }
-    if (sb.c_out != 0.0) {
-        double F = f[0], Fp = fp[0];
+    double x = 0.0;
+    if (MODE != kPassPlain) {
+        x = lg.G == 1 ? sum4(xl) : lg.sum4(xl[0]);
+        if (lg.any(bad != 0u)) x = em_sum_slow<NA, MODE>(bins, S, lut, lg);
+    }
+    double t_out = 0.0;
+    if (S.c_out != 0.0) {
+        double F = S.f[0], Fp = S.fp[0];
 #pragma unroll
-        for (int k = 1; k < NA; ++k) { F += f[k]; Fp += fp[k]; }
+        for (int k = 1; k < NA; ++k) { F += S.f[k]; Fp += S.fp[k]; }
         const double inv = rcp_fast(F);
-#pragma unroll
-        for (int k = 0; k < NA; ++k) s[k] += sb.c_out * (f[k] * inv);
-        if (DELTA) delta += sb.c_out * fabs(log_ratio(Fp * inv));
+        t_out = S.c_out * inv;
+        if (DELTA) x += S.c_out * fabs(log_ratio(Fp * inv));
     }
-    return delta;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) s[k] = S.f[k] * ((o_run[k] + sum_others<NA>(a_run, k)) + t_out);
+    return x;
 }
 
 // BV_EM_ABS_INT_TRUNC, the rare case the frequencies cannot decide: is there a bin whose log marginal moved by >= 1?
@@ -400,95 +497,88 @@ __device__ __forceinline__ bool moved_by_one(double m, double mp) {
     return fabs(diff) >= 1.0 && fabs(diff) < 2147483648.0;
 }
 template <int NA>
-__device__ __noinline__ bool em_moved_bin(const uint32_t* bins, const SubsetBins<NA>& sb, const double* lut, const int (&j)[NA],
-                                          const double (&f)[NA], const double (&fp)[NA], const LaneGroup& lg) {
-    if (sb.c_out != 0.0) {   // the bins outside the subset: marginals e3 * F
-        double F = f[0], Fp = fp[0];
+__device__ __noinline__ bool em_moved_bin(const uint32_t* bins, const EmState<NA>& S, const double* lut, const LaneGroup& lg) {
+    if (S.c_out != 0.0) {   // the bins outside the subset: marginals e3 * F
+        double F = S.f[0], Fp = S.fp[0];
 #pragma unroll
-        for (int k = 1; k < NA; ++k) { F += f[k]; Fp += fp[k]; }
+        for (int k = 1; k < NA; ++k) { F += S.f[k]; Fp += S.fp[k]; }
         if (moved_by_one(F, Fp)) return true;
     }
     bool found = false;
-    for (int u = lg.gl; u < sb.n && !found; u += lg.G) {   // (a yes / no answer: the order of the visits does not matter)
-        const uint32_t p = bins[sb.bin_of(u)];
-        const int b = (int)bin_base(p);
-        const uint32_t q = bin_qual(p);
-        const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
-        double m = 0.0, mp = 0.0;
-#pragma unroll
-        for (int k = 0; k < NA; ++k) { const double L = b == j[k] ? ome : e3; m += L * f[k]; mp += L * fp[k]; }
-        found = moved_by_one(m, mp);
+#pragma unroll 1
+    for (int k = 0; k < NA; ++k) {
+        const double fk = pick<NA>(S.f, k), fo = sum_others<NA>(S.f, k), fpk = pick<NA>(S.fp, k), fpo = sum_others<NA>(S.fp, k);
+        const int r1 = pick<NA>(S.r1, k);
+        for (int u = pick<NA>(S.r0, k) + lg.gl; u < r1 && !found; u += lg.G) {   // (a yes / no answer: the order of the visits does not matter)
+            const uint32_t q = bin_qual(bins[u]);
+            const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
+            found = moved_by_one(ome * fk + e3 * fo, ome * fpk + e3 * fpo);
+        }
     }
     return lg.any(found);
 }
 
-// The state of one EM: the subset's alleles, which bins to visit, the frequencies of this and of the previous E-step.
-template <int NA>
-struct EmState {
-    int j[NA];
-    SubsetBins<NA> sb;
-    int st[6];            // first bin of each base (bins are sorted by base), nb
-    double f[NA], fp[NA];
-    double total;
-};
+// first bin of each base (bins are sorted by base) and the number of bins
+__device__ __forceinline__ void bin_starts(const EmSiteHdr& H, int (&st)[6]) {
+    st[0] = 0; st[1] = (int)(H.base_start[0] & 0xffffu); st[2] = (int)(H.base_start[0] >> 16);
+    st[3] = (int)(H.base_start[1] & 0xffffu); st[4] = (int)(H.base_start[1] >> 16); st[5] = (int)H.nb;
+}
 
 template <int NA>
 __device__ __forceinline__ void em_setup(const EmSiteHdr& H, uint32_t subset, EmState<NA>& S) {
     S.total = (double)H.total;
-    S.st[0] = 0; S.st[1] = (int)(H.base_start[0] & 0xffffu); S.st[2] = (int)(H.base_start[0] >> 16);
-    S.st[3] = (int)(H.base_start[1] & 0xffffu); S.st[4] = (int)(H.base_start[1] >> 16); S.st[5] = (int)H.nb;
+    int st[6];
+    bin_starts(H, st);
     uint32_t left = subset;
-    int seen = 0;
     uint32_t c_in = 0;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
-        S.j[k] = __ffs(left) - 1;
+        const int jk = __ffs(left) - 1;
         left &= left - 1u;
         int b0 = 0, b1 = 0;
         uint32_t d = 0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) if (S.j[k] == b) { b0 = S.st[b]; b1 = S.st[b + 1]; d = H.depth[b]; }
+        for (int b = 0; b < 4; ++b) if (jk == b) { b0 = st[b]; b1 = st[b + 1]; d = H.depth[b]; }
         c_in += d;
-        S.sb.off[k] = b0 - seen;
-        seen += b1 - b0;
-        S.sb.cum[k] = seen;
+        S.r0[k] = b0;
+        S.r1[k] = b1;
         // initial frequencies: depth/total for the subset's members, NOT renormalised (src/basetype.cpp:93-103)
         S.f[k] = (double)d / S.total;
         S.fp[k] = S.f[k];
     }
-    S.sb.n = seen;
-    S.sb.c_out = (double)(H.total - c_in);
+    S.c_out = (double)(H.total - c_in);
 }
 
 // The whole EM of one candidate subset (src/algorithm.h:210-255; _f, src/basetype.cpp:105-128).  res: log-likelihood under
 // the second-to-last frequencies (what _f() sums), the estimated frequencies, flags.  resume: the iterations were run by
 // bv_em_iter_kernel, which left the last two frequency vectors in res.
 template <int NA>
-__device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* lut, const EmSiteHdr& H, const uint32_t* bins,
+__device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* lut, const double2* ltab, const EmSiteHdr* Hg, const uint32_t* bins,
                                         uint32_t subset, double* res, const LaneGroup& lg) {
+    // (the header is read where it is needed, not carried in registers through the EM)
     EmState<NA> S;
-    em_setup<NA>(H, subset, S);
-    int (&j)[NA] = S.j;
-    SubsetBins<NA>& sb = S.sb;
-    const int (&st)[6] = S.st;
+    em_setup<NA>(*Hg, subset, S);
     double (&f)[NA] = S.f;
     double (&fp)[NA] = S.fp;
     const double total = S.total;
     double s[NA];
     uint64_t flags = 0;
-    if (a.em_resume) {
+    double ll = 0.0;
+    const bool resume = a.em_resume != 0u;
+    if (resume) {
+        // the log-likelihood under fp: one pass with the previous frequencies in the place of the current ones
 #pragma unroll
-        for (int k = 0; k < NA; ++k) { f[k] = res[k]; fp[k] = res[4 + k]; }
+        for (int k = 0; k < NA; ++k) { f[k] = res[4 + k]; fp[k] = f[k]; }
         flags = (uint64_t)__double_as_longlong(res[8]);
-    } else {
-    em_pass<NA, false>(bins, sb, lut, j, f, fp, s, lg);
-#pragma unroll
-    for (int k = 0; k < NA; ++k) { fp[k] = f[k]; f[k] = s[k] / total; }
+    }
+    bool first = !resume;   // the E-step + M-step in front of EM()'s loop: no convergence test
     int it = a.em_max_iter;
     for (;;) {   // (BV_EM_ABS_INT_TRUNC: with fabs the iterations are bv_em_iter_kernel's, and this function resumes after them)
-        bool more;
-        {
-            em_pass<NA, false>(bins, sb, lut, j, f, fp, s, lg);
+        bool last = resume;
+        if (!resume && !first) {
+            // EM()'s convergence test after the E-step under f compares its log marginals with those of the E-step under fp
+            // (src/algorithm.h:238-250) -- a function of f and fp alone, so it is evaluated BEFORE the E-step, and the E-step that
+            // turns out to be the last also sums the log-likelihood.
             // Every marginal is a non-negative combination of the frequencies, so its ratio between two E-steps lies between
             // the smallest and the largest ratio of the frequencies (e = 2.71828...): all of those inside (1/2.718, 2.718) =>
             // no log marginal moved by 1; all >= 2.7183 or all <= 1/2.7183 => every one did; otherwise the bins decide.
@@ -499,55 +589,33 @@ __device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* l
                 up = up && f[k] >= 2.7183 * fp[k] && fp[k] > 0.0 && f[k] < 1e300;
                 down = down && fp[k] >= 2.7183 * f[k] && f[k] > 0.0 && fp[k] < 1e300;
             }
-            more = calm ? false : (up || down) ? true : em_moved_bin<NA>(bins, sb, lut, j, f, fp, lg);
+            const bool more = calm ? false : (up || down) ? true : em_moved_bin<NA>(bins, S, lut, lg);
+            last = !more || it == 1;
+        }
+        if (last) ll = em_pass<NA, kPassLL>(bins, S, lut, ltab, s, lg);
+        else em_pass<NA, kPassPlain>(bins, S, lut, ltab, s, lg);
+        if (resume) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) f[k] = res[k];
+            break;
         }
 #pragma unroll
         for (int k = 0; k < NA; ++k) { fp[k] = f[k]; f[k] = s[k] / total; }
+        if (first) { first = false; continue; }
         --it;
         if (it == 0) flags |= BV_FLAG_EM_MAXITER;
-        if (!more || it == 0) break;
+        if (last) break;
     }
-    }
-    // Sum of c * log marginal under fp, the frequencies of the last E-step: one logarithm per bin of the subset's bases;
-    // a bin outside them has the marginal e3(q) * F: log e3 comes from the table, log F is one logarithm for all of them.
-    auto lml_term = [&](int u) {
-        const uint32_t p = bins[sb.bin_of(u)];
-        const int b = (int)bin_base(p);
-        const uint32_t q = bin_qual(p);
-        const double ome = lut[kLutOneMinusEps * kQSlots + q], e3 = lut[kLutEpsThird * kQSlots + q];
-        double m = (b == j[0] ? ome : e3) * fp[0];
-#pragma unroll
-        for (int k = 1; k < NA; ++k) m += (b == j[k] ? ome : e3) * fp[k];
-        return (double)bin_count(p) * log(m);
-    };
-    double ll;
-    if (lg.G == 1) {
-        double lp[4] = {0.0, 0.0, 0.0, 0.0};
-        int u = 0;
-#pragma unroll 1
-        for (; u + 4 <= sb.n; u += 4) {
-#pragma unroll
-            for (int v = 0; v < 4; ++v) lp[v] += lml_term(u + v);
-        }
-#pragma unroll
-        for (int v = 0; v < 3; ++v)
-            if (u + v < sb.n) lp[v] += lml_term(u + v);
-        ll = sum4(lp);
-    } else {
-        double l1 = 0.0;
-#pragma unroll 2
-        for (int u = lg.gl; u < sb.n; u += 4) l1 += lml_term(u);
-        ll = lg.sum4(l1);
-    }
-    if (sb.c_out != 0.0) {
+    // ll: sum of c * log marginal under fp, the frequencies of the last E-step, over the bins of the subset's bases; a bin outside
+    // them has the marginal e3(q) * F: log e3 comes from the table, log F is one logarithm for all of them.
+    if (S.c_out != 0.0) {
         // the bins outside the subset: table look-ups only, summed in bin order by every lane of the group alike
-        uint32_t in_set = 0;
-#pragma unroll
-        for (int k = 0; k < NA; ++k) in_set |= 1u << j[k];
+        int st[6];
+        bin_starts(*Hg, st);
         double lo = 0.0;
 #pragma unroll 1
         for (int b = 0; b < 5; ++b) {
-            if (in_set >> b & 1u) continue;
+            if (subset >> b & 1u) continue;
             for (int i = st[b]; i < st[b + 1]; ++i) {
                 const uint32_t p = bins[i];
                 lo += (double)bin_count(p) * lut[kLutLogMis * kQSlots + bin_qual(p)];
@@ -556,14 +624,17 @@ __device__ __forceinline__ void em_task(const SiteKernelArgs& a, const double* l
         double F = fp[0];
 #pragma unroll
         for (int k = 1; k < NA; ++k) F += fp[k];
-        ll += lo + sb.c_out * log(F);
+        ll += lo + S.c_out * log(F);
     }
     if (lg.gl != 0) return;
     double fo[4] = {0.0, 0.0, 0.0, 0.0};
+    uint32_t left = subset;
 #pragma unroll
     for (int k = 0; k < NA; ++k) {
+        const int jk = __ffs(left) - 1;
+        left &= left - 1u;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) if (j[k] == b) fo[b] = f[k];
+        for (int b = 0; b < 4; ++b) if (jk == b) fo[b] = f[k];
     }
     res[0] = ll; res[1] = fo[0]; res[2] = fo[1]; res[3] = fo[2]; res[4] = fo[3];
     res[5] = __longlong_as_double((long long)flags);
@@ -590,9 +661,9 @@ __device__ __forceinline__ void em_iter_list(const SiteKernelArgs& a, TaskCta& c
     uint64_t flags = 0;
     const uint32_t* bins = my_row;
     EmState<NA> S;
-    S.sb.n = 0; S.sb.c_out = 0.0; S.total = 1.0;
+    S.c_out = 0.0; S.total = 1.0;
 #pragma unroll
-    for (int k = 0; k < NA; ++k) { S.j[k] = k; S.f[k] = 0.0; S.fp[k] = 0.0; S.sb.off[k] = 0; S.sb.cum[k] = 0; }
+    for (int k = 0; k < NA; ++k) { S.f[k] = 0.0; S.fp[k] = 0.0; S.r0[k] = 0; S.r1[k] = 0; }
     for (;;) {
         const uint32_t need = __ballot_sync(kFull, !have && !done);
         if (need) {
@@ -622,7 +693,7 @@ __device__ __forceinline__ void em_iter_list(const SiteKernelArgs& a, TaskCta& c
             continue;
         }
         double s[NA];
-        const double delta = em_pass<NA, true>(bins, S.sb, lut, S.j, S.f, S.fp, s, lg);
+        const double delta = em_pass<NA, kPassDelta>(bins, S, lut, cs.ltab, s, lg);
         if (have) {
 #pragma unroll
             for (int k = 0; k < NA; ++k) { S.fp[k] = S.f[k]; S.f[k] = s[k] / S.total; }
@@ -639,7 +710,9 @@ __device__ __forceinline__ void em_iter_list(const SiteKernelArgs& a, TaskCta& c
                 for (int k = 0; k < NA; ++k) { res[k] = S.f[k]; res[4 + k] = S.fp[k]; }
                 res[8] = __longlong_as_double((long long)flags);
                 have = false;
-                S.sb.n = 0; S.sb.c_out = 0.0;
+                S.c_out = 0.0;
+#pragma unroll
+                for (int k = 0; k < NA; ++k) { S.r0[k] = 0; S.r1[k] = 0; }
             }
         }
     }
@@ -648,6 +721,7 @@ __device__ __forceinline__ void em_iter_list(const SiteKernelArgs& a, TaskCta& c
 __global__ void __launch_bounds__(kTaskThreads) bv_em_iter_kernel(const __grid_constant__ SiteKernelArgs a) {
     TaskCta& cs = *reinterpret_cast<TaskCta*>(bv_smem_raw);
     for (int i = threadIdx.x; i < 4 * kQSlots; i += kTaskThreads) cs.lut[i / kQSlots][i % kQSlots] = a.lut[(i / kQSlots) * kQStride + i % kQSlots];
+    for (int i = threadIdx.x; i < kLogTabEntries; i += kTaskThreads) cs.ltab[i] = a.logtab[i];
     __syncthreads();
     const double* lut = &cs.lut[0][0];
     const uint32_t n2 = min(a.counters[kCntEmTask2], a.em_task_cap[0]), n3 = min(a.counters[kCntEmTask3], a.em_task_cap[1]),
@@ -659,7 +733,36 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_iter_kernel(const __grid_c
 
 // ---- the site's decision, after its last task has finished ----------------------------------------------------------------------
 // Backward elimination (src/basetype.cpp:144-168) on the task results, ALT / AF / QUAL (:170-196), FS of the VCF row.
-__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHdr& H, uint32_t hdr_index) {
+// The strand-bias test of a VCF row whose called ALT set is not "every non-reference base" is a Fisher test of its own (ref vs the
+// called alleles, src/basetype.cpp:244-295, basetype_caller.cpp:1164) -- on a deep pileup a walk of hundreds of steps, 10-100x the
+// rest of a decision, needed by one decided site in three.  Run inside the decision it kept a few lanes of one or two warps busy
+// while the CTA's other warps waited at the round's barrier (a fifth of bv_em_task_kernel's warp time on deep multi-allelic
+// pileups, profiles/r02_k4b_fs_queue.txt).  The sites are queued instead (fs_queue != nullptr), and the CTA runs the tests when a
+// whole CTA of them waits: every lane of every warp on the same path.
+__device__ __forceinline__ void vcf_tables(const bv_site_out* rec, int ref_code, uint32_t alt_set, int& rf, int& rr, int& vf, int& vr,
+                                           int& af_, int& ar) {
+    const uint32_t f[4] = {rec->fwd[0], rec->fwd[1], rec->fwd[2], rec->fwd[3]};
+    const uint32_t rv[4] = {rec->rev[0], rec->rev[1], rec->rev[2], rec->rev[3]};
+    rf = 0; rr = 0; vf = 0; vr = 0; af_ = 0; ar = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (b == ref_code) { rf = (int)f[b]; rr = (int)rv[b]; }
+        else { af_ += (int)f[b]; ar += (int)rv[b]; }
+        if (alt_set >> b & 1u) { vf += (int)f[b]; vr += (int)rv[b]; }
+    }
+}
+// a queued site: the table again from its (decided) record, the test, FS into the record
+__device__ __forceinline__ void fs_vcf_job(const SiteKernelArgs& a, uint32_t site) {
+    bv_site_out* rec = a.out + site;
+    const int ref_code = ref_code_of(a.ref_base[site]);
+    uint32_t alt_set = 0;
+    for (int k = 0; k < (int)rec->n_alt; ++k) alt_set |= 1u << (rec->alt[k] & 3u);
+    int rf, rr, vf, vr, af_, ar;
+    vcf_tables(rec, ref_code, alt_set, rf, rr, vf, vr, af_, ar);
+    rec->fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
+}
+
+__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHdr& H, uint32_t hdr_index, uint32_t* fs_queue_n, uint32_t* fs_queue) {
     const uint32_t site = H.site;
     bv_site_out* rec = a.out + site;
     const int ref_code = ref_code_of(a.ref_base[site]);
@@ -752,17 +855,15 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
         if (n_act == 1 && total > 10 && r > 0.5) { qual = 5000.0; flags |= BV_FLAG_MONO_QUAL; }
         else qual = qual_from_chi(chi);
         // strand bias of the VCF row, ref vs the called ALT alleles (src/basetype.cpp:244-295, basetype_caller.cpp:1164)
-        const uint32_t f[4] = {rec->fwd[0], rec->fwd[1], rec->fwd[2], rec->fwd[3]};
-        const uint32_t rv[4] = {rec->rev[0], rec->rev[1], rec->rev[2], rec->rev[3]};
-        int rf = 0, rr = 0, vf = 0, vr = 0, af_ = 0, ar = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            if (b == ref_code) { rf = (int)f[b]; rr = (int)rv[b]; }
-            else { af_ += (int)f[b]; ar += (int)rv[b]; }
-            if (alt_set >> b & 1u) { vf += (int)f[b]; vr += (int)rv[b]; }
-        }
+        int rf, rr, vf, vr, af_, ar;
+        vcf_tables(rec, ref_code, alt_set, rf, rr, vf, vr, af_, ar);
         if (vf == af_ && vr == ar) fs_vcf = rec->fs_cvg;   // same 2x2 table as the CVG row
-        else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
+        else if ((vf | vr) != 0 && (rf | rr) != 0) {
+            double p;
+            if (fisher_margin1(rf, rr, vf, vr, p)) fs_vcf = fs_from_p(p);
+            else if (fs_queue != nullptr) fs_queue[atomicAdd(fs_queue_n, 1u)] = site;   // fs_vcf_job() completes the record
+            else fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
+        }
     }
     // ---- record: ALT alleles in ACGT order of the active set (src/basetype.cpp:172-177) ----
     uint32_t alts = 0;
@@ -799,11 +900,13 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
     {
         const uint64_t n_all = (uint64_t)min(a.counters[kCntEmTask2], a.em_task_cap[0]) + min(a.counters[kCntEmTask3], a.em_task_cap[1]) +
                                min(a.counters[kCntEmTask4], a.em_task_cap[2]);
-        if ((n_all > (uint64_t)a.em_task_split) != (kMinCtas > 1)) return;
+        if ((n_all > (uint64_t)a.em_task_split) != (kMinCtas == BV_TASK_HI_CTAS)) return;
     }
     TaskCta& cs = *reinterpret_cast<TaskCta*>(bv_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 4 * kQSlots; i += kTaskThreads) cs.lut[i / kQSlots][i % kQSlots] = a.lut[(i / kQSlots) * kQStride + i % kQSlots];
+    for (int i = tid; i < kLogTabEntries; i += kTaskThreads) cs.ltab[i] = a.logtab[i];
+    if (tid == 0) cs.n_fs = 0;
     const double* lut = &cs.lut[0][0];
     // the three task lists, one after the other
     uint32_t n_list[3], blk_end[3], base[3];
@@ -848,8 +951,8 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         const bool valid = word != kEmTaskInvalid;
         const uint32_t hdr = word & 0x0fffffffu, subset = word >> 28;
         EmSiteHdr* const Hg = a.em_hdr + hdr;
-        EmSiteHdr H;
-        if (valid) H = *Hg;
+        uint32_t h_nb = 0, h_off = 0;   // (only these two words of the header are needed here)
+        if (valid) { h_off = Hg->bins_off; h_nb = Hg->nb; }
         // Staging: the tasks of a site are neighbours in the list, so one row serves a run of lanes with the same header; all 32
         // lanes copy it (coalesced), one run after the other.  Lists longer than a row are read from the pool.
         const uint32_t hdr_prev = __shfl_up_sync(kFull, valid ? hdr : kEmTaskInvalid, 1);
@@ -859,20 +962,20 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         __syncwarp();   // the previous round's readers of the warp's rows are done
         for (uint32_t todo = lead; todo; todo &= todo - 1u) {
             const int src = __ffs(todo) - 1;
-            const uint32_t nb = __shfl_sync(kFull, H.nb, src), off = __shfl_sync(kFull, H.bins_off, src);
+            const uint32_t nb = __shfl_sync(kFull, h_nb, src), off = __shfl_sync(kFull, h_off, src);
             const uint32_t r = row0 + (uint32_t)__popc(lead & ((2u << src) - 1u)) - 1u;
             if (nb <= (uint32_t)kStageBins)
                 for (uint32_t i = lane; i < nb; i += 32) cs.bins[r * kStageStride + i] = a.em_pool[off + i];
         }
         const uint32_t* bins = nullptr;
-        if (valid) bins = H.nb <= (uint32_t)kStageBins ? cs.bins + row * kStageStride : a.em_pool + H.bins_off;
+        if (valid) bins = h_nb <= (uint32_t)kStageBins ? cs.bins + row * kStageStride : a.em_pool + h_off;
         __syncwarp();
         bool last = false;
         if (valid) {
             double* res = a.em_res + (size_t)t * kEmResDoubles;
-            if (li == 0) em_task<2>(a, lut, H, bins, subset, res, lg);
-            else if (li == 1) em_task<3>(a, lut, H, bins, subset, res, lg);
-            else em_task<4>(a, lut, H, bins, subset, res, lg);
+            if (li == 0) em_task<2>(a, lut, cs.ltab, Hg, bins, subset, res, lg);
+            else if (li == 1) em_task<3>(a, lut, cs.ltab, Hg, bins, subset, res, lg);
+            else em_task<4>(a, lut, cs.ltab, Hg, bins, subset, res, lg);
             if (lg.gl == 0) {
                 __threadfence();
                 last = atomicSub(&Hg->remaining, 1u) == 1u;   // every task of the site has stored its result
@@ -891,7 +994,7 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
                 const uint32_t d_hdr = cs.dq[tid >> 5][dq_n + (uint32_t)lane];
                 __threadfence();
                 const EmSiteHdr Hd = a.em_hdr[d_hdr];
-                decide_site(a, Hd, d_hdr);
+                decide_site(a, Hd, d_hdr, nullptr, nullptr);
                 __syncwarp();
             }
         }
@@ -900,7 +1003,7 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         const uint32_t d_hdr = cs.dq[tid >> 5][lane];
         __threadfence();
         const EmSiteHdr Hd = a.em_hdr[d_hdr];
-        decide_site(a, Hd, d_hdr);
+        decide_site(a, Hd, d_hdr, nullptr, nullptr);
     }
 #else
     const uint32_t tpc = (uint32_t)(kTaskThreads / lg.G);   // tasks per CTA and round
@@ -917,10 +1020,15 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         const bool valid = word != kEmTaskInvalid;
         const uint32_t hdr = word & 0x0fffffffu, subset = word >> 28;
         __syncthreads();   // the previous round's readers of cs.bins are done (first round: the tables are written)
+        if (cs.n_fs >= (uint32_t)kTaskThreads) {   // (CTA-uniform) a whole CTA of Fisher tests waits: one per thread
+            fs_vcf_job(a, cs.fs_site[cs.n_fs - (uint32_t)kTaskThreads + (uint32_t)tid]);
+            __syncthreads();
+            if (tid == 0) cs.n_fs -= (uint32_t)kTaskThreads;
+        }
         if (tid == 0) cs.n_decide = 0;
         EmSiteHdr* const Hg = a.em_hdr + hdr;
-        EmSiteHdr H;
-        if (valid) H = *Hg;
+        uint32_t h_nb = 0, h_off = 0;   // (only these two words of the header are needed here)
+        if (valid) { h_off = Hg->bins_off; h_nb = Hg->nb; }
         // Staging, warp by warp: the tasks of a site are neighbours in the list, so one row serves a run of lanes with the same
         // header; all 32 lanes copy it (coalesced), one run after the other.  Lists longer than a row are read from the pool.
         const uint32_t hdr_prev = __shfl_up_sync(kFull, valid ? hdr : kEmTaskInvalid, 1);
@@ -929,24 +1037,23 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         const uint32_t row = (uint32_t)(tid & ~31) + (uint32_t)__popc(lead & ((2u << lane) - 1u)) - 1u;   // row of the last leader up to this lane
         for (uint32_t todo = lead; todo; todo &= todo - 1u) {
             const int src = __ffs(todo) - 1;
-            const uint32_t nb = __shfl_sync(kFull, H.nb, src), off = __shfl_sync(kFull, H.bins_off, src);
+            const uint32_t nb = __shfl_sync(kFull, h_nb, src), off = __shfl_sync(kFull, h_off, src);
             const uint32_t r = (uint32_t)(tid & ~31) + (uint32_t)__popc(lead & ((2u << src) - 1u)) - 1u;
             if (nb <= (uint32_t)kStageBins)
                 for (uint32_t i = lane; i < nb; i += 32) cs.bins[r * kStageStride + i] = a.em_pool[off + i];
         }
         const uint32_t* bins = nullptr;
-        if (valid) bins = H.nb <= (uint32_t)kStageBins ? cs.bins + row * kStageStride : a.em_pool + H.bins_off;
+        if (valid) bins = h_nb <= (uint32_t)kStageBins ? cs.bins + row * kStageStride : a.em_pool + h_off;
         __syncthreads();
         if (valid) {
             double* res = a.em_res + (size_t)t * kEmResDoubles;
-            if (li == 0) em_task<2>(a, lut, H, bins, subset, res, lg);
-            else if (li == 1) em_task<3>(a, lut, H, bins, subset, res, lg);
-            else em_task<4>(a, lut, H, bins, subset, res, lg);
+            if (li == 0) em_task<2>(a, lut, cs.ltab, Hg, bins, subset, res, lg);
+            else if (li == 1) em_task<3>(a, lut, cs.ltab, Hg, bins, subset, res, lg);
+            else em_task<4>(a, lut, cs.ltab, Hg, bins, subset, res, lg);
             if (lg.gl == 0) {
                 __threadfence();
                 if (atomicSub(&Hg->remaining, 1u) == 1u) {   // every task of the site has stored its result: queue the decision
-                    const uint32_t k = atomicAdd(&cs.n_decide, 1u);
-                    cs.decide_hdr[k] = hdr; cs.decide_row[k] = row;
+                    cs.decide_hdr[atomicAdd(&cs.n_decide, 1u)] = hdr;
                 }
             }
         }
@@ -955,9 +1062,11 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         if ((uint32_t)tid < cs.n_decide) {
             __threadfence();
             const EmSiteHdr Hd = a.em_hdr[cs.decide_hdr[tid]];
-            decide_site(a, Hd, cs.decide_hdr[tid]);
+            decide_site(a, Hd, cs.decide_hdr[tid], &cs.n_fs, cs.fs_site);
         }
     }
+    __syncthreads();
+    for (uint32_t k = (uint32_t)tid; k < cs.n_fs; k += (uint32_t)kTaskThreads) fs_vcf_job(a, cs.fs_site[k]);   // the tests still waiting
 #endif
 }
 

@@ -29,22 +29,50 @@ __device__ __forceinline__ void list_append(uint32_t* list, uint32_t* counter, b
     if (pred) list[pos + __popc(m & ((1u << lane) - 1u))] = site;
 }
 
-__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site);
+// Fisher tests that are not closed form wait in two queues of the CTA, by the width of the table's support: <= 24 outcomes (the
+// reference's own walk, kt_fisher_exact) or more (bisection + tail sums, bv_fisher_fast.h).  The two paths share no code and cost
+// 10-100x the rest of a site, so a warp that ran them lane by lane, each lane on its own site, executed both paths for every
+// mixed group of 32 sites -- 8 of 32 lanes active on average on deep pileups.  From the queues every warp runs ONE path with all
+// of its lanes (profiles/r02_k2_queues.txt).
+constexpr int kScalarThreads = 256;
+struct ScalarCta {
+    uint32_t n[2];                         // jobs queued: [0] narrow supports, [1] wide
+    uint32_t site[2][kScalarThreads];
+    int4 table[2][kScalarThreads];         // ref_fwd, ref_rev, alt_fwd, alt_rev
+};
 
-__global__ void __launch_bounds__(256) bv_scalar_kernel(const __grid_constant__ SiteKernelArgs a) {
+__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site, ScalarCta& q);
+
+__global__ void __launch_bounds__(kScalarThreads) bv_scalar_kernel(const __grid_constant__ SiteKernelArgs a) {
+    __shared__ ScalarCta q;
     const uint32_t n_slow = a.counters[kCntSlow];
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n_slow; i += stride) {   // warp-uniform trips
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n_slow; i0 += stride) {   // CTA-uniform trips
+        const uint32_t i = i0 + threadIdx.x;
+        if (threadIdx.x < 2) q.n[threadIdx.x] = 0;
+        __syncthreads();
         const bool valid = i < n_slow;
         const uint32_t site = valid ? a.list_slow[i] : 0u;
-        const uint32_t state = valid ? scalar_site(a, site) : kStateDone;
+        const uint32_t state = valid ? scalar_site(a, site, q) : kStateDone;
         list_append(a.list_bound, a.counters + kCntBound, state == kStateBound, site);
         list_append(a.list_em, a.counters + kCntEm, state == kStateEM, site);
+        __syncthreads();
+        // the queued tests: the wide ones on the first warps, the narrow ones on whole warps after them
+        const uint32_t n_wide = q.n[1], first_narrow = (n_wide + 31u) & ~31u, n_jobs = first_narrow + q.n[0];
+        for (uint32_t j = threadIdx.x; j < n_jobs; j += kScalarThreads) {
+            const int c = j < first_narrow ? 1 : 0;
+            const uint32_t k = c ? j : j - first_narrow;
+            if (c == 0 || k < n_wide) {
+                const int4 t = q.table[c][k];
+                reinterpret_cast<double*>(a.out + q.site[c][k])[14] = fs_from_table(a.logfact, t.x, t.y, t.z, t.w);   // fs_cvg
+            }
+        }
+        __syncthreads();
     }
 }
 
 // returns the site's new state
-__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site) {
+__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site, ScalarCta& q) {
     uint32_t* rec = reinterpret_cast<uint32_t*>(a.out + site);
     const uint4 w0 = reinterpret_cast<const uint4*>(rec)[0];   // depth[4]
     const uint4 w1 = reinterpret_cast<const uint4*>(rec)[1];   // other, state, fwd[0..1]
@@ -74,7 +102,18 @@ __device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_
         const int rr = ref_code < 0 ? 0 : (int)sel4u(ref_code, r0, r1, r2, r3);
         const int af_ = (int)(f0 + f1 + f2 + f3) - rf, ar = (int)(r0 + r1 + r2 + r3) - rr;
         // a table with an empty row or column has a single possible outcome: p == 1, FS == 0 (kfunc.c:256)
-        if ((af_ | ar) != 0 && (rf | rr) != 0) fs_cvg = fs_from_table(a.logfact, rf, rr, af_, ar);
+        if ((af_ | ar) != 0 && (rf | rr) != 0) {
+            double p;
+            if (fisher_margin1(rf, rr, af_, ar, p)) fs_cvg = fs_from_p(p);
+            else {
+                // queued by the width of the support [max(0, n1_ + n_1 - n), min(n1_, n_1)]; the record's FS is written from the queue
+                const int n1_ = rf + rr, n_1 = rf + af_, n = n1_ + af_ + ar;
+                const int c = (min(n1_, n_1) - max(0, n1_ + n_1 - n) > kFisherNarrowSupport) ? 1 : 0;
+                const uint32_t k = atomicAdd(&q.n[c], 1u);
+                q.site[c][k] = site;
+                q.table[c][k] = make_int4(rf, rr, af_, ar);
+            }
+        }
     }
     uint32_t state = need_qual ? kStateEM : kStateDone;
     // the active set travels in bits 8-11 of the alt word (K4a), the minor allele of a bound site in bits 0-1 (K3)

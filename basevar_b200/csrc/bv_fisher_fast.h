@@ -60,7 +60,8 @@ BV_FN double ff_pmf(const LF& lf, const EXP& ex, int i, int n1_, int n_1, int n)
 // The fast path is used for wide supports only, and not for astronomically small q: below ~1e-250 the reference's
 // incremental products run into denormals and its sum loses terms (it can even return 0, i.e. FS = 10000, where the
 // true p is 1e-305); parity there needs its own operation sequence, which the callers keep for exactly that case.
-BV_FN bool fisher_fast_applicable(int lo, int hi, double q) { return hi - lo > 24 && q > 1e-250; }
+constexpr int kFisherNarrowSupport = 24;   // supports up to this wide are walked as the reference does
+BV_FN bool fisher_fast_applicable(int lo, int hi, double q) { return hi - lo > kFisherNarrowSupport && q > 1e-250; }
 
 // Two-sided p of the table (n11 n12 / n21 n22); q_in = pmf(n11) already computed by the caller (> 0), lo < hi.
 template <class LF, class EXP>

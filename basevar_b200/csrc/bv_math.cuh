@@ -171,14 +171,17 @@ __device__ __forceinline__ bool fisher_margin1(int a, int b, int c, int d, doubl
 }
 
 // src/basetype.cpp:277-283
-__device__ __noinline__ double fs_from_table(const double* __restrict__ lf, int rf, int rr, int af, int ar) {
-    double p;
-    if (!fisher_margin1(rf, rr, af, ar, p)) p = fisher_two_sided(lf, rf, rr, af, ar);
+__device__ __forceinline__ double fs_from_p(double p) {
     if (p == 1.0) return 0.0;   // -10*log10(1) = -0.0, scrubbed to +0.0 by the reference's `fs == 0` branch
     double fs = -10 * nlog10(p);
     if (isinf(fs)) fs = 10000;
     else if (fs == 0) fs = 0.0;
     return fs;
+}
+__device__ __noinline__ double fs_from_table(const double* __restrict__ lf, int rf, int rr, int af, int ar) {
+    double p;
+    if (!fisher_margin1(rf, rr, af, ar, p)) p = fisher_two_sided(lf, rf, rr, af, ar);
+    return fs_from_p(p);
 }
 
 // ---- warp reductions ------------------------------------------------------------------------------------

@@ -61,7 +61,18 @@ def test_random_tables_against_the_oracle(built_lib, oracle_lib):
     finally:
         eng.close()
     want = np.empty(len(tables))
+    atol = np.full(len(tables), util.FS_ATOL)
     for i, (a, b, c, d) in enumerate(tables.tolist()):
         # strand_bias() runs the test on every table (an empty row gives p == 1)
-        want[i] = _fs_of_p(oracle_lib.bvo_fisher_two_sided(a, b, c, d))
-    assert util.close(got, want, util.RTOL, util.FS_ATOL).all(), np.nonzero(~util.close(got, want, util.RTOL, util.FS_ATOL))[0][:10]
+        p = oracle_lib.bvo_fisher_two_sided(a, b, c, d)
+        want[i] = _fs_of_p(p)
+        if 0 < p < 2.3e-308:
+            # A p-value in the denormal range is a sum of hypergeometric terms that are each a few hundred to a few thousand steps
+            # of the denormal grid (4.9e-324): the reference's own sum is that coarse, and below ~4,000 steps its very first term
+            # -- exp() of the observed table's log-probability -- is 0 or not by the last bit of exp (device: FS = 10000, the
+            # reference's rule for p == 0).  Measured on a ladder of such tables: tools/fs_probe.py, profiles/r02_fs_probe.txt.
+            steps = p / 4.94e-324
+            atol[i] = 10 / math.log(10) * 4096 / steps if steps > 4096 else np.inf
+    ok = (np.abs(got - want) <= atol + util.RTOL * np.abs(want)) | (np.isinf(atol) & ((got == 10000.0) | (np.abs(got - want) < 5)))
+    bad = np.nonzero(~ok)[0][:10]
+    assert ok.all(), (bad, tables[bad], got[bad], want[bad])
