@@ -140,6 +140,7 @@ _SIGNATURES = [
     ("bv_set_profiling", C.c_int, [C.c_void_p, C.c_int]),
     ("bv_last_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("bv_last_em_kernel_times", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    ("bv_last_fisher_kernel_time", C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     ("bv_tile_submit", C.c_int, [C.c_void_p, C.c_int, C.POINTER(BvTile)]),
     ("bv_tile_wait", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("bv_tile_wait_compact", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]),

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) bv_synth_rpr_kernel(const bv_synth_model*
 // Scratch of one in-flight tile: work lists and counters (K1 -> K2 -> K3 -> K4) and the EM kernel's spill space.
 // Kernels of different tiles may overlap, so every slot (and the device-resident path) owns one.
 struct bv_scratch {
-    uint32_t* d_lists = nullptr;      // 4 x cap site indices
+    uint32_t* d_lists = nullptr;      // 6 x cap site indices (list_fisher takes two)
     uint32_t* d_counters = nullptr;   // kNumCounters x u32
     uint32_t* d_bin_spill = nullptr;
     double* d_lml_spill = nullptr;
@@ -176,7 +176,7 @@ struct bv_ctx {
     bool zero_copy_qual = true;       // BASEVAR_B200_ZERO_COPY_QUAL=0 uploads the whole qual plane instead
     uint64_t h2d_bytes_total = 0;
     bool profiling = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     long long task_split_override = -1;   // BASEVAR_B200_TASK_SPLIT (tuning): tiles with more EM tasks than this run the high-occupancy build
     int task_ctas_per_sm = 3;         // resident CTAs per SM of bv_em_task_kernel<BV_TASK_LO_CTAS> (asked of the runtime in bv_create) ...
     int task_ctas_per_sm_hi = 4;      // ... and of bv_em_task_kernel<BV_TASK_HI_CTAS>, the build for tiles with many EM tasks
@@ -241,7 +241,7 @@ static int scratch_reserve(bv_ctx* ctx, bv_scratch& sc, uint32_t n_sites) {
         if (sc.d_lists) BV_CUDA(ctx, cudaFree(sc.d_lists));
         sc.d_lists = nullptr;
         sc.cap = 0;
-        BV_CUDA(ctx, cudaMalloc(&sc.d_lists, 4 * (size_t)n_sites * sizeof(uint32_t)));
+        BV_CUDA(ctx, cudaMalloc(&sc.d_lists, 6 * (size_t)n_sites * sizeof(uint32_t)));
         // EM scratch: room for every site to be an EM site; 64 bins and 3 tasks per site of the tile on average (a deep,
         // multi-allelic pileup needs 25 and 1; what does not fit is finished inside K4a, see bv_em_kernels.cuh)
         cudaFree(sc.d_em_hdr); cudaFree(sc.d_em_pool); cudaFree(sc.d_em_tasks); cudaFree(sc.d_em_res); cudaFree(sc.d_em_single);
@@ -287,6 +287,7 @@ static int fill_kernel_args(bv_ctx* ctx, const bv_tile* t, bv_site_out* d_out, b
     a->list_slow = sc.d_lists;
     a->list_bound = sc.d_lists + sc.cap;
     a->list_em = sc.d_lists + 2 * (size_t)sc.cap;
+    a->list_fisher = sc.d_lists + 4 * (size_t)sc.cap;   // [2 * n_sites] of its 2 * cap words
     a->counters = sc.d_counters;
     a->em_hdr = sc.d_em_hdr; a->em_pool = sc.d_em_pool; a->em_tasks = sc.d_em_tasks; a->em_res = sc.d_em_res; a->em_single = sc.d_em_single;
     a->em_pool_cap = sc.em_pool_cap;
@@ -400,8 +401,14 @@ static int launch_site_kernel(bv_ctx* ctx, const bv::SiteKernelArgs& a, cudaStre
     bv::bv_em_task_kernel<BV_TASK_HI_CTAS><<<grid_hi, bv::kTaskThreads, bv::kTaskSmemBytes, stream>>>(b);
     ctx->launches += 1;
     BV_CUDA(ctx, cudaGetLastError());
-    if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[5], stream)); ctx->ev_valid = true; }
-    ctx->launches += 5;
+    if (prof) BV_CUDA(ctx, cudaEventRecord(ctx->ev[5], stream));
+    // the Fisher tests K2 and K4 listed (as many as two per site; the counts are on the device): grid-stride
+    grid = (4u * a.n_sites + bv::kFisherThreads - 1) / bv::kFisherThreads;   // (a pair of lanes per test)
+    if (grid > (uint32_t)ctx->num_sms * BV_SCALAR_CTAS_PER_SM) grid = (uint32_t)ctx->num_sms * BV_SCALAR_CTAS_PER_SM;
+    bv::bv_fisher_kernel<<<grid, bv::kFisherThreads, 0, stream>>>(a);
+    BV_CUDA(ctx, cudaGetLastError());
+    if (prof) { BV_CUDA(ctx, cudaEventRecord(ctx->ev[6], stream)); ctx->ev_valid = true; }
+    ctx->launches += 6;
     if (a.list_called) {
         // K5 / K6: the called sites (a few per mille of the tile at 0.1x); grids sized for the worst case, warps
         // without work leave at once
@@ -490,7 +497,7 @@ int bv_set_profiling(bv_ctx* ctx, int on) {
     if (!ctx) return set_err(nullptr, BV_ERR_ARG, "null context");
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
     if (on && !ctx->ev[0]) {
-        for (int i = 0; i < 6; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
+        for (int i = 0; i < 7; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev[i]));
         for (int i = 0; i < 3; ++i) BV_CUDA(ctx, cudaEventCreate(&ctx->ev_call[i]));
     }
     ctx->profiling = on != 0;
@@ -524,6 +531,15 @@ int bv_last_em_kernel_times(bv_ctx* ctx, float ms[2]) {
     BV_CUDA(ctx, cudaSetDevice(ctx->device));
     BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[5]));
     for (int i = 0; i < 2; ++i) BV_CUDA(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[3 + i], ctx->ev[4 + i]));
+    return BV_OK;
+}
+
+int bv_last_fisher_kernel_time(bv_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return set_err(ctx, BV_ERR_ARG, "null argument");
+    if (!ctx->ev_valid) return set_err(ctx, BV_ERR_STATE, "no profiled tile yet (bv_set_profiling)");
+    BV_CUDA(ctx, cudaSetDevice(ctx->device));
+    BV_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+    BV_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev[5], ctx->ev[6]));
     return BV_OK;
 }
 
@@ -675,7 +691,7 @@ void bv_destroy(bv_ctx* ctx) {
     }
     cudaFree(ctx->d_lut); cudaFree(ctx->d_logfact); cudaFree(ctx->d_model); cudaFree(ctx->d_group);
     scratch_free(ctx->dev_scratch);
-    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 7; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 3; ++i) if (ctx->ev_call[i]) cudaEventDestroy(ctx->ev_call[i]);
     if (ctx->ev_trace0) cudaEventDestroy(ctx->ev_trace0);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }

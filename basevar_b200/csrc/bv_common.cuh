@@ -8,16 +8,21 @@
 //   K1  bv_count_kernel   (bv_count_kernel.cuh)    every site, every cell: streams the base + strand planes through
 //        per-warp TMA rings and counts -- per-base depths and the 2x4 strand table.  Sites whose reads all equal REF get
 //        their final record here; the others get their counts and the state BV_STATE_SCALAR.
-//   K2  bv_scalar_kernel  (bv_finish_kernels.cuh)  one THREAD per site in state SCALAR: active alleles, strand-bias
-//        Fisher test; final record unless the result depends on base qualities (then state BOUND or EM).
+//   K2  bv_scalar_kernel  (bv_finish_kernels.cuh)  one THREAD per site in state SCALAR: active alleles, the strand-bias test
+//        of the CVG row where it is closed form (else it is listed for KF); final record unless the result depends on base
+//        qualities (then state BOUND or EM).
 //   K3  bv_bound_kernel   (bv_finish_kernels.cuh)  one warp per site in state BOUND (REF plus one minor allele carried by
 //        a few reads -- sequencing errors): fetches the row's base + qual planes and settles the LRT by a rigorous bound
 //        on the likelihood ratio, without running the EM; what the bound cannot decide goes to state EM.
 //   K4a bv_hist_kernel    (bv_em_kernels.cuh)      one warp per site in state EM: (base, phred) histogram of the row, compact
 //        bins, one EM task per candidate subset of the active alleles.
 //   K4b bv_em_task_kernel (bv_em_kernels.cuh)      one THREAD per EM task (the whole EM of one subset on the site's bins); the
-//        thread that finishes a site's last task replays the LRT elimination on the results and completes the record (QUAL,
-//        Fisher test of the VCF row).  bv_em_iter_kernel runs the iterations first when the convergence test uses fabs.
+//        thread that finishes a site's last task replays the LRT elimination on the results and completes the record (ALT, AF,
+//        QUAL; the Fisher test of the VCF row is listed for KF).  bv_em_iter_kernel runs the iterations first when the
+//        convergence test uses fabs.
+//   KF  bv_fisher_kernel  (bv_finish_kernels.cuh)  the two-sided Fisher exact tests K2 and K4 listed, a pair of lanes per test
+//        (one per tail), the tests over wide supports (bisection + tail sums) apart from those over narrow ones (the
+//        reference's walk), so that every warp runs one path.
 //   K5 / K6 (bv_call_kernels.cuh) rank sums and population-group frequencies of the called sites; K7 bv_pack_kernel
 //        (bv_finish_kernels.cuh) the compact result transport.
 //
@@ -56,6 +61,7 @@ constexpr int kCntEmHdr = 7, kCntEmPool = 8;                              // K4a
 constexpr int kCntEmTask2 = 9, kCntEmTask3 = 11, kCntEmTask4 = 12;        // EM tasks by number of alleles in the candidate subset
 constexpr int kCntFull = 13;                                              // full records of a compact tile (bv_pack_kernel)
 constexpr int kCntEmFallback = 10;                                        // EM sites finished inside K4a (scratch pools full)
+constexpr int kCntFisherNarrow = 14, kCntFisherWide = 15;                   // queued Fisher tests (K2, K4b -> bv_fisher_kernel)
 constexpr int kCntEmFetch2 = 16, kCntEmFetch3 = 17, kCntEmFetch4 = 18;      // next task of each list (bv_em_iter_kernel)
 constexpr int kNumCounters = 24;
 
@@ -79,6 +85,8 @@ static_assert(sizeof(EmSiteHdr) == 64, "EmSiteHdr layout");
 constexpr int kEmResDoubles = 10;            // per EM task: log-likelihood, f[4], flags (as bits of a u64); between bv_em_iter_kernel
                                              // and bv_em_task_kernel: f[k], fp[k] (k-th allele of the subset) in [0..3], [4..7], flags in [8]
 constexpr uint32_t kEmTaskInvalid = 0xffffffffu;
+constexpr uint32_t kFisherVcfRow = 1u << 24;   // list_fisher entry: the test of the VCF row (ref vs called ALT), else that of the CVG row
+constexpr uint32_t kFisherWide = 1u << 25;     // (in the queues of a CTA only) the table's support is wider than kFisherNarrowSupport
 
 struct SiteKernelArgs {
     const uint8_t* base;
@@ -94,8 +102,10 @@ struct SiteKernelArgs {
     uint32_t* list_slow;     // work lists (site indices), each with room for n_sites entries: K1 -> K2,
     uint32_t* list_bound;    //   K2 -> K3,
     uint32_t* list_em;       //   K2 and K3 -> K4
+    uint32_t* list_fisher;   //   K2 and K4b -> bv_fisher_kernel: [2 * n_sites] queued Fisher tests (site | kFisherVcfRow), those over narrow
+                             //   supports from the front, those over wide supports from the back
     uint32_t* counters;      // [kNumCounters], zeroed before K1
-    // K4a -> K4b -> K4c (bv_em_kernels.cuh)
+    // K4a -> K4b (bv_em_kernels.cuh)
     EmSiteHdr* em_hdr;       // [n_sites]
     uint32_t* em_pool;       // [em_pool_cap] compact bins of the EM sites, allocated with kCntEmPool
     uint32_t* em_tasks;      // hdr index | subset << 28; three lists one after the other: 2-, 3- and 4-allele subsets,

@@ -147,7 +147,8 @@ __device__ __noinline__ void hist_site(uint32_t site) {
 
     // ---- ALT / QUAL (src/basetype.cpp:170-196) ----
     // Here only the rule that needs no arithmetic (mono-allelic 5000); the chi-square survival function and the Fisher
-    // test of the VCF row are scalar work: the site is queued and vcf_flush() does them one thread per site.
+    // test of the VCF row are scalar work: the site is queued and vcf_flush() does them one thread per site (the test itself:
+    // bv_fisher_kernel).
     const int ref_code = ref_code_of(cs.a.ref_base[site]);
     const uint32_t ref_bit = ref_code >= 0 ? (1u << ref_code) : 0u;
     const uint32_t alt_set = act & ~ref_bit;
@@ -263,8 +264,8 @@ struct __align__(16) TaskCta {
     double2 ltab[kLogTabEntries];     // log_tab()'s table
     uint32_t n_decide;                // sites whose last task finished in this round of the CTA ...
     uint32_t decide_hdr[kTaskThreads];   // ... their headers: decided one thread per site after the round
-    uint32_t n_fs;                    // decided sites whose VCF row needs a Fisher test of its own (FsQueue) ...
-    uint32_t fs_site[2 * kTaskThreads];  // ... waiting until a whole CTA of them is there
+    uint32_t n_fs;                    // Fisher tests of the VCF rows of decided sites, listed by decide_site ...
+    uint32_t fs_site[2 * kTaskThreads];  // ... on their way to list_fisher, a CTA of them at a time
 #if BV_TASK_WARP_ROUNDS
     uint32_t dq[kTaskThreads / 32][64];  // per warp: headers of completed sites waiting for their decision
 #endif
@@ -734,34 +735,10 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_iter_kernel(const __grid_c
 // ---- the site's decision, after its last task has finished ----------------------------------------------------------------------
 // Backward elimination (src/basetype.cpp:144-168) on the task results, ALT / AF / QUAL (:170-196), FS of the VCF row.
 // The strand-bias test of a VCF row whose called ALT set is not "every non-reference base" is a Fisher test of its own (ref vs the
-// called alleles, src/basetype.cpp:244-295, basetype_caller.cpp:1164) -- on a deep pileup a walk of hundreds of steps, 10-100x the
-// rest of a decision, needed by one decided site in three.  Run inside the decision it kept a few lanes of one or two warps busy
-// while the CTA's other warps waited at the round's barrier (a fifth of bv_em_task_kernel's warp time on deep multi-allelic
-// pileups, profiles/r02_k4b_fs_queue.txt).  The sites are queued instead (fs_queue != nullptr), and the CTA runs the tests when a
-// whole CTA of them waits: every lane of every warp on the same path.
-__device__ __forceinline__ void vcf_tables(const bv_site_out* rec, int ref_code, uint32_t alt_set, int& rf, int& rr, int& vf, int& vr,
-                                           int& af_, int& ar) {
-    const uint32_t f[4] = {rec->fwd[0], rec->fwd[1], rec->fwd[2], rec->fwd[3]};
-    const uint32_t rv[4] = {rec->rev[0], rec->rev[1], rec->rev[2], rec->rev[3]};
-    rf = 0; rr = 0; vf = 0; vr = 0; af_ = 0; ar = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        if (b == ref_code) { rf = (int)f[b]; rr = (int)rv[b]; }
-        else { af_ += (int)f[b]; ar += (int)rv[b]; }
-        if (alt_set >> b & 1u) { vf += (int)f[b]; vr += (int)rv[b]; }
-    }
-}
-// a queued site: the table again from its (decided) record, the test, FS into the record
-__device__ __forceinline__ void fs_vcf_job(const SiteKernelArgs& a, uint32_t site) {
-    bv_site_out* rec = a.out + site;
-    const int ref_code = ref_code_of(a.ref_base[site]);
-    uint32_t alt_set = 0;
-    for (int k = 0; k < (int)rec->n_alt; ++k) alt_set |= 1u << (rec->alt[k] & 3u);
-    int rf, rr, vf, vr, af_, ar;
-    vcf_tables(rec, ref_code, alt_set, rf, rr, vf, vr, af_, ar);
-    rec->fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
-}
-
+// called alleles) -- on a deep pileup a walk of hundreds of steps, needed by one decided site in three.  Run inside the decision it
+// kept a few lanes of one or two warps busy while the CTA's other warps waited at the round's barrier (a fifth of this kernel's warp
+// time on deep multi-allelic pileups).  With fs_queue the decision only lists the test (site | kFisherVcfRow | kFisherWide); the CTA
+// hands its list on to bv_fisher_kernel (see fisher_push in bv_finish_kernels.cuh).
 __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHdr& H, uint32_t hdr_index, uint32_t* fs_queue_n, uint32_t* fs_queue) {
     const uint32_t site = H.site;
     bv_site_out* rec = a.out + site;
@@ -856,12 +833,13 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
         else qual = qual_from_chi(chi);
         // strand bias of the VCF row, ref vs the called ALT alleles (src/basetype.cpp:244-295, basetype_caller.cpp:1164)
         int rf, rr, vf, vr, af_, ar;
-        vcf_tables(rec, ref_code, alt_set, rf, rr, vf, vr, af_, ar);
-        if (vf == af_ && vr == ar) fs_vcf = rec->fs_cvg;   // same 2x2 table as the CVG row
-        else if ((vf | vr) != 0 && (rf | rr) != 0) {
+        strand_tables(rec, ref_code, alt_set, rf, rr, vf, vr, af_, ar);
+        if ((vf | vr) != 0 && (rf | rr) != 0) {
             double p;
             if (fisher_margin1(rf, rr, vf, vr, p)) fs_vcf = fs_from_p(p);
-            else if (fs_queue != nullptr) fs_queue[atomicAdd(fs_queue_n, 1u)] = site;   // fs_vcf_job() completes the record
+            else if (fs_queue != nullptr)   // bv_fisher_kernel completes the record (also when the table is that of the CVG row: its
+                                            // FS is not there yet either)
+                fs_queue[atomicAdd(fs_queue_n, 1u)] = site | kFisherVcfRow | (fisher_support_wide(rf, rr, vf, vr) ? kFisherWide : 0u);
             else fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
         }
     }
@@ -1020,8 +998,9 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         const bool valid = word != kEmTaskInvalid;
         const uint32_t hdr = word & 0x0fffffffu, subset = word >> 28;
         __syncthreads();   // the previous round's readers of cs.bins are done (first round: the tables are written)
-        if (cs.n_fs >= (uint32_t)kTaskThreads) {   // (CTA-uniform) a whole CTA of Fisher tests waits: one per thread
-            fs_vcf_job(a, cs.fs_site[cs.n_fs - (uint32_t)kTaskThreads + (uint32_t)tid]);
+        if (cs.n_fs >= (uint32_t)kTaskThreads) {   // (CTA-uniform) a whole CTA of listed Fisher tests: on to bv_fisher_kernel's list
+            const uint32_t e = cs.fs_site[cs.n_fs - (uint32_t)kTaskThreads + (uint32_t)tid];
+            fisher_push(a, true, (e & kFisherWide) != 0u, e & ~kFisherWide);
             __syncthreads();
             if (tid == 0) cs.n_fs -= (uint32_t)kTaskThreads;
         }
@@ -1066,7 +1045,11 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         }
     }
     __syncthreads();
-    for (uint32_t k = (uint32_t)tid; k < cs.n_fs; k += (uint32_t)kTaskThreads) fs_vcf_job(a, cs.fs_site[k]);   // the tests still waiting
+    for (uint32_t k0 = 0; k0 < cs.n_fs; k0 += (uint32_t)kTaskThreads) {   // the tests still listed here
+        const bool have = k0 + (uint32_t)tid < cs.n_fs;
+        const uint32_t e = have ? cs.fs_site[k0 + (uint32_t)tid] : 0u;
+        fisher_push(a, have, (e & kFisherWide) != 0u, e & ~kFisherWide);
+    }
 #endif
 }
 

@@ -29,50 +29,118 @@ __device__ __forceinline__ void list_append(uint32_t* list, uint32_t* counter, b
     if (pred) list[pos + __popc(m & ((1u << lane) - 1u))] = site;
 }
 
-// Fisher tests that are not closed form wait in two queues of the CTA, by the width of the table's support: <= 24 outcomes (the
-// reference's own walk, kt_fisher_exact) or more (bisection + tail sums, bv_fisher_fast.h).  The two paths share no code and cost
-// 10-100x the rest of a site, so a warp that ran them lane by lane, each lane on its own site, executed both paths for every
-// mixed group of 32 sites -- 8 of 32 lanes active on average on deep pileups.  From the queues every warp runs ONE path with all
-// of its lanes (profiles/r02_k2_queues.txt).
-constexpr int kScalarThreads = 256;
-struct ScalarCta {
-    uint32_t n[2];                         // jobs queued: [0] narrow supports, [1] wide
-    uint32_t site[2][kScalarThreads];
-    int4 table[2][kScalarThreads];         // ref_fwd, ref_rev, alt_fwd, alt_rev
-};
+// Fisher tests that are not closed form are not run where they arise.  A test is a walk over the table's support: <= 24 outcomes
+// the reference's own way (kt_fisher_exact), or bisection + tail sums for wider supports (bv_fisher_fast.h) -- two paths that share
+// no code and cost 10-100x the rest of a site.  Run lane by lane, each lane on its own site, a warp executed both paths for every
+// mixed group of 32 sites (8 of 32 lanes active on deep pileups), and queues per CTA left most warps waiting for the CTA's few wide
+// tests (41 % of K2's warp time at a barrier, profiles/r02_fisher_queues.txt).  So K2 (the CVG row's test) and the decisions of K4b
+// (the VCF row's) only LIST their tests, by support width, and bv_fisher_kernel runs them all after K4b: every warp on one path,
+// the whole GPU on the wide ones first.
+// all 32 lanes call; `entry` of the lanes with pred goes onto the narrow or the wide end of list_fisher
+__device__ __forceinline__ void fisher_push(const SiteKernelArgs& a, bool pred, bool wide, uint32_t entry) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t mn = __ballot_sync(kFull, pred && !wide), mw = __ballot_sync(kFull, pred && wide);
+    if (mn) {
+        uint32_t pos = 0;
+        if (lane == __ffs(mn) - 1) pos = atomicAdd(a.counters + kCntFisherNarrow, (uint32_t)__popc(mn));
+        pos = __shfl_sync(kFull, pos, __ffs(mn) - 1);
+        if (pred && !wide) a.list_fisher[pos + __popc(mn & below)] = entry;
+    }
+    if (mw) {
+        uint32_t pos = 0;
+        if (lane == __ffs(mw) - 1) pos = atomicAdd(a.counters + kCntFisherWide, (uint32_t)__popc(mw));
+        pos = __shfl_sync(kFull, pos, __ffs(mw) - 1);
+        if (pred && wide) a.list_fisher[2u * a.n_sites - 1u - (pos + __popc(mw & below))] = entry;
+    }
+}
+// is the support [max(0, n1_ + n_1 - n), min(n1_, n_1)] of the table (a b / c d) wider than the reference's walk is kept for?
+__device__ __forceinline__ bool fisher_support_wide(int t11, int t12, int t21, int t22) {
+    const int n1_ = t11 + t12, n_1 = t11 + t21, n = n1_ + t21 + t22;
+    return min(n1_, n_1) - max(0, n1_ + n_1 - n) > kFisherNarrowSupport;
+}
 
-__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site, ScalarCta& q);
+// The two strand tables of a site from its record: ref vs every non-reference base (CVG row, basetype_caller.cpp:1236-1245) and ref
+// vs the called ALT alleles (VCF row, :1164); src/basetype.cpp:244-295.
+__device__ __forceinline__ void strand_tables(const bv_site_out* rec, int ref_code, uint32_t alt_set, int& rf, int& rr, int& vf, int& vr,
+                                              int& af_, int& ar) {
+    const uint32_t f[4] = {rec->fwd[0], rec->fwd[1], rec->fwd[2], rec->fwd[3]};
+    const uint32_t rv[4] = {rec->rev[0], rec->rev[1], rec->rev[2], rec->rev[3]};
+    rf = 0; rr = 0; vf = 0; vr = 0; af_ = 0; ar = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (b == ref_code) { rf = (int)f[b]; rr = (int)rv[b]; }
+        else { af_ += (int)f[b]; ar += (int)rv[b]; }
+        if (alt_set >> b & 1u) { vf += (int)f[b]; vr += (int)rv[b]; }
+    }
+}
 
-__global__ void __launch_bounds__(kScalarThreads) bv_scalar_kernel(const __grid_constant__ SiteKernelArgs a) {
-    __shared__ ScalarCta q;
+// One queued test (all 32 lanes call): the table again from the site's (by now final) record, the test, FS into the record.
+// pair: lanes 2k and 2k + 1 share the test, the even lane sums its left tail, the odd one its right tail -- half the latency of the
+// kernel's longest dependency chain, which is all that counts while the tests of a tile leave most of the GPU's threads unused.
+// left + right is the very sum the one-thread test forms, so the value is the same bit for bit in both modes (and in bv_fs_kernel).
+__device__ __forceinline__ void fisher_job(const SiteKernelArgs& a, bool have, uint32_t entry, bool pair) {
+    const int side = pair ? (int)(threadIdx.x & 1u) : kFisherBoth;
+    double part = 0.0;
+    bool whole = false;
+    bv_site_out* rec = nullptr;
+    if (have) {
+        const uint32_t site = entry & 0x00ffffffu;
+        rec = a.out + site;
+        const int ref_code = ref_code_of(a.ref_base[site]);
+        uint32_t alt_set = 0;
+        if (entry & kFisherVcfRow)
+            for (int k = 0; k < (int)rec->n_alt; ++k) alt_set |= 1u << (rec->alt[k] & 3u);
+        int rf, rr, vf, vr, af_, ar;
+        strand_tables(rec, ref_code, alt_set, rf, rr, vf, vr, af_, ar);
+        if (!(entry & kFisherVcfRow)) { vf = af_; vr = ar; }
+        part = fisher_two_sided(a.logfact, rf, rr, vf, vr, side, &whole);   // (margin-1 tables are closed form and never listed)
+    }
+    const double other = __shfl_xor_sync(kFull, part, 1);
+    if (have && side != kFisherRight) {
+        double p = (pair && !whole) ? part + other : part;
+        if (p > 1.) p = 1.;
+        const double fs = fs_from_p(p);
+        if (entry & kFisherVcfRow) rec->fs_vcf = fs; else rec->fs_cvg = fs;
+    }
+}
+
+constexpr int kFisherThreads = 256;
+__global__ void __launch_bounds__(kFisherThreads) bv_fisher_kernel(const __grid_constant__ SiteKernelArgs a) {
+    const uint32_t n_wide = a.counters[kCntFisherWide], n_narrow = a.counters[kCntFisherNarrow];
+    const uint32_t threads = gridDim.x * blockDim.x;
+    const bool pair = 2u * (n_wide + n_narrow + 32u) <= threads;      // a pair of lanes per test while that still is one trip
+    const uint32_t per_warp = pair ? 16u : 32u, shift = pair ? 1u : 0u;
+    const uint32_t first_narrow = (n_wide + per_warp - 1u) & ~(per_warp - 1u), n_jobs = first_narrow + n_narrow;   // the narrow tests
+                                                                                                       // start on a warp of their own
+    for (uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> shift; (j & ~(per_warp - 1u)) < n_jobs; j += threads >> shift) {   // warp-uniform trips
+        bool have = false;
+        uint32_t entry = 0;
+        if (j < first_narrow) {
+            if (j < n_wide) { have = true; entry = a.list_fisher[2u * a.n_sites - 1u - j]; }
+        } else if (j < n_jobs) { have = true; entry = a.list_fisher[j - first_narrow]; }
+        fisher_job(a, have, entry, pair);
+    }
+}
+
+__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site, bool& fs_job, bool& fs_wide);
+
+__global__ void __launch_bounds__(256) bv_scalar_kernel(const __grid_constant__ SiteKernelArgs a) {
     const uint32_t n_slow = a.counters[kCntSlow];
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n_slow; i0 += stride) {   // CTA-uniform trips
-        const uint32_t i = i0 + threadIdx.x;
-        if (threadIdx.x < 2) q.n[threadIdx.x] = 0;
-        __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; (i & ~31u) < n_slow; i += stride) {   // warp-uniform trips
         const bool valid = i < n_slow;
         const uint32_t site = valid ? a.list_slow[i] : 0u;
-        const uint32_t state = valid ? scalar_site(a, site, q) : kStateDone;
+        bool fs_job = false, fs_wide = false;
+        const uint32_t state = valid ? scalar_site(a, site, fs_job, fs_wide) : kStateDone;
         list_append(a.list_bound, a.counters + kCntBound, state == kStateBound, site);
         list_append(a.list_em, a.counters + kCntEm, state == kStateEM, site);
-        __syncthreads();
-        // the queued tests: the wide ones on the first warps, the narrow ones on whole warps after them
-        const uint32_t n_wide = q.n[1], first_narrow = (n_wide + 31u) & ~31u, n_jobs = first_narrow + q.n[0];
-        for (uint32_t j = threadIdx.x; j < n_jobs; j += kScalarThreads) {
-            const int c = j < first_narrow ? 1 : 0;
-            const uint32_t k = c ? j : j - first_narrow;
-            if (c == 0 || k < n_wide) {
-                const int4 t = q.table[c][k];
-                reinterpret_cast<double*>(a.out + q.site[c][k])[14] = fs_from_table(a.logfact, t.x, t.y, t.z, t.w);   // fs_cvg
-            }
-        }
-        __syncthreads();
+        fisher_push(a, fs_job, fs_wide, site);
     }
 }
 
 // returns the site's new state
-__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site, ScalarCta& q) {
+__device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_t site, bool& fs_job, bool& fs_wide) {
     uint32_t* rec = reinterpret_cast<uint32_t*>(a.out + site);
     const uint4 w0 = reinterpret_cast<const uint4*>(rec)[0];   // depth[4]
     const uint4 w1 = reinterpret_cast<const uint4*>(rec)[1];   // other, state, fwd[0..1]
@@ -105,14 +173,7 @@ __device__ __forceinline__ uint32_t scalar_site(const SiteKernelArgs& a, uint32_
         if ((af_ | ar) != 0 && (rf | rr) != 0) {
             double p;
             if (fisher_margin1(rf, rr, af_, ar, p)) fs_cvg = fs_from_p(p);
-            else {
-                // queued by the width of the support [max(0, n1_ + n_1 - n), min(n1_, n_1)]; the record's FS is written from the queue
-                const int n1_ = rf + rr, n_1 = rf + af_, n = n1_ + af_ + ar;
-                const int c = (min(n1_, n_1) - max(0, n1_ + n_1 - n) > kFisherNarrowSupport) ? 1 : 0;
-                const uint32_t k = atomicAdd(&q.n[c], 1u);
-                q.site[c][k] = site;
-                q.table[c][k] = make_int4(rf, rr, af_, ar);
-            }
+            else { fs_job = true; fs_wide = fisher_support_wide(rf, rr, af_, ar); }   // bv_fisher_kernel completes the record
         }
     }
     uint32_t state = need_qual ? kStateEM : kStateDone;
@@ -1068,6 +1129,8 @@ __device__ __noinline__ void vcf_flush() {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n = W.vcf_n;
     __syncwarp();
+    bool job = false, wide = false;
+    uint32_t entry = 0;
     if (lane < n) {
         const uint32_t site = W.vcf_site[lane];
         bv_site_out* rec = cs.a.out + site;
@@ -1075,20 +1138,18 @@ __device__ __noinline__ void vcf_flush() {
         if (!(rec->flags & BV_FLAG_MONO_QUAL)) rec->qual = qual_from_chi(rec->chi2);
         uint32_t alt_set = 0;
         for (int k = 0; k < (int)rec->n_alt; ++k) alt_set |= 1u << (rec->alt[k] & 3u);
-        const uint32_t f[4] = {rec->fwd[0], rec->fwd[1], rec->fwd[2], rec->fwd[3]};
-        const uint32_t rv[4] = {rec->rev[0], rec->rev[1], rec->rev[2], rec->rev[3]};
-        int rf = 0, rr = 0, vf = 0, vr = 0, af_ = 0, ar = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            if (b == ref_code) { rf = (int)f[b]; rr = (int)rv[b]; }
-            else { af_ += (int)f[b]; ar += (int)rv[b]; }
-            if (alt_set >> b & 1u) { vf += (int)f[b]; vr += (int)rv[b]; }
-        }
+        int rf, rr, vf, vr, af_, ar;
+        strand_tables(rec, ref_code, alt_set, rf, rr, vf, vr, af_, ar);
         double fs_vcf = 0.0;
-        if (vf == af_ && vr == ar) fs_vcf = rec->fs_cvg;   // same 2x2 table as the CVG row
-        else if ((vf | vr) != 0 && (rf | rr) != 0) fs_vcf = fs_from_table(cs.a.logfact, rf, rr, vf, vr);
+        if ((vf | vr) != 0 && (rf | rr) != 0) {
+            double p;
+            if (fisher_margin1(rf, rr, vf, vr, p)) fs_vcf = fs_from_p(p);
+            else { job = true; wide = fisher_support_wide(rf, rr, vf, vr); }   // bv_fisher_kernel completes the record
+        }
         rec->fs_vcf = fs_vcf;
+        entry = site | kFisherVcfRow;
     }
+    fisher_push(cs.a, job, wide, entry);
     __syncwarp();
     if (lane == 0) W.vcf_n = 0;
     __syncwarp();

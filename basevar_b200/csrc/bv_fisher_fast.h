@@ -52,9 +52,13 @@ BV_FN double ff_div(double num, double den) {
 #endif
 }
 
+template <class LF>
+BV_FN double ff_lpmf(const LF& lf, int i, int n1_, int n_1, int n) {   // log of the pmf: the argument of kfunc.c:209-212's exp
+    return ff_lbinom(lf, n1_, i) + ff_lbinom(lf, n - n1_, n_1 - i) - ff_lbinom(lf, n, n_1);
+}
 template <class LF, class EXP>
 BV_FN double ff_pmf(const LF& lf, const EXP& ex, int i, int n1_, int n_1, int n) {   // kfunc.c:209-212
-    return ex(ff_lbinom(lf, n1_, i) + ff_lbinom(lf, n - n1_, n_1 - i) - ff_lbinom(lf, n, n_1));
+    return ex(ff_lpmf(lf, i, n1_, n_1, n));
 }
 
 // The fast path is used for wide supports only, and not for astronomically small q: below ~1e-250 the reference's
@@ -64,17 +68,24 @@ constexpr int kFisherNarrowSupport = 24;   // supports up to this wide are walke
 BV_FN bool fisher_fast_applicable(int lo, int hi, double q) { return hi - lo > kFisherNarrowSupport && q > 1e-250; }
 
 // Two-sided p of the table (n11 n12 / n21 n22); q_in = pmf(n11) already computed by the caller (> 0), lo < hi.
+// side: kFisherBoth = the whole test; kFisherLeft / kFisherRight = that tail's sum alone, not clamped -- the two tails share
+// nothing, so two threads can take one each (bv_fisher_kernel); their sum, clamped to 1, is the value of the whole test bit for bit.
+constexpr int kFisherBoth = -1, kFisherLeft = 0, kFisherRight = 1;
 template <class LF, class EXP>
-BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_, int n_1, int n, int lo, int hi, double q) {
-    const double thr_lo = 0.99999999 * q, thr_hi = 1.00000001 * q;
+BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_, int n_1, int n, int lo, int hi, double q,
+                                   int side = kFisherBoth) {
+    const double thr_hi = 1.00000001 * q;
+    // The bisections compare LOGARITHMS of the pmf with log(0.99999999 q): the same decisions (exp is monotone, and its rounding is
+    // eight orders of magnitude below the slack) without an exp per probe -- the exps were a fifth of the test's instructions.
+    const double lthr_lo = ff_lpmf(lf, n11, n1_, n_1, n) + -1.00000000500000003e-8;   // log(0.99999999) = -1.000000005e-8
     int64_t m64 = ((int64_t)n1_ + 1) * ((int64_t)n_1 + 1) / ((int64_t)n + 2);
     int mode = (int)(m64 < lo ? lo : m64 > hi ? hi : m64);
     double two = 0.0;
-    {   // ---- left: first i in [lo, min(n11, mode)] with pmf(i) >= thr_lo (pmf rises there; the end point qualifies)
+    if (side != kFisherRight) {   // ---- left: first i in [lo, min(n11, mode)] with pmf(i) >= thr_lo (pmf rises there; the end point qualifies)
         int a = lo, b = n11 < mode ? n11 : mode;
         while (a < b) {
             const int mid = a + ((b - a) >> 1);
-            if (ff_pmf(lf, ex, mid, n1_, n_1, n) >= thr_lo) b = mid; else a = mid + 1;
+            if (ff_lpmf(lf, mid, n1_, n_1, n) >= lthr_lo) b = mid; else a = mid + 1;
         }
         const int iL = a;
         const double pL = iL == n11 ? q : ff_pmf(lf, ex, iL, n1_, n_1, n);
@@ -93,11 +104,11 @@ BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_
         if (pL < thr_hi) left += pL;
         two += left;
     }
-    {   // ---- right: last i in [max(n11, mode), hi] with pmf(i) >= thr_lo (pmf falls there; the start point qualifies)
+    if (side != kFisherLeft) {   // ---- right: last i in [max(n11, mode), hi] with pmf(i) >= thr_lo (pmf falls there; the start point qualifies)
         int a = n11 > mode ? n11 : mode, b = hi;
         while (a < b) {
             const int mid = a + ((b - a + 1) >> 1);
-            if (ff_pmf(lf, ex, mid, n1_, n_1, n) >= thr_lo) a = mid; else b = mid - 1;
+            if (ff_lpmf(lf, mid, n1_, n_1, n) >= lthr_lo) a = mid; else b = mid - 1;
         }
         const int iR = a;
         const double pR = iR == n11 ? q : ff_pmf(lf, ex, iR, n1_, n_1, n);
@@ -116,7 +127,7 @@ BV_FN double fisher_two_sided_fast(const LF& lf, const EXP& ex, int n11, int n1_
         if (pR < thr_hi) right += pR;
         two += right;
     }
-    return two > 1. ? 1. : two;
+    return (side == kFisherBoth && two > 1.) ? 1. : two;
 }
 
 }  // namespace bv

@@ -101,17 +101,30 @@ __device__ __noinline__ double hypergeo_tab(const double* __restrict__ lf, int n
     return nexp(lbinom_tab(lf, n1_, n11) + lbinom_tab(lf, n - n1_, n_1 - n11) - lbinom_tab(lf, n, n_1));
 }
 
-// kfunc.c:220-243 with only n11 moving
+// kfunc.c:220-243 with only n11 moving.  The step's factor a / n11 * b / n22 is formed as (a * b) * (1 / (n11 * n22)) -- integer
+// products below 2^53, exact, and a Newton reciprocal (ff_div) -- where the reference divides twice: a few ulp per step, far inside
+// the 1e-8 slack of the comparisons the walk feeds, at a third of the instructions (BV_HG_RCP=0: the divisions).
+#ifndef BV_HG_RCP
+#define BV_HG_RCP 1
+#endif
 __device__ __noinline__ double hg_move(const double* __restrict__ lf, HgState& st, int n11) {
     int n22 = n11 + st.n - st.n1_ - st.n_1;
     if ((n11 % 11) && n22) {
         if (n11 == st.n11 + 1) {
+#if BV_HG_RCP
+            st.p *= ff_div((double)(st.n1_ - st.n11) * (double)(st.n_1 - st.n11), (double)n11 * (double)n22);
+#else
             st.p *= (double)(st.n1_ - st.n11) / n11 * (st.n_1 - st.n11) / n22;
+#endif
             st.n11 = n11;
             return st.p;
         }
         if (n11 == st.n11 - 1) {
+#if BV_HG_RCP
+            st.p *= ff_div((double)st.n11 * (double)(st.n11 + st.n - st.n1_ - st.n_1), (double)(st.n1_ - n11) * (double)(st.n_1 - n11));
+#else
             st.p *= (double)st.n11 / (st.n1_ - n11) * (st.n11 + st.n - st.n1_ - st.n_1) / (st.n_1 - n11);
+#endif
             st.n11 = n11;
             return st.p;
         }
@@ -121,35 +134,44 @@ __device__ __noinline__ double hg_move(const double* __restrict__ lf, HgState& s
     return st.p;
 }
 
-__device__ __noinline__ double fisher_two_sided(const double* __restrict__ lf, int n11, int n12, int n21, int n22) {
+// side: see fisher_two_sided_fast -- kFisherBoth returns the test's p; kFisherLeft / kFisherRight return that tail's sum alone
+// (not clamped), or the whole answer with `whole` set when the table needs no sums (one possible outcome; q == 0).
+__device__ __noinline__ double fisher_two_sided(const double* __restrict__ lf, int n11, int n12, int n21, int n22, int side = kFisherBoth,
+                                                bool* whole = nullptr) {
     int n1_ = n11 + n12, n_1 = n11 + n21, n = n11 + n12 + n21 + n22;
     int hi = (n_1 < n1_) ? n_1 : n1_;
     int lo = n1_ + n_1 - n;
     if (lo < 0) lo = 0;
+    if (whole) *whole = true;
     if (lo == hi) return 1.;
     HgState st;
     st.n11 = n11; st.n1_ = n1_; st.n_1 = n_1; st.n = n;
     st.p = hypergeo_tab(lf, n11, n1_, n_1, n);
     double q = st.p;
     if (q == 0.0) return 0.0;
+    if (whole) *whole = false;
     // wide supports (deep or dense pileups): bisection + short tail sums instead of a walk over the whole support
-    if (fisher_fast_applicable(lo, hi, q)) return fisher_two_sided_fast(LogFactTab{lf}, ExpFn{}, n11, n1_, n_1, n, lo, hi, q);
-    double p, left, right;
+    if (fisher_fast_applicable(lo, hi, q)) return fisher_two_sided_fast(LogFactTab{lf}, ExpFn{}, n11, n1_, n_1, n, lo, hi, q, side);
+    double p, left = 0., right = 0.;
     int i, j;
-    p = hg_move(lf, st, lo);
-    for (left = 0., i = lo + 1; p < 0.99999999 * q && i <= hi; ++i) {
-        left += p;
-        p = hg_move(lf, st, i);
+    if (side != kFisherRight) {
+        p = hg_move(lf, st, lo);
+        for (i = lo + 1; p < 0.99999999 * q && i <= hi; ++i) {
+            left += p;
+            p = hg_move(lf, st, i);
+        }
+        if (p < 1.00000001 * q) left += p;
     }
-    if (p < 1.00000001 * q) left += p;
-    p = hg_move(lf, st, hi);
-    for (right = 0., j = hi - 1; p < 0.99999999 * q && j >= 0; --j) {
-        right += p;
-        p = hg_move(lf, st, j);
+    if (side != kFisherLeft) {
+        p = hg_move(lf, st, hi);
+        for (j = hi - 1; p < 0.99999999 * q && j >= 0; --j) {
+            right += p;
+            p = hg_move(lf, st, j);
+        }
+        if (p < 1.00000001 * q) right += p;
     }
-    if (p < 1.00000001 * q) right += p;
     double two = left + right;
-    if (two > 1.) two = 1.;
+    if (side == kFisherBoth && two > 1.) two = 1.;
     return two;
 }
 

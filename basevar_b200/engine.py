@@ -76,12 +76,14 @@ class BaseTypeEngine:
         self._check(self.lib.bv_last_kernel_times(self._ctx, ms), "bv_last_kernel_times")
         return dict(zip(self.KERNEL_NAMES, (float(x) for x in ms)))
 
-    EM_KERNEL_NAMES = ("bv_hist_kernel", "bv_em_task_kernel")
+    EM_KERNEL_NAMES = ("bv_hist_kernel", "bv_em_task_kernel", "bv_fisher_kernel")
 
     def last_em_kernel_times(self):
-        """Durations (ms) of the two kernels K4 consists of (row histograms, EM tasks + decisions) for the same tile."""
-        ms = (C.c_float * 2)()
+        """Durations (ms) of the two kernels K4 consists of (row histograms, EM tasks + decisions) and of the kernel that runs the
+        Fisher tests K2 and K4b listed, for the same tile."""
+        ms = (C.c_float * 3)()
         self._check(self.lib.bv_last_em_kernel_times(self._ctx, ms), "bv_last_em_kernel_times")
+        self._check(self.lib.bv_last_fisher_kernel_time(self._ctx, C.cast(C.byref(ms, 8), C.POINTER(C.c_float))), "bv_last_fisher_kernel_time")
         return dict(zip(self.EM_KERNEL_NAMES, (float(x) for x in ms)))
 
     # -- tiles from host memory --------------------------------------------------------------------

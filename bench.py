@@ -302,7 +302,7 @@ class Resident:
         self.eng.set_profiling(False)
         out = {n: v / steps for n, v in ks.items()}
         out.update({n: v / steps for n, v in es.items()})
-        out["bv_em_kernel"] = out.pop("bv_em_kernel")   # = bv_hist_kernel + bv_em_task_kernel
+        out["bv_em_kernel"] = out.pop("bv_em_kernel")   # = bv_hist_kernel + bv_em_task_kernel (bv_fisher_kernel follows them)
         return out
 
     def records(self):
@@ -321,7 +321,7 @@ class Resident:
         return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": load_traffic(self.name, self.N, self.S), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                 "kernel": "the step's kernels together (K1 bv_count_kernel, K2 bv_scalar_kernel, K3 bv_bound_kernel, K4a bv_hist_kernel, "
-                          "K4b bv_em_task_kernel; bv_em_kernel = K4a + K4b)",
+                          "K4b bv_em_task_kernel, bv_fisher_kernel; bv_em_kernel = K4a + K4b)",
                 "avg_launch_ms": avg_ms, "kernel_ms": kernel_ms,
                 # K1 alone moves 2 of the 3 planes (base + strand; the qual plane is read only where the result depends on it)
                 "k1_bytes": k1b, "k1_achieved": k1, "k1_frac": k1 / peak}

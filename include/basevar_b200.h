@@ -208,11 +208,13 @@ int         bv_set_params(bv_ctx* ctx, const bv_params* params); /* change min_a
 uint64_t    bv_launch_count(const bv_ctx* ctx);                /* kernels launched by this context so far */
 uint64_t    bv_h2d_bytes(const bv_ctx* ctx);                   /* bytes uploaded by bv_tile_submit so far (host tiles) */
 /* Instrumentation: with profiling on, every tile records CUDA events between its kernels (K1 count, K2 scalar,
- * K3 bound, K4 = K4a row histograms + K4b EM tasks and decisions); bv_last_kernel_times() waits for the most recent tile
- * and returns the durations of K1..K4 in ms, bv_last_em_kernel_times() those of K4a and K4b. */
+ * K3 bound, K4 = K4a row histograms + K4b EM tasks and decisions, then the Fisher tests K2 and K4b listed);
+ * bv_last_kernel_times() waits for the most recent tile and returns the durations of K1..K4 in ms,
+ * bv_last_em_kernel_times() those of K4a and K4b, bv_last_fisher_kernel_time() that of bv_fisher_kernel. */
 int         bv_set_profiling(bv_ctx* ctx, int on);
 int         bv_last_kernel_times(bv_ctx* ctx, float ms[4]);
 int         bv_last_em_kernel_times(bv_ctx* ctx, float ms[2]);
+int         bv_last_fisher_kernel_time(bv_ctx* ctx, float* ms);
 int         bv_last_call_kernel_times(bv_ctx* ctx, float ms[2]);   /* K5 rank sums, K6 population groups */
 
 /* ---- tile pipeline (replaces: BatchInfo -> BaseType ctor -> lrt() -> strand_bias per site) ------ */

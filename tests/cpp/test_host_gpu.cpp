@@ -85,7 +85,7 @@ int main(int argc, char** argv) {
     }
     Context ctx(0, maf, (uint32_t)N, S, 2);
     std::vector<bv_site_out> recs = ctx.run(pk.tile());
-    CHECK(ctx.launch_count() == 6);   // K1, K2, K3, K4a, K4b (two builds of it are launched, one of them works)
+    CHECK(ctx.launch_count() == 7);   // K1, K2, K3, K4a, K4b (two builds of it are launched, one of them works), Fisher tests
     int n_var = 0;
     bv_tile t = pk.tile();
     for (int s = 0; s < S; ++s) {
@@ -151,7 +151,7 @@ int main(int argc, char** argv) {
         CHECK(sp.n_sites() == (uint32_t)S && sp.n_cells() > 0 && sp.n_cells() < (size_t)S * N);
         const uint64_t l0 = ctx.launch_count();
         std::vector<bv_site_out> srecs = ctx.run(sp.tile());
-        CHECK(ctx.launch_count() - l0 == 7);   // K0 expand + K1..K3, K4a, K4b x 2
+        CHECK(ctx.launch_count() - l0 == 8);   // K0 expand + K1..K3, K4a, K4b x 2, Fisher tests
         CHECK(memcmp(srecs.data(), recs.data(), sizeof(bv_site_out) * S) == 0);
         printf("sparse transport: %zu cells for %d x %zu sample-sites, records identical\n", sp.n_cells(), S, N);
     }

@@ -115,7 +115,7 @@ def test_calls_pinned_planes_zero_copy_and_no_groups(engine):
     assert pinned_bytes < pageable_bytes / 2, (pinned_bytes, pageable_bytes)
     launches = engine.launch_count
     engine.call_host_calls(pb[:100], pq[:100], ps[:100], r[:100], pm[:100], pr[:100], N)
-    assert engine.launch_count - launches == 7   # K1..K3, K4a, K4b (two builds, one of them works) + K5
+    assert engine.launch_count - launches == 8   # K1..K3, K4a, K4b (two builds, one of them works), Fisher tests + K5
 
 
 def test_calls_device_resident_equals_host_path(engine):

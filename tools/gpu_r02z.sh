@@ -12,7 +12,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$O/smoke.log" 
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > "$O/bench_reference.json" 2> "$O/bench_reference.err"
 timeout 900 python bench.py > "$O/bench.json" 2> "$O/bench.err"; tail -2 "$O/bench.err"
 python tools/bench_show.py "$O/bench.json"
-for cfg in "C2 1000000 0" "C3 100000 0" "C5 200000 0" "C5 200000 1" "C4 9472 0"; do
+for cfg in "C2 1000000 0" "C3 100000 0" "C5 200000 0" "C5 1000000 0" "C5 200000 1" "C4 9472 0"; do
   set -- $cfg
   timeout 300 python tools/run_kernel.py --config $1 --sites $2 --abs-mode $3 --launches 5 2>&1 | tee -a "$O/run_kernel.log"
 done
@@ -21,7 +21,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
 python tools/ncu_launches.py "$O/launches.csv" > "$O/launches_by_kernel.txt" 2>&1; head -20 "$O/launches_by_kernel.txt"
 for cfg in "C2 1000000" "C5 200000" "C4 9472"; do
   set -- $cfg
-  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:bv_(count|scalar|bound|hist|em_task)_kernel" -s 6 -c 6 -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:bv_(count|scalar|bound|hist|em_task|fisher)_kernel" -s 7 -c 7 -f \
       -o "$O/prof_$1_step" python tools/run_kernel.py --config $1 --sites $2 --launches 2 > "$O/ncu_$1.log" 2>&1
   tail -1 "$O/ncu_$1.log"
 done
