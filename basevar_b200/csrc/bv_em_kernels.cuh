@@ -737,9 +737,9 @@ __global__ void __launch_bounds__(kTaskThreads) bv_em_iter_kernel(const __grid_c
 // The strand-bias test of a VCF row whose called ALT set is not "every non-reference base" is a Fisher test of its own (ref vs the
 // called alleles) -- on a deep pileup a walk of hundreds of steps, needed by one decided site in three.  Run inside the decision it
 // kept a few lanes of one or two warps busy while the CTA's other warps waited at the round's barrier (a fifth of this kernel's warp
-// time on deep multi-allelic pileups).  With fs_queue the decision only lists the test (site | kFisherVcfRow | kFisherWide); the CTA
-// hands its list on to bv_fisher_kernel (see fisher_push in bv_finish_kernels.cuh).
-__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHdr& H, uint32_t hdr_index, uint32_t* fs_queue_n, uint32_t* fs_queue) {
+// time on deep multi-allelic pileups).  The decision only names the test (fs_entry = site | kFisherVcfRow | kFisherWide, 0 = none);
+// the caller hands it on to bv_fisher_kernel's list (fisher_push in bv_finish_kernels.cuh).
+__device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHdr& H, uint32_t hdr_index, uint32_t& fs_entry) {
     const uint32_t site = H.site;
     bv_site_out* rec = a.out + site;
     const int ref_code = ref_code_of(a.ref_base[site]);
@@ -837,10 +837,8 @@ __device__ __noinline__ void decide_site(const SiteKernelArgs& a, const EmSiteHd
         if ((vf | vr) != 0 && (rf | rr) != 0) {
             double p;
             if (fisher_margin1(rf, rr, vf, vr, p)) fs_vcf = fs_from_p(p);
-            else if (fs_queue != nullptr)   // bv_fisher_kernel completes the record (also when the table is that of the CVG row: its
-                                            // FS is not there yet either)
-                fs_queue[atomicAdd(fs_queue_n, 1u)] = site | kFisherVcfRow | (fisher_support_wide(rf, rr, vf, vr) ? kFisherWide : 0u);
-            else fs_vcf = fs_from_table(a.logfact, rf, rr, vf, vr);
+            else   // bv_fisher_kernel completes the record (also when the table is that of the CVG row: its FS is not there yet either)
+                fs_entry = site | kFisherVcfRow | (fisher_support_wide(rf, rr, vf, vr) ? kFisherWide : 0u);
         }
     }
     // ---- record: ALT alleles in ACGT order of the active set (src/basetype.cpp:172-177) ----
@@ -972,16 +970,23 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
                 const uint32_t d_hdr = cs.dq[tid >> 5][dq_n + (uint32_t)lane];
                 __threadfence();
                 const EmSiteHdr Hd = a.em_hdr[d_hdr];
-                decide_site(a, Hd, d_hdr, nullptr, nullptr);
+                uint32_t e = 0;
+                decide_site(a, Hd, d_hdr, e);
                 __syncwarp();
+                fisher_push(a, e != 0u, (e & kFisherWide) != 0u, e & ~kFisherWide);
             }
         }
     }
-    if ((uint32_t)lane < dq_n) {
-        const uint32_t d_hdr = cs.dq[tid >> 5][lane];
-        __threadfence();
-        const EmSiteHdr Hd = a.em_hdr[d_hdr];
-        decide_site(a, Hd, d_hdr, nullptr, nullptr);
+    {
+        uint32_t e = 0;
+        if ((uint32_t)lane < dq_n) {
+            const uint32_t d_hdr = cs.dq[tid >> 5][lane];
+            __threadfence();
+            const EmSiteHdr Hd = a.em_hdr[d_hdr];
+            decide_site(a, Hd, d_hdr, e);
+        }
+        __syncwarp();
+        fisher_push(a, e != 0u, (e & kFisherWide) != 0u, e & ~kFisherWide);
     }
 #else
     const uint32_t tpc = (uint32_t)(kTaskThreads / lg.G);   // tasks per CTA and round
@@ -1041,7 +1046,9 @@ __global__ void __launch_bounds__(kTaskThreads, kMinCtas) bv_em_task_kernel(cons
         if ((uint32_t)tid < cs.n_decide) {
             __threadfence();
             const EmSiteHdr Hd = a.em_hdr[cs.decide_hdr[tid]];
-            decide_site(a, Hd, cs.decide_hdr[tid], &cs.n_fs, cs.fs_site);
+            uint32_t e = 0;
+            decide_site(a, Hd, cs.decide_hdr[tid], e);
+            if (e) cs.fs_site[atomicAdd(&cs.n_fs, 1u)] = e;
         }
     }
     __syncthreads();

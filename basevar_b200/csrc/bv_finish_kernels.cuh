@@ -54,10 +54,16 @@ __device__ __forceinline__ void fisher_push(const SiteKernelArgs& a, bool pred, 
         if (pred && wide) a.list_fisher[2u * a.n_sites - 1u - (pos + __popc(mw & below))] = entry;
     }
 }
-// is the support [max(0, n1_ + n_1 - n), min(n1_, n_1)] of the table (a b / c d) wider than the reference's walk is kept for?
+// Which end of the list: is the support [max(0, n1_ + n_1 - n), min(n1_, n_1)] of the table (a b / c d) wider than BV_FISHER_LIST_WIDE
+// outcomes?  24 = where the algorithm changes (fisher_fast_applicable): the reference's walk on one end, bisection + tails on the
+// other.  Splitting later (48, 96, 200: the cheap bisections with the walks, only the long tails apart) measured slower on deep pileups
+// (bv_fisher_kernel on C5: 0.256 / 0.279 / 0.315 / 0.342 ms per 10^6 sites), equal elsewhere (profiles/r02_fisher_queues.txt).
+#ifndef BV_FISHER_LIST_WIDE
+#define BV_FISHER_LIST_WIDE 24
+#endif
 __device__ __forceinline__ bool fisher_support_wide(int t11, int t12, int t21, int t22) {
     const int n1_ = t11 + t12, n_1 = t11 + t21, n = n1_ + t21 + t22;
-    return min(n1_, n_1) - max(0, n1_ + n_1 - n) > kFisherNarrowSupport;
+    return min(n1_, n_1) - max(0, n1_ + n_1 - n) > BV_FISHER_LIST_WIDE;
 }
 
 // The two strand tables of a site from its record: ref vs every non-reference base (CVG row, basetype_caller.cpp:1236-1245) and ref
