@@ -429,7 +429,8 @@ std::string BaseTypeRunner::usage() {
            "  --filename-has-samplename    Take the sample id from a file name like 'SampleID.xxxx.bam'.\n"
            "  --smart-rerun                Accepted and ignored.\n"
            "  --gpus=LIST                  Comma delimited CUDA devices to shard the regions over. [0]\n"
-           "  --tile-sites=INT             Positions per GPU tile. [8192]\n"
+           "  --tile-sites=INT             Positions per GPU tile. [8192; fewer for cohorts of more than ~40,000 samples:\n"
+           "                               2 GiB of device planes per tile]\n"
            "  --dense-upload               Upload the packed planes of a tile instead of its covered cells.\n"
            "  --workers-per-gpu=INT        Host workers per GPU, each with its own region shard (pileup, text). [thread / 2]\n"
            "  --timing                     Print the wall seconds per stage of the host pipeline (JSON, stderr).\n"
@@ -480,7 +481,7 @@ void BaseTypeRunner::set_arguments(int argc, char* argv[]) {
                     if (!tok.empty()) a.devices.push_back(std::stoi(tok));
                 break;
             }
-            case '6': ss >> a.tile_sites; break;
+            case '6': ss >> a.tile_sites; a.tile_sites_given = true; break;
             case '7': a.dense_upload = true; break;
             case '8': a.flip_log = optarg; break;
             case '9': a.timing = true; break;
@@ -664,6 +665,12 @@ void BaseTypeRunner::run() {
             for (int k = 0; k < w; ++k) devices.push_back(g);
     }
     const size_t N = args_.input_bf.size();
+    if (!args_.tile_sites_given) {
+        // A tile's device planes are 6 bytes per sample and position (base, qual, strand + the called-site planes), per slot and
+        // worker: 8,192 positions of 100,000 samples are 4.9 GB, of a million samples 49 GB.  Keep a tile at 2 GiB unless told otherwise.
+        const uint64_t fit = (2ull << 30) / (6ull * ((N + 15) / 16 * 16 + 16));
+        args_.tile_sites = (uint32_t)std::min<uint64_t>(args_.tile_sites, std::max<uint64_t>(fit, 64));
+    }
     // positions decoded per pass: bounded by the reference's own step and by the memory of the per-sample cell lists
     const uint64_t span_len = std::max<uint64_t>(args_.tile_sites, std::min<uint64_t>(PILEUP_STEP_REGION_LEN, (uint64_t)4e8 / std::max<size_t>(N, 1)));
     std::string flips;   // positions flagged NEAR_LRT / LRT_TIE, in coordinate order

@@ -96,6 +96,7 @@ struct BaseTypeARGS {   // src/basetype_utils.h:74-96
     // additions
     std::vector<int> devices;   // GPUs to shard the calling intervals over (empty: device 0)
     uint32_t tile_sites = 8192;
+    bool tile_sites_given = false;   // --tile-sites on the command line: taken as is; else lowered for very wide cohorts (run())
     int em_abs_mode = BV_EM_ABS_INT_TRUNC;
     bool dense_upload = false;   // upload the packed planes instead of the covered cells (bv_tile instead of bv_sparse_tile)
     std::string flip_log;        // file for the positions flagged NEAR_LRT / LRT_TIE (CHROM, POS, FLAGS); empty: count only
