@@ -18,8 +18,9 @@
 //                          lanes per task; the sums are formed in the same order either way.)
 //                          The thread that stores the LAST result of a site then decides it: replays the elimination
 //                          loop on the table of task results (first-minimum argmin in the reference's subset order,
-//                          threshold, flags), ALT / AF / QUAL (chi-square survival function) and the strand-bias
-//                          Fisher test of the VCF row -- scalar work that overlaps with the EMs of other warps.
+//                          threshold, flags), ALT / AF / QUAL (chi-square survival function) -- scalar work that overlaps
+//                          with the EMs of other warps.  The strand-bias Fisher test of the VCF row is only listed here;
+//                          bv_fisher_kernel (bv_finish_kernels.cuh) runs the listed tests of a tile together.
 //
 // At most 3 of the 11 tasks of a 4-allele site are never consulted (the elimination needs <= 8 EMs); evaluating them
 // anyway removes every dependency between EMs.  A flag an unconsulted task raises (BV_FLAG_EM_MAXITER) is not reported.

@@ -45,3 +45,12 @@ def test_c5_full_size_both_abs_modes(built_lib, oracle_lib, abs_mode):
     assert r["sites"] == 1_000_000 and r["n_samples"] == 2_000
     _assert_ok(r)
     assert r["variant_sites"] > 200_000
+
+
+def test_fisher_kernel_modes_leave_no_trace(built_lib, oracle_lib):
+    """bv_fisher_kernel gives a test a pair of lanes (one tail each) while that is one trip of its grid, else one thread: one tile
+    of 160,000 deep multi-allelic sites lists ~200,000 tests (one thread each), the same sites in tiles of 16,000 list ~20,000 per
+    tile (lane pairs) -- and the records are the same, bit for bit (left + right is the same sum either way)."""
+    r = full_configs.run_config("C5", max_sites=160_000, tile_sites=160_000, tile_sites_b=16_000, spot=1000)
+    assert r["sites"] == 160_000
+    _assert_ok(r)
