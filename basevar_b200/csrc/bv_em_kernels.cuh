@@ -318,7 +318,7 @@ __device__ __forceinline__ double log_ratio(double r) {
 // log(1 + r) is six terms of its series (the next one is below 3e-18).  Absolute error <= 1 ulp of the result, 2e-17 near
 // x = 1 (checked against 80-bit logl on 2e7 arguments, tools/log_tab_check.c) -- the accuracy of the libdevice logarithm it
 // replaces in the EM's sums, at a third of its instructions and WITHOUT A BRANCH: the four bins a thread works on side by side
-// stay one straight-line block whose dependency chains the compiler interleaves.  Zero, denormal, negative, inf and NaN
+// stay one straight-line block (no divergence regions between them) for the scheduler to overlap.  Zero, denormal, negative, inf and NaN
 // arguments raise `bad` (the value returned for them means nothing); the caller then forms its sum again with the library
 // function (em_sum_slow).
 __device__ __forceinline__ double log_tab(double x, const double2* tab, uint32_t& bad) {

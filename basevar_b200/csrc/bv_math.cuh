@@ -163,6 +163,10 @@ __device__ __noinline__ double fisher_two_sided(const double* __restrict__ lf, i
         if (p < 1.00000001 * q) left += p;
     }
     if (side != kFisherLeft) {
+        // The right walk starts from the observed table again, not from where the left walk stopped (the reference carries its
+        // state over, which matters only when the left walk ends next to hi: an incremental step from there instead of a direct
+        // evaluation, 1e-15 relative).  So the two tails share nothing and a lane pair forms the same value as one thread.
+        st.n11 = n11; st.p = q;
         p = hg_move(lf, st, hi);
         for (j = hi - 1; p < 0.99999999 * q && j >= 0; --j) {
             right += p;

@@ -282,7 +282,7 @@ StrandBiasInfo strand_bias(const char ref_base, const std::string alt_bases_stri
     else if (rec.n_alt && ((alt_set ^ vcf_set) & covered) == 0) s.fs = rec.fs_vcf;
     else if ((s.alt_fwd | s.alt_rev) == 0 || (s.ref_fwd | s.ref_rev) == 0) s.fs = 0.0;   // one possible table: p == 1
     else {
-        // neither of the two sets the record carries FS for: the 2x2 table goes to the device (bv_fisher_fs, the code of kernel K2)
+        // neither of the two sets the record carries FS for: the 2x2 table goes to the device (bv_fisher_fs, the code of bv_fisher_kernel)
         const uint32_t reads = (uint32_t)(s.ref_fwd + s.ref_rev + s.alt_fwd + s.alt_rev);
         if (!ctx) {
             if (!t_one.ctx || t_one.ctx->max_samples() + 1 < reads) {

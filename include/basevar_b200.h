@@ -339,7 +339,7 @@ int bv_synth_fill_host(const bv_synth_model* model, uint64_t site0, uint32_t n_s
 /* ---- strand-bias statistic of arbitrary 2x2 tables ------------------------------------------------ */
 /* strand_bias() (src/basetype.cpp:244-295) takes ANY set of ALT bases; the records carry FS for the two sets the caller
  * asks for (all non-REF bases: CVG row; the called ALT alleles: VCF row).  For any other set the 2x2 table follows from the
- * record's per-base strand counts and this call computes its FS on the device with the code of kernel K2 (two-sided Fisher
+ * record's per-base strand counts and this call computes its FS on the device with the code of kernel KF, bv_fisher_kernel (two-sided Fisher
  * exact test restated from htslib/kfunc.c:245-313, FS rule src/basetype.cpp:277-283).  tables: n x {ref_fwd, ref_rev,
  * alt_fwd, alt_rev} in host memory, every table's total <= bv_params::max_samples + 1; fs_out: n doubles (host).
  * Blocking; a table with an empty row gives 0 (one possible outcome, p == 1). */
