@@ -47,10 +47,12 @@ def test_c5_full_size_both_abs_modes(built_lib, oracle_lib, abs_mode):
     assert r["variant_sites"] > 200_000
 
 
-def test_fisher_kernel_modes_leave_no_trace(built_lib, oracle_lib):
-    """bv_fisher_kernel gives a test a pair of lanes (one tail each) while that is one trip of its grid, else one thread: one tile
-    of 160,000 deep multi-allelic sites lists ~200,000 tests (one thread each), the same sites in tiles of 16,000 list ~20,000 per
-    tile (lane pairs) -- and the records are the same, bit for bit (left + right is the same sum either way)."""
-    r = full_configs.run_config("C5", max_sites=160_000, tile_sites=160_000, tile_sites_b=16_000, spot=1000)
+def test_kernel_modes_leave_no_trace(built_lib, oracle_lib):
+    """Work that is shaped by the size of a tile, on the same 160,000 deep multi-allelic sites as one tile and in tiles of 8,000:
+    bv_fisher_kernel gives a test a pair of lanes (one tail each) while that is one trip of its grid, else one thread (~200,000
+    listed tests in the large tile, ~10,000 per small one); bv_em_task_kernel runs its high-occupancy build with a thread per EM
+    task on the large tile (~148,000 tasks) and the other build with four lanes per task on the small ones (~7,400).  The records
+    are the same, bit for bit: every sum is formed in the same order in either mode."""
+    r = full_configs.run_config("C5", max_sites=160_000, tile_sites=160_000, tile_sites_b=8_000, spot=1000)
     assert r["sites"] == 160_000
     _assert_ok(r)
